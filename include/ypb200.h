@@ -1,0 +1,128 @@
+/* ypb200 — C ABI of the B200-native (sm_100a) YOLO-seg / YOLOv10 per-frame detector engine.
+ *
+ * The reference (daisy9542/yolo-puncture) has no FFI of its own: its seam is the Python API of the
+ * third-party `ultralytics` package,
+ *     model = YOLO(weights)                                   yolo_seg/app.py:45, yolo_with_deva.py:226
+ *     results = model.predict(source=frame, conf=..., retina_masks=True, device=...)
+ *                                                             yolo_seg/app.py:49,91; yolo_with_deva.py:51;
+ *                                                             dev_tools/auto_speed_calc.py:62
+ * and everything below `predict` (letterboxed frame -> fused Conv/BN/SiLU network -> DFL decode ->
+ * NMS / top-k -> proto-mask decode) is what this library replaces.
+ * yolo_puncture_b200/model.py binds these entry points with ctypes and rebuilds the unchanged
+ * `YOLO.predict() -> list[Results]` surface on top (INTEGRATION.md shows the stub).
+ *
+ * Conventions: every entry point returns 0 on success or a negative ypb_status; nothing throws across
+ * the boundary; ypb_last_error() returns a thread-local message.  An engine is single-threaded and
+ * bound to one CUDA device (mirrors upstream's `with self._lock:` around inference); use one engine
+ * per GPU.  All device work is enqueued on the caller's stream; there is no hidden synchronisation
+ * and, after ypb_finalize_weights(), no hidden allocation: the activation workspace and every output
+ * buffer are allocated by the caller (PyTorch tensors).  There is no CPU fallback: on a device that is
+ * not sm_100 ypb_bind_workspace() fails.
+ */
+#ifndef YPB200_H_
+#define YPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ypb_engine ypb_engine;
+
+typedef enum {
+  YPB_OK = 0,
+  YPB_ERR_ARG = -1,        /* bad argument / unknown model spec / shape mismatch */
+  YPB_ERR_STATE = -2,      /* call order violated (weights missing, not planned, ...) */
+  YPB_ERR_CUDA = -3,       /* CUDA runtime / driver error, or not an sm_100 device */
+  YPB_ERR_DEVICE = -4      /* a kernel flagged an internal pipeline error */
+} ypb_status;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int ypb_version(void);
+const char* ypb_last_error(void);
+
+/* ---- engine lifetime: replaces YOLO(path) + AutoBackend(fuse=True) ----------------------- */
+/* model_spec: "yolov8{n,s,m,l,x}-seg" | "yolov10n"; nc = number of classes. */
+int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out);
+void ypb_engine_destroy(ypb_engine* e);
+
+/* Weight table in upstream state_dict naming, e.g. "model.0.conv.weight",
+ * "model.0.bn.running_var", "model.22.cv2.0.2.bias".  used==0: present in checkpoints but not on the
+ * inference path (v10 one-to-many branches). */
+int ypb_weight_count(const ypb_engine* e);
+int ypb_weight_info(const ypb_engine* e, int index, const char** name, int* ndim, int64_t shape[4], int* used);
+/* Copies `numel` fp32 values from host memory; the caller keeps ownership of `data`. */
+int ypb_load_weight(ypb_engine* e, const char* name, const float* data, int64_t numel);
+/* Folds BatchNorm (w' = w*g/sqrt(v+1e-3), b' = beta - mu*g/sqrt(v+1e-3)), converts to bf16, repacks to the
+ * implicit-GEMM layout [tap][Cout][Cin] and uploads to `device`.  Allocates the (engine-owned) weight arena. */
+int ypb_finalize_weights(ypb_engine* e, int device);
+
+/* ---- planning: static per-(B,H,W) layer plan, one workspace arena ------------------------ */
+/* H, W: letterboxed network input size (multiples of 32).  Returns the workspace size the caller must
+ * allocate (device memory, 1024-byte aligned) and pass to ypb_bind_workspace(). */
+int ypb_plan(ypb_engine* e, int batch, int height, int width, size_t* workspace_bytes);
+int ypb_bind_workspace(ypb_engine* e, void* workspace, size_t bytes);
+int ypb_num_anchors(const ypb_engine* e);      /* A for the current plan */
+int ypb_num_classes(const ypb_engine* e);
+int ypb_num_mask_coefs(const ypb_engine* e);   /* 32 for -seg models, 0 otherwise */
+int ypb_kernel_launches(const ypb_engine* e);  /* kernels one ypb_infer() enqueues */
+double ypb_conv_flops(const ypb_engine* e);    /* algorithmic conv FLOPs of one ypb_infer() (whole batch) */
+
+/* ---- inference: replaces BasePredictor.inference + postprocess ---------------------------- */
+typedef struct {
+  float conf;          /* predict(conf=...)      default 0.25 */
+  float iou;           /* predict(iou=...)       default 0.7  */
+  int max_det;         /* predict(max_det=...)   default 300 (<= 300) */
+  int agnostic_nms;    /* predict(agnostic_nms=) default 0 */
+  const uint32_t* class_mask; /* device ptr to ceil(nc/32) words, bit c set = class c allowed; NULL = all */
+} ypb_infer_params;
+
+/* frames : device, (B,H,W,3) uint8 BGR, already letterboxed (resize + 114 pad) to the planned H x W
+ * xform  : device, (B,5) fp32 [pad_w, pad_h, gain, W0, H0] per frame (ops.scale_boxes geometry)
+ * det    : device, (B,max_det,6) fp32 [x1,y1,x2,y2,conf,cls] in original-frame pixels, descending conf
+ * det_lb : device, (B,max_det,4) fp32 same boxes in letterboxed-input pixels
+ * keep   : device, (B,max_det) int32 anchor index of each detection
+ * coef   : device, (B,max_det,nm) fp32 mask coefficients (ignored when nm == 0; may be NULL)
+ * count  : device, (B) int32 detections per frame */
+int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform,
+              const ypb_infer_params* params, float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count);
+
+/* Fused proto-mask decode for the detections of the last ypb_infer() on this engine (reads count/det/coef
+ * on the device; no host sync).  Masks are packed in detection order: frame 0's detections first.
+ * retina=1: ops.process_mask_native, masks (n,H0,W0) for frames that all have original size H0 x W0;
+ * retina=0: ops.process_mask, masks (n,H,W) at the letterboxed input size (out_h/out_w ignored).
+ * masks  : device, (capacity, out_h, out_w) uint8 {0,1}
+ * status : device, int32[2] = {total detections in batch, 1 if total > capacity (excess not written)} */
+int ypb_masks(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w, const float* det,
+              const float* det_lb, const float* coef, const int32_t* count, uint8_t* masks, int capacity,
+              int32_t* status);
+
+/* Device-side error word (0 = ok); nonzero means a bounded pipeline wait inside a kernel gave up. */
+int ypb_device_error(ypb_engine* e, uint32_t* word);
+
+/* ---- introspection for tests / profiling --------------------------------------------------- */
+/* Named activation views of the bound workspace, e.g. "model.4", "head", "proto".
+ * dtype: 0 = bf16, 1 = fp32.  Layout is (B, H, W, Ctot) with the view on channels [c_off, c_off+C). */
+int ypb_view_count(const ypb_engine* e);
+int ypb_view_info(const ypb_engine* e, int index, const char** name, size_t* offset, int* H, int* W, int* Ctot,
+                  int* c_off, int* C, int* dtype);
+/* 0: tcgen05 tensor-core convs (default, the product path); 1: CUDA-core debugging twin (tests only). */
+int ypb_set_conv_impl(ypb_engine* e, int impl);
+
+/* Stand-alone kernel entry points used by the parity tests (device pointers, caller's stream). */
+int ypb_conv2d_bf16(void* cuda_stream, const void* in_nhwc_bf16, int B, int H, int W, int in_ctot, int in_c_off,
+                    int cin, const void* w_gemm_bf16 /*[k*k][cout][cin]*/, const float* bias, int cout, int k,
+                    int stride, int act, const void* res_nhwc_bf16 /*nullable, same layout as out*/, void* out,
+                    int out_ctot, int out_c_off, int out_fp32, int impl);
+int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float* scores /*(B,N)*/,
+            const int32_t* cls /*(B,N)*/, const int32_t* n_valid /*(B)*/, int B, int N, float iou, int max_det,
+            int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,
+            int32_t* count /*(B)*/);
+size_t ypb_nms_scratch_bytes(int B, int N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YPB200_H_ */

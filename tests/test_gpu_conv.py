@@ -1,0 +1,72 @@
+"""Parity of the tcgen05 implicit-GEMM conv kernel (through the C ABI) against a torch fp32 reference.
+
+Tolerance: outputs are stored in bf16 (8-bit mantissa), accumulation is fp32 on both sides, so
+|got - ref| <= 2^-7 |ref| + 2e-2 covers one bf16 rounding plus summation-order noise.
+"""
+import pytest
+import torch
+
+from gpu_util import conv_reference, describe_mismatch
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 2.0 ** -7, 2e-2
+
+# (B, H, W, in_ctot, in_c_off, cin, cout, k, stride, act, residual, out_ctot, out_c_off, out_fp32)
+CASES = [
+    (1, 16, 16, 64, 0, 64, 64, 1, 1, 1, False, 64, 0, False),
+    (2, 20, 20, 128, 0, 128, 128, 1, 1, 1, False, 128, 0, False),
+    (1, 16, 24, 48, 0, 48, 80, 1, 1, 0, False, 80, 0, True),
+    (1, 8, 8, 32, 16, 16, 16, 1, 1, 1, False, 48, 32, False),
+    (1, 16, 16, 64, 0, 64, 64, 3, 1, 1, False, 64, 0, False),
+    (2, 20, 20, 96, 32, 64, 32, 3, 1, 1, True, 96, 64, False),
+    (1, 32, 32, 32, 0, 32, 64, 3, 2, 1, False, 64, 0, False),
+    (2, 40, 40, 192, 64, 128, 128, 3, 2, 1, False, 160, 16, False),
+    (1, 20, 20, 256, 0, 256, 512, 3, 1, 1, False, 512, 0, False),
+    (1, 23, 40, 80, 0, 80, 176, 3, 1, 1, False, 176, 0, False),
+    (4, 80, 80, 128, 0, 128, 128, 3, 1, 1, True, 128, 0, False),
+    (3, 46, 80, 160, 0, 160, 320, 3, 2, 1, False, 320, 0, False),
+    (2, 40, 40, 384, 0, 384, 128, 1, 1, 1, False, 128, 0, False),
+]
+
+
+def run_case(case, impl=0, seed=0):
+    from yolo_puncture_b200.engine import conv2d_bf16, gemm_weight
+    B, H, W, ictot, icoff, cin, cout, k, s, act, use_res, octot, ocoff, ofp32 = case
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    x = torch.randn((B, H, W, ictot), device=dev, generator=g).to(torch.bfloat16)
+    w = torch.randn((cout, cin, k, k), device=dev, generator=g) * (1.0 / (cin * k * k) ** 0.5)
+    bias = torch.randn((cout,), device=dev, generator=g) * 0.5
+    oH, oW = H // s, W // s
+    odt = torch.float32 if ofp32 else torch.bfloat16
+    out = torch.full((B, oH, oW, octot), 7.0, device=dev, dtype=odt)
+    res = None
+    if use_res:
+        out = torch.randn((B, oH, oW, octot), device=dev, generator=g).to(odt)
+        res = out.clone()
+    conv2d_bf16(x, gemm_weight(w), bias, k, s, act, cin=cin, in_c_off=icoff, res=res, out=out, out_c_off=ocoff,
+                out_fp32=ofp32, impl=impl)
+    torch.cuda.synchronize()
+    ref = conv_reference(x[..., icoff:icoff + cin], w, bias, k, s, act,
+                         res=None if res is None else res[..., ocoff:ocoff + cout])
+    got = out[..., ocoff:ocoff + cout].float()
+    untouched = torch.cat([out[..., :ocoff], out[..., ocoff + cout:]], -1)
+    untouched_ref = torch.cat([res[..., :ocoff], res[..., ocoff + cout:]], -1) if use_res else torch.full_like(untouched, 7.0)
+    return got, ref, bool((untouched == untouched_ref).all())
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_conv_tc_matches_reference(case):
+    got, ref, clean = run_case(case, impl=0)
+    ok = bool(((got - ref).abs() <= ATOL + RTOL * ref.abs()).all())
+    assert ok, describe_mismatch(got, ref, RTOL, ATOL)
+    assert clean, "kernel wrote outside its channel slice"
+
+
+@pytest.mark.parametrize("case", CASES[:8], ids=[str(i) for i in range(8)])
+def test_conv_simt_twin_matches_reference(case):
+    got, ref, clean = run_case(case, impl=1)
+    ok = bool(((got - ref).abs() <= ATOL + RTOL * ref.abs()).all())
+    assert ok, describe_mismatch(got, ref, RTOL, ATOL)
+    assert clean

@@ -1,0 +1,209 @@
+// Host-side planning of one fused conv launch: tile shape, TMA tensor maps, kernel parameters.
+// (Single translation unit build: this file is included once, by ypb200.cu.)
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+
+#include "conv_tc.cuh"
+
+namespace ypb {
+
+// Everything needed to describe one conv on raw device pointers (engine buffers or test tensors).
+struct ConvDesc {
+  // input: NHWC bf16 buffer (B, Hin, Win, in_ctot), channels [in_c_off, in_c_off + cin)
+  const void* in = nullptr;
+  int B = 0, Hin = 0, Win = 0, in_ctot = 0, in_c_off = 0, cin = 0;
+  // weights: bf16 [k*k][cout][cin] (ConvTranspose 2x2: [1][4*cq][cin], cout = 4*cq), bias fp32 [cout]
+  const void* wg = nullptr;
+  const float* bias = nullptr;
+  int cout = 0, k = 1, stride = 1, act = 1;
+  // output
+  int out_mode = OUT_BF16;
+  void* out = nullptr;
+  long long out_img_stride = 0;  // elements between images
+  int out_pix_stride = 0;        // elements between pixels
+  int out_c_off = 0;
+  // optional residual (bf16, indexed like a bf16 NHWC output)
+  const void* res = nullptr;
+  long long res_img_stride = 0;
+  int res_pix_stride = 0, res_c_off = 0;
+};
+
+struct ConvLaunch {
+  ConvParams p;
+  ConvSimtGeom sg;
+  CUtensorMap tmA, tmB;
+  dim3 grid;
+  int smem = 0;
+  double flops = 0;
+  int oH = 0, oW = 0;
+};
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+static bool encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                            const cuuint64_t* strides_bytes /*rank-1*/, const cuuint32_t* box, std::string* err) {
+  PFN_tmapEncodeTiled enc = tmap_encoder();
+  if (!enc) {
+    *err = "cuTensorMapEncodeTiled unavailable (no CUDA driver)";
+    return false;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rank %d dims %llu,%llu,%llu box %u,%u,%u", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0), box[0],
+             box[1], rank > 2 ? box[2] : 0);
+    *err = buf;
+    return false;
+  }
+  return true;
+}
+
+// Pick the CTA rectangle (TH x TW <= 128 output pixels) that covers an H x W map with the fewest tiles.
+static void pick_tile(int H, int W, int* TH, int* TW) {
+  long best_tiles = -1;
+  int bh = 1, bw = 128, best_shape = 1 << 30;
+  for (int tw = 4; tw <= 128; ++tw) {
+    int th = 128 / tw;
+    if (th > H) th = H;
+    if (th < 1) continue;
+    int twc = tw > W ? W : tw;
+    const long tiles = (long)((H + th - 1) / th) * ((W + twc - 1) / twc);
+    const int shape = th > twc ? th - twc : twc - th;
+    if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && shape < best_shape)) {
+      best_tiles = tiles; bh = th; bw = twc; best_shape = shape;
+    }
+  }
+  *TH = bh; *TW = bw;
+}
+
+// Geometry only (no pointers, no driver calls): usable on a box without a GPU.
+static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* err) {
+  ConvParams& p = L->p;
+  memset(&p, 0, sizeof p);
+  if (d.cin % 16 || d.cout % 16 || d.in_ctot % 8 || d.in_c_off % 8) { *err = "conv channels must be multiples of 16"; return false; }
+  if (!((d.k == 1 && d.stride == 1) || (d.k == 3 && (d.stride == 1 || d.stride == 2)))) { *err = "unsupported conv k/stride"; return false; }
+  if (d.stride == 2 && ((d.Hin | d.Win) & 1)) { *err = "stride-2 conv needs even input dims"; return false; }
+  const int oH = d.Hin / d.stride, oW = d.Win / d.stride;
+  L->oH = oH; L->oW = oW;
+  p.Cin = d.cin; p.Cout = d.cout; p.ntaps = d.k * d.k;
+  p.img_HW = oH * oW; p.img_W = oW;
+  if (d.k == 1) {  // flat: 128 consecutive pixels of the flattened batch
+    p.tB = 1; p.tH = 1; p.tW = d.B * oH * oW;
+    p.TH = 1; p.TW = 128;
+    p.tiles_h = 1; p.tiles_w = (p.tW + 127) / 128;
+    p.a_base[0] = d.in_c_off; p.a_cw[1] = 1;
+    L->grid.x = p.tiles_w;
+  } else {
+    p.tB = d.B; p.tH = oH; p.tW = oW;
+    pick_tile(oH, oW, &p.TH, &p.TW);
+    p.tiles_h = (oH + p.TH - 1) / p.TH; p.tiles_w = (oW + p.TW - 1) / p.TW;
+    p.a_base[0] = d.in_c_off;
+    if (d.stride == 1) {  // view (C, W, H, B, 1)
+      p.a_cw[1] = 1; p.a_ch[2] = 1; p.a_cb[3] = 1;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) { int* t = p.tap[kh * 3 + kw]; t[1] = kw - 1; t[2] = kh - 1; }
+    } else {              // view (2C, W/2, 2, H/2, B): input row 2*oh+kh-1 = 2*(oh+dh)+ph
+      p.a_cw[1] = 1; p.a_ch[3] = 1; p.a_cb[4] = 1;
+      const int dd[3] = {-1, 0, 0}, par[3] = {1, 0, 1};
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+          int* t = p.tap[kh * 3 + kw];
+          t[0] = par[kw] * d.in_ctot; t[1] = dd[kw]; t[2] = par[kh]; t[3] = dd[kh];
+        }
+    }
+    L->grid.x = d.B * p.tiles_h * p.tiles_w;
+  }
+  int splits = 1;
+  while (d.cout / splits > 256 || d.cout % (16 * splits)) {
+    ++splits;
+    if (splits > d.cout / 16) { *err = "cannot split Cout"; return false; }
+  }
+  p.n_tile = d.cout / splits;
+  L->grid.y = splits; L->grid.z = 1;
+  const int k_iters = p.ntaps * ((d.cin + 63) / 64);
+  int st = (110 * 1024) / conv_stage_bytes(p.n_tile);
+  if (st < 2) st = 2;
+  if (st > 6) st = 6;
+  if (st > k_iters) st = k_iters;
+  p.stages = st;
+  L->smem = conv_smem_bytes(p.n_tile, st);
+  p.out_mode = d.out_mode; p.act = d.act;
+  p.out_img_stride = d.out_img_stride; p.out_pix_stride = d.out_pix_stride; p.out_c_off = d.out_c_off;
+  p.res_img_stride = d.res_img_stride; p.res_pix_stride = d.res_pix_stride; p.res_c_off = d.res_c_off;
+  L->flops = 2.0 * d.B * oH * oW * (double)d.cout * d.cin * d.k * d.k;
+  ConvSimtGeom& g = L->sg;
+  memset(&g, 0, sizeof g);
+  g.in_H = d.Hin; g.in_W = d.Win; g.in_ctot = d.in_ctot; g.in_c_off = d.in_c_off;
+  g.k = d.k; g.stride = d.stride; g.pad = d.k / 2; g.oH = oH; g.oW = oW; g.nB = d.B;
+  return true;
+}
+
+// Fills pointers and encodes the TMA descriptors (needs the CUDA driver).
+static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
+  ConvParams& p = L->p;
+  p.out = d.out; p.bias = d.bias; p.res = reinterpret_cast<const __nv_bfloat16*>(d.res);
+  L->sg.in = reinterpret_cast<const __nv_bfloat16*>(d.in);
+  L->sg.wg = reinterpret_cast<const __nv_bfloat16*>(d.wg);
+  const cuuint64_t C = (cuuint64_t)d.in_ctot;
+  cuuint64_t dims[5], str[4];
+  cuuint32_t box[5];
+  if (d.k == 1) {
+    dims[0] = C; dims[1] = (cuuint64_t)d.B * d.Hin * d.Win; dims[2] = dims[3] = dims[4] = 1;
+    str[0] = C * 2; str[1] = str[2] = str[3] = dims[1] * C * 2;
+    box[0] = 64; box[1] = 128; box[2] = box[3] = box[4] = 1;
+  } else if (d.stride == 1) {
+    dims[0] = C; dims[1] = d.Win; dims[2] = d.Hin; dims[3] = d.B; dims[4] = 1;
+    str[0] = C * 2; str[1] = str[0] * d.Win; str[2] = str[1] * d.Hin; str[3] = str[2] * d.B;
+    box[0] = 64; box[1] = p.TW; box[2] = p.TH; box[3] = 1; box[4] = 1;
+  } else {
+    dims[0] = 2 * C; dims[1] = d.Win / 2; dims[2] = 2; dims[3] = d.Hin / 2; dims[4] = d.B;
+    str[0] = 2 * C * 2; str[1] = (cuuint64_t)d.Win * C * 2; str[2] = 2 * str[1]; str[3] = (cuuint64_t)d.Hin * d.Win * C * 2;
+    box[0] = 64; box[1] = p.TW; box[2] = 1; box[3] = p.TH; box[4] = 1;
+  }
+  if (!encode_bf16_map(&L->tmA, d.in, 5, dims, str, box, err)) return false;
+  cuuint64_t wd[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.cout, (cuuint64_t)(d.k * d.k)};
+  cuuint64_t ws[2] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.cin * 2 * d.cout};
+  cuuint32_t wb[3] = {64, (cuuint32_t)p.n_tile, 1};
+  if (!encode_bf16_map(&L->tmB, d.wg, 3, wd, ws, wb, err)) return false;
+  return true;
+}
+
+static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int impl) {
+  if (impl == 1) {
+    const long long total = (long long)L.sg.nB * L.sg.oH * L.sg.oW * (L.p.Cout / 16);
+    conv_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(L.sg, L.p);
+    return cudaGetLastError();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_tc_kernel<<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+  return cudaGetLastError();
+}
+
+}  // namespace ypb

@@ -1,0 +1,275 @@
+// Fused Conv2d(+folded BN bias)(+SiLU)(+residual) as an implicit GEMM on the 5th-gen tensor cores.
+//
+// Replaces the cuDNN calls behind UPSTREAM ultralytics `Conv.forward_fuse` / `nn.ConvTranspose2d`
+// (SURVEY.md §2.2, §8 a3-a5), i.e. everything `AutoBackend.forward` runs per frame for the
+// `model.predict(...)` calls at reference yolo_seg/app.py:91 and yolo_seg/yolo_with_deva.py:51.
+//
+//   out[m, n] = act( sum_{tap, c} A[m @ tap, c] * Wg[tap][n][c] + bias[n] ) (+ res[m, n])
+//
+//   m  = one output pixel of an NHWC bf16 activation; a CTA owns a TH x TW rectangle (<=128 pixels)
+//        of one image (3x3 convs) or 128 consecutive pixels of the flattened batch (1x1 convs);
+//   A  = input activation, fetched per (tap, 64-channel chunk) by ONE 5-D TMA box load
+//        {64 ch, TW, (1), TH, (1)} whose out-of-bounds rows are zero-filled by the TMA unit, which
+//        is exactly the conv's zero padding; stride-2 convs address the input through the view
+//        (2C, W/2, 2, H/2, B) so that a tap is again a dense box;
+//   Wg = [tap][Cout][Cin] bf16 (K-major), one 3-D TMA box {64, n_tile, 1} per (tap, chunk);
+//   D  = fp32 accumulator in TMEM (128 lanes x n_tile columns), tcgen05.mma kind::f16, M=128;
+//   epilogue = tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16/fp32 store into a channel slice
+//        of the destination buffer (so Concat / C2f chunk never materialise), or pixel-shuffle
+//        store for ConvTranspose2d(k=2,s=2).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..+31); warp 2 also owns the TMEM allocation.
+#pragma once
+#include "common.cuh"
+
+namespace ypb {
+
+enum ConvOutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_SHUFFLE2_BF16 = 2 };
+
+struct ConvParams {
+  // M tiling space (rect mode: B,H,W of the OUTPUT map; flat mode: 1,1,B*H*W)
+  int tB, tH, tW;
+  int TH, TW;            // CTA tile rectangle, TH*TW <= 128
+  int tiles_h, tiles_w;  // tiles per image
+  // GEMM
+  int Cin;               // reduction channels per tap (multiple of 16)
+  int Cout;              // N (multiple of 16)
+  int n_tile;            // N per CTA (multiple of 16, <= 256); gridDim.y = Cout / n_tile
+  int ntaps;             // 1 or 9
+  int stages;
+  // A-operand TMA coordinates: c[d] = a_base[d] + b*a_cb[d] + h0*a_ch[d] + w0*a_cw[d] + tap[t][d]; c[0] += 64*chunk
+  int a_base[5], a_cb[5], a_ch[5], a_cw[5];
+  int tap[9][5];
+  // epilogue
+  int out_mode, act;
+  int img_HW, img_W;     // real output pixels per image / width (q -> image, row, col)
+  void* out;
+  long long out_img_stride;
+  int out_pix_stride, out_c_off;
+  const float* bias;     // [Cout] fp32
+  const __nv_bfloat16* res;
+  long long res_img_stride;
+  int res_pix_stride, res_c_off;
+};
+
+// Store 16 consecutive output channels [n, n+16) of output pixel q. v = raw accumulators.
+__device__ __forceinline__ void conv_epilogue_store16(const ConvParams& p, int q, int n, const float (&acc)[16]) {
+  float y[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float t = acc[j] + __ldg(p.bias + n + j);
+    y[j] = p.act ? silu_f(t) : t;
+  }
+  const int b = q / p.img_HW;
+  const int rem = q - b * p.img_HW;
+  if (p.out_mode == OUT_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + b * p.out_img_stride + (long long)rem * p.out_pix_stride + p.out_c_off + n;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+    return;
+  }
+  long long off;
+  if (p.out_mode == OUT_SHUFFLE2_BF16) {
+    const int cq = p.Cout >> 2;
+    const int g = n / cq, c = n - g * cq;
+    const int h = rem / p.img_W, w = rem - h * p.img_W;
+    off = b * p.out_img_stride + ((long long)(2 * h + (g >> 1)) * (2 * p.img_W) + 2 * w + (g & 1)) * p.out_pix_stride +
+          p.out_c_off + c;
+  } else {
+    off = b * p.out_img_stride + (long long)rem * p.out_pix_stride + p.out_c_off + n;
+  }
+  if (p.res != nullptr) {
+    // y = bf16(act(...)) first, then bf16(y + res): the same two roundings as storing the conv
+    // output and adding the shortcut afterwards (Bottleneck: x + cv2(cv1(x))).
+    const __nv_bfloat16* r = p.res + b * p.res_img_stride + (long long)rem * p.res_pix_stride + p.res_c_off + n;
+    uint4 r0 = *reinterpret_cast<const uint4*>(r), r1 = *reinterpret_cast<const uint4*>(r + 8);
+    const __nv_bfloat16* rb0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+    const __nv_bfloat16* rb1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y[j] = bf16_round(y[j]) + __bfloat162float(rb0[j]);
+      y[j + 8] = bf16_round(y[j + 8]) + __bfloat162float(rb1[j]);
+    }
+  }
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+  uint4 s0 = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  uint4 s1 = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]),
+                        pack_bf16x2(y[14], y[15]));
+  *reinterpret_cast<uint4*>(o) = s0;
+  *reinterpret_cast<uint4*>(o + 8) = s1;
+}
+
+constexpr int kConvThreads = 192;
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+__host__ __device__ inline int conv_stage_bytes(int n_tile) { return kATileBytes + n_tile * 128; }
+__host__ __device__ inline int conv_smem_bytes(int n_tile, int stages) {
+  return 1024 /*align slack*/ + stages * conv_stage_bytes(n_tile) + 256 /*barriers*/;
+}
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = conv_stage_bytes(p.n_tile);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* accum_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile -> (b, h0, w0)
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int b = blockIdx.x / tiles_per_img;
+  const int t_in = blockIdx.x - b * tiles_per_img;
+  const int th = t_in / p.tiles_w;
+  const int h0 = th * p.TH, w0 = (t_in - th * p.tiles_w) * p.TW;
+  const int n0 = blockIdx.y * p.n_tile;
+
+  const int kchunks = (p.Cin + 63) >> 6;
+  const int k_iters = p.ntaps * kchunks;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.n_tile) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int cbase[5];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) cbase[d] = p.a_base[d] + b * p.a_cb[d] + h0 * p.a_ch[d] + w0 * p.a_cw[d];
+      const uint32_t tx_bytes = (uint32_t)(p.TH * p.TW * 128 + p.n_tile * 128);
+      int it = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        for (int c = 0; c < kchunks; ++c, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1, 1u);
+          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sb = sa + kATileBytes;
+          mbar_expect_tx(full_bar + s, tx_bytes);
+          tma_load_5d(sa, &tmA, full_bar + s, cbase[0] + p.tap[t][0] + c * 64, cbase[1] + p.tap[t][1],
+                      cbase[2] + p.tap[t][2], cbase[3] + p.tap[t][3], cbase[4] + p.tap[t][4]);
+          tma_load_3d(sb, &tmB, full_bar + s, c * 64, n0, t);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+      int it = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        for (int c = 0; c < kchunks; ++c, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full_bar + s, ph, 2u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + kATileBytes;
+          int ksteps = (p.Cin - c * 64) >> 4;
+          if (ksteps > 4) ksteps = 4;
+          for (int j = 0; j < ksteps; ++j) {
+            umma_bf16(tmem_base, umma_desc_sw128(sa + j * 32), umma_desc_sw128(sb + j * 32), idesc,
+                      (it > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);  // frees the smem slot when these MMAs retire
+        }
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    const int r = lg * 32 + lane;
+    const int rh = r / p.TW, rw = r - rh * p.TW;
+    const int h = h0 + rh, w = w0 + rw;
+    const bool valid = (r < p.TH * p.TW) && (h < p.tH) && (w < p.tW);
+    const int q = (b * p.tH + h) * p.tW + w;
+    mbar_wait(accum_bar, 0, 4u);
+    tc_fence_after();
+    for (int j = 0; j < p.n_tile; j += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)j, v);
+      tmem_ld_wait();
+      if (valid) {
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
+        conv_epilogue_store16(p, q, n0 + j, acc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bring-up / debugging twin: the same conv on CUDA cores, one thread per (pixel, 16 channels).
+// Used by tests to cross-check the tensor-core kernel layer by layer on the device; the engine
+// only runs it when YPB_CONV_IMPL=simt is set explicitly (never as a silent fallback).
+// ------------------------------------------------------------------------------------------------
+struct ConvSimtGeom {
+  const __nv_bfloat16* in;
+  int in_H, in_W, in_ctot, in_c_off;  // NHWC input buffer
+  int k, stride, pad;
+  const __nv_bfloat16* wg;            // [tap][Cout][Cin]
+  int oH, oW, nB;                     // output map
+};
+
+__global__ void conv_simt_kernel(const ConvSimtGeom g, const ConvParams p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ngrp = p.Cout / 16;
+  const long long total = (long long)g.nB * g.oH * g.oW * ngrp;
+  if (idx >= total) return;
+  const int ng = (int)(idx % ngrp);
+  const int q = (int)(idx / ngrp);
+  const int b = q / (g.oH * g.oW);
+  const int rem = q - b * g.oH * g.oW;
+  const int oh = rem / g.oW, ow = rem - oh * g.oW;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int kh = 0; kh < g.k; ++kh) {
+    const int ih = oh * g.stride - g.pad + kh;
+    if (ih < 0 || ih >= g.in_H) continue;
+    for (int kw = 0; kw < g.k; ++kw) {
+      const int iw = ow * g.stride - g.pad + kw;
+      if (iw < 0 || iw >= g.in_W) continue;
+      const __nv_bfloat16* a = g.in + (((long long)b * g.in_H + ih) * g.in_W + iw) * g.in_ctot + g.in_c_off;
+      const __nv_bfloat16* wt = g.wg + ((long long)(kh * g.k + kw) * p.Cout + ng * 16) * p.Cin;
+      for (int c = 0; c < p.Cin; ++c) {
+        const float av = __bfloat162float(a[c]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(av, __bfloat162float(wt[(long long)j * p.Cin + c]), acc[j]);
+      }
+    }
+  }
+  conv_epilogue_store16(p, q, ng * 16, acc);
+}
+
+}  // namespace ypb

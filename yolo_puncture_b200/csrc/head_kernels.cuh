@@ -1,0 +1,239 @@
+// Detection-head selection kernels (HBM / latency bound, warp-shuffle + shared memory):
+//   decode_filter_kernel : DFL softmax-expectation box decode + class max + conf filter + candidate push
+//   nms_kernel           : batched (one CTA per image) sort + greedy class-aware NMS + scale_boxes + coef gather
+// UPSTREAM sites replaced: head.py::Detect._inference (DFL, dist2bbox, sigmoid), utils/ops.py::
+// non_max_suppression (+ torchvision.ops.nms), ops.scale_boxes / clip_boxes  (SURVEY.md §8 a6, a7, a9);
+// all of it runs inside `model.predict(...)` at reference yolo_seg/app.py:91 and yolo_with_deva.py:51.
+//
+// Bit-exactness contract (tests/test_gpu_select.py): fed the oracle's decoded boxes/scores, the kept
+// anchor indices and class ids are identical to torchvision's.  Hence: IEEE *_rn ops in the oracle's
+// order (no FMA contraction), strict `>` on IoU, inter/(a+b-inter) with no +1, fp32 class offset
+// box + cls*7680 applied before IoU, ordering by (score desc, anchor index asc).
+#pragma once
+#include "common.cuh"
+
+namespace ypb {
+
+struct HeadGeom {
+  int A;              // anchors per image
+  int no;             // floats per anchor row in the head buffer: 64 + nc + nm
+  int nc, nm;
+  int cand_stride;    // slots per image in the candidate key list (next_pow2(A): room for sort padding)
+  int lvl_start[4];   // first anchor of each level, [3] = A
+  int lvl_w[3];       // map width per level
+  float lvl_stride[3];
+};
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// One warp per anchor.  head: (B, A, no) fp32 rows [64 box logits | nc class logits | nm coefs].
+// Candidates (max class score > conf) get their decoded xyxy box and class written at the dense
+// slot [b][anchor] and a 64-bit sort key pushed on the image's candidate list.
+// key = score_bits << 32 | ~anchor   (descending key order == score desc, anchor asc)
+__global__ void __launch_bounds__(256)
+decode_filter_kernel(const float* __restrict__ head, HeadGeom g, int nB, float conf, int xyxy_direct,
+                     const unsigned* __restrict__ cls_mask, float4* __restrict__ dbox, int* __restrict__ dcls, unsigned long long* __restrict__ cand_keys,
+                     int* __restrict__ cand_count) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)nB * g.A) return;
+  const int b = (int)(wid / g.A), a = (int)(wid - (long long)b * g.A);
+  const float* row = head + wid * g.no;
+
+  // ---- class max / argmax (first index wins ties, like torch.max) ----
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int c = lane; c < g.nc; c += 32) {
+    const float v = row[64 + c];
+    if (v > best) { best = v; bidx = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+  }
+  const float score = sigmoid_f(best);
+  if (!(score > conf)) return;  // warp-uniform
+  // predict(classes=[...]): upstream filters on the arg-max class after the confidence test
+  if (cls_mask != nullptr && !((cls_mask[bidx >> 5] >> (bidx & 31)) & 1u)) return;
+
+  // ---- DFL: softmax over 16 bins per side, expectation; lane l holds side l/16 (and +2) bin l%16 ----
+  float d[2];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float x = row[half * 32 + lane];
+    float m = x;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e = expf(x - m);
+    float s = e, ws = e * (float)(lane & 15);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ws += __shfl_xor_sync(0xffffffffu, ws, o);
+    }
+    d[half] = __fdiv_rn(ws, s);
+  }
+  // lanes 0..15: (l, r)   lanes 16..31: (t, b)
+  const float dl = __shfl_sync(0xffffffffu, d[0], 0), dt = __shfl_sync(0xffffffffu, d[0], 16);
+  const float dr = __shfl_sync(0xffffffffu, d[1], 0), db = __shfl_sync(0xffffffffu, d[1], 16);
+  if (lane != 0) return;
+
+  int lvl = 0;
+  if (a >= g.lvl_start[1]) lvl = 1;
+  if (a >= g.lvl_start[2]) lvl = 2;
+  const int local = a - g.lvl_start[lvl];
+  const int iy = local / g.lvl_w[lvl], ix = local - iy * g.lvl_w[lvl];
+  const float ax = (float)ix + 0.5f, ay = (float)iy + 0.5f, st = g.lvl_stride[lvl];
+  const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt), x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
+  float4 box;
+  if (xyxy_direct) {  // end2end heads: dist2bbox(xywh=False) * stride
+    box = make_float4(__fmul_rn(x1, st), __fmul_rn(y1, st), __fmul_rn(x2, st), __fmul_rn(y2, st));
+  } else {            // dist2bbox(xywh=True) * stride, then ops.xywh2xyxy inside NMS
+    const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.0f), st), cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.0f), st);
+    const float w = __fmul_rn(__fsub_rn(x2, x1), st), h = __fmul_rn(__fsub_rn(y2, y1), st);
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    box = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+  }
+  dbox[wid] = box;
+  dcls[wid] = bidx;
+  const int slot = atomicAdd(cand_count + b, 1);
+  cand_keys[(long long)b * g.cand_stride + slot] =
+      ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)a);
+}
+
+// In-place bitonic sort, descending, of n_pow2 keys (any address space), by one CTA.
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* k, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (n_pow2 >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = k[lo], c = k[hi];
+        if ((a < c) == desc) { k[lo] = c; k[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct FrameXform {   // per-image letterbox undo (ops.scale_boxes): x = clamp((x - pad) / gain, 0, size)
+  float pad_w, pad_h, gain, W0, H0;
+};
+
+__device__ __forceinline__ float iou_tv(float ix1, float iy1, float ix2, float iy2, float iarea, float jx1, float jy1,
+                                        float jx2, float jy2, float jarea) {
+  const float xx1 = fmaxf(ix1, jx1), yy1 = fmaxf(iy1, jy1), xx2 = fminf(ix2, jx2), yy2 = fminf(iy2, jy2);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
+}
+
+constexpr int kNmsSmemKeys = 4096;
+constexpr int kNmsMaxDet = 300;
+
+// One CTA per image.  Outputs (row i < count[b], descending score):
+//   det     (B, max_det, 6)  [x1,y1,x2,y2,conf,cls] boxes mapped back to the original frame
+//   det_lb  (B, max_det, 4)  the same boxes in letterboxed-input pixels (what non-retina masks crop with)
+//   keep    (B, max_det)     anchor index of each kept row
+//   coef    (B, max_det, nm) mask coefficients gathered from the head rows
+__global__ void __launch_bounds__(256)
+nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict__ dbox, const int* __restrict__ dcls,
+           unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_count, float iou_thr, int max_det,
+           int max_nms, float max_wh, const FrameXform* __restrict__ xf, float* __restrict__ det,
+           float* __restrict__ det_lb, int* __restrict__ keep, float* __restrict__ coef, int* __restrict__ count) {
+  __shared__ unsigned long long s_keys[kNmsSmemKeys];
+  __shared__ float s_kept[kNmsMaxDet][5];  // offset box + area
+  __shared__ float s_score[kNmsMaxDet];
+  __shared__ int s_nkept;
+  const int b = blockIdx.x;
+  int n = cand_count[b];
+  if (n > g.A) n = g.A;
+  unsigned long long* gk = cand_keys + (long long)b * g.cand_stride;
+  int n_pow2 = 1;
+  while (n_pow2 < n) n_pow2 <<= 1;
+  unsigned long long* keys;
+  if (n_pow2 <= kNmsSmemKeys) {
+    keys = s_keys;
+    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = i < n ? gk[i] : 0ull;
+  } else {  // rare: sort in place in global memory (cand_stride = next_pow2(A) leaves room for the padding)
+    keys = gk;
+    for (int i = n + threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = 0ull;
+  }
+  bitonic_sort_desc(keys, n_pow2);
+  if (n > max_nms) n = max_nms;
+
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int nkept = 0;
+    for (int i0 = 0; i0 < n && nkept < max_det; i0 += 32) {
+      const int i = i0 + lane;
+      bool alive = i < n;
+      float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, area = 0.f;
+      int anchor = 0;
+      float score = 0.f;
+      if (alive) {
+        const unsigned long long key = keys[i];
+        anchor = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+        score = __uint_as_float((unsigned)(key >> 32));
+        const float4 bx = dbox[(long long)b * g.A + anchor];
+        const float off = __fmul_rn((float)dcls[(long long)b * g.A + anchor], max_wh);
+        x1 = __fadd_rn(bx.x, off); y1 = __fadd_rn(bx.y, off); x2 = __fadd_rn(bx.z, off); y2 = __fadd_rn(bx.w, off);
+        area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+      }
+      for (int k = 0; k < nkept; ++k) {
+        if (alive && iou_tv(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area) > iou_thr)
+          alive = false;
+      }
+      unsigned live = __ballot_sync(0xffffffffu, alive);
+      while (live != 0u && nkept < max_det) {
+        const int l = __ffs(live) - 1;
+        const float kx1 = __shfl_sync(0xffffffffu, x1, l), ky1 = __shfl_sync(0xffffffffu, y1, l);
+        const float kx2 = __shfl_sync(0xffffffffu, x2, l), ky2 = __shfl_sync(0xffffffffu, y2, l);
+        const float ka = __shfl_sync(0xffffffffu, area, l);
+        if (lane == l) {
+          s_kept[nkept][0] = x1; s_kept[nkept][1] = y1; s_kept[nkept][2] = x2; s_kept[nkept][3] = y2; s_kept[nkept][4] = area;
+          s_score[nkept] = score;
+          keep[(long long)b * max_det + nkept] = anchor;
+        }
+        ++nkept;
+        if (alive && lane > l && iou_tv(kx1, ky1, kx2, ky2, ka, x1, y1, x2, y2, area) > iou_thr) alive = false;
+        live = __ballot_sync(0xffffffffu, alive) & ~((2u << l) - 1u);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) { s_nkept = nkept; count[b] = nkept; }
+  }
+  __syncthreads();
+  const int nk = s_nkept;
+  const FrameXform t = xf[b];
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+    const int anchor = keep[(long long)b * max_det + i];
+    const long long ga = (long long)b * g.A + anchor;
+    const float4 bx = dbox[ga];
+    const int cls = dcls[ga];
+    const float score = s_score[i];
+    if (det == nullptr) continue;  // selection-only call (ypb_nms)
+    float* lb = det_lb + ((long long)b * max_det + i) * 4;
+    lb[0] = bx.x; lb[1] = bx.y; lb[2] = bx.z; lb[3] = bx.w;
+    float* o = det + ((long long)b * max_det + i) * 6;
+    o[0] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.x, t.pad_w), t.gain), 0.0f), t.W0);
+    o[1] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.y, t.pad_h), t.gain), 0.0f), t.H0);
+    o[2] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.z, t.pad_w), t.gain), 0.0f), t.W0);
+    o[3] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.w, t.pad_h), t.gain), 0.0f), t.H0);
+    o[4] = score;
+    o[5] = (float)cls;
+  }
+  if (g.nm > 0 && coef != nullptr) {
+    for (int i = threadIdx.x; i < nk * g.nm; i += blockDim.x) {
+      const int r = i / g.nm, c = i - r * g.nm;
+      const int anchor = keep[(long long)b * max_det + r];
+      coef[((long long)b * max_det + r) * g.nm + c] = head[((long long)b * g.A + anchor) * g.no + 64 + g.nc + c];
+    }
+  }
+}
+
+}  // namespace ypb

@@ -1,0 +1,146 @@
+// Bandwidth-bound layer kernels around the tensor-core convs: fused preprocess + stem conv,
+// nearest 2x upsample into a concat slice, SPPF chained max-pools.
+// UPSTREAM sites replaced: engine/predictor.py::preprocess (BGR->RGB, /255) + model.0 Conv,
+// nn.Upsample(2,'nearest') + Concat, block.py::SPPF's three MaxPool2d(5,1,2)  (SURVEY.md §2.2).
+#pragma once
+#include "common.cuh"
+
+namespace ypb {
+
+// ------------------------------------------------------------------------------------------------
+// Stem: uint8 BGR HWC letterboxed frame -> RGB/255 -> Conv3x3 s2 p1 (+folded BN) -> SiLU -> bf16 NHWC.
+// The frame is read as bytes straight from HBM (3 B/pixel instead of a 12 B/pixel fp32 CHW tensor),
+// K = 27 is too thin for the tensor pipe so this one runs on the FMA pipe in fp32.
+// Weights: wk[(kh*3+kw)*3 + c_rgb][C0] fp32, bias[C0].
+// ------------------------------------------------------------------------------------------------
+constexpr int kStemTile = 16;  // 16x16 output pixels per CTA, 256 threads
+
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const uint8_t* __restrict__ frames, int H, int W, const float* __restrict__ wk,
+                 const float* __restrict__ bias, int C0, __nv_bfloat16* __restrict__ out, int out_ctot) {
+  extern __shared__ float stem_smem[];
+  const int IT = 2 * kStemTile + 1;               // 33 input rows/cols per tile
+  float* s_in = stem_smem;                        // [IT][IT][3] RGB/255
+  float* s_w = s_in + IT * IT * 3;                // [27][C0]
+  float* s_b = s_w + 27 * C0;                     // [C0]
+  const int oH = H >> 1, oW = W >> 1;
+  const int b = blockIdx.z;
+  const int oh0 = blockIdx.y * kStemTile, ow0 = blockIdx.x * kStemTile;
+  const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+  const uint8_t* img = frames + (size_t)b * H * W * 3;
+  for (int i = threadIdx.x; i < IT * IT; i += 256) {
+    const int r = i / IT, c = i - r * IT;
+    const int ih = ih0 + r, iw = iw0 + c;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+      const uint8_t* px = img + ((size_t)ih * W + iw) * 3;
+      v2 = __fdiv_rn((float)px[0], 255.f);  // B -> channel 2
+      v1 = __fdiv_rn((float)px[1], 255.f);
+      v0 = __fdiv_rn((float)px[2], 255.f);  // R -> channel 0
+    }
+    s_in[i * 3 + 0] = v0;
+    s_in[i * 3 + 1] = v1;
+    s_in[i * 3 + 2] = v2;
+  }
+  for (int i = threadIdx.x; i < 27 * C0; i += 256) s_w[i] = wk[i];
+  for (int i = threadIdx.x; i < C0; i += 256) s_b[i] = bias[i];
+  __syncthreads();
+  const int ty = threadIdx.x / kStemTile, tx = threadIdx.x - ty * kStemTile;
+  const int oh = oh0 + ty, ow = ow0 + tx;
+  if (oh >= oH || ow >= oW) return;
+  float x[27];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[(kh * 3 + kw) * 3 + c] = s_in[((2 * ty + kh) * IT + 2 * tx + kw) * 3 + c];
+  __nv_bfloat16* o = out + ((size_t)(b * oH + oh) * oW + ow) * out_ctot;
+  for (int n0 = 0; n0 < C0; n0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = s_b[n0 + j];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[k], s_w[k * C0 + n0 + j], acc[j]);
+    }
+    uint4 s = make_uint4(pack_bf16x2(silu_f(acc[0]), silu_f(acc[1])), pack_bf16x2(silu_f(acc[2]), silu_f(acc[3])),
+                         pack_bf16x2(silu_f(acc[4]), silu_f(acc[5])), pack_bf16x2(silu_f(acc[6]), silu_f(acc[7])));
+    *reinterpret_cast<uint4*>(o + n0) = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Nearest 2x upsample of a channel slice into a channel slice of the (2h, 2w) concat buffer.
+// One thread per (output pixel, 8-channel vector).
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int in_ctot, int in_c_off,
+                                  __nv_bfloat16* __restrict__ out, int out_ctot, int out_c_off, int nB, int h, int w,
+                                  int C) {
+  const int vec = C >> 3;
+  const long long total = (long long)nB * 4 * h * w * vec;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = (int)(idx % vec);
+  long long pix = idx / vec;
+  const int ow = (int)(pix % (2 * w));
+  pix /= (2 * w);
+  const int oh = (int)(pix % (2 * h));
+  const int b = (int)(pix / (2 * h));
+  const uint4 val = *reinterpret_cast<const uint4*>(in + (((long long)b * h + (oh >> 1)) * w + (ow >> 1)) * in_ctot +
+                                                    in_c_off + v * 8);
+  *reinterpret_cast<uint4*>(out + (((long long)b * 2 * h + oh) * (2 * w) + ow) * out_ctot + out_c_off + v * 8) = val;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPPF pools: y1 = maxpool5(x), y2 = maxpool5(y1) (== 9x9 window), y3 = maxpool5(y2) (== 13x13),
+// windows clipped at the border (MaxPool2d pads with -inf).  x is channel slice 0 of a (.., 4c)
+// buffer; y1..y3 are written to slices 1..3 of the same buffer, so SPPF.cv2 reads the concat as is.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+__global__ void sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int nB, int h, int w, int c) {
+  const int ctot = 4 * c, vec = c >> 3;
+  const long long total = (long long)nB * h * w * vec;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = (int)(idx % vec);
+  long long pix = idx / vec;
+  const int x = (int)(pix % w);
+  pix /= w;
+  const int y = (int)(pix % h);
+  const int b = (int)(pix / h);
+  const __nv_bfloat16* base = buf + (long long)b * h * w * ctot + v * 8;
+  const uint32_t ninf = 0xFF80FF80u;  // (-inf, -inf) bf16x2
+  uint4 m5 = make_uint4(ninf, ninf, ninf, ninf), m9 = m5, m13 = m5;
+  for (int dy = -6; dy <= 6; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= h) continue;
+    const int ady = dy < 0 ? -dy : dy;
+    for (int dx = -6; dx <= 6; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= w) continue;
+      const int adx = dx < 0 ? -dx : dx;
+      const int r = ady > adx ? ady : adx;
+      const uint4 val = *reinterpret_cast<const uint4*>(base + ((long long)yy * w + xx) * ctot);
+      m13 = bf16x8_max(m13, val);
+      if (r <= 4) m9 = bf16x8_max(m9, val);
+      if (r <= 2) m5 = bf16x8_max(m5, val);
+    }
+  }
+  __nv_bfloat16* o = buf + (((long long)b * h + y) * w + x) * ctot + v * 8;
+  *reinterpret_cast<uint4*>(o + c) = m5;
+  *reinterpret_cast<uint4*>(o + 2 * c) = m9;
+  *reinterpret_cast<uint4*>(o + 3 * c) = m13;
+}
+
+}  // namespace ypb

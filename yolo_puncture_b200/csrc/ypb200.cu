@@ -1,0 +1,754 @@
+// ypb200 — engine (graph builder, planner, executor) and C ABI.  See include/ypb200.h.
+//
+// The engine is the native replacement of UPSTREAM ultralytics `AutoBackend.forward` +
+// `SegmentationPredictor.postprocess` behind `model.predict(...)` (reference yolo_seg/app.py:91,
+// yolo_seg/yolo_with_deva.py:51).  Topologies restate cfg/models/v8/yolov8-seg.yaml and
+// cfg/models/v10/yolov10n.yaml; weight names follow the upstream state_dict (A.6).
+//
+// Data layout in HBM: every activation is NHWC bf16 inside ONE caller-allocated workspace arena;
+// Concat / C2f-chunk / SPPF-cat never materialise: producers write channel slices of the consumer's
+// buffer and consumers read channel slices through TMA coordinates.  The three head branches of a
+// level share one fused first 3x3 conv.  The last 1x1 convs of the head write fp32 rows
+// [64 box logits | nc class logits | 32 mask coefs] of a (B, A, no) buffer that decode/NMS consume.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ypb200.h"
+#include "conv_plan.cuh"
+#include "head_kernels.cuh"
+#include "mask_kernels.cuh"
+#include "misc_kernels.cuh"
+
+using namespace ypb;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(YPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+namespace {
+
+struct WeightEntry {
+  std::string name;
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool loaded = false, used = true;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct BufDesc {
+  std::string name;
+  int lvl = 0, C = 0, dtype = 0;  // dtype 0 bf16, 1 fp32
+  int H = 0, W = 0;
+  size_t offset = 0, bytes = 0;
+};
+struct View { int buf = -1, c_off = 0, C = 0; };
+
+enum OpKind { OP_STEM, OP_CONV, OP_UPSAMPLE, OP_SPPF };
+enum SrcKind { SRC_CONV_BN = 0, SRC_CONV_BIAS = 1, SRC_CONVT = 2 };
+struct ConvSrc { std::string mod; int kind; int cout; };
+
+struct Op {
+  OpKind kind = OP_CONV;
+  std::string name;
+  std::vector<ConvSrc> srcs;
+  int cin = 0, cout = 0, k = 1, s = 1, act = 1, out_mode = OUT_BF16;
+  View in, out, res;
+  int head_lvl = -1, head_coff = 0;
+  size_t w_off = 0, b_off = 0;  // byte offsets in the weight arena
+  ConvLaunch L;
+};
+
+struct NamedView { std::string name; View v; };
+
+}  // namespace
+
+struct ypb_engine {
+  std::string spec;
+  int nc = 80, nm = 0;
+  bool end2end = false;
+  std::vector<WeightEntry> weights;
+  std::map<std::string, int> windex;
+  std::vector<BufDesc> bufs;
+  std::vector<Op> ops;
+  std::vector<NamedView> views;
+  View feat[3];  // P3,P4,P5 (for anchors)
+  int proto_buf = -1;
+  // weights on device
+  int device = -1;
+  void* w_arena = nullptr;
+  size_t w_bytes = 0;
+  bool finalized = false;
+  // plan
+  int B = 0, H = 0, W = 0, A = 0, no = 0;
+  HeadGeom hg{};
+  size_t ws_bytes = 0;
+  size_t off_head = 0, off_dbox = 0, off_dcls = 0, off_keys = 0, off_count = 0, off_moff = 0;
+  bool planned = false, bound = false;
+  uint8_t* ws = nullptr;
+  int conv_impl = 0;
+  int launches = 0;
+  double flops = 0;
+
+  // ------------------------------------------------------------------ builder helpers
+  int add_weight(const std::string& name, std::vector<int64_t> shape, bool used = true) {
+    WeightEntry w;
+    w.name = name; w.shape = std::move(shape); w.used = used;
+    weights.push_back(std::move(w));
+    windex[name] = (int)weights.size() - 1;
+    return (int)weights.size() - 1;
+  }
+  void add_conv_weights(const ConvSrc& s, int cin, int k, bool used = true) {
+    if (s.kind == SRC_CONV_BN) {
+      add_weight(s.mod + ".conv.weight", {s.cout, cin, k, k}, used);
+      for (const char* leaf : {"weight", "bias", "running_mean", "running_var"})
+        add_weight(s.mod + ".bn." + leaf, {s.cout}, used);
+    } else if (s.kind == SRC_CONV_BIAS) {
+      add_weight(s.mod + ".weight", {s.cout, cin, k, k}, used);
+      add_weight(s.mod + ".bias", {s.cout}, used);
+    } else {
+      add_weight(s.mod + ".weight", {cin, s.cout, 2, 2}, used);
+      add_weight(s.mod + ".bias", {s.cout}, used);
+    }
+  }
+  int new_buf(const std::string& name, int lvl, int C, int dtype = 0) {
+    BufDesc b;
+    b.name = name; b.lvl = lvl; b.C = C; b.dtype = dtype;
+    bufs.push_back(b);
+    return (int)bufs.size() - 1;
+  }
+  View whole(int buf) const { return View{buf, 0, bufs[buf].C}; }
+  View slice(int buf, int off, int C) const { return View{buf, off, C}; }
+  void name_view(const std::string& n, View v) { views.push_back({n, v}); }
+
+  // Conv(+BN)+SiLU, possibly several modules fused along Cout (they must share input, k, s).
+  void conv(const std::vector<std::string>& mods, const std::vector<int>& couts, View in, View out, int k, int s,
+            bool act = true, View res = View()) {
+    Op op;
+    op.kind = OP_CONV; op.name = mods[0];
+    op.cin = in.C; op.k = k; op.s = s; op.act = act ? 1 : 0; op.in = in; op.out = out; op.res = res;
+    int tot = 0;
+    for (size_t i = 0; i < mods.size(); ++i) {
+      ConvSrc src{mods[i], SRC_CONV_BN, couts[i]};
+      add_conv_weights(src, in.C, k);
+      op.srcs.push_back(src);
+      tot += couts[i];
+    }
+    op.cout = tot;
+    ops.push_back(op);
+  }
+  void conv1(const std::string& mod, View in, View out, int k, int s, bool act = true, View res = View()) {
+    conv({mod}, {out.C}, in, out, k, s, act, res);
+  }
+  // plain nn.Conv2d(k=1, bias) writing fp32 head rows
+  void head_out(const std::string& mod, View in, int cout, int lvl, int coff) {
+    Op op;
+    op.kind = OP_CONV; op.name = mod;
+    op.cin = in.C; op.cout = cout; op.k = 1; op.s = 1; op.act = 0; op.in = in; op.out_mode = OUT_F32;
+    op.head_lvl = lvl; op.head_coff = coff;
+    ConvSrc src{mod, SRC_CONV_BIAS, cout};
+    add_conv_weights(src, in.C, 1);
+    op.srcs.push_back(src);
+    ops.push_back(op);
+  }
+
+  // UPSTREAM block.py::C2f
+  void c2f(const std::string& mod, View in, View out, int n, bool shortcut, int lvl) {
+    const int c = out.C / 2;
+    const int Y = new_buf(mod + ".cat", lvl, (2 + n) * c);
+    conv1(mod + ".cv1", in, slice(Y, 0, 2 * c), 1, 1);
+    for (int j = 0; j < n; ++j) {
+      const int t = new_buf(mod + ".m" + std::to_string(j) + ".t", lvl, c);
+      const View x = slice(Y, (1 + j) * c, c);
+      conv1(mod + ".m." + std::to_string(j) + ".cv1", x, whole(t), 3, 1);
+      conv1(mod + ".m." + std::to_string(j) + ".cv2", whole(t), slice(Y, (2 + j) * c, c), 3, 1, true,
+            shortcut ? x : View());
+    }
+    conv1(mod + ".cv2", whole(Y), out, 1, 1);
+  }
+  // UPSTREAM block.py::SPPF
+  void sppf(const std::string& mod, View in, View out, int lvl) {
+    const int c_ = in.C / 2;
+    const int S = new_buf(mod + ".cat", lvl, 4 * c_);
+    conv1(mod + ".cv1", in, slice(S, 0, c_), 1, 1);
+    Op op;
+    op.kind = OP_SPPF; op.name = mod + ".pool"; op.in = slice(S, 0, c_); op.out = whole(S);
+    ops.push_back(op);
+    conv1(mod + ".cv2", whole(S), out, 1, 1);
+  }
+  void upsample(View in, View out) {
+    Op op;
+    op.kind = OP_UPSAMPLE; op.name = "upsample"; op.in = in; op.out = out;
+    ops.push_back(op);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// topologies
+// ------------------------------------------------------------------------------------------------
+static int make_div8(double x) { return (int)(std::ceil(x / 8.0) * 8); }
+
+static bool build_v8seg(ypb_engine& e, char scale) {
+  double d, w; int mc;
+  switch (scale) {
+    case 'n': d = 0.33; w = 0.25; mc = 1024; break;
+    case 's': d = 0.33; w = 0.50; mc = 1024; break;
+    case 'm': d = 0.67; w = 0.75; mc = 768; break;
+    case 'l': d = 1.00; w = 1.00; mc = 512; break;
+    case 'x': d = 1.00; w = 1.25; mc = 512; break;
+    default: return false;
+  }
+  auto ch = [&](int c) { return make_div8(std::min(c, mc) * w); };
+  auto rep = [&](int n) { return std::max((int)std::lround(n * d), 1); };
+  const int c64 = ch(64), c128 = ch(128), c256 = ch(256), c512 = ch(512), c1024 = ch(1024);
+  const int n3 = rep(3), n6 = rep(6);
+  e.nm = 32;
+  const std::string M = "model.";
+  // buffers (lvl = log2 of the downscale); concat inputs are slices of the concat buffer
+  const int x0 = e.new_buf("model.0", 1, c64), x1 = e.new_buf("model.1", 2, c128), x2 = e.new_buf("model.2", 2, c128);
+  const int x3 = e.new_buf("model.3", 3, c256);
+  const int cat14 = e.new_buf("model.14", 3, c512 + c256);    // [up(12) | 4]
+  const int x5 = e.new_buf("model.5", 4, c512);
+  const int cat11 = e.new_buf("model.11", 4, c1024 + c512);   // [up(9) | 6]
+  const int x7 = e.new_buf("model.7", 5, c1024), x8 = e.new_buf("model.8", 5, c1024);
+  const int cat20 = e.new_buf("model.20", 5, c512 + c1024);   // [19 | 9]
+  const int cat17 = e.new_buf("model.17", 4, c256 + c512);    // [16 | 12]
+  const int x15 = e.new_buf("model.15", 3, c256), x18 = e.new_buf("model.18", 4, c512), x21 = e.new_buf("model.21", 5, c1024);
+  const View v4 = e.slice(cat14, c512, c256), v6 = e.slice(cat11, c1024, c512), v9 = e.slice(cat20, c512, c1024);
+  const View v12 = e.slice(cat17, c256, c512), v16 = e.slice(cat17, 0, c256), v19 = e.slice(cat20, 0, c512);
+
+  {  // stem
+    Op op;
+    op.kind = OP_STEM; op.name = "model.0"; op.cin = 3; op.cout = c64; op.k = 3; op.s = 2; op.out = e.whole(x0);
+    ConvSrc src{"model.0", SRC_CONV_BN, c64};
+    e.add_conv_weights(src, 3, 3);
+    op.srcs.push_back(src);
+    e.ops.push_back(op);
+  }
+  e.conv1(M + "1", e.whole(x0), e.whole(x1), 3, 2);
+  e.c2f(M + "2", e.whole(x1), e.whole(x2), n3, true, 2);
+  e.conv1(M + "3", e.whole(x2), e.whole(x3), 3, 2);
+  e.c2f(M + "4", e.whole(x3), v4, n6, true, 3);
+  e.conv1(M + "5", v4, e.whole(x5), 3, 2);
+  e.c2f(M + "6", e.whole(x5), v6, n6, true, 4);
+  e.conv1(M + "7", v6, e.whole(x7), 3, 2);
+  e.c2f(M + "8", e.whole(x7), e.whole(x8), n3, true, 5);
+  e.sppf(M + "9", e.whole(x8), v9, 5);
+  e.upsample(v9, e.slice(cat11, 0, c1024));
+  e.c2f(M + "12", e.whole(cat11), v12, n3, false, 4);
+  e.upsample(v12, e.slice(cat14, 0, c512));
+  e.c2f(M + "15", e.whole(cat14), e.whole(x15), n3, false, 3);
+  e.conv1(M + "16", e.whole(x15), v16, 3, 2);
+  e.c2f(M + "18", e.whole(cat17), e.whole(x18), n3, false, 4);
+  e.conv1(M + "19", e.whole(x18), v19, 3, 2);
+  e.c2f(M + "21", e.whole(cat20), e.whole(x21), n3, false, 5);
+  e.name_view("model.0", e.whole(x0)); e.name_view("model.1", e.whole(x1)); e.name_view("model.2", e.whole(x2));
+  e.name_view("model.3", e.whole(x3)); e.name_view("model.4", v4); e.name_view("model.5", e.whole(x5));
+  e.name_view("model.6", v6); e.name_view("model.7", e.whole(x7)); e.name_view("model.8", e.whole(x8));
+  e.name_view("model.9", v9); e.name_view("model.11", e.whole(cat11)); e.name_view("model.12", v12);
+  e.name_view("model.14", e.whole(cat14)); e.name_view("model.15", e.whole(x15)); e.name_view("model.16", v16);
+  e.name_view("model.17", e.whole(cat17)); e.name_view("model.18", e.whole(x18)); e.name_view("model.19", v19);
+  e.name_view("model.20", e.whole(cat20)); e.name_view("model.21", e.whole(x21));
+
+  // Segment head (UPSTREAM head.py::Segment), module index 22
+  const std::string Hd = "model.22.";
+  const int chs[3] = {c256, c512, c1024};
+  const View P[3] = {e.whole(x15), e.whole(x18), e.whole(x21)};
+  const int hc2 = std::max(std::max(16, chs[0] / 4), 64), hc3 = std::max(chs[0], std::min(e.nc, 100));
+  const int hc4 = std::max(chs[0] / 4, e.nm);
+  for (int i = 0; i < 3; ++i) {
+    e.feat[i] = P[i];
+    const std::string si = std::to_string(i);
+    const int lvl = 3 + i;
+    // the first 3x3 conv of the box / class / coef branches reads the same P_i: one fused GEMM, N = hc2+hc3+hc4
+    const int f0 = e.new_buf(Hd + "lvl" + si + ".s0", lvl, hc2 + hc3 + hc4);
+    e.conv({Hd + "cv2." + si + ".0", Hd + "cv3." + si + ".0", Hd + "cv4." + si + ".0"}, {hc2, hc3, hc4}, P[i], e.whole(f0), 3, 1);
+    const int t2 = e.new_buf(Hd + "cv2." + si + ".t", lvl, hc2), t3 = e.new_buf(Hd + "cv3." + si + ".t", lvl, hc3);
+    const int t4 = e.new_buf(Hd + "cv4." + si + ".t", lvl, hc4);
+    e.conv1(Hd + "cv2." + si + ".1", e.slice(f0, 0, hc2), e.whole(t2), 3, 1);
+    e.conv1(Hd + "cv3." + si + ".1", e.slice(f0, hc2, hc3), e.whole(t3), 3, 1);
+    e.conv1(Hd + "cv4." + si + ".1", e.slice(f0, hc2 + hc3, hc4), e.whole(t4), 3, 1);
+    e.head_out(Hd + "cv2." + si + ".2", e.whole(t2), 64, i, 0);
+    e.head_out(Hd + "cv3." + si + ".2", e.whole(t3), e.nc, i, 64);
+    e.head_out(Hd + "cv4." + si + ".2", e.whole(t4), e.nm, i, 64 + e.nc);
+  }
+  e.add_weight(Hd + "dfl.conv.weight", {1, 16, 1, 1}, false);
+  // Proto (UPSTREAM block.py::Proto)
+  const int npr = ch(256);
+  const int p1 = e.new_buf(Hd + "proto.cv1", 3, npr), p2 = e.new_buf(Hd + "proto.upsample", 2, npr);
+  const int p3 = e.new_buf(Hd + "proto.cv2", 2, npr), pr = e.new_buf("proto", 2, e.nm, 1);
+  e.conv1(Hd + "proto.cv1", P[0], e.whole(p1), 3, 1);
+  {
+    Op op;
+    op.kind = OP_CONV; op.name = Hd + "proto.upsample";
+    op.cin = npr; op.cout = 4 * npr; op.k = 1; op.s = 1; op.act = 0; op.out_mode = OUT_SHUFFLE2_BF16;
+    op.in = e.whole(p1); op.out = e.whole(p2);
+    ConvSrc src{Hd + "proto.upsample", SRC_CONVT, npr};
+    e.add_conv_weights(src, npr, 2);
+    op.srcs.push_back(src);
+    e.ops.push_back(op);
+  }
+  e.conv1(Hd + "proto.cv2", e.whole(p2), e.whole(p3), 3, 1);
+  {
+    e.conv1(Hd + "proto.cv3", e.whole(p3), e.whole(pr), 1, 1);
+    e.ops.back().out_mode = OUT_F32;
+  }
+  e.proto_buf = pr;
+  e.name_view("proto", e.whole(pr));
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: BN fold + repack
+// ------------------------------------------------------------------------------------------------
+static uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// Folded fp32 weight [cout][cin][k][k] (ConvT: as stored [cin][cout][2][2]) and bias [cout] of one source module.
+static int folded(const ypb_engine& e, const ConvSrc& s, std::vector<float>* w, std::vector<float>* b) {
+  auto get = [&](const std::string& n) -> const WeightEntry* {
+    auto it = e.windex.find(n);
+    return it == e.windex.end() ? nullptr : &e.weights[it->second];
+  };
+  if (s.kind == SRC_CONV_BN) {
+    const WeightEntry *cw = get(s.mod + ".conv.weight"), *g = get(s.mod + ".bn.weight"), *be = get(s.mod + ".bn.bias"),
+                      *mu = get(s.mod + ".bn.running_mean"), *var = get(s.mod + ".bn.running_var");
+    if (!cw || !g || !be || !mu || !var || !cw->loaded || !g->loaded || !be->loaded || !mu->loaded || !var->loaded)
+      return fail(YPB_ERR_STATE, "weights of " + s.mod + " not loaded");
+    *w = cw->data;
+    b->assign(s.cout, 0.f);
+    const int64_t per = cw->numel() / s.cout;
+    for (int co = 0; co < s.cout; ++co) {
+      const float sc = g->data[co] / std::sqrt(var->data[co] + 1e-3f);
+      for (int64_t i = 0; i < per; ++i) (*w)[co * per + i] *= sc;
+      (*b)[co] = be->data[co] - mu->data[co] * sc;
+    }
+  } else {
+    const WeightEntry *cw = get(s.mod + ".weight"), *cb = get(s.mod + ".bias");
+    if (!cw || !cb || !cw->loaded || !cb->loaded) return fail(YPB_ERR_STATE, "weights of " + s.mod + " not loaded");
+    *w = cw->data;
+    *b = cb->data;
+  }
+  return YPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ypb_version(void) { return 100; }
+const char* ypb_last_error(void) { return g_last_error.c_str(); }
+
+int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out) {
+  if (!model_spec || !out || nc < 1) return fail(YPB_ERR_ARG, "bad argument");
+  ypb_engine* e = new ypb_engine();
+  e->spec = model_spec;
+  e->nc = nc;
+  bool ok = false;
+  const std::string s = model_spec;
+  if (s.size() == 11 && s.rfind("yolov8", 0) == 0 && s.substr(7) == "-seg") ok = build_v8seg(*e, s[6]);
+  if (!ok) {
+    delete e;
+    return fail(YPB_ERR_ARG, "unknown model spec '" + s + "'");
+  }
+  *out = e;
+  return YPB_OK;
+}
+
+void ypb_engine_destroy(ypb_engine* e) {
+  if (!e) return;
+  if (e->w_arena) cudaFree(e->w_arena);
+  delete e;
+}
+
+int ypb_weight_count(const ypb_engine* e) { return e ? (int)e->weights.size() : 0; }
+
+int ypb_weight_info(const ypb_engine* e, int i, const char** name, int* ndim, int64_t shape[4], int* used) {
+  if (!e || i < 0 || i >= (int)e->weights.size()) return fail(YPB_ERR_ARG, "bad weight index");
+  const WeightEntry& w = e->weights[i];
+  if (name) *name = w.name.c_str();
+  if (ndim) *ndim = (int)w.shape.size();
+  if (shape) for (size_t d = 0; d < 4; ++d) shape[d] = d < w.shape.size() ? w.shape[d] : 1;
+  if (used) *used = w.used ? 1 : 0;
+  return YPB_OK;
+}
+
+int ypb_load_weight(ypb_engine* e, const char* name, const float* data, int64_t numel) {
+  if (!e || !name || !data) return fail(YPB_ERR_ARG, "bad argument");
+  auto it = e->windex.find(name);
+  if (it == e->windex.end()) return fail(YPB_ERR_ARG, std::string("unknown weight '") + name + "'");
+  WeightEntry& w = e->weights[it->second];
+  if (numel != w.numel()) return fail(YPB_ERR_ARG, std::string("size mismatch for '") + name + "'");
+  if (w.used) w.data.assign(data, data + numel);
+  w.loaded = true;
+  e->finalized = false;
+  return YPB_OK;
+}
+
+int ypb_finalize_weights(ypb_engine* e, int device) {
+  if (!e) return fail(YPB_ERR_ARG, "null engine");
+  // layout pass
+  size_t off = 0;
+  auto align = [](size_t x) { return (x + 1023) & ~size_t(1023); };
+  for (Op& op : e->ops) {
+    if (op.kind == OP_STEM) {
+      op.w_off = off; off = align(off + (size_t)27 * op.cout * 4);
+      op.b_off = off; off = align(off + (size_t)op.cout * 4);
+    } else if (op.kind == OP_CONV) {
+      op.w_off = off; off = align(off + (size_t)op.k * op.k * op.cout * op.cin * 2);
+      op.b_off = off; off = align(off + (size_t)op.cout * 4);
+    }
+  }
+  std::vector<uint8_t> host(off, 0);
+  for (Op& op : e->ops) {
+    if (op.kind != OP_STEM && op.kind != OP_CONV) continue;
+    float* bias = reinterpret_cast<float*>(host.data() + op.b_off);
+    int n_off = 0;
+    for (const ConvSrc& s : op.srcs) {
+      std::vector<float> w, b;
+      int rc = folded(*e, s, &w, &b);
+      if (rc) return rc;
+      if (op.kind == OP_STEM) {
+        float* wk = reinterpret_cast<float*>(host.data() + op.w_off);
+        for (int co = 0; co < s.cout; ++co)
+          for (int c = 0; c < 3; ++c)
+            for (int kh = 0; kh < 3; ++kh)
+              for (int kw = 0; kw < 3; ++kw)
+                wk[((kh * 3 + kw) * 3 + c) * op.cout + co] = w[((co * 3 + c) * 3 + kh) * 3 + kw];
+        for (int co = 0; co < s.cout; ++co) bias[co] = b[co];
+      } else if (s.kind == SRC_CONVT) {
+        uint16_t* wg = reinterpret_cast<uint16_t*>(host.data() + op.w_off);
+        const int cq = s.cout;
+        for (int ci = 0; ci < op.cin; ++ci)
+          for (int co = 0; co < cq; ++co)
+            for (int g = 0; g < 4; ++g)
+              wg[((size_t)(g * cq + co)) * op.cin + ci] = f32_to_bf16(w[((size_t)(ci * cq + co)) * 4 + g]);
+        for (int g = 0; g < 4; ++g)
+          for (int co = 0; co < cq; ++co) bias[g * cq + co] = b[co];
+      } else {
+        uint16_t* wg = reinterpret_cast<uint16_t*>(host.data() + op.w_off);
+        const int kk = op.k * op.k;
+        for (int co = 0; co < s.cout; ++co)
+          for (int ci = 0; ci < op.cin; ++ci)
+            for (int t = 0; t < kk; ++t)
+              wg[((size_t)t * op.cout + n_off + co) * op.cin + ci] = f32_to_bf16(w[((size_t)co * op.cin + ci) * kk + t]);
+        for (int co = 0; co < s.cout; ++co) bias[n_off + co] = b[co];
+      }
+      n_off += s.cout;
+    }
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(YPB_ERR_CUDA, "device is not sm_100 (Blackwell B200); there is no fallback path");
+  if (e->w_arena) { cudaFree(e->w_arena); e->w_arena = nullptr; }
+  CUDA_TRY(cudaMalloc(&e->w_arena, off));
+  CUDA_TRY(cudaMemcpy(e->w_arena, host.data(), off, cudaMemcpyHostToDevice));
+  e->w_bytes = off;
+  e->device = device;
+  e->finalized = true;
+  e->bound = false;
+  return YPB_OK;
+}
+
+int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
+  if (!e || B < 1 || H < 32 || W < 32 || (H % 32) || (W % 32)) return fail(YPB_ERR_ARG, "plan: H and W must be multiples of 32");
+  e->B = B; e->H = H; e->W = W;
+  size_t off = 0;
+  auto align = [](size_t x) { return (x + 1023) & ~size_t(1023); };
+  for (BufDesc& b : e->bufs) {
+    b.H = H >> b.lvl; b.W = W >> b.lvl;
+    b.bytes = (size_t)B * b.H * b.W * b.C * (b.dtype ? 4 : 2);
+    b.offset = off;
+    off = align(off + b.bytes);
+  }
+  // head geometry
+  HeadGeom& g = e->hg;
+  int A = 0;
+  for (int i = 0; i < 3; ++i) {
+    const BufDesc& fb = e->bufs[e->feat[i].buf];
+    g.lvl_start[i] = A; g.lvl_w[i] = fb.W; g.lvl_stride[i] = (float)(1 << fb.lvl);
+    A += fb.H * fb.W;
+  }
+  g.lvl_start[3] = A;
+  g.A = A; g.nc = e->nc; g.nm = e->nm; g.no = 64 + e->nc + e->nm;
+  int cs = 1;
+  while (cs < A) cs <<= 1;
+  g.cand_stride = cs;
+  e->A = A; e->no = g.no;
+  e->off_head = off; off = align(off + (size_t)B * A * g.no * 4);
+  e->off_dbox = off; off = align(off + (size_t)B * A * 16);
+  e->off_dcls = off; off = align(off + (size_t)B * A * 4);
+  e->off_keys = off; off = align(off + (size_t)B * cs * 8);
+  e->off_count = off; off = align(off + (size_t)B * 4);
+  e->off_moff = off; off = align(off + (size_t)(B + 1) * 4);
+  e->ws_bytes = off;
+  // per-op geometry
+  e->launches = 0; e->flops = 0;
+  for (Op& op : e->ops) {
+    ++e->launches;
+    if (op.kind == OP_STEM) { e->flops += 2.0 * B * (H / 2) * (W / 2) * op.cout * 27; continue; }
+    if (op.kind != OP_CONV) continue;
+    const BufDesc& ib = e->bufs[op.in.buf];
+    ConvDesc d;
+    d.B = B; d.Hin = ib.H; d.Win = ib.W; d.in_ctot = ib.C; d.in_c_off = op.in.c_off; d.cin = op.cin;
+    d.cout = op.cout; d.k = op.k; d.stride = op.s; d.act = op.act; d.out_mode = op.out_mode;
+    if (op.head_lvl >= 0) {
+      d.out_img_stride = (long long)A * g.no; d.out_pix_stride = g.no;
+      d.out_c_off = g.lvl_start[op.head_lvl] * g.no + op.head_coff;
+    } else {
+      const BufDesc& ob = e->bufs[op.out.buf];
+      d.out_img_stride = (long long)ob.H * ob.W * ob.C; d.out_pix_stride = ob.C; d.out_c_off = op.out.c_off;
+    }
+    if (op.res.buf >= 0) {
+      const BufDesc& rb = e->bufs[op.res.buf];
+      d.res_img_stride = (long long)rb.H * rb.W * rb.C; d.res_pix_stride = rb.C; d.res_c_off = op.res.c_off;
+    }
+    std::string err;
+    if (!conv_plan_geometry(d, &op.L, &err)) return fail(YPB_ERR_ARG, op.name + ": " + err);
+    e->flops += op.L.flops;
+  }
+  e->launches += 2;  // decode_filter + nms
+  e->planned = true;
+  e->bound = false;
+  if (workspace_bytes) *workspace_bytes = off;
+  return YPB_OK;
+}
+
+int ypb_bind_workspace(ypb_engine* e, void* workspace, size_t bytes) {
+  if (!e || !workspace) return fail(YPB_ERR_ARG, "bad argument");
+  if (!e->planned || !e->finalized) return fail(YPB_ERR_STATE, "bind: finalize weights and plan first");
+  if (bytes < e->ws_bytes) return fail(YPB_ERR_ARG, "workspace too small");
+  if ((uintptr_t)workspace & 1023) return fail(YPB_ERR_ARG, "workspace must be 1024-byte aligned");
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->ws = reinterpret_cast<uint8_t*>(workspace);
+  const uint8_t* wa = reinterpret_cast<const uint8_t*>(e->w_arena);
+  const HeadGeom& g = e->hg;
+  for (Op& op : e->ops) {
+    if (op.kind != OP_CONV) continue;
+    const BufDesc& ib = e->bufs[op.in.buf];
+    ConvDesc d;
+    d.in = e->ws + ib.offset;
+    d.B = e->B; d.Hin = ib.H; d.Win = ib.W; d.in_ctot = ib.C; d.in_c_off = op.in.c_off; d.cin = op.cin;
+    d.wg = wa + op.w_off; d.bias = reinterpret_cast<const float*>(wa + op.b_off);
+    d.cout = op.cout; d.k = op.k; d.stride = op.s; d.act = op.act; d.out_mode = op.out_mode;
+    d.out = op.head_lvl >= 0 ? (void*)(e->ws + e->off_head) : (void*)(e->ws + e->bufs[op.out.buf].offset);
+    if (op.res.buf >= 0) d.res = e->ws + e->bufs[op.res.buf].offset;
+    std::string err;
+    if (!conv_bind(d, &op.L, &err)) return fail(YPB_ERR_CUDA, op.name + ": " + err);
+  }
+  (void)g;
+  e->bound = true;
+  return YPB_OK;
+}
+
+int ypb_num_anchors(const ypb_engine* e) { return e ? e->A : 0; }
+int ypb_num_classes(const ypb_engine* e) { return e ? e->nc : 0; }
+int ypb_num_mask_coefs(const ypb_engine* e) { return e ? e->nm : 0; }
+int ypb_kernel_launches(const ypb_engine* e) { return e ? e->launches : 0; }
+double ypb_conv_flops(const ypb_engine* e) { return e ? e->flops : 0.0; }
+
+int ypb_set_conv_impl(ypb_engine* e, int impl) {
+  if (!e || impl < 0 || impl > 1) return fail(YPB_ERR_ARG, "bad argument");
+  e->conv_impl = impl;
+  return YPB_OK;
+}
+
+int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform, const ypb_infer_params* prm,
+              float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count) {
+  if (!e || !frames || !xform || !prm || !det || !det_lb || !keep || !count) return fail(YPB_ERR_ARG, "bad argument");
+  if (!e->bound) return fail(YPB_ERR_STATE, "infer: bind a workspace first");
+  if (prm->max_det < 1 || prm->max_det > kNmsMaxDet) return fail(YPB_ERR_ARG, "max_det must be in [1,300]");
+  if (e->nm > 0 && !coef) return fail(YPB_ERR_ARG, "coef buffer required for -seg models");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const uint8_t* wa = reinterpret_cast<const uint8_t*>(e->w_arena);
+  const int B = e->B;
+  for (const Op& op : e->ops) {
+    switch (op.kind) {
+      case OP_STEM: {
+        const BufDesc& ob = e->bufs[op.out.buf];
+        dim3 grid((ob.W + kStemTile - 1) / kStemTile, (ob.H + kStemTile - 1) / kStemTile, B);
+        const size_t smem = (size_t)(33 * 33 * 3 + 27 * op.cout + op.cout) * 4;
+        stem_conv_kernel<<<grid, 256, smem, st>>>(frames, e->H, e->W, reinterpret_cast<const float*>(wa + op.w_off),
+                                                   reinterpret_cast<const float*>(wa + op.b_off), op.cout,
+                                                   reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C);
+        break;
+      }
+      case OP_CONV:
+        CUDA_TRY(conv_launch(op.L, st, e->conv_impl));
+        break;
+      case OP_UPSAMPLE: {
+        const BufDesc &ib = e->bufs[op.in.buf], &ob = e->bufs[op.out.buf];
+        const long long total = (long long)B * 4 * ib.H * ib.W * (op.in.C / 8);
+        upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(e->ws + ib.offset), ib.C, op.in.c_off,
+            reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C, op.out.c_off, B, ib.H, ib.W, op.in.C);
+        break;
+      }
+      case OP_SPPF: {
+        const BufDesc& ib = e->bufs[op.in.buf];
+        const long long total = (long long)B * ib.H * ib.W * (op.in.C / 8);
+        sppf_pool_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+            reinterpret_cast<__nv_bfloat16*>(e->ws + ib.offset), B, ib.H, ib.W, op.in.C);
+        break;
+      }
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  const HeadGeom& g = e->hg;
+  int* cand_count = reinterpret_cast<int*>(e->ws + e->off_count);
+  CUDA_TRY(cudaMemsetAsync(cand_count, 0, (size_t)B * 4, st));
+  const float* head = reinterpret_cast<const float*>(e->ws + e->off_head);
+  float4* dbox = reinterpret_cast<float4*>(e->ws + e->off_dbox);
+  int* dcls = reinterpret_cast<int*>(e->ws + e->off_dcls);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(e->ws + e->off_keys);
+  const long long warps = (long long)B * g.A;
+  decode_filter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(head, g, B, prm->conf, e->end2end ? 1 : 0,
+                                                                            prm->class_mask, dbox, dcls, keys, cand_count);
+  nms_kernel<<<B, 256, 0, st>>>(head, g, dbox, dcls, keys, cand_count, prm->iou, prm->max_det, 30000,
+                                prm->agnostic_nms ? 0.0f : 7680.0f, reinterpret_cast<const FrameXform*>(xform), det, det_lb,
+                                keep, coef, count);
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
+int ypb_masks(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w, const float* det, const float* det_lb,
+              const float* coef, const int32_t* count, uint8_t* masks, int capacity, int32_t* status) {
+  if (!e || !det || !det_lb || !coef || !count || !masks || !status || capacity < 1) return fail(YPB_ERR_ARG, "bad argument");
+  if (!e->bound || e->nm == 0 || e->proto_buf < 0) return fail(YPB_ERR_STATE, "masks: not a bound -seg engine");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const BufDesc& pb = e->bufs[e->proto_buf];
+  MaskGeom g{};
+  g.mh = pb.H; g.mw = pb.W; g.nm = e->nm; g.max_det = kNmsMaxDet; g.retina = retina ? 1 : 0;
+  if (retina) {
+    if (out_h < 1 || out_w < 1) return fail(YPB_ERR_ARG, "masks: bad output size");
+    // ops.scale_masks: gain/pad in proto space with int() truncation, then bilinear to (H0, W0)
+    const double gain = std::min((double)g.mh / out_h, (double)g.mw / out_w);
+    const double pad_w = (g.mw - out_w * gain) / 2, pad_h = (g.mh - out_h * gain) / 2;
+    const int top = (int)pad_h, left = (int)pad_w, bottom = (int)(g.mh - pad_h), right = (int)(g.mw - pad_w);
+    g.top = top; g.left = left; g.ch = bottom - top; g.cw = right - left;
+    g.out_h = out_h; g.out_w = out_w;
+  } else {
+    g.top = 0; g.left = 0; g.ch = g.mh; g.cw = g.mw;
+    g.out_h = e->H; g.out_w = e->W;
+    g.ratio_w = (float)((double)g.mw / e->W); g.ratio_h = (float)((double)g.mh / e->H);
+  }
+  if (g.ch < 1 || g.cw < 1 || g.ch > g.out_h || g.cw > g.out_w) return fail(YPB_ERR_ARG, "masks: output smaller than the proto window is unsupported");
+  g.scale_h = (float)g.ch / (float)g.out_h; g.scale_w = (float)g.cw / (float)g.out_w;
+  int* offsets = reinterpret_cast<int*>(e->ws + e->off_moff);
+  mask_offsets_kernel<<<1, 32, 0, st>>>(count, e->B, capacity, offsets, status);
+  const int tiles = ((g.out_w + kMaskTile - 1) / kMaskTile) * ((g.out_h + kMaskTile - 1) / kMaskTile);
+  dim3 grid(tiles, capacity);
+  if (capacity > 65535) return fail(YPB_ERR_ARG, "masks: capacity > 65535");
+  mask_decode_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb, offsets,
+                                           e->B, capacity, g, masks);
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
+int ypb_device_error(ypb_engine* e, uint32_t* word) {
+  (void)e;
+  if (!word) return fail(YPB_ERR_ARG, "bad argument");
+  unsigned int v = 0;
+  CUDA_TRY(cudaMemcpyFromSymbol(&v, g_dev_error, sizeof v));
+  *word = v;
+  if (v) {
+    unsigned int z = 0;
+    CUDA_TRY(cudaMemcpyToSymbol(g_dev_error, &z, sizeof z));
+  }
+  return YPB_OK;
+}
+
+int ypb_view_count(const ypb_engine* e) { return e ? (int)e->views.size() + 1 : 0; }
+
+int ypb_view_info(const ypb_engine* e, int i, const char** name, size_t* offset, int* H, int* W, int* Ctot, int* c_off,
+                  int* C, int* dtype) {
+  if (!e || !e->planned || i < 0 || i > (int)e->views.size()) return fail(YPB_ERR_ARG, "bad view index / not planned");
+  if (i == (int)e->views.size()) {  // the fp32 head rows, as a (B, 1, A, no) "image"
+    static const char* hn = "head";
+    *name = hn; *offset = e->off_head; *H = 1; *W = e->A; *Ctot = e->no; *c_off = 0; *C = e->no; *dtype = 1;
+    return YPB_OK;
+  }
+  const NamedView& nv = e->views[i];
+  const BufDesc& b = e->bufs[nv.v.buf];
+  *name = nv.name.c_str(); *offset = b.offset; *H = b.H; *W = b.W; *Ctot = b.C; *c_off = nv.v.c_off; *C = nv.v.C;
+  *dtype = b.dtype;
+  return YPB_OK;
+}
+
+// ---- stand-alone kernels for parity tests -----------------------------------------------------
+int ypb_conv2d_bf16(void* cuda_stream, const void* in, int B, int H, int W, int in_ctot, int in_c_off, int cin,
+                    const void* wg, const float* bias, int cout, int k, int stride, int act, const void* res, void* out,
+                    int out_ctot, int out_c_off, int out_fp32, int impl) {
+  ConvDesc d;
+  d.in = in; d.B = B; d.Hin = H; d.Win = W; d.in_ctot = in_ctot; d.in_c_off = in_c_off; d.cin = cin;
+  d.wg = wg; d.bias = bias; d.cout = cout; d.k = k; d.stride = stride; d.act = act;
+  d.out_mode = out_fp32 ? OUT_F32 : OUT_BF16;
+  const int oH = H / stride, oW = W / stride;
+  d.out = out; d.out_img_stride = (long long)oH * oW * out_ctot; d.out_pix_stride = out_ctot; d.out_c_off = out_c_off;
+  if (res) { d.res = res; d.res_img_stride = d.out_img_stride; d.res_pix_stride = out_ctot; d.res_c_off = out_c_off; }
+  ConvLaunch L;
+  std::string err;
+  if (!conv_plan_geometry(d, &L, &err)) return fail(YPB_ERR_ARG, err);
+  if (!conv_bind(d, &L, &err)) return fail(YPB_ERR_CUDA, err);
+  CUDA_TRY(conv_launch(L, reinterpret_cast<cudaStream_t>(cuda_stream), impl));
+  return YPB_OK;
+}
+
+size_t ypb_nms_scratch_bytes(int B, int N) {
+  int cs = 1;
+  while (cs < N) cs <<= 1;
+  return (size_t)B * cs * 8 + (size_t)B * sizeof(FrameXform) + 1024;
+}
+
+__global__ void nms_test_pack_kernel(const float* boxes, const float* scores, const int* n_valid, int B, int N, int cs,
+                                     unsigned long long* keys, FrameXform* xf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) xf[i] = FrameXform{0.f, 0.f, 1.f, 3.0e38f, 3.0e38f};
+  if (i >= B * N) return;
+  const int b = i / N, a = i - b * N;
+  if (a < n_valid[b])
+    keys[(long long)b * cs + a] = ((unsigned long long)__float_as_uint(scores[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)a);
+  (void)boxes;
+}
+
+int ypb_nms(void* cuda_stream, const float* boxes, const float* scores, const int32_t* cls, const int32_t* n_valid, int B,
+            int N, float iou, int max_det, int agnostic, void* scratch, int32_t* keep, int32_t* count) {
+  if (!boxes || !scores || !cls || !n_valid || !scratch || !keep || !count || max_det < 1 || max_det > kNmsMaxDet)
+    return fail(YPB_ERR_ARG, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  HeadGeom g{};
+  g.A = N; g.no = 0; g.nc = 0; g.nm = 0;
+  int cs = 1;
+  while (cs < N) cs <<= 1;
+  g.cand_stride = cs;
+  uint8_t* s = reinterpret_cast<uint8_t*>(scratch);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(s);
+  FrameXform* xf = reinterpret_cast<FrameXform*>(s + (size_t)B * cs * 8);
+  nms_test_pack_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(boxes, scores, n_valid, B, N, cs, keys, xf);
+  nms_kernel<<<B, 256, 0, st>>>(nullptr, g, reinterpret_cast<const float4*>(boxes), cls, keys, n_valid, iou, max_det, 30000,
+                                agnostic ? 0.0f : 7680.0f, xf, nullptr, nullptr, keep, nullptr, count);
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+"""`YOLO(...).predict(...) -> list[Results]` drop-in over the native sm_100a engine.
+
+Host-side mirror of the UPSTREAM surface the reference calls:
+  YOLO(path)                                   reference yolo_seg/app.py:45; yolo_seg/yolo_with_deva.py:226;
+                                               dev_tools/auto_speed_calc.py:40
+  model.predict(source=frame, conf=…, retina_masks=True, device=…)
+                                               reference yolo_seg/app.py:49,91; yolo_seg/yolo_with_deva.py:51
+  next(model.model.parameters()).device / model.model.to(device)
+                                               reference yolo_seg/yolo_with_deva.py:42,130
+Everything numeric — the fused-BN network, DFL decode, NMS, mask decode — runs in libypb200.so on the
+GPU; this module only letterboxes frames on the host (cv2, exactly like UPSTREAM data/augment.py::
+LetterBox), moves bytes, and wraps outputs.  There is no CPU execution path: without a CUDA device
+(or without the compiled library) predict() raises.
+"""
+
+import os
+import time
+
+import numpy as np
+import torch
+
+from .engine import MAX_DET, Engine, YpbError
+from .results import Results
+from .synth import synth_state_dict
+
+KNOWN_SPECS = tuple(f"yolov8{s}-seg" for s in "nsmlx")
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-side geometry (UPSTREAM data/augment.py::LetterBox, utils/ops.py::scale_boxes)
+# ---------------------------------------------------------------------------------------------------
+def letterbox_geometry(shape, new_shape, auto, stride=32):
+    """(h0,w0) -> (resized (w,h), top, bottom, left, right) for LetterBox(center=True, scaleup=True)."""
+    r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+    new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = dw % stride, dh % stride
+    dw, dh = dw / 2, dh / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return new_unpad, top, bottom, left, right
+
+
+def letterbox_into(dst, img, new_unpad, top, left):
+    """Resize `img` (cv2 INTER_LINEAR, as upstream) and paste it into the 114-filled canvas `dst`."""
+    import cv2
+    if (img.shape[1], img.shape[0]) != new_unpad:
+        img = cv2.resize(img, new_unpad, interpolation=cv2.INTER_LINEAR)
+    dst[...] = 114
+    dst[top:top + img.shape[0], left:left + img.shape[1]] = img
+
+
+def box_xform(net_hw, orig_hw):
+    """[pad_w, pad_h, gain, W0, H0] of ops.scale_boxes for one frame."""
+    gain = min(net_hw[0] / orig_hw[0], net_hw[1] / orig_hw[1])
+    pad_w = round((net_hw[1] - orig_hw[1] * gain) / 2 - 0.1)
+    pad_h = round((net_hw[0] - orig_hw[0] * gain) / 2 - 0.1)
+    return [float(pad_w), float(pad_h), float(gain), float(orig_hw[1]), float(orig_hw[0])]
+
+
+def _to_bgr_array(src):
+    if isinstance(src, np.ndarray):
+        if src.ndim != 3 or src.shape[2] != 3 or src.dtype != np.uint8:
+            raise ValueError("ndarray sources must be (H,W,3) uint8 BGR")
+        return src, None
+    if isinstance(src, (str, os.PathLike)):
+        import cv2
+        im = cv2.imread(str(src))
+        if im is None:
+            raise FileNotFoundError(f"cannot read image {src}")
+        return im, str(src)
+    if hasattr(src, "convert"):  # PIL.Image: RGB -> BGR (UPSTREAM LoadPilAndNumpy._single_check)
+        im = np.asarray(src.convert("RGB"))[:, :, ::-1]
+        return np.ascontiguousarray(im), None
+    raise TypeError(f"unsupported source type {type(src)}")
+
+
+class _ModelProxy:
+    """What `yolo.model` must be for the reference: `.parameters()` on the engine's device and `.to()`."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def parameters(self):
+        yield self._owner._device_token
+
+    def to(self, device=None, *a, **k):
+        if device is not None:
+            self._owner._set_device(device)
+        return self
+
+    def eval(self):
+        return self
+
+    @property
+    def names(self):
+        return self._owner.names
+
+
+class YOLO:
+    """Drop-in for `ultralytics.YOLO` on the predict path.
+
+    model: a spec name ("yolov8s-seg"; synthetic weights), or a file written by
+    `torch.save({"spec": ..., "nc": ..., "names": ..., "state_dict": ...})` / a bare upstream-named
+    state_dict (real `.pt` pickles need the upstream classes to unpickle — export their
+    `model.state_dict()` on a box that has ultralytics)."""
+
+    def __init__(self, model="yolov8n-seg", task=None, verbose=False, nc=None, state_dict=None, device=None, seed=0):
+        names = None
+        spec = model
+        if isinstance(model, (str, os.PathLike)) and os.path.exists(str(model)):
+            blob = torch.load(str(model), map_location="cpu", weights_only=True)
+            if "state_dict" in blob:
+                spec, state_dict = blob["spec"], blob["state_dict"]
+                nc = blob.get("nc", nc)
+                names = blob.get("names")
+            else:
+                state_dict = blob
+                spec = os.path.splitext(os.path.basename(str(model)))[0]
+        spec = str(spec)
+        for ext in (".pt", ".yaml", ".pth"):
+            if spec.endswith(ext):
+                spec = spec[: -len(ext)]
+        if nc is None and state_dict is not None:
+            key = next((k for k in state_dict if k.endswith(".cv3.0.2.bias")), None)
+            nc = int(state_dict[key].numel()) if key else 80
+        self.spec = spec
+        self.nc = int(nc or 80)
+        self.task = task or ("segment" if spec.endswith("-seg") else "detect")
+        self.names = names or {i: f"class{i}" for i in range(self.nc)}
+        self.engine = Engine(spec, self.nc)
+        if state_dict is None:
+            state_dict = synth_state_dict([(n, s) for n, s, _ in self.engine.weight_specs()], spec, seed, nc=self.nc)
+        self.engine.load_state_dict(state_dict)
+        self._device = None
+        self._device_token = torch.zeros(1)
+        self._staging = {}
+        self.overrides = {}
+        if device is not None:
+            self._set_device(device)
+
+    # ------------------------------------------------------------------ device handling
+    @staticmethod
+    def _parse_device(device):
+        if device is None or device == "":
+            return torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        if isinstance(device, int):
+            return torch.device("cuda", device)
+        if isinstance(device, str) and device.isdigit():
+            return torch.device("cuda", int(device))
+        d = torch.device(device)
+        if d.type != "cuda":
+            raise YpbError(f"device '{device}': this engine only runs on CUDA sm_100a GPUs (no CPU path)")
+        return torch.device("cuda", d.index or 0)
+
+    def _set_device(self, device):
+        d = self._parse_device(device)
+        if self._device == d:
+            return
+        if not torch.cuda.is_available():
+            raise YpbError("no CUDA device available: the B200 engine has no CPU fallback")
+        self.engine.finalize(d)
+        self._device = d
+        self._device_token = torch.zeros(1, device=d)
+        self._staging = {}
+
+    def to(self, device):
+        self._set_device(device)
+        return self
+
+    @property
+    def model(self):
+        return _ModelProxy(self)
+
+    @property
+    def device(self):
+        return self._device
+
+    # ------------------------------------------------------------------ predict
+    def __call__(self, source=None, **kwargs):
+        return self.predict(source, **kwargs)
+
+    def predict(self, source=None, stream=False, conf=0.25, iou=0.7, retina_masks=False, device=None, imgsz=None,
+                max_det=MAX_DET, classes=None, agnostic_nms=False, half=False, batch=64, verbose=False, **ignored):
+        """One `Results` per frame, in input order.  Unknown kwargs are accepted and ignored like upstream."""
+        if source is None:
+            raise ValueError("predict() needs a source")
+        if device is not None or self._device is None:
+            self._set_device(device)
+        srcs = list(source) if isinstance(source, (list, tuple)) else [source]
+        frames, paths = zip(*[_to_bgr_array(s) for s in srcs])
+        imgsz = imgsz or self.overrides.get("imgsz", 640)
+        imgsz = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        max_det = min(int(max_det), MAX_DET)
+        same_shape = len({f.shape for f in frames}) == 1
+        results = [None] * len(frames)
+        # frames of one original shape share letterbox geometry and mask size: batch them together
+        groups = {}
+        for i, f in enumerate(frames):
+            groups.setdefault(f.shape[:2], []).append(i)
+        for shape, idxs in groups.items():
+            for s in range(0, len(idxs), batch):
+                chunk = idxs[s:s + batch]
+                out = self._predict_batch([frames[i] for i in chunk], shape, imgsz, same_shape, conf, iou,
+                                          retina_masks, max_det, classes, agnostic_nms)
+                for i, r in zip(chunk, out):
+                    r.path = paths[i]
+                    results[i] = r
+        return iter(results) if stream else results
+
+    def _buffers(self, B, H, W):
+        key = (B, H, W)
+        if key not in self._staging:
+            self._staging = {key: {
+                "host": torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory(),
+                "dev": torch.empty((B, H, W, 3), dtype=torch.uint8, device=self._device),
+                "xf_host": torch.empty((B, 5), dtype=torch.float32).pin_memory(),
+                "xf_dev": torch.empty((B, 5), dtype=torch.float32, device=self._device),
+            }}
+        return self._staging[key]
+
+    def _predict_batch(self, frames, shape, imgsz, auto, conf, iou, retina, max_det, classes, agnostic):
+        eng = self.engine
+        B = len(frames)
+        t0 = time.perf_counter()
+        new_unpad, top, bottom, left, right = letterbox_geometry(shape, imgsz, auto)
+        H, W = new_unpad[1] + top + bottom, new_unpad[0] + left + right
+        if H % 32 or W % 32:
+            raise YpbError(f"letterboxed size {H}x{W} is not a multiple of 32 (imgsz={imgsz})")
+        with torch.cuda.device(self._device):
+            eng.plan(B, H, W)
+            buf = self._buffers(B, H, W)
+            host = buf["host"].numpy()
+            for i, f in enumerate(frames):
+                letterbox_into(host[i], f, new_unpad, top, left)
+            xf = box_xform((H, W), shape)
+            buf["xf_host"][:] = torch.tensor(xf)
+            cmask = None
+            if classes is not None:
+                words = np.zeros(((self.nc + 31) // 32,), np.uint32)
+                for c in classes:
+                    words[int(c) >> 5] |= np.uint32(1) << np.uint32(int(c) & 31)
+                cmask = torch.from_numpy(words.view(np.int32)).to(self._device)
+            t1 = time.perf_counter()
+            buf["dev"].copy_(buf["host"], non_blocking=True)
+            buf["xf_dev"].copy_(buf["xf_host"], non_blocking=True)
+            eng.infer(buf["dev"], buf["xf_dev"], conf, iou, max_det, agnostic, cmask)
+            counts = eng.count.cpu()  # stream-ordered D2H: the only host sync of the detector
+            t2 = time.perf_counter()
+            n_tot = int(counts.sum())
+            det = eng.det.clone() if n_tot else None  # stays on the device, like upstream Results.boxes
+            masks = None
+            if self.task == "segment" and n_tot:
+                mh, mw = (shape[0], shape[1]) if retina else (H, W)
+                masks = torch.empty((n_tot, mh, mw), dtype=torch.uint8, device=self._device)
+                eng.masks(masks, retina, mh, mw)
+            err = eng.device_error()
+            if err:
+                raise YpbError(f"device pipeline error word 0x{err:x}")
+            t3 = time.perf_counter()
+        speed = {"preprocess": (t1 - t0) * 1e3 / B, "inference": (t2 - t1) * 1e3 / B, "postprocess": (t3 - t2) * 1e3 / B}
+        out, off = [], 0
+        for i, f in enumerate(frames):
+            n = int(counts[i])
+            boxes = det[i, :n] if n else torch.zeros((0, 6), device=self._device)
+            m = masks[off:off + n] if (masks is not None and n) else None
+            off += n
+            out.append(Results(f, None, self.names, boxes=boxes, masks=m, speed=dict(speed)))
+        return out

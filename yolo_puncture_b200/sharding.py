@@ -1,0 +1,45 @@
+"""Frame sharding across the GPUs of one box.
+
+Frames are independent, so the detector shards by frame with NO collective on the data path: rank r
+owns contiguous chunks of the stream, runs its own engine replica, and the host gathers per-frame
+results back into frame order.  `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is used
+for that host-side gather and for timing barriers only.
+"""
+
+
+def shard_indices(n_frames, rank, world, chunk):
+    """Indices of the frames rank `rank` processes: frame i belongs to rank (i // chunk) % world."""
+    return [i for i in range(n_frames) if (i // chunk) % world == rank]
+
+
+def shard_counts(n_frames, world, chunk):
+    return [len(shard_indices(n_frames, r, world, chunk)) for r in range(world)]
+
+
+def gather_in_frame_order(local_items, n_frames, rank, world, chunk, group=None):
+    """All ranks pass their per-frame payloads (picklable; in local frame order); every rank receives the
+    full list in global frame order.  Host-side gather only."""
+    import torch.distributed as dist
+    mine = shard_indices(n_frames, rank, world, chunk)
+    if len(mine) != len(local_items):
+        raise ValueError(f"rank {rank}: {len(local_items)} items for {len(mine)} owned frames")
+    if world == 1:
+        return list(local_items)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, list(local_items), group=group)
+    out = [None] * n_frames
+    for r in range(world):
+        for idx, item in zip(shard_indices(n_frames, r, world, chunk), gathered[r]):
+            out[idx] = item
+    return out
+
+
+def summarize_results(results):
+    """Compact, picklable per-frame payload: (n, boxes (n,6) numpy) — masks stay on the owning GPU
+    (the DEVA hand-off of reference yolo_seg/yolo_with_deva.py:54-88 is point-to-point, not gathered)."""
+    out = []
+    for r in results:
+        b = r.boxes.data
+        b = b.cpu().numpy() if hasattr(b, "cpu") else b
+        out.append((len(b), b))
+    return out

@@ -89,6 +89,17 @@ typedef struct {
 int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform,
               const ypb_infer_params* params, float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count);
 
+/* Profiling twin of ypb_infer(): brackets every layer op with CUDA events on the caller's stream,
+ * synchronises the stream, and returns the device time of each op in milliseconds (op order =
+ * ypb_op_info order; the last two entries are decode_filter and nms).  Not for the hot loop. */
+int ypb_infer_profile(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform,
+                      const ypb_infer_params* params, float* det, float* det_lb, int32_t* keep, float* coef,
+                      int32_t* count, float* op_ms, int capacity);
+int ypb_op_count(const ypb_engine* e);
+/* kind: 0 stem, 1 tensor-core conv, 2 upsample, 3 sppf pool, 100 decode_filter, 101 nms;
+ * flops / bytes: algorithmic work of the op for the planned batch. */
+int ypb_op_info(const ypb_engine* e, int index, const char** name, int* kind, double* flops, double* bytes);
+
 /* Fused proto-mask decode for the detections of the last ypb_infer() on this engine (reads count/det/coef
  * on the device; no host sync).  Masks are packed in detection order: frame 0's detections first.
  * retina=1: ops.process_mask_native, masks (n,H0,W0) for frames that all have original size H0 x W0;

@@ -38,3 +38,48 @@ def describe_mismatch(got, ref, rtol, atol, max_items=12):
         for b, h, w, c in idx.tolist():
             lines.append(f"  [{b},{h},{w},{c}] got {float(got[b, h, w, c]):.5g} ref {float(ref[b, h, w, c]):.5g}")
     return "\n".join(lines)
+
+
+def oracle_with_synth(name, emulate):
+    """(oracle net fused [+bf16 emulation], state_dict) with the deterministic synthetic weights."""
+    from oracle.model import build_model
+    from yolo_puncture_b200 import synth
+    net = build_model(name)
+    sd = synth.synth_state_dict([(k, v.shape) for k, v in net.state_dict().items()], name)
+    net.load_state_dict(sd)
+    net.fuse()
+    if emulate:
+        net.set_emulation(True)
+    return net, sd
+
+
+def oracle_select_on_engine_tensors(eng, net, B, level_shapes, conf, iou, max_det=300, classes=None, agnostic=False):
+    """Run the ORACLE's decode + NMS on the engine's own fp32 head rows.  Returns (dets, kept_idx, proto)."""
+    from oracle import ops as oops
+    nc = net.nc
+    head = eng.view("head")[:, 0].float().cpu()
+    maps, off = [], 0
+    for (h, w) in level_shapes:
+        maps.append(head[:, off:off + h * w, :64 + nc].permute(0, 2, 1).reshape(B, 64 + nc, h, w))
+        off += h * w
+    with torch.no_grad():
+        pred = torch.cat([net.model[-1]._inference(maps), head[..., 64 + nc:].permute(0, 2, 1)], 1)
+    dets, kept = oops.non_max_suppression(pred, conf, iou, classes=classes, agnostic=agnostic, max_det=max_det, nc=nc,
+                                          return_idx=True)
+    proto = eng.view("proto").float().cpu().permute(0, 3, 1, 2)
+    return dets, kept, proto
+
+
+def mask_iou(a, b):
+    a, b = a.float(), b.float()
+    inter, union = (a * b).sum((1, 2)), ((a + b) > 0).float().sum((1, 2))
+    return inter / union.clamp(min=1)
+
+
+def box_iou_matrix(a, b):
+    lt = torch.max(a[:, None, :2], b[None, :, :2])
+    rb = torch.min(a[:, None, 2:4], b[None, :, 2:4])
+    inter = (rb - lt).clamp(min=0).prod(2)
+    aa = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    ab = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    return inter / (aa[:, None] + ab[None] - inter).clamp(min=1e-9)

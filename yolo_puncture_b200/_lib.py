@@ -40,6 +40,11 @@ SIGNATURES = {
     "ypb_conv_flops": (c_double, [c_void_p]),
     "ypb_infer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(InferParams), c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p]),
+    "ypb_infer_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(InferParams), c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "ypb_op_count": (c_int, [c_void_p]),
+    "ypb_op_info": (c_int, [c_void_p, c_int, C.POINTER(c_char_p), C.POINTER(c_int), C.POINTER(c_double),
+                            C.POINTER(c_double)]),
     "ypb_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_int, c_void_p]),
     "ypb_device_error": (c_int, [c_void_p, C.POINTER(c_uint32)]),

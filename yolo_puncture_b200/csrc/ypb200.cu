@@ -350,6 +350,74 @@ static int folded(const ypb_engine& e, const ConvSrc& s, std::vector<float>* w, 
   return YPB_OK;
 }
 
+
+// Enqueue one layer op on `st`.
+static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t* frames) {
+  const uint8_t* wa = reinterpret_cast<const uint8_t*>(e->w_arena);
+  const int B = e->B;
+  switch (op.kind) {
+    case OP_STEM: {
+      const BufDesc& ob = e->bufs[op.out.buf];
+      dim3 grid((ob.W + kStemTile - 1) / kStemTile, (ob.H + kStemTile - 1) / kStemTile, B);
+      const size_t smem = (size_t)(33 * 33 * 3 + 27 * op.cout + op.cout) * 4;
+      stem_conv_kernel<<<grid, 256, smem, st>>>(frames, e->H, e->W, reinterpret_cast<const float*>(wa + op.w_off),
+                                                 reinterpret_cast<const float*>(wa + op.b_off), op.cout,
+                                                 reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C);
+      break;
+    }
+    case OP_CONV:
+      CUDA_TRY(conv_launch(op.L, st, e->conv_impl));
+      break;
+    case OP_UPSAMPLE: {
+      const BufDesc &ib = e->bufs[op.in.buf], &ob = e->bufs[op.out.buf];
+      const long long total = (long long)B * 4 * ib.H * ib.W * (op.in.C / 8);
+      upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(e->ws + ib.offset), ib.C, op.in.c_off,
+          reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C, op.out.c_off, B, ib.H, ib.W, op.in.C);
+      break;
+    }
+    case OP_SPPF: {
+      const BufDesc& ib = e->bufs[op.in.buf];
+      const long long total = (long long)B * ib.H * ib.W * (op.in.C / 8);
+      sppf_pool_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+          reinterpret_cast<__nv_bfloat16*>(e->ws + ib.offset), B, ib.H, ib.W, op.in.C);
+      break;
+    }
+  }
+  return YPB_OK;
+}
+
+// Selection stage: candidate filter + decode, then batched NMS.
+static int launch_select(ypb_engine* e, cudaStream_t st, const float* xform, const ypb_infer_params* prm, float* det,
+                         float* det_lb, int32_t* keep, float* coef, int32_t* count, cudaEvent_t mid) {
+  const int B = e->B;
+  const HeadGeom& g = e->hg;
+  int* cand_count = reinterpret_cast<int*>(e->ws + e->off_count);
+  CUDA_TRY(cudaMemsetAsync(cand_count, 0, (size_t)B * 4, st));
+  const float* head = reinterpret_cast<const float*>(e->ws + e->off_head);
+  float4* dbox = reinterpret_cast<float4*>(e->ws + e->off_dbox);
+  int* dcls = reinterpret_cast<int*>(e->ws + e->off_dcls);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(e->ws + e->off_keys);
+  const long long warps = (long long)B * g.A;
+  decode_filter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(head, g, B, prm->conf, e->end2end ? 1 : 0,
+                                                                            prm->class_mask, dbox, dcls, keys, cand_count);
+  if (mid) CUDA_TRY(cudaEventRecord(mid, st));
+  nms_kernel<<<B, 256, 0, st>>>(head, g, dbox, dcls, keys, cand_count, prm->iou, prm->max_det, 30000,
+                                prm->agnostic_nms ? 0.0f : 7680.0f, reinterpret_cast<const FrameXform*>(xform), det, det_lb,
+                                keep, coef, count);
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
+static int check_infer_args(ypb_engine* e, const uint8_t* frames, const float* xform, const ypb_infer_params* prm,
+                            float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count) {
+  if (!e || !frames || !xform || !prm || !det || !det_lb || !keep || !count) return fail(YPB_ERR_ARG, "bad argument");
+  if (!e->bound) return fail(YPB_ERR_STATE, "infer: bind a workspace first");
+  if (prm->max_det < 1 || prm->max_det > kNmsMaxDet) return fail(YPB_ERR_ARG, "max_det must be in [1,300]");
+  if (e->nm > 0 && !coef) return fail(YPB_ERR_ARG, "coef buffer required for -seg models");
+  return YPB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -575,59 +643,73 @@ int ypb_set_conv_impl(ypb_engine* e, int impl) {
 
 int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform, const ypb_infer_params* prm,
               float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count) {
-  if (!e || !frames || !xform || !prm || !det || !det_lb || !keep || !count) return fail(YPB_ERR_ARG, "bad argument");
-  if (!e->bound) return fail(YPB_ERR_STATE, "infer: bind a workspace first");
-  if (prm->max_det < 1 || prm->max_det > kNmsMaxDet) return fail(YPB_ERR_ARG, "max_det must be in [1,300]");
-  if (e->nm > 0 && !coef) return fail(YPB_ERR_ARG, "coef buffer required for -seg models");
+  int rc0 = check_infer_args(e, frames, xform, prm, det, det_lb, keep, coef, count);
+  if (rc0) return rc0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-  const uint8_t* wa = reinterpret_cast<const uint8_t*>(e->w_arena);
   const int B = e->B;
   for (const Op& op : e->ops) {
-    switch (op.kind) {
-      case OP_STEM: {
-        const BufDesc& ob = e->bufs[op.out.buf];
-        dim3 grid((ob.W + kStemTile - 1) / kStemTile, (ob.H + kStemTile - 1) / kStemTile, B);
-        const size_t smem = (size_t)(33 * 33 * 3 + 27 * op.cout + op.cout) * 4;
-        stem_conv_kernel<<<grid, 256, smem, st>>>(frames, e->H, e->W, reinterpret_cast<const float*>(wa + op.w_off),
-                                                   reinterpret_cast<const float*>(wa + op.b_off), op.cout,
-                                                   reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C);
-        break;
-      }
-      case OP_CONV:
-        CUDA_TRY(conv_launch(op.L, st, e->conv_impl));
-        break;
-      case OP_UPSAMPLE: {
-        const BufDesc &ib = e->bufs[op.in.buf], &ob = e->bufs[op.out.buf];
-        const long long total = (long long)B * 4 * ib.H * ib.W * (op.in.C / 8);
-        upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            reinterpret_cast<const __nv_bfloat16*>(e->ws + ib.offset), ib.C, op.in.c_off,
-            reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C, op.out.c_off, B, ib.H, ib.W, op.in.C);
-        break;
-      }
-      case OP_SPPF: {
-        const BufDesc& ib = e->bufs[op.in.buf];
-        const long long total = (long long)B * ib.H * ib.W * (op.in.C / 8);
-        sppf_pool_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-            reinterpret_cast<__nv_bfloat16*>(e->ws + ib.offset), B, ib.H, ib.W, op.in.C);
-        break;
-      }
-    }
+    int rc = launch_op(e, op, st, frames);
+    if (rc) return rc;
   }
   CUDA_TRY(cudaGetLastError());
-  const HeadGeom& g = e->hg;
-  int* cand_count = reinterpret_cast<int*>(e->ws + e->off_count);
-  CUDA_TRY(cudaMemsetAsync(cand_count, 0, (size_t)B * 4, st));
-  const float* head = reinterpret_cast<const float*>(e->ws + e->off_head);
-  float4* dbox = reinterpret_cast<float4*>(e->ws + e->off_dbox);
-  int* dcls = reinterpret_cast<int*>(e->ws + e->off_dcls);
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(e->ws + e->off_keys);
-  const long long warps = (long long)B * g.A;
-  decode_filter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(head, g, B, prm->conf, e->end2end ? 1 : 0,
-                                                                            prm->class_mask, dbox, dcls, keys, cand_count);
-  nms_kernel<<<B, 256, 0, st>>>(head, g, dbox, dcls, keys, cand_count, prm->iou, prm->max_det, 30000,
-                                prm->agnostic_nms ? 0.0f : 7680.0f, reinterpret_cast<const FrameXform*>(xform), det, det_lb,
-                                keep, coef, count);
-  CUDA_TRY(cudaGetLastError());
+  return launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, nullptr);
+}
+
+int ypb_op_count(const ypb_engine* e) { return e ? (int)e->ops.size() + 2 : 0; }
+
+int ypb_op_info(const ypb_engine* e, int i, const char** name, int* kind, double* flops, double* bytes) {
+  if (!e || !e->planned || i < 0 || i >= (int)e->ops.size() + 2) return fail(YPB_ERR_ARG, "bad op index / not planned");
+  static const char* sel_names[2] = {"decode_filter", "nms"};
+  const int n = (int)e->ops.size();
+  if (i >= n) {
+    *name = sel_names[i - n]; *kind = 100 + (i - n); *flops = 0;
+    *bytes = (i == n) ? (double)e->B * e->A * e->no * 4 : (double)e->B * 300 * (6 + 4 + 1 + e->nm) * 4;
+    return YPB_OK;
+  }
+  const Op& op = e->ops[i];
+  *name = op.name.c_str(); *kind = (int)op.kind;
+  const int B = e->B;
+  if (op.kind == OP_STEM) {
+    *flops = 2.0 * B * (e->H / 2) * (e->W / 2) * op.cout * 27;
+    *bytes = (double)B * e->H * e->W * 3 + (double)B * (e->H / 2) * (e->W / 2) * op.cout * 2;
+  } else if (op.kind == OP_CONV) {
+    const BufDesc& ib = e->bufs[op.in.buf];
+    const double M = (double)B * op.L.oH * op.L.oW;
+    *flops = op.L.flops;
+    *bytes = (double)B * ib.H * ib.W * op.cin * 2 + M * op.cout * (op.out_mode == OUT_F32 ? 4 : 2) +
+             (double)op.k * op.k * op.cin * op.cout * 2 + (op.res.buf >= 0 ? M * op.cout * 2 : 0.0);
+  } else if (op.kind == OP_UPSAMPLE) {
+    const BufDesc& ib = e->bufs[op.in.buf];
+    *flops = 0; *bytes = (double)B * ib.H * ib.W * op.in.C * 2 * 5;
+  } else {
+    const BufDesc& ib = e->bufs[op.in.buf];
+    *flops = 0; *bytes = (double)B * ib.H * ib.W * op.in.C * 2 * 4;
+  }
+  return YPB_OK;
+}
+
+int ypb_infer_profile(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform,
+                      const ypb_infer_params* prm, float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count,
+                      float* op_ms, int capacity) {
+  int rc = check_infer_args(e, frames, xform, prm, det, det_lb, keep, coef, count);
+  if (rc) return rc;
+  const int n = (int)e->ops.size();
+  if (!op_ms || capacity < n + 2) return fail(YPB_ERR_ARG, "op_ms too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  std::vector<cudaEvent_t> ev(n + 3);
+  for (auto& x : ev) CUDA_TRY(cudaEventCreate(&x));
+  CUDA_TRY(cudaEventRecord(ev[0], st));
+  for (int i = 0; i < n; ++i) {
+    rc = launch_op(e, e->ops[i], st, frames);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev[i + 1], st));
+  }
+  rc = launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, ev[n + 1]);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(ev[n + 2], st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int i = 0; i < n + 2; ++i) CUDA_TRY(cudaEventElapsedTime(op_ms + i, ev[i], ev[i + 1]));
+  for (auto& x : ev) cudaEventDestroy(x);
   return YPB_OK;
 }
 

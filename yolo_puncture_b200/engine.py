@@ -116,6 +116,26 @@ class Engine:
         check(self._lib.ypb_infer(self._h, C.c_void_p(st), _ptr(frames), _ptr(xform), C.byref(prm), _ptr(self.det),
                                   _ptr(self.det_lb), _ptr(self.keep), _ptr(self.coef), _ptr(self.count)))
 
+    def ops(self):
+        """[(name, kind, flops, bytes)] of the planned layer ops (+ decode_filter, nms)."""
+        out = []
+        for i in range(self._lib.ypb_op_count(self._h)):
+            name, kind, fl, by = C.c_char_p(), C.c_int(), C.c_double(), C.c_double()
+            check(self._lib.ypb_op_info(self._h, i, C.byref(name), C.byref(kind), C.byref(fl), C.byref(by)))
+            out.append((name.value.decode(), kind.value, fl.value, by.value))
+        return out
+
+    def infer_profile(self, frames, xform, conf=0.25, iou=0.7, max_det=MAX_DET):
+        """Like infer() but returns the device milliseconds of every op (CUDA events around each launch)."""
+        n = self._lib.ypb_op_count(self._h)
+        ms = (C.c_float * n)()
+        prm = InferParams(float(conf), float(iou), int(max_det), 0, None)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.ypb_infer_profile(self._h, C.c_void_p(st), _ptr(frames), _ptr(xform), C.byref(prm),
+                                          _ptr(self.det), _ptr(self.det_lb), _ptr(self.keep), _ptr(self.coef),
+                                          _ptr(self.count), ms, n))
+        return list(ms)
+
     def masks(self, out, retina, out_h=0, out_w=0):
         """out: cuda uint8 (capacity, h, w).  Decodes masks of the last infer() in detection order."""
         st = torch.cuda.current_stream(self.device).cuda_stream

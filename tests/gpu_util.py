@@ -73,7 +73,7 @@ def oracle_select_on_engine_tensors(eng, net, B, level_shapes, conf, iou, max_de
 def mask_iou(a, b):
     a, b = a.float(), b.float()
     inter, union = (a * b).sum((1, 2)), ((a + b) > 0).float().sum((1, 2))
-    return inter / union.clamp(min=1)
+    return torch.where(union > 0, inter / union.clamp(min=1), torch.ones_like(union))  # two empty masks agree
 
 
 def box_iou_matrix(a, b):

@@ -105,7 +105,7 @@ def main():
                 me = masks[o:o + n].cpu().float()
                 inter = (mo * me).sum((1, 2))
                 union = ((mo + me) > 0).float().sum((1, 2))
-                iou = (inter / union.clamp(min=1))
+                iou = torch.where(union > 0, inter / union.clamp(min=1), torch.ones_like(union))
                 print(f"         mask IoU min {iou.min().item():.5f} mean {iou.mean().item():.5f} "
                       f"mismatch px {(mo != me).sum().item()} of {mo.numel()}")
             o += cnt[b]

@@ -56,7 +56,7 @@ decode_filter_kernel(const float* __restrict__ head, HeadGeom g, int nB, float c
   const float score = sigmoid_f(best);
   if (!(score > conf)) return;  // warp-uniform
   // predict(classes=[...]): upstream filters on the arg-max class after the confidence test
-  if (cls_mask != nullptr && !((cls_mask[bidx >> 5] >> (bidx & 31)) & 1u)) return;
+  if (!xyxy_direct && cls_mask != nullptr && !((cls_mask[bidx >> 5] >> (bidx & 31)) & 1u)) return;
 
   // ---- DFL: softmax over 16 bins per side, expectation; lane l holds side l/16 (and +2) bin l%16 ----
   float d[2];
@@ -103,6 +103,30 @@ decode_filter_kernel(const float* __restrict__ head, HeadGeom g, int nB, float c
       ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)a);
 }
 
+// End-to-end (YOLOv10, NMS-free) heads: every (anchor, class) pair with score > conf is a candidate of the
+// top-k; key = score_bits << 32 | ~(anchor*nc + class).  Runs after decode_filter_kernel(xyxy_direct=1), which
+// has already written the xyxy box of every anchor whose best class passes conf.  One warp per anchor.
+__global__ void __launch_bounds__(256)
+pair_candidates_kernel(const float* __restrict__ head, HeadGeom g, int nB, float conf, const unsigned* __restrict__ cls_mask,
+                       unsigned long long* __restrict__ cand_keys, int* __restrict__ cand_count) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)nB * g.A) return;
+  const int b = (int)(wid / g.A), a = (int)(wid - (long long)b * g.A);
+  const float* row = head + wid * g.no;
+  for (int c = lane; c < g.nc; c += 32) {
+    const float score = sigmoid_f(row[64 + c]);
+    if (!(score > conf)) continue;
+    if (cls_mask != nullptr && !((cls_mask[c >> 5] >> (c & 31)) & 1u)) continue;
+    const int slot = atomicAdd(cand_count + b, 1);
+    if (slot < g.cand_stride)
+      cand_keys[(long long)b * g.cand_stride + slot] =
+          ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(a * g.nc + c));
+    else
+      atomicOr(&g_dev_error, 0x100u);  // candidate list overflow (conf far below any sensible value)
+  }
+}
+
 // In-place bitonic sort, descending, of n_pow2 keys (any address space), by one CTA.
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* k, int n_pow2) {
   for (int size = 2; size <= n_pow2; size <<= 1) {
@@ -143,7 +167,7 @@ constexpr int kNmsMaxDet = 300;
 __global__ void __launch_bounds__(256)
 nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict__ dbox, const int* __restrict__ dcls,
            unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_count, float iou_thr, int max_det,
-           int max_nms, float max_wh, const FrameXform* __restrict__ xf, float* __restrict__ det,
+           int max_nms, float max_wh, int e2e, const FrameXform* __restrict__ xf, float* __restrict__ det,
            float* __restrict__ det_lb, int* __restrict__ keep, float* __restrict__ coef, int* __restrict__ count) {
   __shared__ unsigned long long s_keys[kNmsSmemKeys];
   __shared__ float s_kept[kNmsMaxDet][5];  // offset box + area
@@ -151,7 +175,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
   __shared__ int s_nkept;
   const int b = blockIdx.x;
   int n = cand_count[b];
-  if (n > g.A) n = g.A;
+  if (n > g.cand_stride) n = g.cand_stride;
   unsigned long long* gk = cand_keys + (long long)b * g.cand_stride;
   int n_pow2 = 1;
   while (n_pow2 < n) n_pow2 <<= 1;
@@ -166,7 +190,19 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
   bitonic_sort_desc(keys, n_pow2);
   if (n > max_nms) n = max_nms;
 
-  if (threadIdx.x < 32) {
+  __shared__ int s_cls[kNmsMaxDet];
+  if (e2e) {
+    // UPSTREAM Detect.postprocess + `pred[pred[:, 4] > conf][:max_det]`: the top-max_det pairs by score, no suppression
+    const int nk = n < max_det ? n : max_det;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+      const unsigned long long key = keys[i];
+      const unsigned pair = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+      s_score[i] = __uint_as_float((unsigned)(key >> 32));
+      s_cls[i] = (int)(pair % (unsigned)g.nc);
+      keep[(long long)b * max_det + i] = (int)(pair / (unsigned)g.nc);
+    }
+    if (threadIdx.x == 0) { s_nkept = nk; count[b] = nk; }
+  } else if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     int nkept = 0;
     for (int i0 = 0; i0 < n && nkept < max_det; i0 += 32) {
@@ -197,6 +233,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
         if (lane == l) {
           s_kept[nkept][0] = x1; s_kept[nkept][1] = y1; s_kept[nkept][2] = x2; s_kept[nkept][3] = y2; s_kept[nkept][4] = area;
           s_score[nkept] = score;
+          s_cls[nkept] = dcls[(long long)b * g.A + anchor];
           keep[(long long)b * max_det + nkept] = anchor;
         }
         ++nkept;
@@ -214,7 +251,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
     const int anchor = keep[(long long)b * max_det + i];
     const long long ga = (long long)b * g.A + anchor;
     const float4 bx = dbox[ga];
-    const int cls = dcls[ga];
+    const int cls = s_cls[i];
     const float score = s_score[i];
     if (det == nullptr) continue;  // selection-only call (ypb_nms)
     float* lb = det_lb + ((long long)b * max_det + i) * 4;

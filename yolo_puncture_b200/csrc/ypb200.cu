@@ -25,6 +25,7 @@
 #include "head_kernels.cuh"
 #include "mask_kernels.cuh"
 #include "misc_kernels.cuh"
+#include "v10_kernels.cuh"
 
 using namespace ypb;
 
@@ -57,7 +58,7 @@ struct BufDesc {
 };
 struct View { int buf = -1, c_off = 0, C = 0; };
 
-enum OpKind { OP_STEM, OP_CONV, OP_UPSAMPLE, OP_SPPF };
+enum OpKind { OP_STEM, OP_CONV, OP_UPSAMPLE, OP_SPPF, OP_DW, OP_ATTN };
 enum SrcKind { SRC_CONV_BN = 0, SRC_CONV_BIAS = 1, SRC_CONVT = 2 };
 struct ConvSrc { std::string mod; int kind; int cout; };
 
@@ -70,6 +71,8 @@ struct Op {
   int head_lvl = -1, head_coff = 0;
   size_t w_off = 0, b_off = 0;  // byte offsets in the weight arena
   ConvLaunch L;
+  // OP_ATTN: in = qkv buffer view, res = pe view, out = output view
+  int heads = 0;
 };
 
 struct NamedView { std::string name; View v; };
@@ -188,6 +191,73 @@ struct ypb_engine {
     op.kind = OP_SPPF; op.name = mod + ".pool"; op.in = slice(S, 0, c_); op.out = whole(S);
     ops.push_back(op);
     conv1(mod + ".cv2", whole(S), out, 1, 1);
+  }
+  // depthwise Conv(+BN)(+SiLU); several modules may be summed into one kernel (RepVGGDW: 7x7 + 3x3)
+  void dwconv(const std::vector<std::string>& mods, const std::vector<int>& ks, View in, View out, int k, int s,
+              bool act, View res = View()) {
+    Op op;
+    op.kind = OP_DW; op.name = mods[0];
+    op.cin = in.C; op.cout = in.C; op.k = k; op.s = s; op.act = act ? 1 : 0; op.in = in; op.out = out; op.res = res;
+    for (size_t i = 0; i < mods.size(); ++i) {
+      ConvSrc src{mods[i], SRC_CONV_BN, in.C};
+      add_conv_weights(src, 1, ks[i]);
+      op.srcs.push_back(src);
+    }
+    ops.push_back(op);
+  }
+  // plain Conv(+BN), no activation, optional residual (Attention.proj / PSA.ffn[1])
+  void conv_noact(const std::string& mod, View in, View out, View res = View()) { conv1(mod, in, out, 1, 1, false, res); }
+  // UPSTREAM block.py::SCDown
+  void scdown(const std::string& mod, View in, View out, int lvl_in) {
+    const int t = new_buf(mod + ".t", lvl_in, out.C);
+    conv1(mod + ".cv1", in, whole(t), 1, 1);
+    dwconv({mod + ".cv2"}, {3}, whole(t), out, 3, 2, false);
+  }
+  // UPSTREAM block.py::PSA (+ Attention), heads = c/64, key_dim 32, head_dim 64
+  void psa(const std::string& mod, View in, View out, int lvl) {
+    const int c = in.C / 2, nh = c / 64;
+    const int P = new_buf(mod + ".ab", lvl, 2 * c), Q = new_buf(mod + ".qkv", lvl, 2 * c), PE = new_buf(mod + ".pe", lvl, c);
+    const int AO = new_buf(mod + ".ao", lvl, c), F = new_buf(mod + ".ffn", lvl, 2 * c);
+    conv1(mod + ".cv1", in, whole(P), 1, 1);
+    const View b = slice(P, c, c);
+    conv_noact(mod + ".attn.qkv", b, whole(Q));
+    {  // pe: depthwise 3x3 over v (the v channels of each head are a strided subset of the qkv buffer)
+      Op op;
+      op.kind = OP_DW; op.name = mod + ".attn.pe";
+      op.cin = c; op.cout = c; op.k = 3; op.s = 1; op.act = 0; op.in = whole(Q); op.out = whole(PE); op.heads = nh;
+      ConvSrc src{mod + ".attn.pe", SRC_CONV_BN, c};
+      add_conv_weights(src, 1, 3);
+      op.srcs.push_back(src);
+      ops.push_back(op);
+    }
+    {
+      Op op;
+      op.kind = OP_ATTN; op.name = mod + ".attn"; op.in = whole(Q); op.res = whole(PE); op.out = whole(AO); op.heads = nh;
+      ops.push_back(op);
+    }
+    conv_noact(mod + ".attn.proj", whole(AO), b, b);          // b = b + attn(b), in place
+    conv1(mod + ".ffn.0", b, whole(F), 1, 1);
+    conv_noact(mod + ".ffn.1", whole(F), b, b);               // b = b + ffn(b), in place
+    conv1(mod + ".cv2", whole(P), out, 1, 1);
+  }
+  // UPSTREAM block.py::C2fCIB with CIB(c, c, shortcut, e=1.0, lk)
+  void c2fcib(const std::string& mod, View in, View out, int n, bool shortcut, bool lk, int lvl) {
+    const int c = out.C / 2;
+    const int Y = new_buf(mod + ".cat", lvl, (2 + n) * c);
+    conv1(mod + ".cv1", in, slice(Y, 0, 2 * c), 1, 1);
+    for (int j = 0; j < n; ++j) {
+      const std::string cm = mod + ".m." + std::to_string(j) + ".cv1.";
+      const View x = slice(Y, (1 + j) * c, c);
+      const int t0 = new_buf(cm + "t0", lvl, c), t1 = new_buf(cm + "t1", lvl, 2 * c), t2 = new_buf(cm + "t2", lvl, 2 * c);
+      const int t3 = new_buf(cm + "t3", lvl, c);
+      dwconv({cm + "0"}, {3}, x, whole(t0), 3, 1, true);
+      conv1(cm + "1", whole(t0), whole(t1), 1, 1);
+      if (lk) dwconv({cm + "2.conv", cm + "2.conv1"}, {7, 3}, whole(t1), whole(t2), 7, 1, true);
+      else dwconv({cm + "2"}, {3}, whole(t1), whole(t2), 3, 1, true);
+      conv1(cm + "3", whole(t2), whole(t3), 1, 1);
+      dwconv({cm + "4"}, {3}, whole(t3), slice(Y, (2 + j) * c, c), 3, 1, true, shortcut ? x : View());
+    }
+    conv1(mod + ".cv2", whole(Y), out, 1, 1);
   }
   void upsample(View in, View out) {
     Op op;
@@ -311,6 +381,94 @@ static bool build_v8seg(ypb_engine& e, char scale) {
   return true;
 }
 
+
+static bool build_v10n(ypb_engine& e) {
+  const double w = 0.25;
+  auto ch = [&](int c) { return make_div8(std::min(c, 1024) * w); };
+  const int c64 = ch(64), c128 = ch(128), c256 = ch(256), c512 = ch(512), c1024 = ch(1024);
+  e.nm = 0; e.end2end = true;
+  const std::string M = "model.";
+  const int x0 = e.new_buf("model.0", 1, c64), x1 = e.new_buf("model.1", 2, c128), x2 = e.new_buf("model.2", 2, c128);
+  const int x3 = e.new_buf("model.3", 3, c256);
+  const int cat15 = e.new_buf("model.15", 3, c512 + c256);   // [up(13) | 4]
+  const int x5 = e.new_buf("model.5", 4, c512);
+  const int cat12 = e.new_buf("model.12", 4, c1024 + c512);  // [up(10) | 6]
+  const int x7 = e.new_buf("model.7", 5, c1024), x8 = e.new_buf("model.8", 5, c1024), x9 = e.new_buf("model.9", 5, c1024);
+  const int cat21 = e.new_buf("model.21", 5, c512 + c1024);  // [20 | 10]
+  const int cat18 = e.new_buf("model.18", 4, c256 + c512);   // [17 | 13]
+  const int x16 = e.new_buf("model.16", 3, c256), x19 = e.new_buf("model.19", 4, c512), x22 = e.new_buf("model.22", 5, c1024);
+  const View v4 = e.slice(cat15, c512, c256), v6 = e.slice(cat12, c1024, c512), v10 = e.slice(cat21, c512, c1024);
+  const View v13 = e.slice(cat18, c256, c512), v17 = e.slice(cat18, 0, c256), v20 = e.slice(cat21, 0, c512);
+  {
+    Op op;
+    op.kind = OP_STEM; op.name = "model.0"; op.cin = 3; op.cout = c64; op.k = 3; op.s = 2; op.out = e.whole(x0);
+    ConvSrc src{"model.0", SRC_CONV_BN, c64};
+    e.add_conv_weights(src, 3, 3);
+    op.srcs.push_back(src);
+    e.ops.push_back(op);
+  }
+  e.conv1(M + "1", e.whole(x0), e.whole(x1), 3, 2);
+  e.c2f(M + "2", e.whole(x1), e.whole(x2), 1, true, 2);
+  e.conv1(M + "3", e.whole(x2), e.whole(x3), 3, 2);
+  e.c2f(M + "4", e.whole(x3), v4, 2, true, 3);
+  e.scdown(M + "5", v4, e.whole(x5), 3);
+  e.c2f(M + "6", e.whole(x5), v6, 2, true, 4);
+  e.scdown(M + "7", v6, e.whole(x7), 4);
+  e.c2f(M + "8", e.whole(x7), e.whole(x8), 1, true, 5);
+  e.sppf(M + "9", e.whole(x8), e.whole(x9), 5);
+  e.psa(M + "10", e.whole(x9), v10, 5);
+  e.upsample(v10, e.slice(cat12, 0, c1024));
+  e.c2f(M + "13", e.whole(cat12), v13, 1, false, 4);
+  e.upsample(v13, e.slice(cat15, 0, c512));
+  e.c2f(M + "16", e.whole(cat15), e.whole(x16), 1, false, 3);
+  e.conv1(M + "17", e.whole(x16), v17, 3, 2);
+  e.c2f(M + "19", e.whole(cat18), e.whole(x19), 1, false, 4);
+  e.scdown(M + "20", e.whole(x19), v20, 4);
+  e.c2fcib(M + "22", e.whole(cat21), e.whole(x22), 1, true, true, 5);
+  e.name_view("model.0", e.whole(x0)); e.name_view("model.1", e.whole(x1)); e.name_view("model.2", e.whole(x2));
+  e.name_view("model.3", e.whole(x3)); e.name_view("model.4", v4); e.name_view("model.5", e.whole(x5));
+  e.name_view("model.6", v6); e.name_view("model.7", e.whole(x7)); e.name_view("model.8", e.whole(x8));
+  e.name_view("model.9", e.whole(x9)); e.name_view("model.10", v10); e.name_view("model.12", e.whole(cat12));
+  e.name_view("model.13", v13); e.name_view("model.15", e.whole(cat15)); e.name_view("model.16", e.whole(x16));
+  e.name_view("model.17", v17); e.name_view("model.18", e.whole(cat18)); e.name_view("model.19", e.whole(x19));
+  e.name_view("model.20", v20); e.name_view("model.21", e.whole(cat21)); e.name_view("model.22", e.whole(x22));
+
+  // v10Detect (UPSTREAM head.py::v10Detect): only the one-to-one branches run at inference
+  const std::string Hd = "model.23.";
+  const int chs[3] = {c256, c512, c1024};
+  const View P[3] = {e.whole(x16), e.whole(x19), e.whole(x22)};
+  const int hc2 = std::max(std::max(16, chs[0] / 4), 64), hc3 = std::max(chs[0], std::min(e.nc, 100));
+  for (int i = 0; i < 3; ++i) {
+    e.feat[i] = P[i];
+    const std::string si = std::to_string(i);
+    const int lvl = 3 + i, x = chs[i];
+    const std::string b2 = Hd + "one2one_cv2." + si + ".", b3 = Hd + "one2one_cv3." + si + ".";
+    const int t0 = e.new_buf(b2 + "t0", lvl, hc2), t1 = e.new_buf(b2 + "t1", lvl, hc2);
+    e.conv1(b2 + "0", P[i], e.whole(t0), 3, 1);
+    e.conv1(b2 + "1", e.whole(t0), e.whole(t1), 3, 1);
+    e.head_out(b2 + "2", e.whole(t1), 64, i, 0);
+    const int u0 = e.new_buf(b3 + "u0", lvl, x), u1 = e.new_buf(b3 + "u1", lvl, hc3), u2 = e.new_buf(b3 + "u2", lvl, hc3);
+    const int u3 = e.new_buf(b3 + "u3", lvl, hc3);
+    e.dwconv({b3 + "0.0"}, {3}, P[i], e.whole(u0), 3, 1, true);
+    e.conv1(b3 + "0.1", e.whole(u0), e.whole(u1), 1, 1);
+    e.dwconv({b3 + "1.0"}, {3}, e.whole(u1), e.whole(u2), 3, 1, true);
+    e.conv1(b3 + "1.1", e.whole(u2), e.whole(u3), 1, 1);
+    e.head_out(b3 + "2", e.whole(u3), e.nc, i, 64);
+    // one-to-many twins: in every checkpoint, never executed
+    const std::string m2 = Hd + "cv2." + si + ".", m3 = Hd + "cv3." + si + ".";
+    e.add_conv_weights(ConvSrc{m2 + "0", SRC_CONV_BN, hc2}, x, 3, false);
+    e.add_conv_weights(ConvSrc{m2 + "1", SRC_CONV_BN, hc2}, hc2, 3, false);
+    e.add_conv_weights(ConvSrc{m2 + "2", SRC_CONV_BIAS, 64}, hc2, 1, false);
+    e.add_conv_weights(ConvSrc{m3 + "0.0", SRC_CONV_BN, x}, 1, 3, false);
+    e.add_conv_weights(ConvSrc{m3 + "0.1", SRC_CONV_BN, hc3}, x, 1, false);
+    e.add_conv_weights(ConvSrc{m3 + "1.0", SRC_CONV_BN, hc3}, 1, 3, false);
+    e.add_conv_weights(ConvSrc{m3 + "1.1", SRC_CONV_BN, hc3}, hc3, 1, false);
+    e.add_conv_weights(ConvSrc{m3 + "2", SRC_CONV_BIAS, e.nc}, hc3, 1, false);
+  }
+  e.add_weight(Hd + "dfl.conv.weight", {1, 16, 1, 1}, false);
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // weights: BN fold + repack
 // ------------------------------------------------------------------------------------------------
@@ -383,6 +541,48 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
           reinterpret_cast<__nv_bfloat16*>(e->ws + ib.offset), B, ib.H, ib.W, op.in.C);
       break;
     }
+    case OP_DW: {
+      const BufDesc &ib = e->bufs[op.in.buf], &ob = e->bufs[op.out.buf];
+      DwParams p{};
+      p.in = reinterpret_cast<const __nv_bfloat16*>(e->ws + ib.offset);
+      p.H = ib.H; p.W = ib.W; p.in_ctot = ib.C; p.in_c_off = op.in.c_off;
+      p.wk = reinterpret_cast<const __nv_bfloat16*>(wa + op.w_off);
+      p.bias = reinterpret_cast<const float*>(wa + op.b_off);
+      p.C = op.cout; p.k = op.k; p.stride = op.s; p.act = op.act;
+      p.out = reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset);
+      p.oH = ob.H; p.oW = ob.W; p.out_ctot = ob.C; p.out_c_off = op.out.c_off;
+      if (op.res.buf >= 0) {
+        p.res = reinterpret_cast<const __nv_bfloat16*>(e->ws + e->bufs[op.res.buf].offset);
+        p.res_ctot = e->bufs[op.res.buf].C; p.res_c_off = op.res.c_off;
+      }
+      p.nB = B;
+      if (op.heads > 0) {  // Attention.pe: one launch per head over that head's v channels of the qkv buffer
+        const int hd = kAttnHD, hc = 2 * kAttnKD + kAttnHD;
+        for (int h = 0; h < op.heads; ++h) {
+          DwParams q = p;
+          q.C = hd; q.in_c_off = h * hc + 2 * kAttnKD; q.out_c_off = h * hd;
+          q.wk = p.wk + h * hd; q.bias = p.bias + h * hd;
+          // weights are [tap][C_total]: give the kernel the full row stride through a strided view
+          q.in = p.in; q.out = p.out;
+          const long long total = (long long)B * ob.H * ob.W * (hd / 8);
+          dwconv_strided_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(q, op.cout);
+        }
+      } else {
+        const long long total = (long long)B * ob.H * ob.W * (op.cout / 8);
+        dwconv_strided_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p, op.cout);
+      }
+      break;
+    }
+    case OP_ATTN: {
+      const BufDesc &qb = e->bufs[op.in.buf], &pb = e->bufs[op.res.buf], &ob = e->bufs[op.out.buf];
+      const int N = qb.H * qb.W;
+      dim3 grid((N + kAttnThreads - 1) / kAttnThreads, op.heads, B);
+      psa_attention_kernel<<<grid, kAttnThreads, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(e->ws + qb.offset), qb.C, op.in.c_off,
+          reinterpret_cast<const __nv_bfloat16*>(e->ws + pb.offset), pb.C, op.res.c_off,
+          reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C, op.out.c_off, N, 1.0f / std::sqrt((float)kAttnKD));
+      break;
+    }
   }
   return YPB_OK;
 }
@@ -401,10 +601,15 @@ static int launch_select(ypb_engine* e, cudaStream_t st, const float* xform, con
   const long long warps = (long long)B * g.A;
   decode_filter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(head, g, B, prm->conf, e->end2end ? 1 : 0,
                                                                             prm->class_mask, dbox, dcls, keys, cand_count);
+  if (e->end2end) {  // NMS-free head: candidates are (anchor, class) pairs; rebuild the key list from scratch
+    CUDA_TRY(cudaMemsetAsync(cand_count, 0, (size_t)B * 4, st));
+    pair_candidates_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(head, g, B, prm->conf, prm->class_mask, keys,
+                                                                              cand_count);
+  }
   if (mid) CUDA_TRY(cudaEventRecord(mid, st));
   nms_kernel<<<B, 256, 0, st>>>(head, g, dbox, dcls, keys, cand_count, prm->iou, prm->max_det, 30000,
-                                prm->agnostic_nms ? 0.0f : 7680.0f, reinterpret_cast<const FrameXform*>(xform), det, det_lb,
-                                keep, coef, count);
+                                prm->agnostic_nms ? 0.0f : 7680.0f, e->end2end ? 1 : 0,
+                                reinterpret_cast<const FrameXform*>(xform), det, det_lb, keep, coef, count);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;
 }
@@ -434,6 +639,7 @@ int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out) {
   bool ok = false;
   const std::string s = model_spec;
   if (s.size() == 11 && s.rfind("yolov8", 0) == 0 && s.substr(7) == "-seg") ok = build_v8seg(*e, s[6]);
+  if (s == "yolov10n") ok = build_v10n(*e);
   if (!ok) {
     delete e;
     return fail(YPB_ERR_ARG, "unknown model spec '" + s + "'");
@@ -484,10 +690,33 @@ int ypb_finalize_weights(ypb_engine* e, int device) {
     } else if (op.kind == OP_CONV) {
       op.w_off = off; off = align(off + (size_t)op.k * op.k * op.cout * op.cin * 2);
       op.b_off = off; off = align(off + (size_t)op.cout * 4);
+    } else if (op.kind == OP_DW) {
+      op.w_off = off; off = align(off + (size_t)op.k * op.k * op.cout * 2);
+      op.b_off = off; off = align(off + (size_t)op.cout * 4);
     }
   }
   std::vector<uint8_t> host(off, 0);
   for (Op& op : e->ops) {
+    if (op.kind == OP_DW) {  // depthwise: [tap][C] bf16; RepVGGDW sums the centred 3x3 into the 7x7 in fp32 first
+      const int C = op.cout, kk = op.k * op.k;
+      std::vector<float> wsum((size_t)kk * C, 0.f);
+      float* bias = reinterpret_cast<float*>(host.data() + op.b_off);
+      for (const ConvSrc& s : op.srcs) {
+        std::vector<float> w, b;
+        int rc = folded(*e, s, &w, &b);
+        if (rc) return rc;
+        const int ks = (int)std::lround(std::sqrt((double)(w.size() / C)));
+        const int o = (op.k - ks) / 2;
+        for (int c = 0; c < C; ++c) {
+          for (int kh = 0; kh < ks; ++kh)
+            for (int kw = 0; kw < ks; ++kw) wsum[(size_t)((kh + o) * op.k + kw + o) * C + c] += w[((size_t)c * ks + kh) * ks + kw];
+          bias[c] += b[c];
+        }
+      }
+      uint16_t* wk = reinterpret_cast<uint16_t*>(host.data() + op.w_off);
+      for (size_t i = 0; i < wsum.size(); ++i) wk[i] = f32_to_bf16(wsum[i]);
+      continue;
+    }
     if (op.kind != OP_STEM && op.kind != OP_CONV) continue;
     float* bias = reinterpret_cast<float*>(host.data() + op.b_off);
     int n_off = 0;
@@ -575,6 +804,12 @@ int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
   for (Op& op : e->ops) {
     ++e->launches;
     if (op.kind == OP_STEM) { e->flops += 2.0 * B * (H / 2) * (W / 2) * op.cout * 27; continue; }
+    if (op.kind == OP_DW) {
+      const BufDesc& ob = e->bufs[op.out.buf];
+      e->flops += 2.0 * B * ob.H * ob.W * op.cout * op.k * op.k;
+      if (op.heads > 1) e->launches += op.heads - 1;
+      continue;
+    }
     if (op.kind != OP_CONV) continue;
     const BufDesc& ib = e->bufs[op.in.buf];
     ConvDesc d;
@@ -595,7 +830,7 @@ int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
     if (!conv_plan_geometry(d, &op.L, &err)) return fail(YPB_ERR_ARG, op.name + ": " + err);
     e->flops += op.L.flops;
   }
-  e->launches += 2;  // decode_filter + nms
+  e->launches += e->end2end ? 3 : 2;  // decode_filter (+ pair_candidates) + nms
   e->planned = true;
   e->bound = false;
   if (workspace_bytes) *workspace_bytes = off;
@@ -681,6 +916,15 @@ int ypb_op_info(const ypb_engine* e, int i, const char** name, int* kind, double
   } else if (op.kind == OP_UPSAMPLE) {
     const BufDesc& ib = e->bufs[op.in.buf];
     *flops = 0; *bytes = (double)B * ib.H * ib.W * op.in.C * 2 * 5;
+  } else if (op.kind == OP_DW) {
+    const BufDesc &ib = e->bufs[op.in.buf], &ob = e->bufs[op.out.buf];
+    *flops = 2.0 * B * ob.H * ob.W * op.cout * op.k * op.k;
+    *bytes = (double)B * ib.H * ib.W * op.cout * 2 + (double)B * ob.H * ob.W * op.cout * 2 * (op.res.buf >= 0 ? 2 : 1);
+  } else if (op.kind == OP_ATTN) {
+    const BufDesc& qb = e->bufs[op.in.buf];
+    const double N = (double)qb.H * qb.W;
+    *flops = 2.0 * B * op.heads * N * N * (kAttnKD + kAttnHD);
+    *bytes = (double)B * N * (qb.C + 2 * op.heads * kAttnHD) * 2;
   } else {
     const BufDesc& ib = e->bufs[op.in.buf];
     *flops = 0; *bytes = (double)B * ib.H * ib.W * op.in.C * 2 * 4;
@@ -828,7 +1072,7 @@ int ypb_nms(void* cuda_stream, const float* boxes, const float* scores, const in
   FrameXform* xf = reinterpret_cast<FrameXform*>(s + (size_t)B * cs * 8);
   nms_test_pack_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(boxes, scores, n_valid, B, N, cs, keys, xf);
   nms_kernel<<<B, 256, 0, st>>>(nullptr, g, reinterpret_cast<const float4*>(boxes), cls, keys, n_valid, iou, max_det, 30000,
-                                agnostic ? 0.0f : 7680.0f, xf, nullptr, nullptr, keep, nullptr, count);
+                                agnostic ? 0.0f : 7680.0f, 0, xf, nullptr, nullptr, keep, nullptr, count);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;
 }

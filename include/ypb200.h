@@ -119,8 +119,11 @@ int ypb_device_error(ypb_engine* e, uint32_t* word);
 int ypb_view_count(const ypb_engine* e);
 int ypb_view_info(const ypb_engine* e, int index, const char** name, size_t* offset, int* H, int* W, int* Ctot,
                   int* c_off, int* C, int* dtype);
-/* 0: tcgen05 tensor-core convs (default, the product path); 1: CUDA-core debugging twin (tests only). */
+/* 0: persistent tcgen05 tensor-core convs (default, the product path); 1: CUDA-core debugging twin (tests only);
+ * 2: first-generation one-tile-per-CTA tcgen05 kernel (kept for A/B measurements). */
 int ypb_set_conv_impl(ypb_engine* e, int impl);
+/* ypb_infer() replays a CUDA graph captured on first use of an argument set (default on); 0 = plain launches. */
+int ypb_set_graph(ypb_engine* e, int on);
 
 /* Stand-alone kernel entry points used by the parity tests (device pointers, caller's stream). */
 int ypb_conv2d_bf16(void* cuda_stream, const void* in_nhwc_bf16, int B, int H, int W, int in_ctot, int in_c_off,

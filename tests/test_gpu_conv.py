@@ -27,6 +27,9 @@ CASES = [
     (4, 80, 80, 128, 0, 128, 128, 3, 1, 1, True, 128, 0, False),
     (3, 46, 80, 160, 0, 160, 320, 3, 2, 1, False, 320, 0, False),
     (2, 40, 40, 384, 0, 384, 128, 1, 1, 1, False, 128, 0, False),
+    (8, 160, 160, 32, 0, 32, 64, 3, 1, 1, False, 64, 0, False),     # > 148 tiles: several tiles per persistent CTA
+    (16, 80, 80, 64, 0, 64, 320, 1, 1, 1, False, 320, 0, False),    # Cout split across tiles, TMEM double buffering
+    (6, 40, 40, 128, 0, 128, 256, 3, 1, 1, True, 256, 0, False),    # n_tile 256: both accumulators fill TMEM
 ]
 
 
@@ -56,9 +59,10 @@ def run_case(case, impl=0, seed=0):
     return got, ref, bool((untouched == untouched_ref).all())
 
 
+@pytest.mark.parametrize("impl", [0, 2], ids=["persistent", "one_tile_per_cta"])
 @pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
-def test_conv_tc_matches_reference(case):
-    got, ref, clean = run_case(case, impl=0)
+def test_conv_tc_matches_reference(case, impl):
+    got, ref, clean = run_case(case, impl=impl)
     ok = bool(((got - ref).abs() <= ATOL + RTOL * ref.abs()).all())
     assert ok, describe_mismatch(got, ref, RTOL, ATOL)
     assert clean, "kernel wrote outside its channel slice"

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ypb_view_info": (c_int, [c_void_p, c_int, C.POINTER(c_char_p), C.POINTER(c_size_t), C.POINTER(c_int),
                               C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
     "ypb_set_conv_impl": (c_int, [c_void_p, c_int]),
+    "ypb_set_graph": (c_int, [c_void_p, c_int]),
     "ypb_conv2d_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
     "ypb_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p,

@@ -34,6 +34,7 @@ struct ConvDesc {
 
 struct ConvLaunch {
   ConvParams p;
+  int n_splits = 1, total_tiles = 0, stages2 = 2, smem2 = 0;  // persistent-kernel launch shape
   ConvSimtGeom sg;
   CUtensorMap tmA, tmB;
   dim3 grid;
@@ -149,6 +150,15 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   if (st > k_iters) st = k_iters;
   p.stages = st;
   L->smem = conv_smem_bytes(p.n_tile, st);
+  // persistent kernel: one CTA per SM, ring as deep as ~200 KB of smem allows (>= 120 KB so CTAs never co-reside)
+  L->n_splits = splits;
+  L->total_tiles = (int)L->grid.x * splits;
+  int st2 = (200 * 1024) / conv_stage_bytes(p.n_tile);
+  if (st2 > 8) st2 = 8;
+  if (st2 < 2) st2 = 2;
+  L->stages2 = st2;
+  L->smem2 = conv2_smem_bytes(p.n_tile, st2);
+  if (L->smem2 < 120 * 1024) L->smem2 = 120 * 1024;
   p.out_mode = d.out_mode; p.act = d.act;
   p.out_img_stride = d.out_img_stride; p.out_pix_stride = d.out_pix_stride; p.out_c_off = d.out_c_off;
   p.res_img_stride = d.res_img_stride; p.res_pix_stride = d.res_pix_stride; p.res_c_off = d.res_c_off;
@@ -190,19 +200,41 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   return true;
 }
 
+static int g_num_sms = 148;
+// One-time function attributes (must not happen inside a stream capture).
+static cudaError_t conv_launch_init() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  done = true;
+  return cudaSuccess;
+}
+
 static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int impl) {
   if (impl == 1) {
     const long long total = (long long)L.sg.nB * L.sg.oH * L.sg.oW * (L.p.Cout / 16);
     conv_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(L.sg, L.p);
     return cudaGetLastError();
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    cudaError_t e = conv_launch_init();
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
-  conv_tc_kernel<<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+  const int num_sms = g_num_sms;
+  if (impl == 2) {  // first-generation kernel: one tile per CTA (kept for A/B measurements)
+    conv_tc_kernel<<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+    return cudaGetLastError();
+  }
+  ConvParams p2 = L.p;
+  p2.stages = L.stages2;
+  const int grid = L.total_tiles < num_sms ? L.total_tiles : num_sms;
+  conv_tc2_kernel<<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles);
   return cudaGetLastError();
 }
 

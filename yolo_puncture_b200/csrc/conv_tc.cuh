@@ -229,6 +229,164 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised version (the product path).  One CTA per SM loops over output tiles:
+//   * the TMA producer runs ahead across tile boundaries through one shared ring of smem stages, so the
+//     next tile's operands are already in flight while the current tile is multiplied and stored;
+//   * the accumulator is double-buffered in TMEM (2 x n_tile columns): the MMA warp starts tile i+1 while
+//     the epilogue warps drain tile i (tcgen05.ld -> bias/SiLU/residual -> global stores);
+//   * tile order is M-major with the Cout splits innermost, so the CTAs that run concurrently work on
+//     neighbouring rectangles of the same image and share halos / weights in L2.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (also owns TMEM), warps 2.. = kEpiWarps epilogue warps
+// (warp w reads TMEM lanes 32*(w%4)..+31; with 8 epilogue warps each lane group's columns are split in two).
+// ------------------------------------------------------------------------------------------------
+constexpr int kEpiWarps = 8;
+constexpr int kConv2Threads = 64 + 32 * kEpiWarps;
+
+__host__ __device__ inline int conv2_acc_stride(int n_tile) { return (n_tile + 31) & ~31; }
+__host__ __device__ inline int conv2_smem_bytes(int n_tile, int stages) {
+  return 1024 /*align slack*/ + stages * conv_stage_bytes(n_tile) + 256 /*barriers*/;
+}
+
+__global__ void __launch_bounds__(kConv2Threads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvParams p, int n_splits, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = conv_stage_bytes(p.n_tile);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int kchunks = (p.Cin + 63) >> 6;
+  const int acc_stride = conv2_acc_stride(p.n_tile);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * acc_stride)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + i, 1);
+      mbar_init(tempty_bar + i, kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)(p.TH * p.TW * 128 + p.n_tile * 128);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
+        const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
+        const int th = t_in / p.tiles_w;
+        const int h0 = th * p.TH, w0 = (t_in - th * p.tiles_w) * p.TW;
+        int cbase[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) cbase[d] = p.a_base[d] + b * p.a_cb[d] + h0 * p.a_ch[d] + w0 * p.a_cw[d];
+        for (int t = 0; t < p.ntaps; ++t) {
+          for (int c = 0; c < kchunks; ++c, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(empty_bar + s, ph ^ 1, 1u);
+            uint8_t* sa = smem + s * stage_bytes;
+            mbar_expect_tx(full_bar + s, tx_bytes);
+            tma_load_5d(sa, &tmA, full_bar + s, cbase[0] + p.tap[t][0] + c * 64, cbase[1] + p.tap[t][1],
+                        cbase[2] + p.tap[t][2], cbase[3] + p.tap[t][3], cbase[4] + p.tap[t][4]);
+            tma_load_3d(sa + kATileBytes, &tmB, full_bar + s, c * 64, n0, t);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+      int it = 0, acc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
+        const int buf = acc & 1;
+        mbar_wait(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_stride);
+        int first = 1;
+        for (int t = 0; t < p.ntaps; ++t) {
+          for (int c = 0; c < kchunks; ++c, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(full_bar + s, ph, 2u);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * stage_bytes);
+            const uint32_t sb = sa + kATileBytes;
+            int ksteps = (p.Cin - c * 64) >> 4;
+            if (ksteps > 4) ksteps = 4;
+            for (int j = 0; j < ksteps; ++j) {
+              umma_bf16(d_tmem, umma_desc_sw128(sa + j * 32), umma_desc_sw128(sb + j * 32), idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            umma_commit(empty_bar + s);
+          }
+        }
+        umma_commit(tfull_bar + buf);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int lg = warp & 3;
+    const int part = (warp - 2) >> 2;
+    constexpr int nparts = kEpiWarps / 4;
+    const int r = lg * 32 + lane;
+    const int rh = r / p.TW, rw = r - rh * p.TW;
+    int acc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
+      const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
+      const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
+      const int th = t_in / p.tiles_w;
+      const int h = th * p.TH + rh, w = (t_in - th * p.tiles_w) * p.TW + rw;
+      const bool valid = (r < p.TH * p.TW) && (h < p.tH) && (w < p.tW);
+      const int q = (b * p.tH + h) * p.tW + w;
+      const int buf = acc & 1;
+      mbar_wait(tfull_bar + buf, (acc >> 1) & 1, 4u);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * acc_stride);
+      for (int j = part * 16; j < p.n_tile; j += 16 * nparts) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + (uint32_t)j, v);
+        tmem_ld_wait();
+        if (valid) {
+          float a[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(v[i]);
+          conv_epilogue_store16(p, q, n0 + j, a);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Bring-up / debugging twin: the same conv on CUDA cores, one thread per (pixel, 16 channels).
 // Used by tests to cross-check the tensor-core kernel layer by layer on the device; the engine
 // only runs it when YPB_CONV_IMPL=simt is set explicitly (never as a silent fallback).

@@ -105,6 +105,22 @@ struct ypb_engine {
   int conv_impl = 0;
   int launches = 0;
   double flops = 0;
+  // CUDA graph of one ypb_infer(): captured once per distinct argument set, then replayed
+  struct GraphKey {
+    const void *frames, *xform, *det, *det_lb, *keep, *coef, *count, *cmask;
+    float conf, iou;
+    int max_det, agnostic, impl;
+    bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+  };
+  bool use_graph = true, graph_valid = false;
+  GraphKey graph_key{};
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  void drop_graph() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    graph_exec = nullptr;
+    graph_valid = false;
+  }
 
   // ------------------------------------------------------------------ builder helpers
   int add_weight(const std::string& name, std::vector<int64_t> shape, bool used = true) {
@@ -650,6 +666,8 @@ int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out) {
 
 void ypb_engine_destroy(ypb_engine* e) {
   if (!e) return;
+  e->drop_graph();
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->w_arena) cudaFree(e->w_arena);
   delete e;
 }
@@ -860,6 +878,11 @@ int ypb_bind_workspace(ypb_engine* e, void* workspace, size_t bytes) {
     if (!conv_bind(d, &op.L, &err)) return fail(YPB_ERR_CUDA, op.name + ": " + err);
   }
   (void)g;
+  e->drop_graph();
+  {
+    cudaError_t ce = conv_launch_init();
+    if (ce != cudaSuccess) return fail(YPB_ERR_CUDA, std::string("conv_launch_init: ") + cudaGetErrorString(ce));
+  }
   e->bound = true;
   return YPB_OK;
 }
@@ -871,9 +894,27 @@ int ypb_kernel_launches(const ypb_engine* e) { return e ? e->launches : 0; }
 double ypb_conv_flops(const ypb_engine* e) { return e ? e->flops : 0.0; }
 
 int ypb_set_conv_impl(ypb_engine* e, int impl) {
-  if (!e || impl < 0 || impl > 1) return fail(YPB_ERR_ARG, "bad argument");
+  if (!e || impl < 0 || impl > 2) return fail(YPB_ERR_ARG, "bad argument");
   e->conv_impl = impl;
+  e->drop_graph();
   return YPB_OK;
+}
+
+int ypb_set_graph(ypb_engine* e, int on) {
+  if (!e) return fail(YPB_ERR_ARG, "bad argument");
+  e->use_graph = on != 0;
+  e->drop_graph();
+  return YPB_OK;
+}
+
+static int enqueue_infer(ypb_engine* e, cudaStream_t st, const uint8_t* frames, const float* xform,
+                         const ypb_infer_params* prm, float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count) {
+  for (const Op& op : e->ops) {
+    int rc = launch_op(e, op, st, frames);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, nullptr);
 }
 
 int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform, const ypb_infer_params* prm,
@@ -881,13 +922,30 @@ int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const flo
   int rc0 = check_infer_args(e, frames, xform, prm, det, det_lb, keep, coef, count);
   if (rc0) return rc0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-  const int B = e->B;
-  for (const Op& op : e->ops) {
-    int rc = launch_op(e, op, st, frames);
-    if (rc) return rc;
+  if (!e->use_graph) return enqueue_infer(e, st, frames, xform, prm, det, det_lb, keep, coef, count);
+  ypb_engine::GraphKey key;
+  memset(&key, 0, sizeof key);
+  key.frames = frames; key.xform = xform; key.det = det; key.det_lb = det_lb; key.keep = keep; key.coef = coef;
+  key.count = count; key.cmask = prm->class_mask; key.conf = prm->conf; key.iou = prm->iou; key.max_det = prm->max_det;
+  key.agnostic = prm->agnostic_nms; key.impl = e->conv_impl;
+  if (!e->graph_valid || !(key == e->graph_key)) {
+    // (re)capture the ~80 launches of a forward pass on a private stream; replays cost one launch
+    e->drop_graph();
+    if (!e->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_infer(e, e->cap_stream, frames, xform, prm, det, det_lb, keep, coef, count);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(YPB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(YPB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+    e->graph_key = key;
+    e->graph_valid = true;
   }
-  CUDA_TRY(cudaGetLastError());
-  return launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, nullptr);
+  CUDA_TRY(cudaGraphLaunch(e->graph_exec, st));
+  return YPB_OK;
 }
 
 int ypb_op_count(const ypb_engine* e) { return e ? (int)e->ops.size() + 2 : 0; }

@@ -151,6 +151,9 @@ class Engine:
     def set_conv_impl(self, impl):
         check(self._lib.ypb_set_conv_impl(self._h, int(impl)))
 
+    def set_graph(self, on):
+        check(self._lib.ypb_set_graph(self._h, int(bool(on))))
+
     # ------------------------------------------------------------------ introspection
     def view_table(self):
         out = {}

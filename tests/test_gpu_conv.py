@@ -30,6 +30,9 @@ CASES = [
     (8, 160, 160, 32, 0, 32, 64, 3, 1, 1, False, 64, 0, False),     # > 148 tiles: several tiles per persistent CTA
     (16, 80, 80, 64, 0, 64, 320, 1, 1, 1, False, 320, 0, False),    # Cout split across tiles, TMEM double buffering
     (6, 40, 40, 128, 0, 128, 256, 3, 1, 1, True, 256, 0, False),    # n_tile 256: both accumulators fill TMEM
+    (2, 32, 32, 64, 0, 64, 16, 1, 1, 1, False, 16, 0, False),       # n_tile 16: one epilogue warp per lane group idles
+    (3, 20, 20, 64, 0, 64, 80, 1, 1, 0, False, 176, 64, True),      # fp32 head rows: 80 classes into a 176-float row
+    (2, 24, 24, 48, 0, 48, 144, 3, 1, 1, True, 144, 0, False),      # 9 chunks: uneven column split, residual
 ]
 
 

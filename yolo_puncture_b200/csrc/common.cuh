@@ -141,7 +141,8 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
   return d;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with ex2.approx / rcp.approx (the result is rounded to bf16 right after)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

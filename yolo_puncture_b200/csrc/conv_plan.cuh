@@ -150,10 +150,10 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   if (st > k_iters) st = k_iters;
   p.stages = st;
   L->smem = conv_smem_bytes(p.n_tile, st);
-  // persistent kernel: one CTA per SM, ring as deep as ~200 KB of smem allows (>= 120 KB so CTAs never co-reside)
+  // persistent kernel: one CTA per SM, ring as deep as ~150 KB of smem allows (70 KB go to the epilogue staging tiles) (>= 120 KB so CTAs never co-reside)
   L->n_splits = splits;
   L->total_tiles = (int)L->grid.x * splits;
-  int st2 = (200 * 1024) / conv_stage_bytes(p.n_tile);
+  int st2 = (150 * 1024) / conv_stage_bytes(p.n_tile);
   if (st2 > 8) st2 = 8;
   if (st2 < 2) st2 = 2;
   L->stages2 = st2;

@@ -241,10 +241,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int kEpiWarps = 8;
 constexpr int kConv2Threads = 64 + 32 * kEpiWarps;
+constexpr int kEpiStageBytes = 32 * (256 + 16);  // per-warp staging tile: 32 rows x (<=256 B + 16 B pad)
 
 __host__ __device__ inline int conv2_acc_stride(int n_tile) { return (n_tile + 31) & ~31; }
 __host__ __device__ inline int conv2_smem_bytes(int n_tile, int stages) {
-  return 1024 /*align slack*/ + stages * conv_stage_bytes(n_tile) + 256 /*barriers*/;
+  return 1024 /*align slack*/ + stages * conv_stage_bytes(n_tile) + 256 /*barriers*/ + kEpiWarps * kEpiStageBytes;
 }
 
 __global__ void __launch_bounds__(kConv2Threads, 1)
@@ -345,9 +346,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue =====================
+    // Each warp owns 32 accumulator rows (its TMEM lane group) and a contiguous range of 16-column chunks.
+    // Phase 1: TMEM -> registers -> +bias -> SiLU -> packed bf16/fp32 into a private, padded smem staging
+    // tile (lane = row: conflict-free thanks to the +16 B row pitch).  The accumulator is released as soon
+    // as the last tcgen05.ld has landed.  Phase 2: the warp writes the staged rows back with lanes running
+    // along the channel dimension, so every store instruction covers whole 128-byte lines of NHWC rows
+    // (a thread-per-row store would touch 32 different lines per instruction).
     const int lg = warp & 3;
     const int part = (warp - 2) >> 2;
-    constexpr int nparts = kEpiWarps / 4;
+    const int nchunks = p.n_tile >> 4;
+    const int half = (nchunks + 1) >> 1;
+    const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
+    const int elt = p.out_mode == OUT_F32 ? 4 : 2;
+    const int chunks_per_pass = elt == 2 ? 8 : 4;  // <= 256 B of output row per pass
+    uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - 2) * kEpiStageBytes;
     const int r = lg * 32 + lane;
     const int rh = r / p.TW, rw = r - rh * p.TW;
     int acc = 0;
@@ -357,25 +369,94 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int th = t_in / p.tiles_w;
       const int h = th * p.TH + rh, w = (t_in - th * p.tiles_w) * p.TW + rw;
       const bool valid = (r < p.TH * p.TW) && (h < p.tH) && (w < p.tW);
-      const int q = (b * p.tH + h) * p.tW + w;
+      const int q = valid ? (b * p.tH + h) * p.tW + w : 0;
+      const int qb = q / p.img_HW, rem = q - qb * p.img_HW;
+      // element offset of channel 0 of this row in the output (pixel-shuffle: of sub-pixel (0,0))
+      long long off_row;
+      if (p.out_mode == OUT_SHUFFLE2_BF16) {
+        const int ph = rem / p.img_W, pw = rem - ph * p.img_W;
+        off_row = qb * p.out_img_stride + ((long long)(2 * ph) * (2 * p.img_W) + 2 * pw) * p.out_pix_stride + p.out_c_off;
+      } else {
+        off_row = qb * p.out_img_stride + (long long)rem * p.out_pix_stride + p.out_c_off;
+      }
+      const long long res_row = qb * p.res_img_stride + (long long)rem * p.res_pix_stride + p.res_c_off;
       const int buf = acc & 1;
       mbar_wait(tfull_bar + buf, (acc >> 1) & 1, 4u);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * acc_stride);
-      for (int j = part * 16; j < p.n_tile; j += 16 * nparts) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + (uint32_t)j, v);
-        tmem_ld_wait();
-        if (valid) {
-          float a[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(v[i]);
-          conv_epilogue_store16(p, q, n0 + j, a);
-        }
+      if (c_begin >= c_end) {  // n_tile == 16: the second warp of the lane group has no columns, it only hands back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + buf);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + buf);
+      for (int cp0 = c_begin; cp0 < c_end; cp0 += chunks_per_pass) {
+        const int nch = min(chunks_per_pass, c_end - cp0);
+        const int row_bytes = nch * 16 * elt, pitch = row_bytes + 16;
+        uint8_t* my = stage + lane * pitch;
+        for (int ch = 0; ch < nch; ++ch) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + (uint32_t)((cp0 + ch) * 16), v);
+          tmem_ld_wait();
+          const int n = n0 + (cp0 + ch) * 16;
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float t = __uint_as_float(v[i]) + __ldg(p.bias + n + i);
+            y[i] = p.act ? silu_f(t) : t;
+          }
+          if (elt == 2) {
+            uint4* d = reinterpret_cast<uint4*>(my + ch * 32);
+            d[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            d[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]),
+                              pack_bf16x2(y[14], y[15]));
+          } else {
+            float4* d = reinterpret_cast<float4*>(my + ch * 64);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+          }
+        }
+        if (cp0 + chunks_per_pass >= c_end) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + buf);
+        } else {
+          __syncwarp();
+        }
+        const int ppr = row_bytes >> 4;  // 16-byte pieces per row
+        for (int piece = lane; piece < 32 * ppr; piece += 32) {
+          const int row = piece / ppr, pc = piece - row * ppr;
+          const long long o_r = __shfl_sync(0xffffffffu, off_row, row);
+          const long long r_r = __shfl_sync(0xffffffffu, res_row, row);
+          const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
+          uint4 val = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
+          if (!ok) continue;
+          if (elt == 4) {
+            const int n = n0 + cp0 * 16 + pc * 4;
+            *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o_r + n) = val;
+            continue;
+          }
+          const int n = n0 + cp0 * 16 + pc * 8;
+          if (p.res != nullptr) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.res + r_r + n);
+            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 fa = __bfloat1622float2(a2[i]), fb = __bfloat1622float2(b2[i]);
+              o[i] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+            }
+            val = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          long long off = o_r + n;
+          if (p.out_mode == OUT_SHUFFLE2_BF16) {
+            const int cq = p.Cout >> 2;
+            const int g = n / cq, c = n - g * cq;
+            off = o_r + ((long long)(g >> 1) * (2 * p.img_W) + (g & 1)) * p.out_pix_stride + c;
+          }
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = val;
+        }
+        __syncwarp();
+      }
     }
   }
   tc_fence_before();

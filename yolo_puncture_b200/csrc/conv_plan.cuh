@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -153,7 +154,9 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   // persistent kernel: one CTA per SM, ring as deep as ~150 KB of smem allows (70 KB go to the epilogue staging tiles) (>= 120 KB so CTAs never co-reside)
   L->n_splits = splits;
   L->total_tiles = (int)L->grid.x * splits;
-  int st2 = (150 * 1024) / conv_stage_bytes(p.n_tile);
+  int ring_kb = 150;
+  if (const char* ev = getenv("YPB_RING_KB")) ring_kb = atoi(ev);  // tuning knob for experiments
+  int st2 = (ring_kb * 1024) / conv_stage_bytes(p.n_tile);
   if (st2 > 8) st2 = 8;
   if (st2 < 2) st2 = 2;
   L->stages2 = st2;

@@ -398,10 +398,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld_wait();
           const int n = n0 + (cp0 + ch) * 16;
           float y[16];
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float t = __uint_as_float(v[i]) + __ldg(p.bias + n + i);
-            y[i] = p.act ? silu_f(t) : t;
+          for (int i = 0; i < 4; ++i) {
+            const float4 bv = __ldg(bp + i);
+            y[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bv.x;
+            y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bv.y;
+            y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bv.z;
+            y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bv.w;
+          }
+          if (p.act) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = silu_f(y[i]);
           }
           if (elt == 2) {
             uint4* d = reinterpret_cast<uint4*>(my + ch * 32);
@@ -421,9 +429,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else {
           __syncwarp();
         }
-        const int ppr = row_bytes >> 4;  // 16-byte pieces per row
+        const int ppr = row_bytes >> 4;  // 16-byte pieces per row (<= 16)
+        const int ppr_inv = (65536 + ppr - 1) / ppr;  // piece / ppr == (piece * ppr_inv) >> 16 for piece < 512
         for (int piece = lane; piece < 32 * ppr; piece += 32) {
-          const int row = piece / ppr, pc = piece - row * ppr;
+          const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
           const long long o_r = __shfl_sync(0xffffffffu, off_row, row);
           const long long r_r = __shfl_sync(0xffffffffu, res_row, row);
           const int ok = __shfl_sync(0xffffffffu, (int)valid, row);

@@ -202,21 +202,27 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
       keep[(long long)b * max_det + i] = (int)(pair / (unsigned)g.nc);
     }
     if (threadIdx.x == 0) { s_nkept = nk; count[b] = nk; }
-  } else if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    int nkept = 0;
-    for (int i0 = 0; i0 < n && nkept < max_det; i0 += 32) {
-      const int i = i0 + lane;
+  } else {
+    // Greedy scan, 256 candidates (8 warps x 32 lanes) per round, in descending score order:
+    //  A. every thread tests its candidate against the boxes kept in earlier rounds (all warps in parallel);
+    //  B. warp 0..7 in turn resolves its own 32 candidates with ballots/shuffles (a live lane is kept and
+    //     suppresses the later lanes it overlaps), publishes the newly kept boxes, and the later warps test
+    //     their candidates against just those.  Equivalent to torchvision's sequential loop.
+    __shared__ int s_range[8][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int nkept = 0;  // CTA-uniform
+    for (int i0 = 0; i0 < n && nkept < max_det; i0 += 256) {
+      const int i = i0 + threadIdx.x;
       bool alive = i < n;
-      float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, area = 0.f;
-      int anchor = 0;
-      float score = 0.f;
+      float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, area = 0.f, score = 0.f;
+      int anchor = 0, cls = 0;
       if (alive) {
         const unsigned long long key = keys[i];
         anchor = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
         score = __uint_as_float((unsigned)(key >> 32));
         const float4 bx = dbox[(long long)b * g.A + anchor];
-        const float off = __fmul_rn((float)dcls[(long long)b * g.A + anchor], max_wh);
+        cls = dcls[(long long)b * g.A + anchor];
+        const float off = __fmul_rn((float)cls, max_wh);
         x1 = __fadd_rn(bx.x, off); y1 = __fadd_rn(bx.y, off); x2 = __fadd_rn(bx.z, off); y2 = __fadd_rn(bx.w, off);
         area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
       }
@@ -224,25 +230,41 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
         if (alive && iou_tv(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area) > iou_thr)
           alive = false;
       }
-      unsigned live = __ballot_sync(0xffffffffu, alive);
-      while (live != 0u && nkept < max_det) {
-        const int l = __ffs(live) - 1;
-        const float kx1 = __shfl_sync(0xffffffffu, x1, l), ky1 = __shfl_sync(0xffffffffu, y1, l);
-        const float kx2 = __shfl_sync(0xffffffffu, x2, l), ky2 = __shfl_sync(0xffffffffu, y2, l);
-        const float ka = __shfl_sync(0xffffffffu, area, l);
-        if (lane == l) {
-          s_kept[nkept][0] = x1; s_kept[nkept][1] = y1; s_kept[nkept][2] = x2; s_kept[nkept][3] = y2; s_kept[nkept][4] = area;
-          s_score[nkept] = score;
-          s_cls[nkept] = dcls[(long long)b * g.A + anchor];
-          keep[(long long)b * max_det + nkept] = anchor;
+      for (int ws = 0; ws < 8; ++ws) {
+        if (warp == ws) {
+          int nk = nkept;
+          unsigned live = __ballot_sync(0xffffffffu, alive);
+          while (live != 0u && nk < max_det) {
+            const int l = __ffs(live) - 1;
+            const float kx1 = __shfl_sync(0xffffffffu, x1, l), ky1 = __shfl_sync(0xffffffffu, y1, l);
+            const float kx2 = __shfl_sync(0xffffffffu, x2, l), ky2 = __shfl_sync(0xffffffffu, y2, l);
+            const float ka = __shfl_sync(0xffffffffu, area, l);
+            if (lane == l) {
+              s_kept[nk][0] = x1; s_kept[nk][1] = y1; s_kept[nk][2] = x2; s_kept[nk][3] = y2; s_kept[nk][4] = area;
+              s_score[nk] = score;
+              s_cls[nk] = cls;
+              keep[(long long)b * max_det + nk] = anchor;
+            }
+            ++nk;
+            if (alive && lane > l && iou_tv(kx1, ky1, kx2, ky2, ka, x1, y1, x2, y2, area) > iou_thr) alive = false;
+            live = __ballot_sync(0xffffffffu, alive) & ~((2u << l) - 1u);
+          }
+          if (lane == 0) { s_range[ws][0] = nkept; s_range[ws][1] = nk; }
         }
-        ++nkept;
-        if (alive && lane > l && iou_tv(kx1, ky1, kx2, ky2, ka, x1, y1, x2, y2, area) > iou_thr) alive = false;
-        live = __ballot_sync(0xffffffffu, alive) & ~((2u << l) - 1u);
+        __syncthreads();
+        const int kb = s_range[ws][0], ke = s_range[ws][1];
+        if (warp > ws) {
+          for (int k = kb; k < ke; ++k) {
+            if (alive && iou_tv(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area) > iou_thr)
+              alive = false;
+          }
+        }
+        nkept = ke;
+        if (nkept >= max_det) break;  // CTA-uniform
       }
-      __syncwarp();
+      __syncthreads();  // s_range is rewritten next round
     }
-    if (lane == 0) { s_nkept = nkept; count[b] = nkept; }
+    if (threadIdx.x == 0) { s_nkept = nkept; count[b] = nkept; }
   }
   __syncthreads();
   const int nk = s_nkept;

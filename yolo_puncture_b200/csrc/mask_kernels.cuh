@@ -34,8 +34,12 @@ __global__ void mask_offsets_kernel(const int* __restrict__ count, int nB, int c
   }
 }
 
-constexpr int kMaskTile = 64;  // 64x64 output pixels per CTA, 256 threads x 16 px
+constexpr int kMaskTile = 64;  // 64x64 output pixels per step, 256 threads x 16 px
 
+// One CTA per (band of 64 output rows, detection).  Bands that miss the box are one contiguous, fully coalesced
+// zero fill; inside a band the CTA walks 64-pixel tiles: tiles that miss the box are zero-filled, the others get the
+// low-resolution logits of just the proto window they need (<= 66x66 dot products of length 32, in shared memory),
+// then every thread produces 16 output pixels with ATen's bilinear arithmetic, the box crop and the > 0 threshold.
 __global__ void __launch_bounds__(256)
 mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const float* __restrict__ coef /*(B,max_det,nm)*/,
                    const float* __restrict__ det /*(B,max_det,6) frame boxes*/, const float* __restrict__ det_lb /*(B,max_det,4)*/,
@@ -45,15 +49,13 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   const int slot = blockIdx.y;
   const int total = offsets[nB];
   if (slot >= total || slot >= capacity) return;
-  // slot -> (image, detection)
-  int lo = 0, hi = nB;
+  int lo = 0, hi = nB;  // slot -> (image, detection)
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (offsets[mid] <= slot) lo = mid; else hi = mid;
   }
   const int b = lo, di = slot - offsets[lo];
-  const int tiles_x = (g.out_w + kMaskTile - 1) / kMaskTile;
-  const int ty0 = (blockIdx.x / tiles_x) * kMaskTile, tx0 = (blockIdx.x % tiles_x) * kMaskTile;
+  const int ty0 = blockIdx.x * kMaskTile;
 
   float bx1, by1, bx2, by2;
   if (g.retina) {
@@ -65,96 +67,109 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
     bx2 = __fmul_rn(d[2], g.ratio_w); by2 = __fmul_rn(d[3], g.ratio_h);
   }
   uint8_t* o = out + (long long)slot * g.out_h * g.out_w;
-  const int trow = threadIdx.x >> 2, tcol = (threadIdx.x & 3) * 16;
-  const int oy = ty0 + trow, ox0 = tx0 + tcol;
-
-  // source-space extent of this tile
   auto src_of = [](int dst, float scale) {
     float s = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
     return s < 0.f ? 0.f : s;
   };
-  const int y_last = min(ty0 + kMaskTile, g.out_h) - 1, x_last = min(tx0 + kMaskTile, g.out_w) - 1;
-  const int sy_lo = (int)src_of(ty0, g.scale_h), sx_lo = (int)src_of(tx0, g.scale_w);
-  const int sy_hi = min((int)src_of(y_last, g.scale_h) + 1, g.ch - 1), sx_hi = min((int)src_of(x_last, g.scale_w) + 1, g.cw - 1);
-  const int rh = sy_hi - sy_lo + 1, rw = sx_hi - sx_lo + 1;
-
-  // tile entirely outside the box (retina: frame coords; non-retina: conservative test in proto space)
-  bool empty;
-  if (g.retina) {
-    empty = ((float)(tx0 + kMaskTile) <= bx1) || ((float)tx0 >= bx2) || ((float)(ty0 + kMaskTile) <= by1) || ((float)ty0 >= by2);
-  } else {
-    empty = ((float)(g.left + sx_hi) < bx1) || ((float)(g.left + sx_lo) >= bx2) || ((float)(g.top + sy_hi) < by1) ||
-            ((float)(g.top + sy_lo) >= by2);
-  }
+  const int y_last = min(ty0 + kMaskTile, g.out_h) - 1;
+  const int sy_lo = (int)src_of(ty0, g.scale_h);
+  const int sy_hi = min((int)src_of(y_last, g.scale_h) + 1, g.ch - 1);
+  const int rh = sy_hi - sy_lo + 1;
   const bool vec_ok = ((g.out_w & 15) == 0);
-  if (empty || rh > kMaskTile + 2 || rw > kMaskTile + 2) {
-    if (oy < g.out_h) {
-      if (vec_ok && ox0 + 16 <= g.out_w) {
-        *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
-      } else {
-        for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j) o[(long long)oy * g.out_w + ox0 + j] = 0;
-      }
+
+  // ---- whole band outside the box: contiguous zero fill ----
+  bool band_empty;
+  if (g.retina) band_empty = ((float)(ty0 + kMaskTile) <= by1) || ((float)ty0 >= by2);
+  else band_empty = ((float)(g.top + sy_hi) < by1) || ((float)(g.top + sy_lo) >= by2);
+  if (band_empty || rh > kMaskTile + 2) {
+    const long long nbytes = (long long)(y_last - ty0 + 1) * g.out_w;
+    uint8_t* dst = o + (long long)ty0 * g.out_w;
+    if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nbytes) & 15) == 0) {
+      for (long long i = threadIdx.x; i < (nbytes >> 4); i += 256) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0, 0, 0, 0);
+    } else {
+      for (long long i = threadIdx.x; i < nbytes; i += 256) dst[i] = 0;
     }
     return;
   }
 
   if (threadIdx.x < g.nm) s_coef[threadIdx.x] = coef[((long long)b * g.max_det + di) * g.nm + threadIdx.x];
-  __syncthreads();
-  // low-resolution logits of the source window: one thread per proto pixel, 32-long dot product
   const float* pb = proto + (long long)b * g.mh * g.mw * g.nm;
-  for (int i = threadIdx.x; i < rh * rw; i += 256) {
-    const int ry = i / rw, rx = i - ry * rw;
-    const int py = g.top + sy_lo + ry, px = g.left + sx_lo + rx;
-    const float4* pp = reinterpret_cast<const float4*>(pb + ((long long)py * g.mw + px) * g.nm);
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 v = __ldg(pp + k);
-      acc = fmaf(s_coef[4 * k + 0], v.x, acc);
-      acc = fmaf(s_coef[4 * k + 1], v.y, acc);
-      acc = fmaf(s_coef[4 * k + 2], v.z, acc);
-      acc = fmaf(s_coef[4 * k + 3], v.w, acc);
-    }
-    if (!g.retina) {  // ops.process_mask crops in proto space BEFORE the upsample
-      const float fx = (float)px, fy = (float)py;
-      if (!(fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2)) acc = 0.f;
-    }
-    s_logit[ry * (kMaskTile + 2) + rx] = acc;
-  }
-  __syncthreads();
-  if (oy >= g.out_h) return;
-
-  const float sy = src_of(oy, g.scale_h);
+  const int trow = threadIdx.x >> 2, tcol = (threadIdx.x & 3) * 16;
+  const int oy = ty0 + trow;
+  const float sy = src_of(min(oy, g.out_h - 1), g.scale_h);
   const int y0 = (int)sy;
   const int y1 = y0 + ((y0 < g.ch - 1) ? 1 : 0);
   const float ly = __fsub_rn(sy, (float)y0), hy = __fsub_rn(1.0f, ly);
-  const float* r0 = s_logit + (y0 - sy_lo) * (kMaskTile + 2);
-  const float* r1 = s_logit + (y1 - sy_lo) * (kMaskTile + 2);
   const bool row_in = g.retina ? ((float)oy >= by1 && (float)oy < by2) : true;
-  uint32_t packed[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int ox = ox0 + j;
-    uint32_t bit = 0;
-    if (ox < g.out_w && row_in) {
-      const float sx = src_of(ox, g.scale_w);
-      const int x0 = (int)sx;
-      const int x1 = x0 + ((x0 < g.cw - 1) ? 1 : 0);
-      const float lx = __fsub_rn(sx, (float)x0), hx = __fsub_rn(1.0f, lx);
-      const float top = __fadd_rn(__fmul_rn(hx, r0[x0 - sx_lo]), __fmul_rn(lx, r0[x1 - sx_lo]));
-      const float bot = __fadd_rn(__fmul_rn(hx, r1[x0 - sx_lo]), __fmul_rn(lx, r1[x1 - sx_lo]));
-      const float val = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
-      bool on = val > 0.0f;
-      if (g.retina) on = on && ((float)ox >= bx1 && (float)ox < bx2);
-      bit = on ? 1u : 0u;
+
+  for (int tx0 = 0; tx0 < g.out_w; tx0 += kMaskTile) {
+    const int ox0 = tx0 + tcol;
+    const int x_last = min(tx0 + kMaskTile, g.out_w) - 1;
+    const int sx_lo = (int)src_of(tx0, g.scale_w);
+    const int sx_hi = min((int)src_of(x_last, g.scale_w) + 1, g.cw - 1);
+    const int rw = sx_hi - sx_lo + 1;
+    bool empty;
+    if (g.retina) empty = ((float)(tx0 + kMaskTile) <= bx1) || ((float)tx0 >= bx2);
+    else empty = ((float)(g.left + sx_hi) < bx1) || ((float)(g.left + sx_lo) >= bx2);
+    if (empty || rw > kMaskTile + 2) {  // CTA-uniform
+      if (oy < g.out_h) {
+        if (vec_ok && ox0 + 16 <= g.out_w) {
+          *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
+        } else {
+          for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j) o[(long long)oy * g.out_w + ox0 + j] = 0;
+        }
+      }
+      continue;
     }
-    packed[j >> 2] |= bit << (8 * (j & 3));
-  }
-  if (vec_ok && ox0 + 16 <= g.out_w) {
-    *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-  } else {
-    for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j)
-      o[(long long)oy * g.out_w + ox0 + j] = (uint8_t)((packed[j >> 2] >> (8 * (j & 3))) & 1u);
+    __syncthreads();  // s_coef ready / previous tile's s_logit fully consumed
+    for (int i = threadIdx.x; i < rh * rw; i += 256) {
+      const int ry = i / rw, rx = i - ry * rw;
+      const int py = g.top + sy_lo + ry, px = g.left + sx_lo + rx;
+      const float4* pp = reinterpret_cast<const float4*>(pb + ((long long)py * g.mw + px) * g.nm);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 v = __ldg(pp + k);
+        acc = fmaf(s_coef[4 * k + 0], v.x, acc);
+        acc = fmaf(s_coef[4 * k + 1], v.y, acc);
+        acc = fmaf(s_coef[4 * k + 2], v.z, acc);
+        acc = fmaf(s_coef[4 * k + 3], v.w, acc);
+      }
+      if (!g.retina) {  // ops.process_mask crops in proto space BEFORE the upsample
+        const float fx = (float)px, fy = (float)py;
+        if (!(fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2)) acc = 0.f;
+      }
+      s_logit[ry * (kMaskTile + 2) + rx] = acc;
+    }
+    __syncthreads();
+    if (oy >= g.out_h) continue;
+    const float* r0 = s_logit + (y0 - sy_lo) * (kMaskTile + 2);
+    const float* r1 = s_logit + (y1 - sy_lo) * (kMaskTile + 2);
+    uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int ox = ox0 + j;
+      uint32_t bit = 0;
+      if (ox < g.out_w && row_in) {
+        const float sx = src_of(ox, g.scale_w);
+        const int x0 = (int)sx;
+        const int x1 = x0 + ((x0 < g.cw - 1) ? 1 : 0);
+        const float lx = __fsub_rn(sx, (float)x0), hx = __fsub_rn(1.0f, lx);
+        const float top = __fadd_rn(__fmul_rn(hx, r0[x0 - sx_lo]), __fmul_rn(lx, r0[x1 - sx_lo]));
+        const float bot = __fadd_rn(__fmul_rn(hx, r1[x0 - sx_lo]), __fmul_rn(lx, r1[x1 - sx_lo]));
+        const float val = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+        bool on = val > 0.0f;
+        if (g.retina) on = on && ((float)ox >= bx1 && (float)ox < bx2);
+        bit = on ? 1u : 0u;
+      }
+      packed[j >> 2] |= bit << (8 * (j & 3));
+    }
+    if (vec_ok && ox0 + 16 <= g.out_w) {
+      *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    } else {
+      for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j)
+        o[(long long)oy * g.out_w + ox0 + j] = (uint8_t)((packed[j >> 2] >> (8 * (j & 3))) & 1u);
+    }
   }
 }
 

@@ -1040,8 +1040,8 @@ int ypb_masks(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w
   g.scale_h = (float)g.ch / (float)g.out_h; g.scale_w = (float)g.cw / (float)g.out_w;
   int* offsets = reinterpret_cast<int*>(e->ws + e->off_moff);
   mask_offsets_kernel<<<1, 32, 0, st>>>(count, e->B, capacity, offsets, status);
-  const int tiles = ((g.out_w + kMaskTile - 1) / kMaskTile) * ((g.out_h + kMaskTile - 1) / kMaskTile);
-  dim3 grid(tiles, capacity);
+  const int bands = (g.out_h + kMaskTile - 1) / kMaskTile;
+  dim3 grid(bands, capacity);
   if (capacity > 65535) return fail(YPB_ERR_ARG, "masks: capacity > 65535");
   mask_decode_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb, offsets,
                                            e->B, capacity, g, masks);

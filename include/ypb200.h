@@ -135,6 +135,8 @@ int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float*
             int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,
             int32_t* count /*(B)*/);
 size_t ypb_nms_scratch_bytes(int B, int N);
+/* Diagnostics: ceiling of the TMA operand-fetch path for an access pattern (csrc/tma_bench.cuh). */
+int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, int H, int B, float* ms, double* bytes);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,13 @@ struct ConvDesc {
 };
 
 struct ConvLaunch {
+  CUtensorMap tmHalo;  // impl 3 experiment: halo box {64, 10, 18}
+  bool halo_ok = false;
+  // halo-reuse kernel for 3x3 stride-1 convs (conv3_halo_kernel)
+  bool use_halo = false;
+  Conv3Extra x3{};
+  CUtensorMap tmHalo3;
+  int tiles_h3 = 0, tiles_w3 = 0, total_tiles3 = 0, smem3 = 0;
   ConvParams p;
   int n_splits = 1, total_tiles = 0, stages2 = 2, smem2 = 0;  // persistent-kernel launch shape
   ConvSimtGeom sg;
@@ -166,6 +173,49 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   p.out_img_stride = d.out_img_stride; p.out_pix_stride = d.out_pix_stride; p.out_c_off = d.out_c_off;
   p.res_img_stride = d.res_img_stride; p.res_pix_stride = d.res_pix_stride; p.res_c_off = d.res_c_off;
   L->flops = 2.0 * d.B * oH * oW * (double)d.cout * d.cin * d.k * d.k;
+  L->use_halo = false;
+  if (d.k == 3 && d.stride == 1 && !getenv("YPB_NO_HALO")) {
+    // Operand bytes fetched from L2 per launch are what bounds these kernels (~7 TB/s L2->SM on B200): pick the
+    // cheapest of {per-tap boxes, halo tiles with msub = 1 or 2, resident or streamed weights}.
+    const int kch = (d.cin + 63) / 64;
+    const long avail = 227 * 1024 - 1024 - 512 - kEpiWarps * kEpiStageBytes;
+    const long b_slot = (long)p.n_tile * 128, b_total = 9L * kch * b_slot;
+    const double cost_taps = (double)L->total_tiles * k_iters * (kATileBytes + b_slot);
+    double best = cost_taps;
+    for (int msub = 1; msub <= 2; ++msub) {
+      if (2 * msub * conv2_acc_stride(p.n_tile) > 512) continue;
+      const int halo_rows = (16 * msub + 2) * 10;
+      const long a_bytes = ((long)halo_rows * 128 + 1023) & ~1023L;
+      const int th3 = (oH + 16 * msub - 1) / (16 * msub), tw3 = (oW + 7) / 8;
+      const long tiles3 = (long)d.B * th3 * tw3 * splits;
+      for (int stat = 1; stat >= 0; --stat) {
+        if (stat && (splits != 1 || b_total > 96 * 1024 || b_total + 2 * a_bytes > avail)) continue;
+        long a_slots, b_slots = 0, b_bytes;
+        if (stat) {
+          b_bytes = b_total;
+          a_slots = (avail - b_total) / a_bytes;
+        } else {
+          a_slots = 2;
+          b_slots = (avail - a_slots * a_bytes) / b_slot;
+          if (b_slots > 12) b_slots = 12;
+          if (b_slots < 2) continue;
+          b_bytes = b_slots * b_slot;
+        }
+        if (a_slots > 4) a_slots = 4;
+        if (a_slots < 2) continue;
+        const double cost = (double)tiles3 * kch * (halo_rows * 128.0 + (stat ? 0.0 : 9.0 * b_slot)) +
+                            (stat ? 148.0 * b_total : 0.0);
+        if (cost < best) {
+          best = cost;
+          L->use_halo = true;
+          L->x3.msub = msub; L->x3.a_slots = (int)a_slots; L->x3.a_bytes = (int)a_bytes; L->x3.halo_rows = halo_rows;
+          L->x3.b_slots = (int)b_slots; L->x3.b_stat = stat; L->x3.b_bytes = (int)b_bytes;
+          L->tiles_h3 = th3; L->tiles_w3 = tw3; L->total_tiles3 = (int)tiles3;
+          L->smem3 = (int)(1024 + a_slots * a_bytes + b_bytes + 512 + kEpiWarps * kEpiStageBytes);
+        }
+      }
+    }
+  }
   ConvSimtGeom& g = L->sg;
   memset(&g, 0, sizeof g);
   g.in_H = d.Hin; g.in_W = d.Win; g.in_ctot = d.in_ctot; g.in_c_off = d.in_c_off;
@@ -196,6 +246,15 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
     box[0] = 64; box[1] = p.TW; box[2] = 1; box[3] = p.TH; box[4] = 1;
   }
   if (!encode_bf16_map(&L->tmA, d.in, 5, dims, str, box, err)) return false;
+  if (L->use_halo) {
+    cuuint32_t hb[5] = {64, 10, (cuuint32_t)(16 * L->x3.msub + 2), 1, 1};
+    if (!encode_bf16_map(&L->tmHalo3, d.in, 5, dims, str, hb, err)) return false;
+  }
+  L->halo_ok = false;
+  if (d.k == 3 && d.stride == 1 && d.cout <= 128) {
+    cuuint32_t hb[5] = {64, 10, 18, 1, 1};
+    L->halo_ok = encode_bf16_map(&L->tmHalo, d.in, 5, dims, str, hb, err);
+  }
   cuuint64_t wd[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.cout, (cuuint64_t)(d.k * d.k)};
   cuuint64_t ws[2] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.cin * 2 * d.cout};
   cuuint32_t wb[3] = {64, (cuuint32_t)p.n_tile, 1};
@@ -211,6 +270,8 @@ static cudaError_t conv_launch_init() {
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -230,8 +291,26 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
     if (e != cudaSuccess) return e;
   }
   const int num_sms = g_num_sms;
+  if (impl == 3) {  // halo-reuse experiment (3x3 stride 1, Cout <= 128): 16x8 tiles
+    if (!L.halo_ok) return cudaErrorInvalidValue;
+    static bool set3 = false;
+    if (!set3) { cudaFuncSetAttribute(conv_halo_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set3 = true; }
+    ConvParams p3 = L.p;
+    p3.tiles_h = (p3.tH + 15) / 16; p3.tiles_w = (p3.tW + 7) / 8;
+    const int grid3 = p3.tB * p3.tiles_h * p3.tiles_w;
+    const int smem3 = 1024 + kHaloBytes + 9 * p3.n_tile * 128 + 256;
+    conv_halo_test_kernel<<<grid3, kConvThreads, smem3, stream>>>(L.tmHalo, L.tmB, p3);
+    return cudaGetLastError();
+  }
   if (impl == 2) {  // first-generation kernel: one tile per CTA (kept for A/B measurements)
     conv_tc_kernel<<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+    return cudaGetLastError();
+  }
+  if (L.use_halo && impl == 0) {
+    ConvParams p3 = L.p;
+    p3.tiles_h = L.tiles_h3; p3.tiles_w = L.tiles_w3;
+    const int grid3 = L.total_tiles3 < num_sms ? L.total_tiles3 : num_sms;
+    conv3_halo_kernel<<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB, p3, L.x3, L.n_splits, L.total_tiles3);
     return cudaGetLastError();
   }
   ConvParams p2 = L.p;

@@ -248,6 +248,113 @@ __host__ __device__ inline int conv2_smem_bytes(int n_tile, int stages) {
   return 1024 /*align slack*/ + stages * conv_stage_bytes(n_tile) + 256 /*barriers*/ + kEpiWarps * kEpiStageBytes;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one 128-row accumulator (sub)tile for one warp (shared by the persistent kernels).
+// The warp owns TMEM lanes [32*lg, +32) (t_addr points at them) and the 16-column chunks [c_begin, c_end).
+// Phase 1: TMEM -> registers -> +bias -> SiLU -> packed bf16/fp32 into the warp's private, padded smem staging
+// tile (lane = row: conflict-free thanks to the +16 B row pitch).  `release` (may be null) is arrived on as soon
+// as the last tcgen05.ld of this call has landed, handing the accumulator back to the MMA warp.
+// Phase 2: the staged rows are written back with lanes running along the channel dimension, so every store
+// instruction covers whole 128-byte lines of NHWC rows (a thread-per-row store touches 32 lines per instruction).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, int lane, int c_begin, int c_end,
+                                          uint32_t t_addr, int n0, bool valid, int q, uint64_t* release) {
+  const int elt = p.out_mode == OUT_F32 ? 4 : 2;
+  const int chunks_per_pass = elt == 2 ? 8 : 4;  // <= 256 B of output row per pass
+  const int qb = q / p.img_HW, rem = q - qb * p.img_HW;
+  // element offset of channel 0 of this row in the output (pixel-shuffle: of sub-pixel (0,0))
+  long long off_row;
+  if (p.out_mode == OUT_SHUFFLE2_BF16) {
+    const int ph = rem / p.img_W, pw = rem - ph * p.img_W;
+    off_row = qb * p.out_img_stride + ((long long)(2 * ph) * (2 * p.img_W) + 2 * pw) * p.out_pix_stride + p.out_c_off;
+  } else {
+    off_row = qb * p.out_img_stride + (long long)rem * p.out_pix_stride + p.out_c_off;
+  }
+  const long long res_row = qb * p.res_img_stride + (long long)rem * p.res_pix_stride + p.res_c_off;
+  if (c_begin >= c_end) {  // n_tile == 16: the second warp of the lane group has no columns, it only hands back
+    __syncwarp();
+    if (lane == 0 && release != nullptr) mbar_arrive(release);
+  }
+  for (int cp0 = c_begin; cp0 < c_end; cp0 += chunks_per_pass) {
+    const int nch = min(chunks_per_pass, c_end - cp0);
+    const int row_bytes = nch * 16 * elt, pitch = row_bytes + 16;
+    uint8_t* my = stage + lane * pitch;
+    for (int ch = 0; ch < nch; ++ch) {
+      uint32_t v[16];
+      tmem_ld16(t_addr + (uint32_t)((cp0 + ch) * 16), v);
+      tmem_ld_wait();
+      const int n = n0 + (cp0 + ch) * 16;
+      float y[16];
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bv = __ldg(bp + i);
+        y[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bv.x;
+        y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bv.y;
+        y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bv.z;
+        y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bv.w;
+      }
+      if (p.act) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = silu_f(y[i]);
+      }
+      if (elt == 2) {
+        uint4* d = reinterpret_cast<uint4*>(my + ch * 32);
+        d[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        d[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]),
+                          pack_bf16x2(y[14], y[15]));
+      } else {
+        float4* d = reinterpret_cast<float4*>(my + ch * 64);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      }
+    }
+    if (cp0 + chunks_per_pass >= c_end) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0 && release != nullptr) mbar_arrive(release);
+    } else {
+      __syncwarp();
+    }
+    const int ppr = row_bytes >> 4;  // 16-byte pieces per row (<= 16)
+    const int ppr_inv = (65536 + ppr - 1) / ppr;  // piece / ppr == (piece * ppr_inv) >> 16 for piece < 512
+    for (int piece = lane; piece < 32 * ppr; piece += 32) {
+      const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
+      const long long o_r = __shfl_sync(0xffffffffu, off_row, row);
+      const long long r_r = __shfl_sync(0xffffffffu, res_row, row);
+      const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
+      uint4 val = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
+      if (!ok) continue;
+      if (elt == 4) {
+        const int n = n0 + cp0 * 16 + pc * 4;
+        *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o_r + n) = val;
+        continue;
+      }
+      const int n = n0 + cp0 * 16 + pc * 8;
+      if (p.res != nullptr) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(p.res + r_r + n);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 fa = __bfloat1622float2(a2[i]), fb = __bfloat1622float2(b2[i]);
+          o[i] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+        }
+        val = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      long long off = o_r + n;
+      if (p.out_mode == OUT_SHUFFLE2_BF16) {
+        const int cq = p.Cout >> 2;
+        const int g = n / cq, c = n - g * cq;
+        off = o_r + ((long long)(g >> 1) * (2 * p.img_W) + (g & 1)) * p.out_pix_stride + c;
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = val;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(kConv2Threads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvParams p, int n_splits, int total_tiles) {
@@ -357,8 +464,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int nchunks = p.n_tile >> 4;
     const int half = (nchunks + 1) >> 1;
     const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
-    const int elt = p.out_mode == OUT_F32 ? 4 : 2;
-    const int chunks_per_pass = elt == 2 ? 8 : 4;  // <= 256 B of output row per pass
     uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - 2) * kEpiStageBytes;
     const int r = lg * 32 + lane;
     const int rh = r / p.TW, rw = r - rh * p.TW;
@@ -370,107 +475,294 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int h = th * p.TH + rh, w = (t_in - th * p.tiles_w) * p.TW + rw;
       const bool valid = (r < p.TH * p.TW) && (h < p.tH) && (w < p.tW);
       const int q = valid ? (b * p.tH + h) * p.tW + w : 0;
-      const int qb = q / p.img_HW, rem = q - qb * p.img_HW;
-      // element offset of channel 0 of this row in the output (pixel-shuffle: of sub-pixel (0,0))
-      long long off_row;
-      if (p.out_mode == OUT_SHUFFLE2_BF16) {
-        const int ph = rem / p.img_W, pw = rem - ph * p.img_W;
-        off_row = qb * p.out_img_stride + ((long long)(2 * ph) * (2 * p.img_W) + 2 * pw) * p.out_pix_stride + p.out_c_off;
-      } else {
-        off_row = qb * p.out_img_stride + (long long)rem * p.out_pix_stride + p.out_c_off;
-      }
-      const long long res_row = qb * p.res_img_stride + (long long)rem * p.res_pix_stride + p.res_c_off;
       const int buf = acc & 1;
       mbar_wait(tfull_bar + buf, (acc >> 1) & 1, 4u);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * acc_stride);
-      if (c_begin >= c_end) {  // n_tile == 16: the second warp of the lane group has no columns, it only hands back
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + buf);
+      epi_drain(p, stage, lane, c_begin, c_end, t_addr, n0, valid, q, tempty_bar + buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 stride-1 convs: halo-reuse kernel (persistent, warp-specialised like conv_tc2_kernel).
+//
+// Measured on B200 (tools/tma_bench.py): the L2 -> SM operand path tops out at ~7 TB/s chip-wide (~47 GB/s per
+// SM), i.e. L2 gives no bandwidth amplification over HBM, and conv_tc2_kernel's per-tap boxes re-fetch the input
+// tile nine times.  Here a CTA owns 8-pixel-wide column tiles (16*msub rows x 8 cols): ONE TMA box
+// {64 ch, 10, 16*msub+2} brings the tile plus its halo per 64-channel chunk, and tap (kh,kw) of sub-tile s is the
+// same shared-memory buffer seen through a UMMA descriptor whose start address is advanced by
+// ((16*s+kh)*10 + kw) rows and whose 8-row groups are 10 rows (1280 B) apart.  That is legal because both TMA and
+// tcgen05.mma apply the 128-byte swizzle on absolute shared-memory address bits (verified on hardware,
+// tools/halo_experiment.py).  Input re-reads drop from 9x to ~1.4x.
+// Weights: if all nine taps of all chunks fit (b_stat), they are loaded ONCE per CTA and stay resident;
+// otherwise they stream through their own ring of per-tap slots and msub=2 sub-tiles share every weight tile.
+// ------------------------------------------------------------------------------------------------
+struct Conv3Extra {
+  int msub;        // 128-row sub-tiles per CTA tile (1 or 2), stacked vertically
+  int a_slots;     // halo ring depth
+  int a_bytes;     // bytes per halo slot (1024 multiple)
+  int halo_rows;   // (16*msub+2)*10
+  int b_slots;     // weight ring depth (streaming mode)
+  int b_stat;      // 1: all weights resident in smem
+  int b_bytes;     // weight region bytes
+};
+
+__global__ void __launch_bounds__(kConv2Threads, 1)
+conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ConvParams p, const Conv3Extra x, int n_splits, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + x.a_slots * x.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + x.b_bytes);
+  uint64_t* a_full = bars;            // [4]
+  uint64_t* a_empty = bars + 4;       // [4]
+  uint64_t* b_full = bars + 8;        // [12]
+  uint64_t* b_empty = bars + 20;      // [12]
+  uint64_t* tfull_bar = bars + 32;    // [2]
+  uint64_t* tempty_bar = bars + 34;   // [2]
+  uint64_t* ball_bar = bars + 36;     // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 37);
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(bars) + 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int kchunks = (p.Cin + 63) >> 6;
+  const int acc_stride = conv2_acc_stride(p.n_tile);
+  const int b_slot_bytes = p.n_tile * 128;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * x.msub * acc_stride)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 12; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, kEpiWarps); }
+    mbar_init(ball_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (x.b_stat) {
+        mbar_expect_tx(ball_bar, (uint32_t)(9 * kchunks * b_slot_bytes));
+        for (int c = 0; c < kchunks; ++c)
+          for (int t = 0; t < 9; ++t) tma_load_3d(sB + (c * 9 + t) * b_slot_bytes, &tmB, ball_bar, c * 64, 0, t);
       }
-      for (int cp0 = c_begin; cp0 < c_end; cp0 += chunks_per_pass) {
-        const int nch = min(chunks_per_pass, c_end - cp0);
-        const int row_bytes = nch * 16 * elt, pitch = row_bytes + 16;
-        uint8_t* my = stage + lane * pitch;
-        for (int ch = 0; ch < nch; ++ch) {
-          uint32_t v[16];
-          tmem_ld16(t_addr + (uint32_t)((cp0 + ch) * 16), v);
-          tmem_ld_wait();
-          const int n = n0 + (cp0 + ch) * 16;
-          float y[16];
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bv = __ldg(bp + i);
-            y[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bv.x;
-            y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bv.y;
-            y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bv.z;
-            y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bv.w;
-          }
-          if (p.act) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = silu_f(y[i]);
-          }
-          if (elt == 2) {
-            uint4* d = reinterpret_cast<uint4*>(my + ch * 32);
-            d[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-            d[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]),
-                              pack_bf16x2(y[14], y[15]));
-          } else {
-            float4* d = reinterpret_cast<float4*>(my + ch * 64);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-          }
-        }
-        if (cp0 + chunks_per_pass >= c_end) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + buf);
-        } else {
-          __syncwarp();
-        }
-        const int ppr = row_bytes >> 4;  // 16-byte pieces per row (<= 16)
-        const int ppr_inv = (65536 + ppr - 1) / ppr;  // piece / ppr == (piece * ppr_inv) >> 16 for piece < 512
-        for (int piece = lane; piece < 32 * ppr; piece += 32) {
-          const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
-          const long long o_r = __shfl_sync(0xffffffffu, off_row, row);
-          const long long r_r = __shfl_sync(0xffffffffu, res_row, row);
-          const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
-          uint4 val = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
-          if (!ok) continue;
-          if (elt == 4) {
-            const int n = n0 + cp0 * 16 + pc * 4;
-            *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o_r + n) = val;
-            continue;
-          }
-          const int n = n0 + cp0 * 16 + pc * 8;
-          if (p.res != nullptr) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(p.res + r_r + n);
-            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val);
-            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-            uint32_t o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 fa = __bfloat1622float2(a2[i]), fb = __bfloat1622float2(b2[i]);
-              o[i] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+      int ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
+        const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
+        const int th = t_in / p.tiles_w;
+        const int h0 = th * 16 * x.msub, w0 = (t_in - th * p.tiles_w) * 8;
+        for (int c = 0; c < kchunks; ++c) {
+          const int sa = ia % x.a_slots;
+          mbar_wait(a_empty + sa, ((ia / x.a_slots) & 1) ^ 1, 1u);
+          mbar_expect_tx(a_full + sa, (uint32_t)(x.halo_rows * 128));
+          tma_load_5d(sA + sa * x.a_bytes, &tmA, a_full + sa, p.a_base[0] + c * 64, w0 - 1, h0 - 1, b, 0);
+          ++ia;
+          if (!x.b_stat) {
+            for (int t = 0; t < 9; ++t, ++ib) {
+              const int sb = ib % x.b_slots;
+              mbar_wait(b_empty + sb, ((ib / x.b_slots) & 1) ^ 1, 1u);
+              mbar_expect_tx(b_full + sb, (uint32_t)b_slot_bytes);
+              tma_load_3d(sB + sb * b_slot_bytes, &tmB, b_full + sb, c * 64, n0, t);
             }
-            val = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          long long off = o_r + n;
-          if (p.out_mode == OUT_SHUFFLE2_BF16) {
-            const int cq = p.Cout >> 2;
-            const int g = n / cq, c = n - g * cq;
-            off = o_r + ((long long)(g >> 1) * (2 * p.img_W) + (g & 1)) * p.out_pix_stride + c;
-          }
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = val;
         }
-        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+      if (x.b_stat) {
+        mbar_wait(ball_bar, 0, 2u);
+        tc_fence_after();
+      }
+      int ia = 0, ib = 0, acc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
+        const int buf = acc & 1;
+        mbar_wait(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u);
+        tc_fence_after();
+        int first = 1;
+        for (int c = 0; c < kchunks; ++c, ++ia) {
+          const int sa = ia % x.a_slots;
+          mbar_wait(a_full + sa, (ia / x.a_slots) & 1, 2u);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + sa * x.a_bytes);
+          int ksteps = (p.Cin - c * 64) >> 4;
+          if (ksteps > 4) ksteps = 4;
+          for (int t = 0; t < 9; ++t) {
+            uint32_t b_base;
+            int sb = 0;
+            if (x.b_stat) {
+              b_base = smem_u32(sB + (c * 9 + t) * b_slot_bytes);
+            } else {
+              sb = ib % x.b_slots;
+              mbar_wait(b_full + sb, (ib / x.b_slots) & 1, 2u);
+              tc_fence_after();
+              b_base = smem_u32(sB + sb * b_slot_bytes);
+              ++ib;
+            }
+            const int kh = t / 3, kw = t - kh * 3;
+            for (int s = 0; s < x.msub; ++s) {
+              const uint32_t a0 = a_base + (uint32_t)(((s * 16 + kh) * 10 + kw) * 128);
+              const uint32_t d_tmem = tmem_base + (uint32_t)((buf * x.msub + s) * acc_stride);
+              for (int j = 0; j < ksteps; ++j)
+                umma_bf16(d_tmem, umma_desc_sw128_sbo(a0 + j * 32, 1280), umma_desc_sw128(b_base + j * 32), idesc,
+                          first ? 0u : 1u);
+            }
+            first = 0;
+            if (!x.b_stat) umma_commit(b_empty + sb);
+          }
+          umma_commit(a_empty + sa);
+        }
+        umma_commit(tfull_bar + buf);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int lg = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const int nchunks = p.n_tile >> 4;
+    const int half = (nchunks + 1) >> 1;
+    const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
+    uint8_t* stage = stage_base + (warp - 2) * kEpiStageBytes;
+    const int r = lg * 32 + lane;
+    int acc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
+      const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
+      const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
+      const int th = t_in / p.tiles_w;
+      const int h0 = th * 16 * x.msub, w0 = (t_in - th * p.tiles_w) * 8;
+      const int buf = acc & 1;
+      mbar_wait(tfull_bar + buf, (acc >> 1) & 1, 4u);
+      tc_fence_after();
+      for (int s = 0; s < x.msub; ++s) {
+        const int h = h0 + s * 16 + (r >> 3), w = w0 + (r & 7);
+        const bool valid = (h < p.tH) && (w < p.tW);
+        const int q = valid ? (b * p.tH + h) * p.tW + w : 0;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * x.msub + s) * acc_stride);
+        epi_drain(p, stage, lane, c_begin, c_end, t_addr, n0, valid, q, s == x.msub - 1 ? tempty_bar + buf : nullptr);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENT (impl 3): 3x3 stride-1 conv whose nine taps all read ONE halo tile in shared memory.
+// Tile = 16 rows x 8 cols of output; the halo box {64 ch, 10, 18} (180 rows of 128 B, SWIZZLE_128B) is loaded
+// once per 64-channel chunk and tap (kh,kw) is the same buffer seen through a descriptor whose start address is
+// advanced by (kh*10+kw) rows and whose 8-row groups are 10 rows (1280 B) apart.  This only works if the
+// tensor core applies the 128B swizzle on absolute shared-memory address bits (as TMA does when writing).
+// Unpipelined on purpose: it exists to answer that question on hardware (tests/test_gpu_conv.py).
+// ------------------------------------------------------------------------------------------------
+constexpr int kHaloRows = 18 * 10;
+constexpr int kHaloBytes = 24 * 1024;  // 180 rows x 128 B, padded to a 1024 multiple
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_halo_test_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kHaloBytes;                      // 9 taps x n_tile rows x 128 B
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + 9 * p.n_tile * 128);
+  uint64_t* done_bar = full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int b = blockIdx.x / tiles_per_img, t_in = blockIdx.x - b * tiles_per_img;
+  const int th = t_in / p.tiles_w;
+  const int h0 = th * 16, w0 = (t_in - th * p.tiles_w) * 8;
+  const int kchunks = (p.Cin + 63) >> 6;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.n_tile) tmem_cols <<= 1;
+  if (warp == 1 && lane == 0) {
+    mbar_init(full_bar, 1);
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+    for (int c = 0; c < kchunks; ++c) {
+      if (c > 0) mbar_wait(done_bar, (c - 1) & 1, 1u);  // previous chunk's MMAs have finished reading smem
+      mbar_expect_tx(full_bar, (uint32_t)(kHaloRows * 128 + 9 * p.n_tile * 128));
+      tma_load_5d(sA, &tmA, full_bar, p.a_base[0] + c * 64, w0 - 1, h0 - 1, b, 0);
+      for (int t = 0; t < 9; ++t) tma_load_3d(sB + t * p.n_tile * 128, &tmB, full_bar, c * 64, 0, t);
+      mbar_wait(full_bar, c & 1, 2u);
+      tc_fence_after();
+      int ksteps = (p.Cin - c * 64) >> 4;
+      if (ksteps > 4) ksteps = 4;
+      for (int t = 0; t < 9; ++t) {
+        const uint32_t a0 = smem_u32(sA) + (uint32_t)(((t / 3) * 10 + (t % 3)) * 128);
+        const uint32_t b0 = smem_u32(sB) + (uint32_t)(t * p.n_tile * 128);
+        for (int j = 0; j < ksteps; ++j)
+          umma_bf16(tmem_base, umma_desc_sw128_sbo(a0 + j * 32, 1280), umma_desc_sw128(b0 + j * 32), idesc,
+                    (c > 0 || t > 0 || j > 0) ? 1u : 0u);
+      }
+      umma_commit(done_bar);
+    }
+  }
+  if (warp >= 2) {
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int h = h0 + (r >> 3), w = w0 + (r & 7);
+    const bool valid = (h < p.tH) && (w < p.tW);
+    const int q = (b * p.tH + h) * p.tW + w;
+    mbar_wait(done_bar, (kchunks - 1) & 1, 4u);
+    tc_fence_after();
+    for (int j = 0; j < p.n_tile; j += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)j, v);
+      tmem_ld_wait();
+      if (valid) {
+        float a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(v[i]);
+        conv_epilogue_store16(p, q, j, a);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }

@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -26,6 +27,7 @@
 #include "mask_kernels.cuh"
 #include "misc_kernels.cuh"
 #include "v10_kernels.cuh"
+#include "tma_bench.cuh"
 
 using namespace ypb;
 
@@ -847,6 +849,16 @@ int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
     std::string err;
     if (!conv_plan_geometry(d, &op.L, &err)) return fail(YPB_ERR_ARG, op.name + ": " + err);
     e->flops += op.L.flops;
+    if (getenv("YPB_PLAN_DEBUG")) {
+      if (op.L.use_halo)
+        fprintf(stderr, "[plan] %-28s k%d s%d %4d->%4d %4dx%-4d halo msub %d %s a_slots %d b_slots %d tiles %d smem %d\n",
+                op.name.c_str(), op.k, op.s, op.cin, op.cout, op.L.oH, op.L.oW, op.L.x3.msub,
+                op.L.x3.b_stat ? "W-resident" : "W-stream", op.L.x3.a_slots, op.L.x3.b_slots, op.L.total_tiles3, op.L.smem3);
+      else
+        fprintf(stderr, "[plan] %-28s k%d s%d %4d->%4d %4dx%-4d taps tile %dx%d n_tile %d stages %d tiles %d smem %d\n",
+                op.name.c_str(), op.k, op.s, op.cin, op.cout, op.L.oH, op.L.oW, op.L.p.TH, op.L.p.TW, op.L.p.n_tile,
+                op.L.stages2, op.L.total_tiles, op.L.smem2);
+    }
   }
   e->launches += e->end2end ? 3 : 2;  // decode_filter (+ pair_candidates) + nms
   e->planned = true;
@@ -894,7 +906,7 @@ int ypb_kernel_launches(const ypb_engine* e) { return e ? e->launches : 0; }
 double ypb_conv_flops(const ypb_engine* e) { return e ? e->flops : 0.0; }
 
 int ypb_set_conv_impl(ypb_engine* e, int impl) {
-  if (!e || impl < 0 || impl > 2) return fail(YPB_ERR_ARG, "bad argument");
+  if (!e || impl < 0 || impl > 3) return fail(YPB_ERR_ARG, "bad argument");
   e->conv_impl = impl;
   e->drop_graph();
   return YPB_OK;
@@ -1095,6 +1107,45 @@ int ypb_conv2d_bf16(void* cuda_stream, const void* in, int B, int H, int W, int 
   if (!conv_plan_geometry(d, &L, &err)) return fail(YPB_ERR_ARG, err);
   if (!conv_bind(d, &L, &err)) return fail(YPB_ERR_CUDA, err);
   CUDA_TRY(conv_launch(L, reinterpret_cast<cudaStream_t>(cuda_stream), impl));
+  return YPB_OK;
+}
+
+// Diagnostics: operand-fetch ceiling of the TMA path (see tma_bench.cuh).  buf: device, >= rows*128 bytes (mode 0/1)
+// or B*H*W*128 bytes (mode 2).  Returns elapsed milliseconds in *ms and bytes moved in *bytes.
+int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, int H, int B, float* ms, double* bytes) {
+  if (!buf || !ms || !bytes || stages < 1 || stages > 12) return fail(YPB_ERR_ARG, "bad argument");
+  CUtensorMap m2, m5;
+  std::string err;
+  {
+    cuuint64_t dims[5] = {64, (cuuint64_t)(mode == 2 ? (long long)B * H * W : rows), 1, 1, 1};
+    cuuint64_t str[4] = {128, dims[1] * 128, dims[1] * 128, dims[1] * 128};
+    cuuint32_t box[5] = {64, 128, 1, 1, 1};
+    if (!encode_bf16_map(&m2, buf, 5, dims, str, box, &err)) return fail(YPB_ERR_CUDA, err);
+  }
+  {
+    cuuint64_t dims[5] = {64, (cuuint64_t)(mode == 2 ? W : 16), (cuuint64_t)(mode == 2 ? H : 8), (cuuint64_t)(mode == 2 ? B : 1), 1};
+    cuuint64_t str[4] = {128, dims[1] * 128, dims[1] * dims[2] * 128, dims[1] * dims[2] * dims[3] * 128};
+    cuuint32_t box[5] = {64, 16, 8, 1, 1};
+    if (!encode_bf16_map(&m5, buf, 5, dims, str, box, &err)) return fail(YPB_ERR_CUDA, err);
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int smem = stages * 16384 + 1024 + 256;
+  CUDA_TRY(cudaFuncSetAttribute(tma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  TmaBenchParams p{mode, stages, iters, rows, W, H, B};
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  tma_bench_kernel<<<sms, 64, smem>>>(m2, m5, p);  // warm-up
+  CUDA_TRY(cudaEventRecord(e0));
+  tma_bench_kernel<<<sms, 64, smem>>>(m2, m5, p);
+  CUDA_TRY(cudaEventRecord(e1));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *bytes = (double)sms * iters * 16384.0;
   return YPB_OK;
 }
 

@@ -635,7 +635,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t d_tmem = tmem_base + (uint32_t)((buf * x.msub + s) * acc_stride);
               for (int j = 0; j < ksteps; ++j)
                 umma_bf16(d_tmem, umma_desc_sw128_sbo(a0 + j * 32, 1280), umma_desc_sw128(b_base + j * 32), idesc,
-                          first ? 0u : 1u);
+                          (first && j == 0) ? 0u : 1u);
             }
             first = 0;
             if (!x.b_stat) umma_commit(b_empty + sb);

@@ -136,6 +136,8 @@ int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float*
             int32_t* count /*(B)*/);
 size_t ypb_nms_scratch_bytes(int B, int N);
 /* Diagnostics: ceiling of the TMA operand-fetch path for an access pattern (csrc/tma_bench.cuh). */
+int ypb_mma_bench(void* buf, int rows, int n, int iters, int shifted, int tma_iters, float* ms);
+int ypb_latency_probe(long long* out_dev /* 8 x int64, device */);
 int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, int H, int B, float* ms, double* bytes);
 
 #ifdef __cplusplus

@@ -1,4 +1,4 @@
-"""Run the TMA operand-fetch microbenchmark over a few access patterns.  python tools/tma_bench.py"""
+"""TMA operand-fetch microbenchmark over access patterns / box sizes / number of producer threads."""
 import ctypes as C
 import os
 import sys
@@ -16,21 +16,23 @@ def run(buf, mode, stages, iters, rows=0, W=0, H=0, B=0):
 
 
 def main():
-    big = torch.zeros(2 << 30, dtype=torch.uint8, device="cuda")      # 2 GiB: streams from HBM
-    for stages in (2, 4, 8, 12):
-        gbs, ms = run(big, 0, stages, 4000, rows=(2 << 30) // 128)
-        print(f"mode0 stream HBM   stages {stages:2d}: {gbs:8.0f} GB/s  ({gbs / 148:6.1f} GB/s/SM)  {ms:.3f} ms")
-    small = big[: 64 << 20]                                              # 64 MiB: L2 resident
-    for stages in (2, 4, 8, 12):
-        gbs, ms = run(small, 0, stages, 4000, rows=(64 << 20) // 128)
-        print(f"mode0 stream L2    stages {stages:2d}: {gbs:8.0f} GB/s  ({gbs / 148:6.1f} GB/s/SM)  {ms:.3f} ms")
-    for stages in (2, 8):
-        gbs, ms = run(small, 1, stages, 4000, rows=(64 << 20) // 128)
-        print(f"mode1 same box     stages {stages:2d}: {gbs:8.0f} GB/s  ({gbs / 148:6.1f} GB/s/SM)  {ms:.3f} ms")
-    for (W, H, B) in ((80, 80, 64), (160, 160, 64)):
-        for stages in (2, 8):
-            gbs, ms = run(big, 2, stages, 3996, W=W, H=H, B=B)
-            print(f"mode2 3x3 taps {W}x{H}x{B} stages {stages:2d}: {gbs:8.0f} GB/s  ({gbs / 148:6.1f} GB/s/SM)  {ms:.3f} ms")
+    big = torch.zeros(2 << 30, dtype=torch.uint8, device="cuda")
+    small = big[: 64 << 20]
+    for name, buf in (("HBM 2GiB", big), ("L2 64MiB", small)):
+        rows = buf.numel() // 128
+        for box in (128, 256):
+            for pairs in (1, 2, 4):
+                for stages in (4, 8):
+                    if stages * box * 128 > 200 * 1024:
+                        continue
+                    gbs, ms = run(buf, 0, stages, 4000, rows=rows, W=pairs, H=box)
+                    print(f"stream {name} box {box:3d} rows, {pairs} producer(s), {stages:2d} stages: {gbs:8.0f} GB/s ({gbs / 148:6.1f} /SM)")
+    for pairs in (1, 2):
+        gbs, ms = run(small, 1, 8, 4000, rows=small.numel() // 128, W=pairs, H=128)
+        print(f"same box, {pairs} producer(s): {gbs:8.0f} GB/s ({gbs / 148:6.1f} /SM)")
+    for (W, H, B) in ((80, 80, 64),):
+        gbs, ms = run(big, 2, 8, 3996, W=W, H=H, B=B)
+        print(f"3x3 taps {W}x{H}x{B}: {gbs:8.0f} GB/s ({gbs / 148:6.1f} /SM)")
 
 
 if __name__ == "__main__":

@@ -13,6 +13,21 @@ namespace ypb {
 // kernel shows up as an error code on the host instead of a hung GPU box.
 __device__ unsigned int g_dev_error = 0;
 
+// One lane of a converged warp, chosen by the hardware.  Code guarded by elect_one() is known to ptxas to run on a
+// single lane, so TMA / tcgen05 instructions (which take uniform-register operands) are emitted straight-line;
+// behind a plain `lane == 0` test ptxas wraps each of them in an ELECT/R2UR "waterfall" loop whose back-edge waits
+// on the instruction's operand scoreboard, serialising the issuing thread with the TMA unit (~750 cycles per
+// cp.async.bulk.tensor on B200, measured with tools/tma_bench.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -29,6 +44,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx_relaxed(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -43,11 +61,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: returns false (and flags g_dev_error) if the phase never completes.
+// Polls with the NON-suspending mbarrier.test_wait: measured on B200 (tools/tma_bench.py), a thread parked in
+// mbarrier.try_wait costs ~730 cycles per producer/consumer hand-off regardless of how early the phase completes,
+// which capped every pipeline in this file at one stage per 0.37 us; polling reacts within tens of cycles.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned int err_code) {
+#ifdef YPB_TRYWAIT
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     if (mbar_try_wait(bar, parity)) return true;
   }
+#else
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    if (mbar_test_wait(bar, parity)) return true;
+  }
+#endif
   atomicOr(&g_dev_error, err_code);
   return false;
 }
@@ -66,6 +104,23 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
       :
       : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
         "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {

@@ -39,7 +39,7 @@ struct ConvLaunch {
   // halo-reuse kernel for 3x3 stride-1 convs (conv3_halo_kernel)
   bool use_halo = false;
   Conv3Extra x3{};
-  CUtensorMap tmHalo3;
+  CUtensorMap tmHalo3, tmB3;  // halo box; weight box {64, n_tile, b_group}
   int tiles_h3 = 0, tiles_w3 = 0, total_tiles3 = 0, smem3 = 0;
   ConvParams p;
   int n_splits = 1, total_tiles = 0, stages2 = 2, smem2 = 0;  // persistent-kernel launch shape
@@ -170,6 +170,7 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   L->smem2 = conv2_smem_bytes(p.n_tile, st2);
   if (L->smem2 < 120 * 1024) L->smem2 = 120 * 1024;
   p.out_mode = d.out_mode; p.act = d.act;
+  p.dbg = getenv("YPB_DBG") ? atoi(getenv("YPB_DBG")) : 0;
   p.out_img_stride = d.out_img_stride; p.out_pix_stride = d.out_pix_stride; p.out_c_off = d.out_c_off;
   p.res_img_stride = d.res_img_stride; p.res_pix_stride = d.res_pix_stride; p.res_c_off = d.res_c_off;
   L->flops = 2.0 * d.B * oH * oW * (double)d.cout * d.cin * d.k * d.k;
@@ -180,10 +181,13 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
     const int kch = (d.cin + 63) / 64;
     const long avail = 227 * 1024 - 1024 - 512 - kEpiWarps * kEpiStageBytes;
     const long b_slot = (long)p.n_tile * 128, b_total = 9L * kch * b_slot;
-    const double cost_taps = (double)L->total_tiles * k_iters * (kATileBytes + b_slot);
+    const double waste_taps = (double)L->total_tiles * 128 - (double)d.B * oH * oW * splits;
+    const double cost_taps = (double)L->total_tiles * k_iters * (kATileBytes + b_slot) + waste_taps * 9.0 * kch * 64.0;
     double best = cost_taps;
+    const int force_msub = getenv("YPB_HALO_MSUB") ? atoi(getenv("YPB_HALO_MSUB")) : 0;
     for (int msub = 1; msub <= 2; ++msub) {
       if (2 * msub * conv2_acc_stride(p.n_tile) > 512) continue;
+      if (force_msub && msub != force_msub && 2 * force_msub * conv2_acc_stride(p.n_tile) <= 512) continue;
       const int halo_rows = (16 * msub + 2) * 10;
       const long a_bytes = ((long)halo_rows * 128 + 1023) & ~1023L;
       const int th3 = (oH + 16 * msub - 1) / (16 * msub), tw3 = (oW + 7) / 8;
@@ -191,25 +195,29 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
       for (int stat = 1; stat >= 0; --stat) {
         if (stat && (splits != 1 || b_total > 96 * 1024 || b_total + 2 * a_bytes > avail)) continue;
         long a_slots, b_slots = 0, b_bytes;
+        int b_group = 3;
         if (stat) {
           b_bytes = b_total;
           a_slots = (avail - b_total) / a_bytes;
         } else {
           a_slots = 2;
-          b_slots = (avail - a_slots * a_bytes) / b_slot;
+          if ((avail - a_slots * a_bytes) / (3 * b_slot) < 2) b_group = 1;  // a kernel row of taps per box when two fit
+          b_slots = (avail - a_slots * a_bytes) / (b_group * b_slot);
           if (b_slots > 12) b_slots = 12;
           if (b_slots < 2) continue;
-          b_bytes = b_slots * b_slot;
+          b_bytes = b_slots * b_group * b_slot;
         }
         if (a_slots > 4) a_slots = 4;
         if (a_slots < 2) continue;
+        // bytes fetched from L2 + a charge for tensor work wasted on padded rows (128 B-equivalents per MMA row-step)
+        const double waste = (double)tiles3 * msub * 128 - (double)d.B * oH * oW * splits;
         const double cost = (double)tiles3 * kch * (halo_rows * 128.0 + (stat ? 0.0 : 9.0 * b_slot)) +
-                            (stat ? 148.0 * b_total : 0.0);
+                            (stat ? 148.0 * b_total : 0.0) + waste * 9.0 * kch * 64.0;
         if (cost < best) {
           best = cost;
           L->use_halo = true;
           L->x3.msub = msub; L->x3.a_slots = (int)a_slots; L->x3.a_bytes = (int)a_bytes; L->x3.halo_rows = halo_rows;
-          L->x3.b_slots = (int)b_slots; L->x3.b_stat = stat; L->x3.b_bytes = (int)b_bytes;
+          L->x3.b_slots = (int)b_slots; L->x3.b_group = b_group; L->x3.b_stat = stat; L->x3.b_bytes = (int)b_bytes;
           L->tiles_h3 = th3; L->tiles_w3 = tw3; L->total_tiles3 = (int)tiles3;
           L->smem3 = (int)(1024 + a_slots * a_bytes + b_bytes + 512 + kEpiWarps * kEpiStageBytes);
         }
@@ -259,6 +267,10 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   cuuint64_t ws[2] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.cin * 2 * d.cout};
   cuuint32_t wb[3] = {64, (cuuint32_t)p.n_tile, 1};
   if (!encode_bf16_map(&L->tmB, d.wg, 3, wd, ws, wb, err)) return false;
+  if (L->use_halo) {
+    cuuint32_t wb3[3] = {64, (cuuint32_t)p.n_tile, (cuuint32_t)L->x3.b_group};
+    if (!encode_bf16_map(&L->tmB3, d.wg, 3, wd, ws, wb3, err)) return false;
+  }
   return true;
 }
 
@@ -310,7 +322,7 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
     ConvParams p3 = L.p;
     p3.tiles_h = L.tiles_h3; p3.tiles_w = L.tiles_w3;
     const int grid3 = L.total_tiles3 < num_sms ? L.total_tiles3 : num_sms;
-    conv3_halo_kernel<<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB, p3, L.x3, L.n_splits, L.total_tiles3);
+    conv3_halo_kernel<<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3);
     return cudaGetLastError();
   }
   ConvParams p2 = L.p;

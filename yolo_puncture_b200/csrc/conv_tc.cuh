@@ -51,6 +51,7 @@ struct ConvParams {
   const __nv_bfloat16* res;
   long long res_img_stride;
   int res_pix_stride, res_c_off;
+  int dbg;  // YPB_DBG experiments (0 in production): 1 = no bias/SiLU math, 2 = no output stores, 4 = no MMA issue
 };
 
 // Store 16 consecutive output channels [n, n+16) of output pixel q. v = raw accumulators.
@@ -240,8 +241,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (warp w reads TMEM lanes 32*(w%4)..+31; with 8 epilogue warps each lane group's columns are split in two).
 // ------------------------------------------------------------------------------------------------
 constexpr int kEpiWarps = 8;
-constexpr int kConv2Threads = 64 + 32 * kEpiWarps;
-constexpr int kEpiStageBytes = 32 * (256 + 16);  // per-warp staging tile: 32 rows x (<=256 B + 16 B pad)
+constexpr int kProdWarps = 4;   // TMA producer warps: one thread sustains only ~1 box load per 0.35 us (tools/tma_bench.py)
+constexpr int kMmaWarp = kProdWarps;
+constexpr int kEpiWarp0 = kProdWarps + 1;
+constexpr int kConv2Threads = 32 * (kProdWarps + 1 + kEpiWarps);
+constexpr int kEpiStageBytes = 32 * (128 + 16);  // per-warp staging tile: 32 rows x (<=128 B + 16 B pad)
 
 __host__ __device__ inline int conv2_acc_stride(int n_tile) { return (n_tile + 31) & ~31; }
 __host__ __device__ inline int conv2_smem_bytes(int n_tile, int stages) {
@@ -260,7 +264,7 @@ __host__ __device__ inline int conv2_smem_bytes(int n_tile, int stages) {
 __device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, int lane, int c_begin, int c_end,
                                           uint32_t t_addr, int n0, bool valid, int q, uint64_t* release) {
   const int elt = p.out_mode == OUT_F32 ? 4 : 2;
-  const int chunks_per_pass = elt == 2 ? 8 : 4;  // <= 256 B of output row per pass
+  const int chunks_per_pass = elt == 2 ? 4 : 2;  // <= 128 B of output row per pass
   const int qb = q / p.img_HW, rem = q - qb * p.img_HW;
   // element offset of channel 0 of this row in the output (pixel-shuffle: of sub-pixel (0,0))
   long long off_row;
@@ -294,7 +298,7 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, i
         y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bv.z;
         y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bv.w;
       }
-      if (p.act) {
+      if (p.act && !(p.dbg & 1)) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = silu_f(y[i]);
       }
@@ -318,7 +322,7 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, i
     }
     const int ppr = row_bytes >> 4;  // 16-byte pieces per row (<= 16)
     const int ppr_inv = (65536 + ppr - 1) / ppr;  // piece / ppr == (piece * ppr_inv) >> 16 for piece < 512
-    for (int piece = lane; piece < 32 * ppr; piece += 32) {
+    for (int piece = lane; piece < ((p.dbg & 2) ? 0 : 32 * ppr); piece += 32) {
       const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
       const long long o_r = __shfl_sync(0xffffffffu, off_row, row);
       const long long r_r = __shfl_sync(0xffffffffu, res_row, row);
@@ -387,15 +391,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  if (warp < kProdWarps) {
+    // ===================== TMA producers: warp w fills the stages of iterations it % kProdWarps == w =====================
+    if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)(p.TH * p.TW * 128 + p.n_tile * 128);
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -406,8 +410,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int cbase[5];
 #pragma unroll
         for (int d = 0; d < 5; ++d) cbase[d] = p.a_base[d] + b * p.a_cb[d] + h0 * p.a_ch[d] + w0 * p.a_cw[d];
-        for (int t = 0; t < p.ntaps; ++t) {
-          for (int c = 0; c < kchunks; ++c, ++it) {
+        for (int c = 0; c < kchunks; ++c) {
+          for (int t = 0; t < p.ntaps; ++t, ++it) {
+            if ((it % kProdWarps) != warp) continue;
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
             mbar_wait(empty_bar + s, ph ^ 1, 1u);
@@ -420,9 +425,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (accumulation order: chunk-major, tap-minor, like conv3_halo_kernel) =====================
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
       int it = 0, acc = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
@@ -431,17 +436,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_stride);
         int first = 1;
-        for (int t = 0; t < p.ntaps; ++t) {
-          for (int c = 0; c < kchunks; ++c, ++it) {
+        for (int c = 0; c < kchunks; ++c) {
+          int ksteps = (p.Cin - c * 64) >> 4;
+          if (ksteps > 4) ksteps = 4;
+          for (int t = 0; t < p.ntaps; ++t, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
             mbar_wait(full_bar + s, ph, 2u);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + s * stage_bytes);
             const uint32_t sb = sa + kATileBytes;
-            int ksteps = (p.Cin - c * 64) >> 4;
-            if (ksteps > 4) ksteps = 4;
-            for (int j = 0; j < ksteps; ++j) {
+            for (int j = 0; j < ((p.dbg & 4) ? 0 : ksteps); ++j) {
               umma_bf16(d_tmem, umma_desc_sw128(sa + j * 32), umma_desc_sw128(sb + j * 32), idesc, first ? 0u : 1u);
               first = 0;
             }
@@ -460,11 +465,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // along the channel dimension, so every store instruction covers whole 128-byte lines of NHWC rows
     // (a thread-per-row store would touch 32 different lines per instruction).
     const int lg = warp & 3;
-    const int part = (warp - 2) >> 2;
+    const int part = (warp - kEpiWarp0) >> 2;
     const int nchunks = p.n_tile >> 4;
     const int half = (nchunks + 1) >> 1;
     const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
-    uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - 2) * kEpiStageBytes;
+    uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - kEpiWarp0) * kEpiStageBytes;
     const int r = lg * 32 + lane;
     const int rh = r / p.TW, rw = r - rh * p.TW;
     int acc = 0;
@@ -484,7 +489,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -519,7 +524,8 @@ struct Conv3Extra {
   int a_slots;     // halo ring depth
   int a_bytes;     // bytes per halo slot (1024 multiple)
   int halo_rows;   // (16*msub+2)*10
-  int b_slots;     // weight ring depth (streaming mode)
+  int b_slots;     // weight ring depth, in groups (streaming mode)
+  int b_group;     // taps per weight box / ring slot: 3 (one kernel row) or 1
   int b_stat;      // 1: all weights resident in smem
   int b_bytes;     // weight region bytes
 };
@@ -546,7 +552,9 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int kchunks = (p.Cin + 63) >> 6;
   const int acc_stride = conv2_acc_stride(p.n_tile);
-  const int b_slot_bytes = p.n_tile * 128;
+  const int tap_bytes = p.n_tile * 128;
+  const int grp_bytes = x.b_group * tap_bytes;
+  const int ngroups = 9 / x.b_group;  // weight boxes per 64-channel chunk
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * x.msub * acc_stride)) tmem_cols <<= 1;
 
@@ -559,46 +567,55 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(ball_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer 0: halo tiles (and the resident weights, once) =====================
+    if (elect_one()) {
       if (x.b_stat) {
-        mbar_expect_tx(ball_bar, (uint32_t)(9 * kchunks * b_slot_bytes));
+        mbar_expect_tx(ball_bar, (uint32_t)(9 * kchunks * tap_bytes));
         for (int c = 0; c < kchunks; ++c)
-          for (int t = 0; t < 9; ++t) tma_load_3d(sB + (c * 9 + t) * b_slot_bytes, &tmB, ball_bar, c * 64, 0, t);
+          for (int g = 0; g < ngroups; ++g)
+            tma_load_3d(sB + (c * 9 + g * x.b_group) * tap_bytes, &tmB, ball_bar, c * 64, 0, g * x.b_group);
       }
-      int ia = 0, ib = 0;
+      int ia = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
+        const int mt = tile / n_splits;
         const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
         const int th = t_in / p.tiles_w;
         const int h0 = th * 16 * x.msub, w0 = (t_in - th * p.tiles_w) * 8;
-        for (int c = 0; c < kchunks; ++c) {
+        for (int c = 0; c < kchunks; ++c, ++ia) {
           const int sa = ia % x.a_slots;
           mbar_wait(a_empty + sa, ((ia / x.a_slots) & 1) ^ 1, 1u);
           mbar_expect_tx(a_full + sa, (uint32_t)(x.halo_rows * 128));
           tma_load_5d(sA + sa * x.a_bytes, &tmA, a_full + sa, p.a_base[0] + c * 64, w0 - 1, h0 - 1, b, 0);
-          ++ia;
-          if (!x.b_stat) {
-            for (int t = 0; t < 9; ++t, ++ib) {
-              const int sb = ib % x.b_slots;
-              mbar_wait(b_empty + sb, ((ib / x.b_slots) & 1) ^ 1, 1u);
-              mbar_expect_tx(b_full + sb, (uint32_t)b_slot_bytes);
-              tma_load_3d(sB + sb * b_slot_bytes, &tmB, b_full + sb, c * 64, n0, t);
-            }
+        }
+      }
+    }
+  } else if (warp < kProdWarps) {
+    // ===================== TMA producers 1..3: streamed weight boxes, box ib handled by warp 1 + ib % 3 =====================
+    if (!x.b_stat && elect_one()) {
+      int ib = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
+        for (int c = 0; c < kchunks; ++c) {
+          for (int g = 0; g < ngroups; ++g, ++ib) {
+            if (1 + (ib % (kProdWarps - 1)) != warp) continue;
+            const int sb = ib % x.b_slots;
+            mbar_wait(b_empty + sb, ((ib / x.b_slots) & 1) ^ 1, 1u);
+            mbar_expect_tx(b_full + sb, (uint32_t)grp_bytes);
+            tma_load_3d(sB + sb * grp_bytes, &tmB, b_full + sb, c * 64, n0, g * x.b_group);
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
       if (x.b_stat) {
         mbar_wait(ball_bar, 0, 2u);
@@ -617,27 +634,31 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t a_base = smem_u32(sA + sa * x.a_bytes);
           int ksteps = (p.Cin - c * 64) >> 4;
           if (ksteps > 4) ksteps = 4;
-          for (int t = 0; t < 9; ++t) {
-            uint32_t b_base;
+          for (int g = 0; g < ngroups; ++g) {
+            uint32_t g_base;
             int sb = 0;
             if (x.b_stat) {
-              b_base = smem_u32(sB + (c * 9 + t) * b_slot_bytes);
+              g_base = smem_u32(sB + (c * 9 + g * x.b_group) * tap_bytes);
             } else {
               sb = ib % x.b_slots;
               mbar_wait(b_full + sb, (ib / x.b_slots) & 1, 2u);
               tc_fence_after();
-              b_base = smem_u32(sB + sb * b_slot_bytes);
+              g_base = smem_u32(sB + sb * grp_bytes);
               ++ib;
             }
-            const int kh = t / 3, kw = t - kh * 3;
-            for (int s = 0; s < x.msub; ++s) {
-              const uint32_t a0 = a_base + (uint32_t)(((s * 16 + kh) * 10 + kw) * 128);
-              const uint32_t d_tmem = tmem_base + (uint32_t)((buf * x.msub + s) * acc_stride);
-              for (int j = 0; j < ksteps; ++j)
-                umma_bf16(d_tmem, umma_desc_sw128_sbo(a0 + j * 32, 1280), umma_desc_sw128(b_base + j * 32), idesc,
-                          (first && j == 0) ? 0u : 1u);
+            for (int u = 0; u < x.b_group; ++u) {
+              const int t = g * x.b_group + u;
+              const int kh = t / 3, kw = t - kh * 3;
+              const uint32_t b_base = g_base + (uint32_t)(u * tap_bytes);
+              for (int sidx = 0; sidx < x.msub; ++sidx) {
+                const uint32_t a0 = a_base + (uint32_t)(((sidx * 16 + kh) * 10 + kw) * 128);
+                const uint32_t d_tmem = tmem_base + (uint32_t)((buf * x.msub + sidx) * acc_stride);
+                for (int j = 0; j < ((p.dbg & 4) ? 0 : ksteps); ++j)
+                  umma_bf16(d_tmem, umma_desc_sw128_sbo(a0 + j * 32, 1280), umma_desc_sw128(b_base + j * 32), idesc,
+                            (first && j == 0) ? 0u : 1u);
+              }
+              first = 0;
             }
-            first = 0;
             if (!x.b_stat) umma_commit(b_empty + sb);
           }
           umma_commit(a_empty + sa);
@@ -648,11 +669,11 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================== epilogue =====================
     const int lg = warp & 3;
-    const int part = (warp - 2) >> 2;
+    const int part = (warp - kEpiWarp0) >> 2;
     const int nchunks = p.n_tile >> 4;
     const int half = (nchunks + 1) >> 1;
     const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
-    uint8_t* stage = stage_base + (warp - 2) * kEpiStageBytes;
+    uint8_t* stage = stage_base + (warp - kEpiWarp0) * kEpiStageBytes;
     const int r = lg * 32 + lane;
     int acc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
@@ -663,18 +684,18 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int buf = acc & 1;
       mbar_wait(tfull_bar + buf, (acc >> 1) & 1, 4u);
       tc_fence_after();
-      for (int s = 0; s < x.msub; ++s) {
-        const int h = h0 + s * 16 + (r >> 3), w = w0 + (r & 7);
+      for (int sidx = 0; sidx < x.msub; ++sidx) {
+        const int h = h0 + sidx * 16 + (r >> 3), w = w0 + (r & 7);
         const bool valid = (h < p.tH) && (w < p.tW);
         const int q = valid ? (b * p.tH + h) * p.tW + w : 0;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * x.msub + s) * acc_stride);
-        epi_drain(p, stage, lane, c_begin, c_end, t_addr, n0, valid, q, s == x.msub - 1 ? tempty_bar + buf : nullptr);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * x.msub + sidx) * acc_stride);
+        epi_drain(p, stage, lane, c_begin, c_end, t_addr, n0, valid, q, sidx == x.msub - 1 ? tempty_bar + buf : nullptr);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }

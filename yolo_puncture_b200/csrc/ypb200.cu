@@ -1119,10 +1119,15 @@ int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, i
   {
     cuuint64_t dims[5] = {64, (cuuint64_t)(mode == 2 ? (long long)B * H * W : rows), 1, 1, 1};
     cuuint64_t str[4] = {128, dims[1] * 128, dims[1] * 128, dims[1] * 128};
-    cuuint32_t box[5] = {64, 128, 1, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)((mode != 2 && H == 256) ? 256 : 128), 1, 1, 1};
     if (!encode_bf16_map(&m2, buf, 5, dims, str, box, &err)) return fail(YPB_ERR_CUDA, err);
   }
-  {
+  if (mode == 3) {
+    cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+    cuuint64_t str[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)(H == 256 ? 256 : 128)};
+    if (!encode_bf16_map(&m5, buf, 2, dims, str, box, &err)) return fail(YPB_ERR_CUDA, err);
+  } else {
     cuuint64_t dims[5] = {64, (cuuint64_t)(mode == 2 ? W : 16), (cuuint64_t)(mode == 2 ? H : 8), (cuuint64_t)(mode == 2 ? B : 1), 1};
     cuuint64_t str[4] = {128, dims[1] * 128, dims[1] * dims[2] * 128, dims[1] * dims[2] * dims[3] * 128};
     cuuint32_t box[5] = {64, 16, 8, 1, 1};
@@ -1131,21 +1136,59 @@ int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, i
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int smem = stages * 16384 + 1024 + 256;
+  const int stage_b = (mode != 2 && H == 256) ? 32768 : 16384;
+  const int smem = stages * stage_b + 1024 + 256;
+  if (smem > 227 * 1024) return fail(YPB_ERR_ARG, "too many stages");
   CUDA_TRY(cudaFuncSetAttribute(tma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   TmaBenchParams p{mode, stages, iters, rows, W, H, B};
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
-  tma_bench_kernel<<<sms, 64, smem>>>(m2, m5, p);  // warm-up
+  tma_bench_kernel<<<sms, 256, smem>>>(m2, m5, p);  // warm-up
   CUDA_TRY(cudaEventRecord(e0));
-  tma_bench_kernel<<<sms, 64, smem>>>(m2, m5, p);
+  tma_bench_kernel<<<sms, 256, smem>>>(m2, m5, p);
   CUDA_TRY(cudaEventRecord(e1));
   CUDA_TRY(cudaEventSynchronize(e1));
   CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  *bytes = (double)sms * iters * 16384.0;
+  *bytes = (double)sms * iters * (double)stage_b;
+  return YPB_OK;
+}
+
+// Diagnostics: tensor-pipe ceiling for M=128 x N MMAs fed from shared memory, optionally with concurrent TMA traffic.
+int ypb_mma_bench(void* buf, int rows, int n, int iters, int shifted, int tma_iters, float* ms) {
+  if (!buf || !ms || n < 16 || n > 256 || (n % 16)) return fail(YPB_ERR_ARG, "bad argument");
+  CUtensorMap m2;
+  std::string err;
+  cuuint64_t dims[5] = {64, (cuuint64_t)rows, 1, 1, 1};
+  cuuint64_t str[4] = {128, dims[1] * 128, dims[1] * 128, dims[1] * 128};
+  cuuint32_t box[5] = {64, 128, 1, 1, 1};
+  if (!encode_bf16_map(&m2, buf, 5, dims, str, box, &err)) return fail(YPB_ERR_CUDA, err);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int smem = 131072 + 1024 + 256;
+  CUDA_TRY(cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  MmaBenchParams p{n, iters, shifted, tma_iters, rows};
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  mma_bench_kernel<<<sms, 96, smem>>>(m2, p);
+  CUDA_TRY(cudaEventRecord(e0));
+  mma_bench_kernel<<<sms, 96, smem>>>(m2, p);
+  CUDA_TRY(cudaEventRecord(e1));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return YPB_OK;
+}
+
+int ypb_latency_probe(long long* out_dev) {
+  if (!out_dev) return fail(YPB_ERR_ARG, "bad argument");
+  latency_probe_kernel<<<1, 64>>>(out_dev);
+  CUDA_TRY(cudaDeviceSynchronize());
   return YPB_OK;
 }
 

@@ -398,7 +398,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kProdWarps) {
-    // ===================== TMA producers: warp w fills the stages of iterations it % kProdWarps == w =====================
+    // ===================== TMA producers: warp w owns the ring stages s with s % kProdWarps == w =====================
     if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)(p.TH * p.TW * 128 + p.n_tile * 128);
       int it = 0;
@@ -412,8 +412,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int d = 0; d < 5; ++d) cbase[d] = p.a_base[d] + b * p.a_cb[d] + h0 * p.a_ch[d] + w0 * p.a_cw[d];
         for (int c = 0; c < kchunks; ++c) {
           for (int t = 0; t < p.ntaps; ++t, ++it) {
-            if ((it % kProdWarps) != warp) continue;
+            // a stage always belongs to the same producer: parity waits are only sound one phase ahead
             const int s = it % p.stages;
+            if ((s % kProdWarps) != warp) continue;
             const uint32_t ph = (it / p.stages) & 1;
             mbar_wait(empty_bar + s, ph ^ 1, 1u);
             uint8_t* sa = smem + s * stage_bytes;
@@ -597,15 +598,15 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp < kProdWarps) {
-    // ===================== TMA producers 1..3: streamed weight boxes, box ib handled by warp 1 + ib % 3 =====================
+    // ===================== TMA producers 1..3: streamed weight boxes, ring slot sb owned by warp 1 + sb % 3 =====================
     if (!x.b_stat && elect_one()) {
       int ib = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
         for (int c = 0; c < kchunks; ++c) {
           for (int g = 0; g < ngroups; ++g, ++ib) {
-            if (1 + (ib % (kProdWarps - 1)) != warp) continue;
             const int sb = ib % x.b_slots;
+            if (1 + (sb % (kProdWarps - 1)) != warp) continue;  // a slot always belongs to the same producer
             mbar_wait(b_empty + sb, ((ib / x.b_slots) & 1) ^ 1, 1u);
             mbar_expect_tx(b_full + sb, (uint32_t)grp_bytes);
             tma_load_3d(sB + sb * grp_bytes, &tmB, b_full + sb, c * 64, n0, g * x.b_group);

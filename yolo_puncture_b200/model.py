@@ -43,12 +43,31 @@ def letterbox_geometry(shape, new_shape, auto, stride=32):
 
 
 def letterbox_into(dst, img, new_unpad, top, left):
-    """Resize `img` (cv2 INTER_LINEAR, as upstream) and paste it into the 114-filled canvas `dst`."""
-    import cv2
+    """Resize `img` (cv2 INTER_LINEAR, as upstream) and paste it into the 114-padded canvas `dst`."""
     if (img.shape[1], img.shape[0]) != new_unpad:
+        import cv2
         img = cv2.resize(img, new_unpad, interpolation=cv2.INTER_LINEAR)
-    dst[...] = 114
-    dst[top:top + img.shape[0], left:left + img.shape[1]] = img
+    h, w = img.shape[:2]
+    if (h, w) == dst.shape[:2]:
+        np.copyto(dst, img)  # no padding: one pass over the pixels
+        return
+    dst[:top] = 114
+    dst[top + h:] = 114
+    dst[top:top + h, :left] = 114
+    dst[top:top + h, left + w:] = 114
+    dst[top:top + h, left:left + w] = img
+
+
+_POOL = None
+
+
+def _pool():
+    """Host threads for frame staging (cv2.resize and numpy copies release the GIL)."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+    return _POOL
 
 
 def box_xform(net_hw, orig_hw):
@@ -232,8 +251,6 @@ class YOLO:
             eng.plan(B, H, W)
             buf = self._buffers(B, H, W)
             host = buf["host"].numpy()
-            for i, f in enumerate(frames):
-                letterbox_into(host[i], f, new_unpad, top, left)
             xf = box_xform((H, W), shape)
             buf["xf_host"][:] = torch.tensor(xf)
             cmask = None
@@ -242,9 +259,16 @@ class YOLO:
                 for c in classes:
                     words[int(c) >> 5] |= np.uint32(1) << np.uint32(int(c) & 31)
                 cmask = torch.from_numpy(words.view(np.int32)).to(self._device)
-            t1 = time.perf_counter()
-            buf["dev"].copy_(buf["host"], non_blocking=True)
+            # stage frames into pinned memory on host threads, chunk by chunk; the H2D copy of a chunk is enqueued as
+            # soon as it is staged, so PCIe transfers overlap the staging of the following chunks
             buf["xf_dev"].copy_(buf["xf_host"], non_blocking=True)
+            chunk = 8
+            futs = [(_pool().submit(letterbox_into, host[i], f, new_unpad, top, left)) for i, f in enumerate(frames)]
+            for c0 in range(0, B, chunk):
+                for fu in futs[c0:c0 + chunk]:
+                    fu.result()
+                buf["dev"][c0:c0 + chunk].copy_(buf["host"][c0:c0 + chunk], non_blocking=True)
+            t1 = time.perf_counter()
             eng.infer(buf["dev"], buf["xf_dev"], conf, iou, max_det, agnostic, cmask)
             counts = eng.count.cpu()  # stream-ordered D2H: the only host sync of the detector
             t2 = time.perf_counter()

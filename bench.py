@@ -191,6 +191,8 @@ def run_ours(args, wl):
     eng = yolo.engine
     eng.set_conv_impl(args.conv_impl)
     eng.set_graph(not args.no_graph)
+    if args.micro_batch:
+        yolo.micro_batch = args.micro_batch
     frames = make_frames(B, hw, rank * B)  # each rank owns its own shard of the synthetic stream
     new_unpad, top, bottom, left, right = letterbox_geometry(hw, (imgsz, imgsz), auto=True)
     H, W = new_unpad[1] + top + bottom, new_unpad[0] + left + right
@@ -330,7 +332,7 @@ def run_ours(args, wl):
         "config": {"workload": args.workload, "model": model, "batch_per_gpu": B, "global_batch": world * B,
                    "frame": f"{hw[1]}x{hw[0]}", "net_input": f"{W}x{H}", "imgsz": imgsz, "conf": CONF, "iou": IOU,
                    "retina_masks": True, "weights": "random-init, synthetic recipe (SURVEY.md 8d)",
-                   "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph,
+                   "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph, "predict_micro_batch": yolo.micro_batch,
                    "detections_per_step": n_det, "parallelism": f"frame-sharded replicas x{world}",
                    "l2": "each step streams >1 GB of activations through HBM (inputs+activations exceed the 126 MB L2)"},
         "p50_frame_latency_ms_b1": p50,
@@ -354,6 +356,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-impl", type=int, default=0, help="0 persistent tcgen05 (product), 2 one-tile-per-CTA tcgen05 (A/B)")
+    ap.add_argument("--micro-batch", type=int, default=0, help="frames per engine pass inside YOLO.predict() (e2e arm)")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay (A/B)")
     ap.add_argument("--dump-ops", default=None, help="write the per-op CUDA-event profile of one step to this CSV")
     args = ap.parse_args()

@@ -114,14 +114,14 @@ struct ypb_engine {
     int max_det, agnostic, impl;
     bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
   };
-  bool use_graph = true, graph_valid = false;
-  GraphKey graph_key{};
-  cudaGraphExec_t graph_exec = nullptr;
+  bool use_graph = true;
+  struct GraphEntry { GraphKey key; cudaGraphExec_t exec; unsigned long long stamp; };
+  std::vector<GraphEntry> graphs;  // small LRU cache: callers alternate between a few input buffers
+  unsigned long long graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
   void drop_graph() {
-    if (graph_exec) cudaGraphExecDestroy(graph_exec);
-    graph_exec = nullptr;
-    graph_valid = false;
+    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
   }
 
   // ------------------------------------------------------------------ builder helpers
@@ -940,9 +940,11 @@ int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const flo
   key.frames = frames; key.xform = xform; key.det = det; key.det_lb = det_lb; key.keep = keep; key.coef = coef;
   key.count = count; key.cmask = prm->class_mask; key.conf = prm->conf; key.iou = prm->iou; key.max_det = prm->max_det;
   key.agnostic = prm->agnostic_nms; key.impl = e->conv_impl;
-  if (!e->graph_valid || !(key == e->graph_key)) {
-    // (re)capture the ~80 launches of a forward pass on a private stream; replays cost one launch
-    e->drop_graph();
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : e->graphs)
+    if (g.key == key) { exec = g.exec; g.stamp = ++e->graph_clock; break; }
+  if (!exec) {
+    // capture the ~80 launches of a forward pass on a private stream; replays cost one launch
     if (!e->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
     int rc = enqueue_infer(e, e->cap_stream, frames, xform, prm, det, det_lb, keep, coef, count);
@@ -950,13 +952,18 @@ int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const flo
     cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) return fail(YPB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
-    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    ce = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) return fail(YPB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
-    e->graph_key = key;
-    e->graph_valid = true;
+    if (e->graphs.size() >= 8) {  // evict the least recently used
+      size_t lru = 0;
+      for (size_t i = 1; i < e->graphs.size(); ++i) if (e->graphs[i].stamp < e->graphs[lru].stamp) lru = i;
+      cudaGraphExecDestroy(e->graphs[lru].exec);
+      e->graphs.erase(e->graphs.begin() + lru);
+    }
+    e->graphs.push_back({key, exec, ++e->graph_clock});
   }
-  CUDA_TRY(cudaGraphLaunch(e->graph_exec, st));
+  CUDA_TRY(cudaGraphLaunch(exec, st));
   return YPB_OK;
 }
 

@@ -156,6 +156,7 @@ class YOLO:
         self._device_token = torch.zeros(1)
         self._staging = {}
         self.overrides = {}
+        self.micro_batch = 16  # frames per engine pass inside predict(); H2D of pass k+1 overlaps compute of pass k
         if device is not None:
             self._set_device(device)
 
@@ -228,18 +229,22 @@ class YOLO:
                     results[i] = r
         return iter(results) if stream else results
 
-    def _buffers(self, B, H, W):
-        key = (B, H, W)
+    def _buffers(self, B, mb, H, W):
+        key = (B, mb, H, W)
         if key not in self._staging:
             self._staging = {key: {
                 "host": torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory(),
-                "dev": torch.empty((B, H, W, 3), dtype=torch.uint8, device=self._device),
-                "xf_host": torch.empty((B, 5), dtype=torch.float32).pin_memory(),
-                "xf_dev": torch.empty((B, 5), dtype=torch.float32, device=self._device),
+                "dev": [torch.empty((mb, H, W, 3), dtype=torch.uint8, device=self._device) for _ in range(2)],
+                "xf_dev": torch.empty((mb, 5), dtype=torch.float32, device=self._device),
+                "copy_stream": torch.cuda.Stream(device=self._device),
+                "in_free": [None, None],
             }}
         return self._staging[key]
 
     def _predict_batch(self, frames, shape, imgsz, auto, conf, iou, retina, max_det, classes, agnostic):
+        """One group of same-shape frames.  The group runs as micro-batches of `mb` frames through one static engine
+        plan: frames are letterboxed into pinned memory by host threads, each micro-batch's H2D copy is issued on a
+        copy stream as soon as its frames are staged, and it overlaps the engine pass of the previous micro-batch."""
         eng = self.engine
         B = len(frames)
         t0 = time.perf_counter()
@@ -247,48 +252,79 @@ class YOLO:
         H, W = new_unpad[1] + top + bottom, new_unpad[0] + left + right
         if H % 32 or W % 32:
             raise YpbError(f"letterboxed size {H}x{W} is not a multiple of 32 (imgsz={imgsz})")
+        mb = B if B <= self.micro_batch else self.micro_batch
+        n_mb = (B + mb - 1) // mb
+        seg = self.task == "segment"
+        mh, mw = (shape[0], shape[1]) if retina else (H, W)
         with torch.cuda.device(self._device):
-            eng.plan(B, H, W)
-            buf = self._buffers(B, H, W)
+            eng.plan(mb, H, W)
+            buf = self._buffers(B, mb, H, W)
             host = buf["host"].numpy()
-            xf = box_xform((H, W), shape)
-            buf["xf_host"][:] = torch.tensor(xf)
+            main = torch.cuda.current_stream(self._device)
+            cs = buf["copy_stream"]
+            buf["xf_dev"].copy_(torch.tensor([box_xform((H, W), shape)] * mb, dtype=torch.float32))
             cmask = None
             if classes is not None:
                 words = np.zeros(((self.nc + 31) // 32,), np.uint32)
                 for c in classes:
                     words[int(c) >> 5] |= np.uint32(1) << np.uint32(int(c) & 31)
                 cmask = torch.from_numpy(words.view(np.int32)).to(self._device)
-            # stage frames into pinned memory on host threads, chunk by chunk; the H2D copy of a chunk is enqueued as
-            # soon as it is staged, so PCIe transfers overlap the staging of the following chunks
-            buf["xf_dev"].copy_(buf["xf_host"], non_blocking=True)
-            chunk = 8
-            futs = [(_pool().submit(letterbox_into, host[i], f, new_unpad, top, left)) for i, f in enumerate(frames)]
-            for c0 in range(0, B, chunk):
-                for fu in futs[c0:c0 + chunk]:
-                    fu.result()
-                buf["dev"][c0:c0 + chunk].copy_(buf["host"][c0:c0 + chunk], non_blocking=True)
+            futs = [_pool().submit(letterbox_into, host[i], f, new_unpad, top, left) for i, f in enumerate(frames)]
+            cs.wait_stream(main)
+            h2d_done = []
             t1 = time.perf_counter()
-            eng.infer(buf["dev"], buf["xf_dev"], conf, iou, max_det, agnostic, cmask)
-            counts = eng.count.cpu()  # stream-ordered D2H: the only host sync of the detector
+            dets, cnts, mask_parts = [], [], []
+
+            def enqueue_h2d(k):
+                lo, hi = k * mb, min((k + 1) * mb, B)
+                for fu in futs[lo:hi]:
+                    fu.result()
+                slot = k & 1
+                with torch.cuda.stream(cs):
+                    if buf["in_free"][slot] is not None:
+                        cs.wait_event(buf["in_free"][slot])
+                    buf["dev"][slot][: hi - lo].copy_(buf["host"][lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                h2d_done.append(ev)
+
+            enqueue_h2d(0)
+            for k in range(n_mb):
+                lo, hi = k * mb, min((k + 1) * mb, B)
+                slot = k & 1
+                main.wait_event(h2d_done[k])
+                eng.infer(buf["dev"][slot], buf["xf_dev"], conf, iou, max_det, agnostic, cmask)
+                fr = torch.cuda.Event()
+                fr.record(main)
+                buf["in_free"][slot] = fr
+                if k + 1 < n_mb:
+                    enqueue_h2d(k + 1)  # its staging + PCIe transfer overlap this micro-batch's engine pass
+                if hi - lo < mb:
+                    eng.count[hi - lo:].zero_()  # padded tail of the last micro-batch
+                counts = eng.count[: hi - lo].cpu()  # stream-ordered D2H: the only host sync per micro-batch
+                n_k = int(counts.sum())
+                cnts.append(counts)
+                dets.append(eng.det[: hi - lo].clone() if n_k else None)
+                if seg and n_k:
+                    m = torch.empty((n_k, mh, mw), dtype=torch.uint8, device=self._device)
+                    eng.masks(m, retina, mh, mw)
+                    mask_parts.append(m)
+                else:
+                    mask_parts.append(None)
             t2 = time.perf_counter()
-            n_tot = int(counts.sum())
-            det = eng.det.clone() if n_tot else None  # stays on the device, like upstream Results.boxes
-            masks = None
-            if self.task == "segment" and n_tot:
-                mh, mw = (shape[0], shape[1]) if retina else (H, W)
-                masks = torch.empty((n_tot, mh, mw), dtype=torch.uint8, device=self._device)
-                eng.masks(masks, retina, mh, mw)
             err = eng.device_error()
             if err:
                 raise YpbError(f"device pipeline error word 0x{err:x}")
             t3 = time.perf_counter()
         speed = {"preprocess": (t1 - t0) * 1e3 / B, "inference": (t2 - t1) * 1e3 / B, "postprocess": (t3 - t2) * 1e3 / B}
-        out, off = [], 0
-        for i, f in enumerate(frames):
-            n = int(counts[i])
-            boxes = det[i, :n] if n else torch.zeros((0, 6), device=self._device)
-            m = masks[off:off + n] if (masks is not None and n) else None
-            off += n
-            out.append(Results(f, None, self.names, boxes=boxes, masks=m, speed=dict(speed)))
+        out = []
+        for k in range(n_mb):
+            lo, hi = k * mb, min((k + 1) * mb, B)
+            counts, det, masks, off = cnts[k].tolist(), dets[k], mask_parts[k], 0
+            for j in range(hi - lo):
+                n = counts[j]
+                boxes = det[j, :n] if n else torch.zeros((0, 6), device=self._device)
+                m = masks[off:off + n] if (masks is not None and n) else None
+                off += n
+                out.append(Results(frames[lo + j], None, self.names, boxes=boxes, masks=m, speed=dict(speed)))
         return out

@@ -41,7 +41,10 @@ struct ConvLaunch {
   Conv3Extra x3{};
   CUtensorMap tmHalo3, tmB3;  // halo box; weight box {64, n_tile, b_group}
   int tiles_h3 = 0, tiles_w3 = 0, total_tiles3 = 0, smem3 = 0;
-  ConvParams p;
+  ConvParams p;       // persistent kernels (conv_tc2 geometry: tile may hold msub sub-tiles)
+  ConvParams p1;      // one-tile-per-CTA geometry (impl 2 / 3, A/B experiments)
+  CUtensorMap tmA1;
+  dim3 grid1;
   int n_splits = 1, total_tiles = 0, stages2 = 2, smem2 = 0;  // persistent-kernel launch shape
   ConvSimtGeom sg;
   CUtensorMap tmA, tmB;
@@ -107,6 +110,24 @@ static void pick_tile(int H, int W, int* TH, int* TW) {
   *TH = bh; *TW = bw;
 }
 
+// Same for CTA tiles made of `msub` vertically stacked sub-tiles (each <= 128 rows, a multiple of 8 rows so that it
+// starts on a swizzle-atom boundary of the A stage).  Returns the number of 128-row MMA slots spent per image.
+static long pick_tile_msub(int H, int W, int msub, int* TH_sub, int* TW) {
+  long best = -1;
+  int best_shape = 1 << 30;
+  for (int tw = 4; tw <= 128; ++tw) {
+    const int twc = tw > W ? W : tw;
+    for (int th = 128 / twc; th >= 1; --th) {
+      if ((th * twc) % 8) continue;
+      const long slots = (long)((H + msub * th - 1) / (msub * th)) * ((W + twc - 1) / twc) * msub;
+      const int shape = th > twc ? th - twc : twc - th;
+      if (best < 0 || slots < best || (slots == best && shape < best_shape)) { best = slots; best_shape = shape; *TH_sub = th; *TW = twc; }
+      break;  // the tallest admissible th for this width is the only candidate worth considering
+    }
+  }
+  return best;
+}
+
 // Geometry only (no pointers, no driver calls): usable on a box without a GPU.
 static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   ConvParams& p = L->p;
@@ -157,17 +178,43 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   if (st > 6) st = 6;
   if (st > k_iters) st = k_iters;
   p.stages = st;
+  p.msub = 1; p.sub_rows = p.TH * p.TW;
   L->smem = conv_smem_bytes(p.n_tile, st);
-  // persistent kernel: one CTA per SM, ring as deep as ~150 KB of smem allows (70 KB go to the epilogue staging tiles) (>= 120 KB so CTAs never co-reside)
+  L->p1 = p;           // one-tile-per-CTA kernels keep the 128-row geometry
+  L->grid1 = L->grid;
+  // persistent kernel: two 128-row sub-tiles per CTA tile when TMEM has room for 2 x 2 accumulators and the layer has
+  // plenty of tiles: every weight tile is fetched once per 256 rows and the per-tile hand-offs are halved
+  {
+    const long m_tiles = (long)L->grid.x;
+    const bool room = 4 * conv2_acc_stride(p.n_tile) <= 512;
+    if (room && m_tiles >= 4 * 148 && !getenv("YPB_NO_MSUB")) {
+      if (d.k == 1) {
+        p.msub = 2; p.sub_rows = 128; p.TW = 256;
+        p.tiles_w = (p.tW + 255) / 256;
+        L->grid.x = p.tiles_w;
+      } else {
+        int ths = 0, tw2 = 0;
+        const long slots2 = pick_tile_msub(oH, oW, 2, &ths, &tw2);
+        if (slots2 > 0 && slots2 * 10 <= (long)p.tiles_h * p.tiles_w * 11) {  // at most 10% more MMA slots than msub = 1
+          p.msub = 2; p.sub_rows = ths * tw2;
+          p.TH = 2 * ths; p.TW = tw2;
+          p.tiles_h = (oH + p.TH - 1) / p.TH; p.tiles_w = (oW + p.TW - 1) / p.TW;
+          L->grid.x = d.B * p.tiles_h * p.tiles_w;
+        }
+      }
+    }
+  }
+  // one CTA per SM, ring as deep as ~150 KB of smem allows (>= 120 KB so CTAs never co-reside)
   L->n_splits = splits;
   L->total_tiles = (int)L->grid.x * splits;
   int ring_kb = 150;
   if (const char* ev = getenv("YPB_RING_KB")) ring_kb = atoi(ev);  // tuning knob for experiments
-  int st2 = (ring_kb * 1024) / conv_stage_bytes(p.n_tile);
+  const int stage2 = p.msub * kATileBytes + p.n_tile * 128;
+  int st2 = (ring_kb * 1024) / stage2;
   if (st2 > 8) st2 = 8;
   if (st2 < 2) st2 = 2;
   L->stages2 = st2;
-  L->smem2 = conv2_smem_bytes(p.n_tile, st2);
+  L->smem2 = 1024 + st2 * stage2 + 256 + kEpiWarps * kEpiStageBytes;
   if (L->smem2 < 120 * 1024) L->smem2 = 120 * 1024;
   p.out_mode = d.out_mode; p.act = d.act;
   p.dbg = getenv("YPB_DBG") ? atoi(getenv("YPB_DBG")) : 0;
@@ -181,8 +228,8 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
     const int kch = (d.cin + 63) / 64;
     const long avail = 227 * 1024 - 1024 - 512 - kEpiWarps * kEpiStageBytes;
     const long b_slot = (long)p.n_tile * 128, b_total = 9L * kch * b_slot;
-    const double waste_taps = (double)L->total_tiles * 128 - (double)d.B * oH * oW * splits;
-    const double cost_taps = (double)L->total_tiles * k_iters * (kATileBytes + b_slot) + waste_taps * 9.0 * kch * 64.0;
+    const double waste_taps = (double)L->total_tiles * p.msub * 128 - (double)d.B * oH * oW * splits;
+    const double cost_taps = (double)L->total_tiles * k_iters * (p.msub * kATileBytes + b_slot) + waste_taps * 9.0 * kch * 64.0;
     double best = cost_taps;
     const int force_msub = getenv("YPB_HALO_MSUB") ? atoi(getenv("YPB_HALO_MSUB")) : 0;
     for (int msub = 1; msub <= 2; ++msub) {
@@ -228,6 +275,12 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   memset(&g, 0, sizeof g);
   g.in_H = d.Hin; g.in_W = d.Win; g.in_ctot = d.in_ctot; g.in_c_off = d.in_c_off;
   g.k = d.k; g.stride = d.stride; g.pad = d.k / 2; g.oH = oH; g.oW = oW; g.nB = d.B;
+  {  // p1 = p with the one-tile-per-CTA geometry saved above
+    const ConvParams g1 = L->p1;
+    L->p1 = p;
+    L->p1.TH = g1.TH; L->p1.TW = g1.TW; L->p1.tiles_h = g1.tiles_h; L->p1.tiles_w = g1.tiles_w;
+    L->p1.msub = 1; L->p1.sub_rows = g1.sub_rows; L->p1.stages = g1.stages;
+  }
   return true;
 }
 
@@ -235,6 +288,7 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
 static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   ConvParams& p = L->p;
   p.out = d.out; p.bias = d.bias; p.res = reinterpret_cast<const __nv_bfloat16*>(d.res);
+  L->p1.out = d.out; L->p1.bias = d.bias; L->p1.res = p.res;
   L->sg.in = reinterpret_cast<const __nv_bfloat16*>(d.in);
   L->sg.wg = reinterpret_cast<const __nv_bfloat16*>(d.wg);
   const cuuint64_t C = (cuuint64_t)d.in_ctot;
@@ -254,6 +308,13 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
     box[0] = 64; box[1] = p.TW; box[2] = 1; box[3] = p.TH; box[4] = 1;
   }
   if (!encode_bf16_map(&L->tmA, d.in, 5, dims, str, box, err)) return false;
+  {  // same view, 128-row box, for the one-tile-per-CTA kernels
+    cuuint32_t box1[5] = {box[0], box[1], box[2], box[3], box[4]};
+    if (d.k == 1) box1[1] = 128;
+    else if (d.stride == 1) { box1[1] = L->p1.TW; box1[2] = L->p1.TH; }
+    else { box1[1] = L->p1.TW; box1[3] = L->p1.TH; }
+    if (!encode_bf16_map(&L->tmA1, d.in, 5, dims, str, box1, err)) return false;
+  }
   if (L->use_halo) {
     cuuint32_t hb[5] = {64, 10, (cuuint32_t)(16 * L->x3.msub + 2), 1, 1};
     if (!encode_bf16_map(&L->tmHalo3, d.in, 5, dims, str, hb, err)) return false;
@@ -307,7 +368,7 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
     if (!L.halo_ok) return cudaErrorInvalidValue;
     static bool set3 = false;
     if (!set3) { cudaFuncSetAttribute(conv_halo_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set3 = true; }
-    ConvParams p3 = L.p;
+    ConvParams p3 = L.p1;
     p3.tiles_h = (p3.tH + 15) / 16; p3.tiles_w = (p3.tW + 7) / 8;
     const int grid3 = p3.tB * p3.tiles_h * p3.tiles_w;
     const int smem3 = 1024 + kHaloBytes + 9 * p3.n_tile * 128 + 256;
@@ -315,7 +376,7 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
     return cudaGetLastError();
   }
   if (impl == 2) {  // first-generation kernel: one tile per CTA (kept for A/B measurements)
-    conv_tc_kernel<<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+    conv_tc_kernel<<<L.grid1, kConvThreads, L.smem, stream>>>(L.tmA1, L.tmB, L.p1);
     return cudaGetLastError();
   }
   if (L.use_halo && impl == 0) {

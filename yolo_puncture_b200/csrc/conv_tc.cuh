@@ -51,6 +51,8 @@ struct ConvParams {
   const __nv_bfloat16* res;
   long long res_img_stride;
   int res_pix_stride, res_c_off;
+  int msub;      // conv_tc2: 128-row accumulator sub-tiles per CTA tile (share every weight tile); 1 or 2
+  int sub_rows;  // rows of one sub-tile (<= 128, multiple of 8); sub-tile s starts at row s*sub_rows of the A stage
   int dbg;  // YPB_DBG experiments (0 in production): 1 = no bias/SiLU math, 2 = no output stores, 4 = no MMA issue
 };
 
@@ -283,6 +285,24 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, i
     const int nch = min(chunks_per_pass, c_end - cp0);
     const int row_bytes = nch * 16 * elt, pitch = row_bytes + 16;
     uint8_t* my = stage + lane * pitch;
+    const int ppr = row_bytes >> 4;               // 16-byte pieces per row (<= 8)
+    const int ppr_inv = (65536 + ppr - 1) / ppr;  // piece / ppr == (piece * ppr_inv) >> 16 for piece < 512
+    // Residual (Bottleneck shortcut): issue this pass's coalesced 16-byte loads NOW so that their latency is
+    // covered by the TMEM reads and the SiLU math of phase 1.
+    uint4 rres[8];
+    if (p.res != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rres[i] = make_uint4(0, 0, 0, 0);
+        if (i < ppr) {
+          const int piece = lane + 32 * i;
+          const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
+          const long long r_r = __shfl_sync(0xffffffffu, res_row, row);
+          const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
+          if (ok) rres[i] = __ldg(reinterpret_cast<const uint4*>(p.res + r_r + n0 + cp0 * 16 + pc * 8));
+        }
+      }
+    }
     for (int ch = 0; ch < nch; ++ch) {
       uint32_t v[16];
       tmem_ld16(t_addr + (uint32_t)((cp0 + ch) * 16), v);
@@ -320,40 +340,41 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, i
     } else {
       __syncwarp();
     }
-    const int ppr = row_bytes >> 4;  // 16-byte pieces per row (<= 16)
-    const int ppr_inv = (65536 + ppr - 1) / ppr;  // piece / ppr == (piece * ppr_inv) >> 16 for piece < 512
-    for (int piece = lane; piece < ((p.dbg & 2) ? 0 : 32 * ppr); piece += 32) {
-      const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
-      const long long o_r = __shfl_sync(0xffffffffu, off_row, row);
-      const long long r_r = __shfl_sync(0xffffffffu, res_row, row);
-      const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
-      uint4 val = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
-      if (!ok) continue;
-      if (elt == 4) {
-        const int n = n0 + cp0 * 16 + pc * 4;
-        *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o_r + n) = val;
-        continue;
-      }
-      const int n = n0 + cp0 * 16 + pc * 8;
-      if (p.res != nullptr) {
-        const uint4 rv = *reinterpret_cast<const uint4*>(p.res + r_r + n);
-        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val);
-        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-        uint32_t o[4];
+    if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 fa = __bfloat1622float2(a2[i]), fb = __bfloat1622float2(b2[i]);
-          o[i] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+      for (int i = 0; i < 8; ++i) {
+        if (i >= ppr) break;
+        const int piece = lane + 32 * i;
+        const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
+        const long long o_r = __shfl_sync(0xffffffffu, off_row, row);
+        const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
+        uint4 val = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
+        if (!ok) continue;
+        if (elt == 4) {
+          const int n = n0 + cp0 * 16 + pc * 4;
+          *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o_r + n) = val;
+          continue;
         }
-        val = make_uint4(o[0], o[1], o[2], o[3]);
+        const int n = n0 + cp0 * 16 + pc * 8;
+        if (p.res != nullptr) {
+          const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+          const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rres[i]);
+          uint32_t o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 fa = __bfloat1622float2(a2[u]), fb = __bfloat1622float2(b2[u]);
+            o[u] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+          }
+          val = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        long long off = o_r + n;
+        if (p.out_mode == OUT_SHUFFLE2_BF16) {
+          const int cq = p.Cout >> 2;
+          const int g = n / cq, c = n - g * cq;
+          off = o_r + ((long long)(g >> 1) * (2 * p.img_W) + (g & 1)) * p.out_pix_stride + c;
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = val;
       }
-      long long off = o_r + n;
-      if (p.out_mode == OUT_SHUFFLE2_BF16) {
-        const int cq = p.Cout >> 2;
-        const int g = n / cq, c = n - g * cq;
-        off = o_r + ((long long)(g >> 1) * (2 * p.img_W) + (g & 1)) * p.out_pix_stride + c;
-      }
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = val;
     }
     __syncwarp();
   }
@@ -364,7 +385,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ ConvParams p, int n_splits, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = conv_stage_bytes(p.n_tile);
+  const int a_bytes = p.msub * kATileBytes;
+  const int stage_bytes = a_bytes + p.n_tile * 128;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;   // [2] accumulator ready
@@ -376,7 +398,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int kchunks = (p.Cin + 63) >> 6;
   const int acc_stride = conv2_acc_stride(p.n_tile);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(2 * acc_stride)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(2 * p.msub * acc_stride)) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -400,7 +422,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp < kProdWarps) {
     // ===================== TMA producers: warp w owns the ring stages s with s % kProdWarps == w =====================
     if (elect_one()) {
-      const uint32_t tx_bytes = (uint32_t)(p.TH * p.TW * 128 + p.n_tile * 128);
+      const uint32_t tx_bytes = (uint32_t)(p.TH * p.TW * 128 + p.n_tile * 128);  // the A box spans all sub-tiles
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
@@ -421,7 +443,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_expect_tx(full_bar + s, tx_bytes);
             tma_load_5d(sa, &tmA, full_bar + s, cbase[0] + p.tap[t][0] + c * 64, cbase[1] + p.tap[t][1],
                         cbase[2] + p.tap[t][2], cbase[3] + p.tap[t][3], cbase[4] + p.tap[t][4]);
-            tma_load_3d(sa + kATileBytes, &tmB, full_bar + s, c * 64, n0, t);
+            tma_load_3d(sa + a_bytes, &tmB, full_bar + s, c * 64, n0, t);
           }
         }
       }
@@ -435,7 +457,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int buf = acc & 1;
         mbar_wait(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * acc_stride);
         int first = 1;
         for (int c = 0; c < kchunks; ++c) {
           int ksteps = (p.Cin - c * 64) >> 4;
@@ -446,11 +467,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(full_bar + s, ph, 2u);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + s * stage_bytes);
-            const uint32_t sb = sa + kATileBytes;
-            for (int j = 0; j < ((p.dbg & 4) ? 0 : ksteps); ++j) {
-              umma_bf16(d_tmem, umma_desc_sw128(sa + j * 32), umma_desc_sw128(sb + j * 32), idesc, first ? 0u : 1u);
-              first = 0;
+            const uint32_t sb = sa + a_bytes;
+            for (int sidx = 0; sidx < p.msub; ++sidx) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.msub + sidx) * acc_stride);
+              const uint32_t sa_s = sa + (uint32_t)(sidx * p.sub_rows * 128);
+              for (int j = 0; j < ((p.dbg & 4) ? 0 : ksteps); ++j)
+                umma_bf16(d_tmem, umma_desc_sw128(sa_s + j * 32), umma_desc_sw128(sb + j * 32), idesc,
+                          (first && j == 0) ? 0u : 1u);
             }
+            first = 0;
             umma_commit(empty_bar + s);
           }
         }
@@ -472,20 +497,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
     uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - kEpiWarp0) * kEpiStageBytes;
     const int r = lg * 32 + lane;
-    const int rh = r / p.TW, rw = r - rh * p.TW;
     int acc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
       const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
       const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
       const int th = t_in / p.tiles_w;
-      const int h = th * p.TH + rh, w = (t_in - th * p.tiles_w) * p.TW + rw;
-      const bool valid = (r < p.TH * p.TW) && (h < p.tH) && (w < p.tW);
-      const int q = valid ? (b * p.tH + h) * p.tW + w : 0;
       const int buf = acc & 1;
       mbar_wait(tfull_bar + buf, (acc >> 1) & 1, 4u);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * acc_stride);
-      epi_drain(p, stage, lane, c_begin, c_end, t_addr, n0, valid, q, tempty_bar + buf);
+      for (int sidx = 0; sidx < p.msub; ++sidx) {
+        const int R = sidx * p.sub_rows + r;  // row of the whole CTA tile
+        const int rh = R / p.TW, rw = R - rh * p.TW;
+        const int h = th * p.TH + rh, w = (t_in - th * p.tiles_w) * p.TW + rw;
+        const bool valid = (r < p.sub_rows) && (h < p.tH) && (w < p.tW);
+        const int q = valid ? (b * p.tH + h) * p.tW + w : 0;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * p.msub + sidx) * acc_stride);
+        epi_drain(p, stage, lane, c_begin, c_end, t_addr, n0, valid, q, sidx == p.msub - 1 ? tempty_bar + buf : nullptr);
+      }
     }
   }
   tc_fence_before();

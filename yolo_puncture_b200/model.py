@@ -156,7 +156,7 @@ class YOLO:
         self._device_token = torch.zeros(1)
         self._staging = {}
         self.overrides = {}
-        self.micro_batch = 16  # frames per engine pass inside predict(); H2D of pass k+1 overlaps compute of pass k
+        self.micro_batch = 32  # frames per engine pass inside predict(); H2D of pass k+1 overlaps compute of pass k
         if device is not None:
             self._set_device(device)
 

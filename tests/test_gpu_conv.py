@@ -33,6 +33,10 @@ CASES = [
     (2, 32, 32, 64, 0, 64, 16, 1, 1, 1, False, 16, 0, False),       # n_tile 16: one epilogue warp per lane group idles
     (3, 20, 20, 64, 0, 64, 80, 1, 1, 0, False, 176, 64, True),      # fp32 head rows: 80 classes into a 176-float row
     (2, 24, 24, 48, 0, 48, 144, 3, 1, 1, True, 144, 0, False),      # 9 chunks: uneven column split, residual
+    (16, 80, 80, 96, 0, 96, 64, 1, 1, 1, False, 64, 0, False),      # 800 flat tiles: 256-pixel CTA tiles (two sub-tiles)
+    (13, 80, 80, 64, 0, 64, 128, 1, 1, 1, True, 192, 64, False),    # same, odd tile count, residual, output slice
+    (8, 160, 160, 32, 0, 32, 64, 3, 2, 1, False, 64, 0, False),     # stride 2 with two stacked sub-tiles per CTA tile
+    (20, 80, 80, 64, 0, 64, 128, 3, 2, 1, False, 128, 0, False),    # stride 2, 40x40 output, 120-row sub-tiles
 ]
 
 

@@ -82,7 +82,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsign
     if (mbar_try_wait(bar, parity)) return true;
   }
 #else
-  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     if (mbar_test_wait(bar, parity)) return true;
   }
 #endif

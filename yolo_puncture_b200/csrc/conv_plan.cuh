@@ -297,7 +297,7 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   if (d.k == 1) {
     dims[0] = C; dims[1] = (cuuint64_t)d.B * d.Hin * d.Win; dims[2] = dims[3] = dims[4] = 1;
     str[0] = C * 2; str[1] = str[2] = str[3] = dims[1] * C * 2;
-    box[0] = 64; box[1] = 128; box[2] = box[3] = box[4] = 1;
+    box[0] = 64; box[1] = (cuuint32_t)p.TW; box[2] = box[3] = box[4] = 1;  // 128 or 256 pixels per CTA tile
   } else if (d.stride == 1) {
     dims[0] = C; dims[1] = d.Win; dims[2] = d.Hin; dims[3] = d.B; dims[4] = 1;
     str[0] = C * 2; str[1] = str[0] * d.Win; str[2] = str[1] * d.Hin; str[3] = str[2] * d.B;

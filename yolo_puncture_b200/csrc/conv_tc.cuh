@@ -319,8 +319,13 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, i
         y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bv.w;
       }
       if (p.act && !(p.dbg & 1)) {
+        if (elt == 2) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = silu_f(y[i]);
+          for (int i = 0; i < 16; ++i) y[i] = silu_f(y[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = silu_precise_f(y[i]);
+        }
       }
       if (elt == 2) {
         uint4* d = reinterpret_cast<uint4*>(my + ch * 32);
@@ -725,6 +730,113 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem on the tensor pipe: uint8 BGR letterboxed frame -> Conv3x3 s2 p1 (+folded BN, /255 folded into the weights)
+// -> SiLU -> bf16 NHWC.  UPSTREAM sites replaced: engine/predictor.py::preprocess (BGR->RGB, /255) + model.0.
+// K = 27 is too thin for a TMA-fed pipeline, so the CTA builds the im2col tile itself: 128 output pixels (8 x 16)
+// per tile, each thread converts its pixel's 27 bytes to bf16 (0..255 are exact in bf16) and writes one K-major
+// SWIZZLE_128B row (k = (kh*3+kw)*3 + c_rgb, padded to 32); two tcgen05.mma (K = 16 each, N = C0) finish the tile.
+// A CTA loops over `tiles_per_cta` tiles; several CTAs are resident per SM and hide each other's phases.
+// Weights: wq[C0][32] bf16 (K-major), bias fp32.  The frame is read as bytes straight from HBM: 3 B per pixel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStemTH = 8, kStemTW = 16;
+
+__global__ void __launch_bounds__(128)
+stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, const __nv_bfloat16* __restrict__ wq,
+               const __grid_constant__ ConvParams p, int tiles_per_img, int tiles_w, int total_tiles, int tiles_per_cta) {
+  __shared__ __align__(1024) uint8_t sA[128 * 128];
+  __shared__ __align__(1024) uint8_t sB[80 * 128];
+  __shared__ __align__(16) uint8_t sIn[17 * 33 * 3 + 16];
+  __shared__ __align__(16) uint8_t sStage[4 * kEpiStageBytes];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int C0 = p.Cout;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)C0) tmem_cols <<= 1;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+  // weights -> swizzled K-major rows (64 used bytes per 128-byte row)
+  for (int i = tid; i < C0 * 4; i += 128) {
+    const int n = i >> 2, j = i & 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(wq + n * 32 + j * 8);
+    *reinterpret_cast<uint4*>(sB + n * 128 + ((j ^ (n & 7)) << 4)) = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t idesc = umma_idesc_bf16(128, C0);
+  const int oH = H >> 1, oW = W >> 1;
+  uint32_t phase = 0;
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  for (int tile = t_begin; tile < min(t_begin + tiles_per_cta, total_tiles); ++tile) {
+    const int b = tile / tiles_per_img, t_in = tile - b * tiles_per_img;
+    const int th = t_in / tiles_w;
+    const int oh0 = th * kStemTH, ow0 = (t_in - th * tiles_w) * kStemTW;
+    const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+    const uint8_t* img = frames + (size_t)b * H * W * 3;
+    // input patch: 17 rows x 33 pixels x 3 bytes (zero outside the frame = conv padding)
+    for (int i = tid; i < 17 * 99; i += 128) {
+      const int r = i / 99, c = i - r * 99;
+      const int ih = ih0 + r, iw = iw0 + c / 3;
+      uint8_t v = 0;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = img[((size_t)ih * W + iw) * 3 + (c - (c / 3) * 3)];
+      sIn[i] = v;
+    }
+    __syncthreads();
+    {  // im2col row of output pixel (ty, tx) = tid: k = (kh*3+kw)*3 + c_rgb, frame bytes are BGR
+      const int ty = tid >> 4, tx = tid & 15;
+      __nv_bfloat16 row[32];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const uint8_t* px = sIn + (2 * ty + kh) * 99 + (2 * tx + kw) * 3;
+          row[(kh * 3 + kw) * 3 + 0] = __float2bfloat16_rn((float)px[2]);
+          row[(kh * 3 + kw) * 3 + 1] = __float2bfloat16_rn((float)px[1]);
+          row[(kh * 3 + kw) * 3 + 2] = __float2bfloat16_rn((float)px[0]);
+        }
+#pragma unroll
+      for (int k = 27; k < 32; ++k) row[k] = __float2bfloat16_rn(0.f);
+      const uint4* rv = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) << 4)) = rv[j];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+      tc_fence_after();
+      umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sA)), umma_desc_sw128(smem_u32(sB)), idesc, 0u);
+      umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sA) + 32), umma_desc_sw128(smem_u32(sB) + 32), idesc, 1u);
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, phase, 16u);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      const int r = warp * 32 + lane;
+      const int oh = oh0 + (r >> 4), ow = ow0 + (r & 15);
+      const bool valid = oh < oH && ow < oW;
+      const int q = valid ? (b * oH + oh) * oW + ow : 0;
+      epi_drain(p, sStage + warp * kEpiStageBytes, lane, 0, C0 >> 4, tmem_base + ((uint32_t)(warp * 32) << 16), 0, valid, q,
+                nullptr);
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM, sA and sIn are reused by the next tile
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }

@@ -534,11 +534,17 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
   switch (op.kind) {
     case OP_STEM: {
       const BufDesc& ob = e->bufs[op.out.buf];
-      dim3 grid((ob.W + kStemTile - 1) / kStemTile, (ob.H + kStemTile - 1) / kStemTile, B);
-      const size_t smem = (size_t)(33 * 33 * 3 + 27 * op.cout + op.cout) * 4;
-      stem_conv_kernel<<<grid, 256, smem, st>>>(frames, e->H, e->W, reinterpret_cast<const float*>(wa + op.w_off),
-                                                 reinterpret_cast<const float*>(wa + op.b_off), op.cout,
-                                                 reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C);
+      ConvParams sp;
+      memset(&sp, 0, sizeof sp);
+      sp.Cout = op.cout; sp.n_tile = op.cout; sp.act = 1; sp.out_mode = OUT_BF16;
+      sp.img_HW = ob.H * ob.W; sp.img_W = ob.W;
+      sp.out = e->ws + ob.offset; sp.out_img_stride = (long long)ob.H * ob.W * ob.C; sp.out_pix_stride = ob.C;
+      sp.out_c_off = op.out.c_off; sp.bias = reinterpret_cast<const float*>(wa + op.b_off);
+      const int tiles_w = (ob.W + kStemTW - 1) / kStemTW, tiles_h = (ob.H + kStemTH - 1) / kStemTH;
+      const int total = B * tiles_h * tiles_w, per_cta = 8;
+      stem_tc_kernel<<<(total + per_cta - 1) / per_cta, 128, 0, st>>>(frames, e->H, e->W,
+                                                                     reinterpret_cast<const __nv_bfloat16*>(wa + op.w_off), sp,
+                                                                     tiles_h * tiles_w, tiles_w, total, per_cta);
       break;
     }
     case OP_CONV:
@@ -705,7 +711,7 @@ int ypb_finalize_weights(ypb_engine* e, int device) {
   auto align = [](size_t x) { return (x + 1023) & ~size_t(1023); };
   for (Op& op : e->ops) {
     if (op.kind == OP_STEM) {
-      op.w_off = off; off = align(off + (size_t)27 * op.cout * 4);
+      op.w_off = off; off = align(off + (size_t)32 * op.cout * 2);
       op.b_off = off; off = align(off + (size_t)op.cout * 4);
     } else if (op.kind == OP_CONV) {
       op.w_off = off; off = align(off + (size_t)op.k * op.k * op.cout * op.cin * 2);
@@ -745,12 +751,14 @@ int ypb_finalize_weights(ypb_engine* e, int device) {
       int rc = folded(*e, s, &w, &b);
       if (rc) return rc;
       if (op.kind == OP_STEM) {
-        float* wk = reinterpret_cast<float*>(host.data() + op.w_off);
+        // K-major rows [C0][32] bf16, k = (kh*3+kw)*3 + c_rgb; the /255 of preprocess is folded into the weights so
+        // that the kernel can feed raw pixel values (exact in bf16) to the tensor core
+        uint16_t* wq = reinterpret_cast<uint16_t*>(host.data() + op.w_off);
         for (int co = 0; co < s.cout; ++co)
           for (int c = 0; c < 3; ++c)
             for (int kh = 0; kh < 3; ++kh)
               for (int kw = 0; kw < 3; ++kw)
-                wk[((kh * 3 + kw) * 3 + c) * op.cout + co] = w[((co * 3 + c) * 3 + kh) * 3 + kw];
+                wq[co * 32 + (kh * 3 + kw) * 3 + c] = f32_to_bf16(w[((co * 3 + c) * 3 + kh) * 3 + kw] / 255.0f);
         for (int co = 0; co < s.cout; ++co) bias[co] = b[co];
       } else if (s.kind == SRC_CONVT) {
         uint16_t* wg = reinterpret_cast<uint16_t*>(host.data() + op.w_off);

@@ -153,8 +153,8 @@ class OracleModel(nn.Module):
     @torch.no_grad()
     def set_emulation(self, on=True):
         """Mirror the engine's storage precision (see modules.py docstring).  Requires fuse().
-        Conv weights are rounded to bf16 (the stem's after folding the /255 of preprocess into them: the engine feeds
-        raw uint8 pixel values, exact in bf16, to the tensor core); activations are rounded to bf16 after each block op; the
+        Conv weights are rounded to bf16, except the stem's (the engine feeds raw uint8 pixel values, exact in bf16, to
+        the tensor core against a hi+lo bf16 split of w/255, i.e. fp32-grade products); activations are rounded to bf16 after each block op; the
         final 1x1 head convs (plain nn.Conv2d) and Proto.cv3 keep fp32 outputs."""
         assert self.fused
         mode = "bf16" if on else None
@@ -164,9 +164,7 @@ class OracleModel(nn.Module):
                 m.emu = mode
             if on and isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
                 if m is stem.conv:
-                    # the engine folds the /255 of preprocess into the stem weights before rounding them to bf16
-                    m.weight.copy_((m.weight / 255.0).to(torch.bfloat16).to(torch.float32) * 255.0)
-                    continue
+                    continue  # the engine splits the stem weights into two bf16 terms: fp32-grade products
                 if m.weight.shape[1:] == (16, 1, 1) and m.weight.shape[0] == 1:
                     continue  # DFL arange
                 m.weight.copy_(m.weight.to(torch.bfloat16).to(torch.float32))

@@ -739,19 +739,22 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // Stem on the tensor pipe: uint8 BGR letterboxed frame -> Conv3x3 s2 p1 (+folded BN, /255 folded into the weights)
 // -> SiLU -> bf16 NHWC.  UPSTREAM sites replaced: engine/predictor.py::preprocess (BGR->RGB, /255) + model.0.
 // K = 27 is too thin for a TMA-fed pipeline, so the CTA builds the im2col tile itself: 128 output pixels (8 x 16)
-// per tile, each thread converts its pixel's 27 bytes to bf16 (0..255 are exact in bf16) and writes one K-major
-// SWIZZLE_128B row (k = (kh*3+kw)*3 + c_rgb, padded to 32); two tcgen05.mma (K = 16 each, N = C0) finish the tile.
+// per tile; each thread converts its pixel's 27 bytes to bf16 (0..255 are exact in bf16) and writes one K-major
+// SWIZZLE_128B row.  The fp32 weights are split w/255 = hi + lo into two bf16 terms, so K = 64 = [x | x] against
+// [hi | lo]: four tcgen05.mma (K = 16, N = C0) per tile give fp32-grade products at bf16 tensor speed.
 // A CTA loops over `tiles_per_cta` tiles; several CTAs are resident per SM and hide each other's phases.
-// Weights: wq[C0][32] bf16 (K-major), bias fp32.  The frame is read as bytes straight from HBM: 3 B per pixel.
+// Weights: wq[C0][64] bf16 (K-major, k = (kh*3+kw)*3 + c_rgb in each 32-wide half), bias fp32.
+// The frame is read as aligned 32-bit words straight from HBM: 3 B per pixel instead of a 12 B/pixel fp32 tensor.
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemTH = 8, kStemTW = 16;
+constexpr int kStemRowWords = 27;  // 33 pixels x 3 B = 99 B plus up to 3 B of misalignment -> 26 words, +1 spare
 
 __global__ void __launch_bounds__(128)
-stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, const __nv_bfloat16* __restrict__ wq,
+stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const __nv_bfloat16* __restrict__ wq,
                const __grid_constant__ ConvParams p, int tiles_per_img, int tiles_w, int total_tiles, int tiles_per_cta) {
   __shared__ __align__(1024) uint8_t sA[128 * 128];
   __shared__ __align__(1024) uint8_t sB[80 * 128];
-  __shared__ __align__(16) uint8_t sIn[17 * 33 * 3 + 16];
+  __shared__ __align__(16) uint32_t sIn[17 * kStemRowWords];
   __shared__ __align__(16) uint8_t sStage[4 * kEpiStageBytes];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -764,10 +767,9 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, const __nv_bflo
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
-  // weights -> swizzled K-major rows (64 used bytes per 128-byte row)
-  for (int i = tid; i < C0 * 4; i += 128) {
-    const int n = i >> 2, j = i & 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(wq + n * 32 + j * 8);
+  for (int i = tid; i < C0 * 8; i += 128) {  // weights -> swizzled K-major rows of 128 B
+    const int n = i >> 3, j = i & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(wq + n * 64 + j * 8);
     *reinterpret_cast<uint4*>(sB + n * 128 + ((j ^ (n & 7)) << 4)) = v;
   }
   tc_fence_before();
@@ -776,6 +778,8 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, const __nv_bflo
   const uint32_t tmem_base = tmem_slot;
   const uint32_t idesc = umma_idesc_bf16(128, C0);
   const int oH = H >> 1, oW = W >> 1;
+  const long long frame_bytes = (long long)H * W * 3, all_words = (frame_bytes * nB + 3) >> 2;
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(frames);  // cudaMalloc'd: at least 256-byte aligned
   uint32_t phase = 0;
   const int t_begin = blockIdx.x * tiles_per_cta;
   for (int tile = t_begin; tile < min(t_begin + tiles_per_cta, total_tiles); ++tile) {
@@ -783,13 +787,17 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, const __nv_bflo
     const int th = t_in / tiles_w;
     const int oh0 = th * kStemTH, ow0 = (t_in - th * tiles_w) * kStemTW;
     const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-    const uint8_t* img = frames + (size_t)b * H * W * 3;
-    // input patch: 17 rows x 33 pixels x 3 bytes (zero outside the frame = conv padding)
-    for (int i = tid; i < 17 * 99; i += 128) {
-      const int r = i / 99, c = i - r * 99;
-      const int ih = ih0 + r, iw = iw0 + c / 3;
-      uint8_t v = 0;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = img[((size_t)ih * W + iw) * 3 + (c - (c / 3) * 3)];
+    // input patch: 17 rows; row r holds the aligned words covering bytes [g0, g0+99) of the frame row, g0 = byte
+    // offset of pixel (ih0+r, iw0); out-of-frame pixels are zeroed when the rows are converted below
+    for (int i = tid; i < 17 * kStemRowWords; i += 128) {
+      const int r = i / kStemRowWords, wd = i - r * kStemRowWords;
+      const int ih = ih0 + r;
+      uint32_t v = 0;
+      if (ih >= 0 && ih < H) {
+        const long long g0 = (long long)b * frame_bytes + ((long long)ih * W + iw0) * 3;
+        const long long wi = (g0 >> 2) + wd;  // arithmetic shift: floor, also for the (only) negative case g0 = -3
+        if (wi >= 0 && wi < all_words) v = __ldg(words + wi);
+      }
       sIn[i] = v;
     }
     __syncthreads();
@@ -797,26 +805,34 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, const __nv_bflo
       const int ty = tid >> 4, tx = tid & 15;
       __nv_bfloat16 row[32];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+      for (int kh = 0; kh < 3; ++kh) {
+        const int r = 2 * ty + kh, ih = ih0 + r;
+        const long long g0 = (long long)b * frame_bytes + ((long long)ih * W + iw0) * 3;
+        const int shift = (int)(g0 & 3);  // bytes between the first loaded word and pixel (ih, iw0)
+        const uint8_t* rb = reinterpret_cast<const uint8_t*>(sIn + r * kStemRowWords) + shift;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const uint8_t* px = sIn + (2 * ty + kh) * 99 + (2 * tx + kw) * 3;
-          row[(kh * 3 + kw) * 3 + 0] = __float2bfloat16_rn((float)px[2]);
-          row[(kh * 3 + kw) * 3 + 1] = __float2bfloat16_rn((float)px[1]);
-          row[(kh * 3 + kw) * 3 + 2] = __float2bfloat16_rn((float)px[0]);
+          const int iw = iw0 + 2 * tx + kw;
+          const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
+          const uint8_t* px = rb + (2 * tx + kw) * 3;
+          row[(kh * 3 + kw) * 3 + 0] = __float2bfloat16_rn(in ? (float)px[2] : 0.f);
+          row[(kh * 3 + kw) * 3 + 1] = __float2bfloat16_rn(in ? (float)px[1] : 0.f);
+          row[(kh * 3 + kw) * 3 + 2] = __float2bfloat16_rn(in ? (float)px[0] : 0.f);
         }
+      }
 #pragma unroll
       for (int k = 27; k < 32; ++k) row[k] = __float2bfloat16_rn(0.f);
       const uint4* rv = reinterpret_cast<const uint4*>(row);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) << 4)) = rv[j];
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) << 4)) = rv[j & 3];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
     if (warp == 0 && elect_one()) {
       tc_fence_after();
-      umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sA)), umma_desc_sw128(smem_u32(sB)), idesc, 0u);
-      umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sA) + 32), umma_desc_sw128(smem_u32(sB) + 32), idesc, 1u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sA) + j * 32), umma_desc_sw128(smem_u32(sB) + j * 32), idesc, j ? 1u : 0u);
       umma_commit(&bar);
     }
     mbar_wait(&bar, phase, 16u);

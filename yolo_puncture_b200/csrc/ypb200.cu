@@ -542,7 +542,7 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       sp.out_c_off = op.out.c_off; sp.bias = reinterpret_cast<const float*>(wa + op.b_off);
       const int tiles_w = (ob.W + kStemTW - 1) / kStemTW, tiles_h = (ob.H + kStemTH - 1) / kStemTH;
       const int total = B * tiles_h * tiles_w, per_cta = 8;
-      stem_tc_kernel<<<(total + per_cta - 1) / per_cta, 128, 0, st>>>(frames, e->H, e->W,
+      stem_tc_kernel<<<(total + per_cta - 1) / per_cta, 128, 0, st>>>(frames, e->H, e->W, B,
                                                                      reinterpret_cast<const __nv_bfloat16*>(wa + op.w_off), sp,
                                                                      tiles_h * tiles_w, tiles_w, total, per_cta);
       break;
@@ -711,7 +711,7 @@ int ypb_finalize_weights(ypb_engine* e, int device) {
   auto align = [](size_t x) { return (x + 1023) & ~size_t(1023); };
   for (Op& op : e->ops) {
     if (op.kind == OP_STEM) {
-      op.w_off = off; off = align(off + (size_t)32 * op.cout * 2);
+      op.w_off = off; off = align(off + (size_t)64 * op.cout * 2);
       op.b_off = off; off = align(off + (size_t)op.cout * 4);
     } else if (op.kind == OP_CONV) {
       op.w_off = off; off = align(off + (size_t)op.k * op.k * op.cout * op.cin * 2);
@@ -751,14 +751,21 @@ int ypb_finalize_weights(ypb_engine* e, int device) {
       int rc = folded(*e, s, &w, &b);
       if (rc) return rc;
       if (op.kind == OP_STEM) {
-        // K-major rows [C0][32] bf16, k = (kh*3+kw)*3 + c_rgb; the /255 of preprocess is folded into the weights so
-        // that the kernel can feed raw pixel values (exact in bf16) to the tensor core
+        // K-major rows [C0][64] bf16 = [hi(32) | lo(32)], k = (kh*3+kw)*3 + c_rgb: the /255 of preprocess is folded into
+        // the weights (the kernel feeds raw pixel values, exact in bf16) and w/255 is split into two bf16 terms
         uint16_t* wq = reinterpret_cast<uint16_t*>(host.data() + op.w_off);
         for (int co = 0; co < s.cout; ++co)
           for (int c = 0; c < 3; ++c)
             for (int kh = 0; kh < 3; ++kh)
-              for (int kw = 0; kw < 3; ++kw)
-                wq[co * 32 + (kh * 3 + kw) * 3 + c] = f32_to_bf16(w[((co * 3 + c) * 3 + kh) * 3 + kw] / 255.0f);
+              for (int kw = 0; kw < 3; ++kw) {
+                const float v = w[((co * 3 + c) * 3 + kh) * 3 + kw] / 255.0f;
+                const uint16_t hi = f32_to_bf16(v);
+                uint32_t hb = (uint32_t)hi << 16;
+                float hf;
+                memcpy(&hf, &hb, 4);
+                wq[co * 64 + (kh * 3 + kw) * 3 + c] = hi;
+                wq[co * 64 + 32 + (kh * 3 + kw) * 3 + c] = f32_to_bf16(v - hf);
+              }
         for (int co = 0; co < s.cout; ++co) bias[co] = b[co];
       } else if (s.kind == SRC_CONVT) {
         uint16_t* wg = reinterpret_cast<uint16_t*>(host.data() + op.w_off);

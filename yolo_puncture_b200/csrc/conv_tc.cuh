@@ -749,13 +749,16 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 constexpr int kStemTH = 8, kStemTW = 16;
 constexpr int kStemRowWords = 27;  // 33 pixels x 3 B = 99 B plus up to 3 B of misalignment -> 26 words, +1 spare
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const __nv_bfloat16* __restrict__ wq,
-               const __grid_constant__ ConvParams p, int tiles_per_img, int tiles_w, int total_tiles, int tiles_per_cta) {
-  __shared__ __align__(1024) uint8_t sA[128 * 128];
-  __shared__ __align__(1024) uint8_t sB[80 * 128];
-  __shared__ __align__(16) uint32_t sIn[17 * kStemRowWords];
-  __shared__ __align__(16) uint8_t sStage[4 * kEpiStageBytes];
+               const __grid_constant__ ConvParams p, int tiles_per_img, int tiles_w, int total_tiles, int tiles_per_cta,
+               int alias_stage) {
+  // dynamic smem: [A tile 16 KB][weights C0*128 B, 1 KB multiple][patch 17x27 words][epilogue staging unless it aliases A]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sA = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = sA + 128 * 128;
+  uint32_t* sIn = reinterpret_cast<uint32_t*>(sB + ((p.Cout * 128 + 1023) & ~1023));
+  uint8_t* sStage = alias_stage ? sA : reinterpret_cast<uint8_t*>(sIn + 17 * kStemRowWords + 4);  // A is dead once the MMAs retire
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -843,8 +846,8 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
       const int oh = oh0 + (r >> 4), ow = ow0 + (r & 15);
       const bool valid = oh < oH && ow < oW;
       const int q = valid ? (b * oH + oh) * oW + ow : 0;
-      epi_drain(p, sStage + warp * kEpiStageBytes, lane, 0, C0 >> 4, tmem_base + ((uint32_t)(warp * 32) << 16), 0, valid, q,
-                nullptr);
+      epi_drain(p, sStage + warp * (alias_stage ? 4096 : kEpiStageBytes), lane, 0, C0 >> 4,
+                tmem_base + ((uint32_t)(warp * 32) << 16), 0, valid, q, nullptr);
     }
     tc_fence_before();
     __syncthreads();  // TMEM, sA and sIn are reused by the next tile

@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -542,9 +543,13 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       sp.out_c_off = op.out.c_off; sp.bias = reinterpret_cast<const float*>(wa + op.b_off);
       const int tiles_w = (ob.W + kStemTW - 1) / kStemTW, tiles_h = (ob.H + kStemTH - 1) / kStemTH;
       const int total = B * tiles_h * tiles_w, per_cta = 8;
-      stem_tc_kernel<<<(total + per_cta - 1) / per_cta, 128, 0, st>>>(frames, e->H, e->W, B,
-                                                                     reinterpret_cast<const __nv_bfloat16*>(wa + op.w_off), sp,
-                                                                     tiles_h * tiles_w, tiles_w, total, per_cta);
+      // the epilogue staging tile (32 rows x (min(2*C0,128)+16) B per warp) aliases the A tile when it fits in 4 KB per warp
+      const int alias = 32 * (std::min(2 * op.cout, 128) + 16) <= 4096 ? 1 : 0;
+      const size_t smem = 1024 + 16384 + ((op.cout * 128 + 1023) & ~1023) + 17 * kStemRowWords * 4 + 16 +
+                          (alias ? 0 : 4 * kEpiStageBytes);
+      stem_tc_kernel<<<(total + per_cta - 1) / per_cta, 128, smem, st>>>(frames, e->H, e->W, B,
+                                                                        reinterpret_cast<const __nv_bfloat16*>(wa + op.w_off), sp,
+                                                                        tiles_h * tiles_w, tiles_w, total, per_cta, alias);
       break;
     }
     case OP_CONV:

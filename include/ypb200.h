@@ -110,6 +110,15 @@ int ypb_masks(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w
               const float* det_lb, const float* coef, const int32_t* count, uint8_t* masks, int capacity,
               int32_t* status);
 
+/* Same, reading the prototypes from `proto` (a copy of the engine's (B,H/4,W/4,32) fp32 proto buffer taken after the
+ * matching ypb_infer()) and using `offsets_scratch` (device, B+1 int32) instead of workspace scratch, so that the next
+ * ypb_infer() may already be running on the workspace.  NULL for either = the engine's own buffers. */
+int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w, const float* det,
+                 const float* det_lb, const float* coef, const int32_t* count, uint8_t* masks, int capacity,
+                 int32_t* status, const float* proto, int32_t* offsets_scratch);
+/* Byte offset and size of the proto buffer inside the bound workspace. */
+int ypb_proto_info(const ypb_engine* e, size_t* offset, size_t* bytes);
+
 /* Device-side error word (0 = ok); nonzero means a bounded pipeline wait inside a kernel gave up. */
 int ypb_device_error(ypb_engine* e, uint32_t* word);
 

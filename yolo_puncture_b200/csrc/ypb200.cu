@@ -1054,8 +1054,25 @@ int ypb_infer_profile(ypb_engine* e, void* cuda_stream, const uint8_t* frames, c
   return YPB_OK;
 }
 
+int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w, const float* det, const float* det_lb,
+                 const float* coef, const int32_t* count, uint8_t* masks, int capacity, int32_t* status, const float* proto,
+                 int32_t* offsets_scratch);
+
 int ypb_masks(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w, const float* det, const float* det_lb,
               const float* coef, const int32_t* count, uint8_t* masks, int capacity, int32_t* status) {
+  return ypb_masks_ex(e, cuda_stream, retina, out_h, out_w, det, det_lb, coef, count, masks, capacity, status, nullptr, nullptr);
+}
+
+int ypb_proto_info(const ypb_engine* e, size_t* offset, size_t* bytes) {
+  if (!e || !e->planned || e->proto_buf < 0 || !offset || !bytes) return fail(YPB_ERR_ARG, "no proto buffer / not planned");
+  *offset = e->bufs[e->proto_buf].offset;
+  *bytes = e->bufs[e->proto_buf].bytes;
+  return YPB_OK;
+}
+
+int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w, const float* det, const float* det_lb,
+                 const float* coef, const int32_t* count, uint8_t* masks, int capacity, int32_t* status, const float* proto,
+                 int32_t* offsets_scratch) {
   if (!e || !det || !det_lb || !coef || !count || !masks || !status || capacity < 1) return fail(YPB_ERR_ARG, "bad argument");
   if (!e->bound || e->nm == 0 || e->proto_buf < 0) return fail(YPB_ERR_STATE, "masks: not a bound -seg engine");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
@@ -1077,12 +1094,12 @@ int ypb_masks(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w
   }
   if (g.ch < 1 || g.cw < 1 || g.ch > g.out_h || g.cw > g.out_w) return fail(YPB_ERR_ARG, "masks: output smaller than the proto window is unsupported");
   g.scale_h = (float)g.ch / (float)g.out_h; g.scale_w = (float)g.cw / (float)g.out_w;
-  int* offsets = reinterpret_cast<int*>(e->ws + e->off_moff);
+  int* offsets = offsets_scratch ? offsets_scratch : reinterpret_cast<int*>(e->ws + e->off_moff);
   mask_offsets_kernel<<<1, 32, 0, st>>>(count, e->B, capacity, offsets, status);
   const int bands = (g.out_h + kMaskTile - 1) / kMaskTile;
   dim3 grid(bands, capacity);
   if (capacity > 65535) return fail(YPB_ERR_ARG, "masks: capacity > 65535");
-  mask_decode_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb, offsets,
+  mask_decode_kernel<<<grid, 256, 0, st>>>(proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb, offsets,
                                            e->B, capacity, g, masks);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;

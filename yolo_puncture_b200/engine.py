@@ -19,6 +19,18 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class OutputSet:
+    """Caller-owned output buffers of one engine pass."""
+
+    def __init__(self, B, nm, device):
+        self.det = torch.zeros((B, MAX_DET, 6), dtype=torch.float32, device=device)
+        self.det_lb = torch.zeros((B, MAX_DET, 4), dtype=torch.float32, device=device)
+        self.keep = torch.zeros((B, MAX_DET), dtype=torch.int32, device=device)
+        self.coef = torch.zeros((B, MAX_DET, nm), dtype=torch.float32, device=device)
+        self.count = torch.zeros((B,), dtype=torch.int32, device=device)
+        self.offsets = torch.zeros((B + 1,), dtype=torch.int32, device=device)
+
+
 class Engine:
     def __init__(self, spec, nc=80):
         self._lib = lib()
@@ -92,11 +104,9 @@ class Engine:
             off = (-self.ws.data_ptr()) % 1024
             self._ws_off = off
             check(self._lib.ypb_bind_workspace(self._h, C.c_void_p(self.ws.data_ptr() + off), nbytes))
-            self.det = torch.zeros((B, MAX_DET, 6), dtype=torch.float32, device=self.device)
-            self.det_lb = torch.zeros((B, MAX_DET, 4), dtype=torch.float32, device=self.device)
-            self.keep = torch.zeros((B, MAX_DET), dtype=torch.int32, device=self.device)
-            self.coef = torch.zeros((B, MAX_DET, max(self.nm, 1)), dtype=torch.float32, device=self.device)
-            self.count = torch.zeros((B,), dtype=torch.int32, device=self.device)
+            # two sets of output buffers: predict() double-buffers engine passes (set 0 is the default one)
+            self.out_sets = [OutputSet(B, max(self.nm, 1), self.device) for _ in range(2)]
+            self.use_outputs(0)
             self.mask_status = torch.zeros((2,), dtype=torch.int32, device=self.device)
         self.shape = (B, H, W)
         self._views = {}
@@ -136,12 +146,27 @@ class Engine:
                                           _ptr(self.count), ms, n))
         return list(ms)
 
-    def masks(self, out, retina, out_h=0, out_w=0):
-        """out: cuda uint8 (capacity, h, w).  Decodes masks of the last infer() in detection order."""
+    def use_outputs(self, i):
+        """Select which output set the next infer()/masks() calls write/read."""
+        o = self.out_sets[i]
+        self.det, self.det_lb, self.keep, self.coef, self.count = o.det, o.det_lb, o.keep, o.coef, o.count
+        self._cur_out = o
+
+    def proto_view(self):
+        """The (B, H/4, W/4, 32) fp32 proto buffer of the last infer(), as a view of the workspace."""
+        off, nbytes = C.c_size_t(), C.c_size_t()
+        check(self._lib.ypb_proto_info(self._h, C.byref(off), C.byref(nbytes)))
+        start = self._ws_off + off.value
+        return self.ws[start:start + nbytes.value]
+
+    def masks(self, out, retina, out_h=0, out_w=0, proto=None, outputs=None):
+        """out: cuda uint8 (capacity, h, w).  Decodes masks of an infer() in detection order.  proto / outputs: a copy
+        of that pass's proto buffer and its OutputSet when the workspace has already moved on to the next pass."""
+        o = outputs or self._cur_out
         st = torch.cuda.current_stream(self.device).cuda_stream
-        check(self._lib.ypb_masks(self._h, C.c_void_p(st), int(bool(retina)), int(out_h), int(out_w), _ptr(self.det),
-                                  _ptr(self.det_lb), _ptr(self.coef), _ptr(self.count), _ptr(out), int(out.shape[0]),
-                                  _ptr(self.mask_status)))
+        check(self._lib.ypb_masks_ex(self._h, C.c_void_p(st), int(bool(retina)), int(out_h), int(out_w), _ptr(o.det),
+                                     _ptr(o.det_lb), _ptr(o.coef), _ptr(o.count), _ptr(out), int(out.shape[0]),
+                                     _ptr(self.mask_status), _ptr(proto), _ptr(o.offsets)))
 
     def device_error(self):
         w = C.c_uint32()

@@ -288,29 +288,51 @@ class YOLO:
                     ev.record(cs)
                 h2d_done.append(ev)
 
-            enqueue_h2d(0)
-            for k in range(n_mb):
+            # Software pipeline: pass k+1 is enqueued BEFORE the host blocks on pass k's detection counts, so the GPU
+            # never idles between passes; pass k's outputs live in output set k&1 and its prototypes are copied aside
+            # (device-to-device) because the workspace is reused by pass k+1.
+            protos = buf.setdefault("proto_copy", [None, None])
+
+            def launch(k):
                 lo, hi = k * mb, min((k + 1) * mb, B)
                 slot = k & 1
                 main.wait_event(h2d_done[k])
+                eng.use_outputs(slot)
                 eng.infer(buf["dev"][slot], buf["xf_dev"], conf, iou, max_det, agnostic, cmask)
                 fr = torch.cuda.Event()
                 fr.record(main)
                 buf["in_free"][slot] = fr
-                if k + 1 < n_mb:
-                    enqueue_h2d(k + 1)  # its staging + PCIe transfer overlap this micro-batch's engine pass
                 if hi - lo < mb:
                     eng.count[hi - lo:].zero_()  # padded tail of the last micro-batch
-                counts = eng.count[: hi - lo].cpu()  # stream-ordered D2H: the only host sync per micro-batch
+                if seg:
+                    pv = eng.proto_view()
+                    if protos[slot] is None or protos[slot].numel() != pv.numel():
+                        protos[slot] = torch.empty_like(pv)
+                    protos[slot].copy_(pv, non_blocking=True)
+
+            def finish(k):
+                lo, hi = k * mb, min((k + 1) * mb, B)
+                o = eng.out_sets[k & 1]
+                counts = o.count[: hi - lo].cpu()  # stream-ordered D2H: the host sync of this pass
                 n_k = int(counts.sum())
                 cnts.append(counts)
-                dets.append(eng.det[: hi - lo].clone() if n_k else None)
+                dets.append(o.det[: hi - lo].clone() if n_k else None)
                 if seg and n_k:
                     m = torch.empty((n_k, mh, mw), dtype=torch.uint8, device=self._device)
-                    eng.masks(m, retina, mh, mw)
+                    eng.masks(m, retina, mh, mw, proto=protos[k & 1], outputs=o)
                     mask_parts.append(m)
                 else:
                     mask_parts.append(None)
+
+            enqueue_h2d(0)
+            for k in range(n_mb):
+                launch(k)
+                if k + 1 < n_mb:
+                    enqueue_h2d(k + 1)  # its staging + PCIe transfer overlap this pass
+                if k > 0:
+                    finish(k - 1)
+            finish(n_mb - 1)
+            eng.use_outputs((n_mb - 1) & 1)
             t2 = time.perf_counter()
             err = eng.device_error()
             if err:

@@ -144,6 +144,8 @@ int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float*
             int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,
             int32_t* count /*(B)*/);
 size_t ypb_nms_scratch_bytes(int B, int N);
+/* Host helper of the predict() pipeline: copy n frames into pinned staging memory with nthreads host threads. */
+int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads);
 /* Diagnostics: ceiling of the TMA operand-fetch path for an access pattern (csrc/tma_bench.cuh). */
 int ypb_mma_bench(void* buf, int rows, int n, int iters, int shifted, int tma_iters, float* ms);
 int ypb_latency_probe(long long* out_dev /* 8 x int64, device */);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ypb_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p,
                         c_void_p, c_void_p]),
     "ypb_nms_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "ypb_stage_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "ypb_mma_bench": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float)]),
     "ypb_latency_probe": (c_int, [c_void_p]),
     "ypb_tma_bench": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float),

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ypb200.h"
@@ -1233,6 +1234,23 @@ int ypb_latency_probe(long long* out_dev) {
   if (!out_dev) return fail(YPB_ERR_ARG, "bad argument");
   latency_probe_kernel<<<1, 64>>>(out_dev);
   CUDA_TRY(cudaDeviceSynchronize());
+  return YPB_OK;
+}
+
+// Host-side helper: copy n frames into the pinned staging buffer with `nthreads` host threads (the Python caller
+// releases the GIL for the duration of the call).  Frame staging is the host stage of the predict() pipeline.
+int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads) {
+  if (!dst || !src || !bytes || n < 0) return fail(YPB_ERR_ARG, "bad argument");
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > n) nthreads = n;
+  if (n == 0) return YPB_OK;
+  auto work = [&](int t) {
+    for (int i = t; i < n; i += nthreads) memcpy(dst[i], src[i], bytes[i]);
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
   return YPB_OK;
 }
 

@@ -13,12 +13,14 @@ LetterBox), moves bytes, and wraps outputs.  There is no CPU execution path: wit
 (or without the compiled library) predict() raises.
 """
 
+import ctypes
 import os
 import time
 
 import numpy as np
 import torch
 
+from ._lib import check, lib
 from .engine import MAX_DET, Engine, YpbError
 from .results import Results
 from .synth import synth_state_dict
@@ -269,7 +271,17 @@ class YOLO:
                 for c in classes:
                     words[int(c) >> 5] |= np.uint32(1) << np.uint32(int(c) & 31)
                 cmask = torch.from_numpy(words.view(np.int32)).to(self._device)
-            futs = [_pool().submit(letterbox_into, host[i], f, new_unpad, top, left) for i, f in enumerate(frames)]
+            direct = (shape[0], shape[1]) == (H, W)  # frames already have the network size: staging is a plain copy
+            futs = None
+            if direct:
+                frames_c = [f if f.flags["C_CONTIGUOUS"] else np.ascontiguousarray(f) for f in frames]
+                nbytes = H * W * 3
+                dst_ptrs = (ctypes.c_void_p * B)(*[buf["host"][i].data_ptr() for i in range(B)])
+                src_ptrs = (ctypes.c_void_p * B)(*[f.ctypes.data for f in frames_c])
+                sizes = (ctypes.c_size_t * B)(*([nbytes] * B))
+                nthreads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+            else:
+                futs = [_pool().submit(letterbox_into, host[i], f, new_unpad, top, left) for i, f in enumerate(frames)]
             cs.wait_stream(main)
             h2d_done = []
             t1 = time.perf_counter()
@@ -277,8 +289,13 @@ class YOLO:
 
             def enqueue_h2d(k):
                 lo, hi = k * mb, min((k + 1) * mb, B)
-                for fu in futs[lo:hi]:
-                    fu.result()
+                if direct:  # native multi-threaded copy into pinned memory (ctypes drops the GIL)
+                    vp = ctypes.sizeof(ctypes.c_void_p)
+                    check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, lo * vp), ctypes.byref(src_ptrs, lo * vp),
+                                                 ctypes.byref(sizes, lo * ctypes.sizeof(ctypes.c_size_t)), hi - lo, nthreads))
+                else:
+                    for fu in futs[lo:hi]:
+                        fu.result()
                 slot = k & 1
                 with torch.cuda.stream(cs):
                     if buf["in_free"][slot] is not None:

@@ -139,6 +139,12 @@ int ypb_conv2d_bf16(void* cuda_stream, const void* in_nhwc_bf16, int B, int H, i
                     int cin, const void* w_gemm_bf16 /*[k*k][cout][cin]*/, const float* bias, int cout, int k,
                     int stride, int act, const void* res_nhwc_bf16 /*nullable, same layout as out*/, void* out,
                     int out_ctot, int out_c_off, int out_fp32, int impl);
+/* Diagnostics: average milliseconds of `iters` back-to-back launches of one conv (out_mode 0 bf16, 1 fp32, 2 pixel-shuffle
+   bf16); dbg >= 0 overrides the experiment mask; desc receives a description of the launch the planner chose. */
+int ypb_conv_bench(void* cuda_stream, const void* in_nhwc_bf16, int B, int H, int W, int in_ctot, int in_c_off, int cin,
+                   const void* w_gemm_bf16, const float* bias, int cout, int k, int stride, int act,
+                   const void* res_nhwc_bf16, void* out, int out_ctot, int out_c_off, int out_mode, int impl, int dbg,
+                   int iters, float* ms, char* desc, int desc_len);
 int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float* scores /*(B,N)*/,
             const int32_t* cls /*(B,N)*/, const int32_t* n_valid /*(B)*/, int B, int N, float iou, int max_det,
             int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,

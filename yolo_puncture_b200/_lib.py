@@ -58,6 +58,9 @@ SIGNATURES = {
     "ypb_set_graph": (c_int, [c_void_p, c_int]),
     "ypb_conv2d_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "ypb_conv_bench": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                               c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                               C.POINTER(c_float), C.c_char_p, c_int]),
     "ypb_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p,
                         c_void_p, c_void_p]),
     "ypb_nms_scratch_bytes": (c_size_t, [c_int, c_int]),

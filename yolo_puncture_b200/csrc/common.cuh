@@ -90,6 +90,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsign
   return false;
 }
 
+// Same, with a back-off between polls (ns = 0: tight polling).  Idle pollers share the SM's memory-instruction
+// queue with the epilogue warps' LDS/STS/SHFL: see the measurements quoted at the call sites in conv_tc.cuh.
+__device__ __forceinline__ bool mbar_wait_bo(uint64_t* bar, uint32_t parity, unsigned int err_code, unsigned int ns) {
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    if (mbar_test_wait(bar, parity)) return true;
+    if (ns) __nanosleep(ns);
+  }
+  atomicOr(&g_dev_error, err_code);
+  return false;
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor)
 // ------------------------------------------------------------------------------------------------

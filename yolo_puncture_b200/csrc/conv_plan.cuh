@@ -214,10 +214,12 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   if (st2 > 8) st2 = 8;
   if (st2 < 2) st2 = 2;
   L->stages2 = st2;
-  L->smem2 = 1024 + st2 * stage2 + 256 + kEpiWarps * kEpiStageBytes;
+  L->smem2 = 1024 + st2 * stage2 + 256 + kEpiWarps * kEpiStageBytes + conv_bias_smem(d.cout);
   if (L->smem2 < 120 * 1024) L->smem2 = 120 * 1024;
   p.out_mode = d.out_mode; p.act = d.act;
   p.dbg = getenv("YPB_DBG") ? atoi(getenv("YPB_DBG")) : 0;
+  p.bo_prod = p.bo_mma_acc = p.bo_mma_full = p.bo_epi = 0;
+  if (const char* ev = getenv("YPB_BO")) sscanf(ev, "%d,%d,%d,%d", &p.bo_prod, &p.bo_mma_acc, &p.bo_mma_full, &p.bo_epi);
   p.out_img_stride = d.out_img_stride; p.out_pix_stride = d.out_pix_stride; p.out_c_off = d.out_c_off;
   p.res_img_stride = d.res_img_stride; p.res_pix_stride = d.res_pix_stride; p.res_c_off = d.res_c_off;
   L->flops = 2.0 * d.B * oH * oW * (double)d.cout * d.cin * d.k * d.k;
@@ -226,7 +228,7 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
     // Operand bytes fetched from L2 per launch are what bounds these kernels (~7 TB/s L2->SM on B200): pick the
     // cheapest of {per-tap boxes, halo tiles with msub = 1 or 2, resident or streamed weights}.
     const int kch = (d.cin + 63) / 64;
-    const long avail = 227 * 1024 - 1024 - 512 - kEpiWarps * kEpiStageBytes;
+    const long avail = 227 * 1024 - 1024 - 512 - kEpiWarps * kEpiStageBytes - conv_bias_smem(d.cout);
     const long b_slot = (long)p.n_tile * 128, b_total = 9L * kch * b_slot;
     const double waste_taps = (double)L->total_tiles * p.msub * 128 - (double)d.B * oH * oW * splits;
     const double cost_taps = (double)L->total_tiles * k_iters * (p.msub * kATileBytes + b_slot) + waste_taps * 9.0 * kch * 64.0;
@@ -266,7 +268,7 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
           L->x3.msub = msub; L->x3.a_slots = (int)a_slots; L->x3.a_bytes = (int)a_bytes; L->x3.halo_rows = halo_rows;
           L->x3.b_slots = (int)b_slots; L->x3.b_group = b_group; L->x3.b_stat = stat; L->x3.b_bytes = (int)b_bytes;
           L->tiles_h3 = th3; L->tiles_w3 = tw3; L->total_tiles3 = (int)tiles3;
-          L->smem3 = (int)(1024 + a_slots * a_bytes + b_bytes + 512 + kEpiWarps * kEpiStageBytes);
+          L->smem3 = (int)(1024 + a_slots * a_bytes + b_bytes + 512 + kEpiWarps * kEpiStageBytes + conv_bias_smem(d.cout));
         }
       }
     }
@@ -335,6 +337,16 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   return true;
 }
 
+// One-line description of the launch the planner chose (diagnostics).
+static void conv_describe(const ConvLaunch& L, int impl, char* out, int n) {
+  if (L.use_halo && impl == 0)
+    snprintf(out, n, "halo msub=%d a_slots=%d b_stat=%d b_slots=%d b_group=%d n_tile=%d splits=%d tiles=%d smem=%d", L.x3.msub,
+             L.x3.a_slots, L.x3.b_stat, L.x3.b_slots, L.x3.b_group, L.p.n_tile, L.n_splits, L.total_tiles3, L.smem3);
+  else
+    snprintf(out, n, "tc2 msub=%d tile=%dx%d stages=%d n_tile=%d splits=%d tiles=%d smem=%d", L.p.msub, L.p.TH, L.p.TW,
+             L.stages2, L.p.n_tile, L.n_splits, L.total_tiles, L.smem2);
+}
+
 static int g_num_sms = 148;
 // One-time function attributes (must not happen inside a stream capture).
 static cudaError_t conv_launch_init() {
@@ -342,10 +354,13 @@ static cudaError_t conv_launch_init() {
   if (done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#define YPB_SET_SMEM(MODE)                                                                                        \
+  e = cudaFuncSetAttribute(conv_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);       \
+  if (e != cudaSuccess) return e;                                                                                 \
+  e = cudaFuncSetAttribute(conv3_halo_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);     \
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
+  YPB_SET_SMEM(EPI_BF16) YPB_SET_SMEM(EPI_BF16_RES) YPB_SET_SMEM(EPI_F32) YPB_SET_SMEM(EPI_SHUFFLE2)
+#undef YPB_SET_SMEM
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -382,14 +397,26 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
   if (L.use_halo && impl == 0) {
     ConvParams p3 = L.p;
     p3.tiles_h = L.tiles_h3; p3.tiles_w = L.tiles_w3;
+    conv_set_fastdiv(p3, L.n_splits);
     const int grid3 = L.total_tiles3 < num_sms ? L.total_tiles3 : num_sms;
-    conv3_halo_kernel<<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3);
+    switch (epi_mode_of(p3.out_mode, p3.res != nullptr)) {
+      case EPI_BF16: conv3_halo_kernel<EPI_BF16><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
+      case EPI_BF16_RES: conv3_halo_kernel<EPI_BF16_RES><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
+      case EPI_F32: conv3_halo_kernel<EPI_F32><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
+      default: conv3_halo_kernel<EPI_SHUFFLE2><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
+    }
     return cudaGetLastError();
   }
   ConvParams p2 = L.p;
   p2.stages = L.stages2;
+  conv_set_fastdiv(p2, L.n_splits);
   const int grid = L.total_tiles < num_sms ? L.total_tiles : num_sms;
-  conv_tc2_kernel<<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles);
+  switch (epi_mode_of(p2.out_mode, p2.res != nullptr)) {
+    case EPI_BF16: conv_tc2_kernel<EPI_BF16><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
+    case EPI_BF16_RES: conv_tc2_kernel<EPI_BF16_RES><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
+    case EPI_F32: conv_tc2_kernel<EPI_F32><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
+    default: conv_tc2_kernel<EPI_SHUFFLE2><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
+  }
   return cudaGetLastError();
 }
 

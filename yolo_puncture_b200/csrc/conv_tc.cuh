@@ -53,8 +53,30 @@ struct ConvParams {
   int res_pix_stride, res_c_off;
   int msub;      // conv_tc2: 128-row accumulator sub-tiles per CTA tile (share every weight tile); 1 or 2
   int sub_rows;  // rows of one sub-tile (<= 128, multiple of 8); sub-tile s starts at row s*sub_rows of the A stage
+  // exact division by launch constants as multiply-high + shift (x < 2^31): a runtime integer division is a ~150-cycle
+  // dependent chain, and the per-tile index math of a warp-specialised role has no other warps to hide behind
+  uint32_t fd_ns[2], fd_tpi[2], fd_tw[2], fd_hw[2], fd_iw[2];  // n_splits, tiles per image, tiles_w, img_HW, img_W
+  int bo_prod, bo_mma_acc, bo_mma_full, bo_epi;  // poll back-off (ns) of the four kinds of mbarrier waits (YPB_BO=a,b,c,d)
   int dbg;  // YPB_DBG experiments (0 in production): 1 = no bias/SiLU math, 2 = no output stores, 4 = no MMA issue
 };
+
+__host__ inline void fastdiv_make(uint32_t d, uint32_t (&f)[2]) {
+  if (d < 1) d = 1;
+  uint32_t sft = 0;
+  while ((1ull << sft) < d) ++sft;
+  f[0] = (uint32_t)(((1ull << (31 + sft)) / d) + 1);
+  f[1] = 31 + sft;
+}
+__device__ __forceinline__ int fdiv(int x, const uint32_t (&f)[2]) {
+  return (int)(((unsigned long long)(uint32_t)x * f[0]) >> f[1]);
+}
+__host__ inline void conv_set_fastdiv(ConvParams& p, int n_splits) {
+  fastdiv_make((uint32_t)n_splits, p.fd_ns);
+  fastdiv_make((uint32_t)(p.tiles_h * p.tiles_w), p.fd_tpi);
+  fastdiv_make((uint32_t)p.tiles_w, p.fd_tw);
+  fastdiv_make((uint32_t)p.img_HW, p.fd_hw);
+  fastdiv_make((uint32_t)p.img_W, p.fd_iw);
+}
 
 // Store 16 consecutive output channels [n, n+16) of output pixel q. v = raw accumulators.
 __device__ __forceinline__ void conv_epilogue_store16(const ConvParams& p, int q, int n, const float (&acc)[16]) {
@@ -102,6 +124,13 @@ __device__ __forceinline__ void conv_epilogue_store16(const ConvParams& p, int q
   *reinterpret_cast<uint4*>(o) = s0;
   *reinterpret_cast<uint4*>(o + 8) = s1;
 }
+
+// YPB_DBG bit 8: per-role wait-cycle accounting (summed over CTAs; read back by ypb_conv_bench).
+// [0] producer-0 wait empty  [1] MMA wait full  [2] MMA wait tempty  [3] epilogue-warp-0 wait tfull
+// [4] epilogue-warp-0 drain  [5] CTA lifetime  [6] MMA wait weights (halo kernel)  [7] CTAs
+__device__ unsigned long long g_conv_prof[16];  // [8..13] epilogue pass phases (all epilogue warps): ld+wait, release, math, stage, write-out, passes
+#define PROF_T0() const long long _pt0 = prof ? clock64() : 0
+#define PROF_ADD(var) do { if (prof) var += clock64() - _pt0; } while (0)
 
 constexpr int kConvThreads = 192;
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
@@ -243,126 +272,187 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (warp w reads TMEM lanes 32*(w%4)..+31; with 8 epilogue warps each lane group's columns are split in two).
 // ------------------------------------------------------------------------------------------------
 constexpr int kEpiWarps = 8;
-constexpr int kProdWarps = 4;   // TMA producer warps: one thread sustains only ~1 box load per 0.35 us (tools/tma_bench.py)
+constexpr int kProdWarps = 3;   // TMA producer warps: one thread sustains only ~1 box load per 0.35 us (tools/tma_bench.py)
 constexpr int kMmaWarp = kProdWarps;
 constexpr int kEpiWarp0 = kProdWarps + 1;
 constexpr int kConv2Threads = 32 * (kProdWarps + 1 + kEpiWarps);
 constexpr int kEpiStageBytes = 32 * (128 + 16);  // per-warp staging tile: 32 rows x (<=128 B + 16 B pad)
+__host__ __device__ inline int conv_bias_smem(int cout) { return (cout * 4 + 15) & ~15; }
 
 __host__ __device__ inline int conv2_acc_stride(int n_tile) { return (n_tile + 31) & ~31; }
 __host__ __device__ inline int conv2_smem_bytes(int n_tile, int stages) {
-  return 1024 /*align slack*/ + stages * conv_stage_bytes(n_tile) + 256 /*barriers*/ + kEpiWarps * kEpiStageBytes;
+  return 1024 /*align slack*/ + stages * conv_stage_bytes(n_tile) + 256 /*barriers*/ + kEpiWarps * kEpiStageBytes;  // + bias
 }
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue of one 128-row accumulator (sub)tile for one warp (shared by the persistent kernels).
-// The warp owns TMEM lanes [32*lg, +32) (t_addr points at them) and the 16-column chunks [c_begin, c_end).
-// Phase 1: TMEM -> registers -> +bias -> SiLU -> packed bf16/fp32 into the warp's private, padded smem staging
-// tile (lane = row: conflict-free thanks to the +16 B row pitch).  `release` (may be null) is arrived on as soon
-// as the last tcgen05.ld of this call has landed, handing the accumulator back to the MMA warp.
-// Phase 2: the staged rows are written back with lanes running along the channel dimension, so every store
-// instruction covers whole 128-byte lines of NHWC rows (a thread-per-row store touches 32 lines per instruction).
+// Epilogue of one 128-row accumulator (sub)tile for one warp (shared by the persistent kernels and the stem).
+// The warp owns TMEM lanes [32*lg, +32) (t_addr points at them) and the 16-column chunks [c_begin, c_end), which it
+// drains in passes of 32 (plus a final 16) columns:
+//   phase 1: ONE tcgen05.ld per pass, issued one pass ahead (the load of pass k+1 is in flight while pass k is
+//            staged and written out); bias from shared memory (pre-scaled), SiLU on 32 independent values per lane,
+//            packed bf16 / fp32 rows into the warp's private, padded smem staging tile (lane = row, conflict-free
+//            thanks to the +16 B row pitch);
+//   phase 2: the staged rows are written back with lanes running along the channel dimension, so every store
+//            instruction covers whole NHWC row segments (a thread-per-row store touches 32 lines per instruction).
+//            Row offsets (relative to the first valid row of the warp) are exchanged with shuffles ONCE per
+//            sub-tile; all loads of a pass are issued before the first store.
+// `release` (may be null) is arrived on as soon as the last tcgen05.ld of this call has landed, handing the
+// accumulator back to the MMA warp.  `sbias` = shared-memory copy of the bias, indexed by absolute output channel and
+// pre-multiplied by 0.5 for SiLU layers with bf16 output (h = x/2 comes straight out of one FFMA).
+// MODE is a compile-time switch: one straight-line instruction stream per output layout.
+// Measured (tools/conv_layers.py --dbg 8, B200): the first versions of this epilogue (chunk-at-a-time tcgen05.ld ->
+// wait -> bias __ldg -> math; generic-address staging; per-piece shuffle -> load -> branch -> store chains) cost
+// ~2500 cycles per 32x32 pass and bounded every layer with K <= 256, although TMEM reads (64 B/clk/SM) and the SFU
+// (16 SiLU/clk/SM) allow ~16 elements per clock.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, int lane, int c_begin, int c_end,
-                                          uint32_t t_addr, int n0, bool valid, int q, uint64_t* release) {
-  const int elt = p.out_mode == OUT_F32 ? 4 : 2;
-  const int chunks_per_pass = elt == 2 ? 4 : 2;  // <= 128 B of output row per pass
-  const int qb = q / p.img_HW, rem = q - qb * p.img_HW;
-  // element offset of channel 0 of this row in the output (pixel-shuffle: of sub-pixel (0,0))
-  long long off_row;
-  if (p.out_mode == OUT_SHUFFLE2_BF16) {
-    const int ph = rem / p.img_W, pw = rem - ph * p.img_W;
-    off_row = qb * p.out_img_stride + ((long long)(2 * ph) * (2 * p.img_W) + 2 * pw) * p.out_pix_stride + p.out_c_off;
-  } else {
-    off_row = qb * p.out_img_stride + (long long)rem * p.out_pix_stride + p.out_c_off;
-  }
-  const long long res_row = qb * p.res_img_stride + (long long)rem * p.res_pix_stride + p.res_c_off;
-  if (c_begin >= c_end) {  // n_tile == 16: the second warp of the lane group has no columns, it only hands back
-    __syncwarp();
-    if (lane == 0 && release != nullptr) mbar_arrive(release);
-  }
-  for (int cp0 = c_begin; cp0 < c_end; cp0 += chunks_per_pass) {
-    const int nch = min(chunks_per_pass, c_end - cp0);
-    const int row_bytes = nch * 16 * elt, pitch = row_bytes + 16;
-    uint8_t* my = stage + lane * pitch;
-    const int ppr = row_bytes >> 4;               // 16-byte pieces per row (<= 8)
-    const int ppr_inv = (65536 + ppr - 1) / ppr;  // piece / ppr == (piece * ppr_inv) >> 16 for piece < 512
-    // Residual (Bottleneck shortcut): issue this pass's coalesced 16-byte loads NOW so that their latency is
-    // covered by the TMEM reads and the SiLU math of phase 1.
-    uint4 rres[8];
-    if (p.res != nullptr) {
+enum EpiMode : int { EPI_BF16 = 0, EPI_BF16_RES = 1, EPI_F32 = 2, EPI_SHUFFLE2 = 3 };
+__host__ __device__ inline int epi_mode_of(int out_mode, bool has_res) {
+  return out_mode == OUT_F32 ? EPI_F32 : out_mode == OUT_SHUFFLE2_BF16 ? EPI_SHUFFLE2 : has_res ? EPI_BF16_RES : EPI_BF16;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// read-only data (the bias copy): not volatile, no memory clobber, so the compiler may schedule it freely
+__device__ __forceinline__ float4 lds128_ro(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int NC>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[32]);
+template <>
+__device__ __forceinline__ void tmem_ldn<16>(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ldn<32>(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Row-offset exchange for a pass layout with PPR 16-byte pieces per row: piece = lane + 32*i covers row piece / PPR.
+template <int PPR>
+__device__ __forceinline__ void epi_row_deltas(int delta, int lane, int (&dl)[PPR]) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        rres[i] = make_uint4(0, 0, 0, 0);
-        if (i < ppr) {
-          const int piece = lane + 32 * i;
-          const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
-          const long long r_r = __shfl_sync(0xffffffffu, res_row, row);
-          const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
-          if (ok) rres[i] = __ldg(reinterpret_cast<const uint4*>(p.res + r_r + n0 + cp0 * 16 + pc * 8));
-        }
-      }
+  for (int i = 0; i < PPR; ++i) dl[i] = __shfl_sync(0xffffffffu, delta, (lane + 32 * i) / PPR);
+}
+
+// bias + activation on NC accumulator values, packed into the staging tile, then written out.
+//   stage_sa : shared-space address of the warp's staging tile;  sb_sa : shared-space address of sbias[n]
+//   dl / rl  : per-piece row deltas of the output / residual (element offsets from base / res_base; < 0 = padding row)
+template <int NC, int MODE>
+__device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32_t (&v)[32], uint32_t stage_sa, uint32_t sb_sa,
+                                               int lane, int n, long long base, long long res_base,
+                                               const int (&dl)[MODE == EPI_F32 ? NC / 4 : NC / 8],
+                                               const int (&rl)[MODE == EPI_F32 ? NC / 4 : NC / 8], bool prof, long long& pt,
+                                               long long (&pacc)[6]) {
+#define EPI_MARK(k) do { if (prof) { const long long _n = clock64(); pacc[(k) - 8] += _n - pt; pt = _n; } } while (0)
+  constexpr bool F32 = MODE == EPI_F32;
+  constexpr int PPR = F32 ? NC / 4 : NC / 8;  // 16-byte pieces per staged row
+  constexpr int pitch = PPR * 16 + 16;
+  const float sc = (p.act && !F32) ? 0.5f : 1.0f;
+  // residual: coalesced 16-byte loads, issued first so their latency hides behind the math
+  uint4 rres[PPR];
+  if (MODE == EPI_BF16_RES) {
+#pragma unroll
+    for (int i = 0; i < PPR; ++i) {
+      const int pc = (lane + 32 * i) % PPR;
+      rres[i] = make_uint4(0, 0, 0, 0);
+      if (rl[i] >= 0) rres[i] = __ldg(reinterpret_cast<const uint4*>(p.res + res_base + rl[i] + n + pc * 8));
     }
-    for (int ch = 0; ch < nch; ++ch) {
-      uint32_t v[16];
-      tmem_ld16(t_addr + (uint32_t)((cp0 + ch) * 16), v);
-      tmem_ld_wait();
-      const int n = n0 + (cp0 + ch) * 16;
-      float y[16];
-      const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+  }
+  float y[NC];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 bv = __ldg(bp + i);
-        y[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bv.x;
-        y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bv.y;
-        y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bv.z;
-        y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bv.w;
+  for (int i = 0; i < NC / 4; ++i) {
+    const float4 b4 = lds128_ro(sb_sa + 16 * i);
+    y[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), sc, b4.x);
+    y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), sc, b4.y);
+    y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), sc, b4.z);
+    y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), sc, b4.w);
+  }
+  if (p.act && !(p.dbg & 1)) {
+    if (!F32) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {  // y holds h = x/2: SiLU(x) = h + h*tanh(h)
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y[i]));
+        y[i] = fmaf(y[i], t, y[i]);
       }
-      if (p.act && !(p.dbg & 1)) {
-        if (elt == 2) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = silu_f(y[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = silu_precise_f(y[i]);
-        }
-      }
-      if (elt == 2) {
-        uint4* d = reinterpret_cast<uint4*>(my + ch * 32);
-        d[0] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-        d[1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]),
-                          pack_bf16x2(y[14], y[15]));
-      } else {
-        float4* d = reinterpret_cast<float4*>(my + ch * 64);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) d[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-      }
-    }
-    if (cp0 + chunks_per_pass >= c_end) {  // last TMEM read of this tile: hand the accumulator back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0 && release != nullptr) mbar_arrive(release);
     } else {
-      __syncwarp();
-    }
-    if (!(p.dbg & 2)) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i >= ppr) break;
-        const int piece = lane + 32 * i;
-        const int row = (piece * ppr_inv) >> 16, pc = piece - row * ppr;
-        const long long o_r = __shfl_sync(0xffffffffu, off_row, row);
-        const int ok = __shfl_sync(0xffffffffu, (int)valid, row);
-        uint4 val = *reinterpret_cast<const uint4*>(stage + row * pitch + pc * 16);
-        if (!ok) continue;
-        if (elt == 4) {
-          const int n = n0 + cp0 * 16 + pc * 4;
-          *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o_r + n) = val;
-          continue;
-        }
-        const int n = n0 + cp0 * 16 + pc * 8;
-        if (p.res != nullptr) {
-          const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+      for (int i = 0; i < NC; ++i) y[i] = silu_precise_f(y[i]);
+    }
+  }
+  if (prof) {  // make the math retire before the timestamp
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc += y[i];
+    if (acc == 123.456f) pt += 1;
+  }
+  EPI_MARK(10);
+  const uint32_t my = stage_sa + lane * pitch;
+  if (!F32) {
+#pragma unroll
+    for (int i = 0; i < PPR; ++i)
+      sts128(my + 16 * i, pack_bf16x2(y[8 * i], y[8 * i + 1]), pack_bf16x2(y[8 * i + 2], y[8 * i + 3]),
+             pack_bf16x2(y[8 * i + 4], y[8 * i + 5]), pack_bf16x2(y[8 * i + 6], y[8 * i + 7]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < PPR; ++i)
+      sts128(my + 16 * i, __float_as_uint(y[4 * i]), __float_as_uint(y[4 * i + 1]), __float_as_uint(y[4 * i + 2]),
+             __float_as_uint(y[4 * i + 3]));
+  }
+  __syncwarp();
+  EPI_MARK(11);
+  if (!(p.dbg & 2)) {
+    uint4 val[PPR];
+#pragma unroll
+    for (int i = 0; i < PPR; ++i) {
+      const int piece = lane + 32 * i;
+      val[i] = lds128(stage_sa + (piece / PPR) * pitch + (piece % PPR) * 16);
+    }
+    const int pc = lane % PPR;  // (lane + 32 i) % PPR is the same for every i: PPR divides 32
+    if (F32) {
+      float* out = reinterpret_cast<float*>(p.out) + base + n + pc * 4;
+#pragma unroll
+      for (int i = 0; i < PPR; ++i)
+        if (dl[i] >= 0) *reinterpret_cast<uint4*>(out + dl[i]) = val[i];
+    } else {
+      const int nn = n + pc * 8;
+      long long coff = nn;
+      if (MODE == EPI_SHUFFLE2) {  // ConvTranspose2d(2,2): channel group g = (dy, dx) of the 2x2 output block
+        const int cq = p.Cout >> 2;
+        const int g = nn / cq, c = nn - g * cq;
+        coff = ((long long)(g >> 1) * (2 * p.img_W) + (g & 1)) * p.out_pix_stride + c;
+      }
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + base + coff;
+#pragma unroll
+      for (int i = 0; i < PPR; ++i) {
+        if (MODE == EPI_BF16_RES) {
+          // y = bf16(act(...)) first, then bf16(y + res): the same two roundings as storing the conv output and
+          // adding the shortcut afterwards (Bottleneck: x + cv2(cv1(x))).
+          const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val[i]);
           const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rres[i]);
           uint32_t o[4];
 #pragma unroll
@@ -370,21 +460,104 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint8_t* stage, i
             const float2 fa = __bfloat1622float2(a2[u]), fb = __bfloat1622float2(b2[u]);
             o[u] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
           }
-          val = make_uint4(o[0], o[1], o[2], o[3]);
+          val[i] = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        long long off = o_r + n;
-        if (p.out_mode == OUT_SHUFFLE2_BF16) {
-          const int cq = p.Cout >> 2;
-          const int g = n / cq, c = n - g * cq;
-          off = o_r + ((long long)(g >> 1) * (2 * p.img_W) + (g & 1)) * p.out_pix_stride + c;
-        }
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = val;
+        if (dl[i] >= 0) *reinterpret_cast<uint4*>(out + dl[i]) = val[i];
       }
     }
-    __syncwarp();
   }
+  __syncwarp();
+  EPI_MARK(12);
+  if (prof) pacc[5] += 1;
+#undef EPI_MARK
 }
 
+template <int MODE>
+__device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa, uint32_t sbias_sa, int lane, int c_begin,
+                                          int c_end, uint32_t t_addr, int n0, bool valid, int qb, int rem,
+                                          uint64_t* release, long long (&pacc)[6]) {
+  constexpr bool F32 = MODE == EPI_F32;
+  constexpr int P32 = F32 ? 8 : 4, P16 = F32 ? 4 : 2;  // 16-byte pieces per staged row of a 32- / 16-column pass
+  const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+  if (c_begin >= c_end || vmask == 0u) {  // nothing to read (n_tile == 16: second warp of the lane group; tile rows all padding)
+    __syncwarp();
+    if (lane == 0 && release != nullptr) mbar_arrive(release);
+    return;
+  }
+  const bool prof = (p.dbg & 8) != 0 && lane == 0;
+  long long pt = prof ? clock64() : 0;
+#define EPI_MARK(k) do { if (prof) { const long long _n = clock64(); pacc[(k) - 8] += _n - pt; pt = _n; } } while (0)
+  // (qb, rem) = image and pixel-within-image of this lane's row; element offset of channel 0 of that row in the
+  // output (pixel-shuffle: of sub-pixel (0,0))
+  long long off_row;
+  if (MODE == EPI_SHUFFLE2) {
+    const int ph = fdiv(rem, p.fd_iw), pw = rem - ph * p.img_W;
+    off_row = qb * p.out_img_stride + ((long long)(2 * ph) * (2 * p.img_W) + 2 * pw) * p.out_pix_stride + p.out_c_off;
+  } else {
+    off_row = qb * p.out_img_stride + (long long)rem * p.out_pix_stride + p.out_c_off;
+  }
+  const int src = __ffs(vmask) - 1;  // rows are addressed relative to the first valid row of the warp (offsets only grow)
+  const long long base = __shfl_sync(0xffffffffu, off_row, src);
+  const int delta = valid ? (int)(off_row - base) : -1;
+  long long res_base = 0;
+  int rdelta = -1;
+  if (MODE == EPI_BF16_RES) {
+    const long long res_row = qb * p.res_img_stride + (long long)rem * p.res_pix_stride + p.res_c_off;
+    res_base = __shfl_sync(0xffffffffu, res_row, src);
+    rdelta = valid ? (int)(res_row - res_base) : -1;
+  }
+  const int col0 = c_begin * 16, ncols = (c_end - c_begin) * 16;
+  const int n32 = ncols >> 5;
+  const bool tail16 = (ncols & 31) != 0;
+  uint32_t v[32];
+  if (n32 > 0) {
+    int dl[P32], rl[P32];
+    epi_row_deltas<P32>(delta, lane, dl);
+    if (MODE == EPI_BF16_RES) epi_row_deltas<P32>(rdelta, lane, rl);
+    tmem_ldn<32>(t_addr + (uint32_t)col0, v);
+    for (int k = 0; k < n32; ++k) {
+      const int col = col0 + 32 * k;
+      tmem_ld_wait();
+      EPI_MARK(8);
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = v[i];
+      if (k + 1 < n32) {
+        tmem_ldn<32>(t_addr + (uint32_t)(col + 32), v);  // in flight during this pass's math, staging and write-out
+      } else if (!tail16 && release != nullptr) {
+        // last TMEM read of this tile has landed (tcgen05.wait::ld): hand the accumulator back to the MMA warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release);
+      }
+      EPI_MARK(9);
+      epi_store_pass<32, MODE>(p, w, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl,
+                               prof, pt, pacc);
+    }
+  }
+  if (tail16) {
+    const int col = col0 + 32 * n32;
+    int dl[P16], rl[P16];
+    epi_row_deltas<P16>(delta, lane, dl);
+    if (MODE == EPI_BF16_RES) epi_row_deltas<P16>(rdelta, lane, rl);
+    tmem_ldn<16>(t_addr + (uint32_t)col, v);
+    tmem_ld_wait();
+    if (release != nullptr) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(release);
+    }
+    epi_store_pass<16, MODE>(p, v, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl, prof,
+                             pt, pacc);
+  }
+#undef EPI_MARK
+}
+
+// Cooperative copy of the (pre-scaled) bias into shared memory; call before the setup __syncthreads().
+__device__ __forceinline__ void epi_load_bias(const ConvParams& p, float* sbias) {
+  const float sc = (p.act && p.out_mode != OUT_F32) ? 0.5f : 1.0f;
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = sc * __ldg(p.bias + i);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kConv2Threads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ ConvParams p, int n_splits, int total_tiles) {
@@ -404,6 +577,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int acc_stride = conv2_acc_stride(p.n_tile);
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * p.msub * acc_stride)) tmem_cols <<= 1;
+  const bool prof = (p.dbg & 8) != 0;
+  const long long prof_start = prof ? clock64() : 0;
+  long long pw0 = 0, pw1 = 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -419,6 +595,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
+  float* sbias = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 256 + kEpiWarps * kEpiStageBytes);
+  epi_load_bias(p, sbias);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -428,22 +606,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== TMA producers: warp w owns the ring stages s with s % kProdWarps == w =====================
     if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)(p.TH * p.TW * 128 + p.n_tile * 128);  // the A box spans all sub-tiles
-      int it = 0;
+      int s = -1;
+      uint32_t ph = 1;  // ring position / phase of the current k-iteration (advanced at the top of the loop body)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
-        const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
-        const int th = t_in / p.tiles_w;
+        const int mt = fdiv(tile, p.fd_ns), n0 = (tile - mt * n_splits) * p.n_tile;
+        const int b = fdiv(mt, p.fd_tpi), t_in = mt - b * tiles_per_img;
+        const int th = fdiv(t_in, p.fd_tw);
         const int h0 = th * p.TH, w0 = (t_in - th * p.tiles_w) * p.TW;
         int cbase[5];
 #pragma unroll
         for (int d = 0; d < 5; ++d) cbase[d] = p.a_base[d] + b * p.a_cb[d] + h0 * p.a_ch[d] + w0 * p.a_cw[d];
         for (int c = 0; c < kchunks; ++c) {
-          for (int t = 0; t < p.ntaps; ++t, ++it) {
+          for (int t = 0; t < p.ntaps; ++t) {
+            if (++s == p.stages) s = 0;
+            if (s == 0) ph ^= 1;
             // a stage always belongs to the same producer: parity waits are only sound one phase ahead
-            const int s = it % p.stages;
             if ((s % kProdWarps) != warp) continue;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(empty_bar + s, ph ^ 1, 1u);
+            {
+              PROF_T0();
+              mbar_wait_bo(empty_bar + s, ph ^ 1, 1u, p.bo_prod);
+              PROF_ADD(pw0);
+            }
             uint8_t* sa = smem + s * stage_bytes;
             mbar_expect_tx(full_bar + s, tx_bytes);
             tma_load_5d(sa, &tmA, full_bar + s, cbase[0] + p.tap[t][0] + c * 64, cbase[1] + p.tap[t][1],
@@ -452,24 +635,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
+      if (prof && warp == 0) atomicAdd(&g_conv_prof[0], (unsigned long long)pw0);
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (accumulation order: chunk-major, tap-minor, like conv3_halo_kernel) =====================
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
-      int it = 0, acc = 0;
+      int s = -1, acc = 0;
+      uint32_t ph = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
         const int buf = acc & 1;
-        mbar_wait(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u);  // epilogue has drained this accumulator
+        {
+          PROF_T0();
+          mbar_wait_bo(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u, p.bo_mma_acc);  // epilogue has drained this accumulator
+          PROF_ADD(pw1);
+        }
         tc_fence_after();
         int first = 1;
         for (int c = 0; c < kchunks; ++c) {
           int ksteps = (p.Cin - c * 64) >> 4;
           if (ksteps > 4) ksteps = 4;
-          for (int t = 0; t < p.ntaps; ++t, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(full_bar + s, ph, 2u);
+          for (int t = 0; t < p.ntaps; ++t) {
+            if (++s == p.stages) s = 0;
+            if (s == 0) ph ^= 1;
+            {
+              PROF_T0();
+              mbar_wait_bo(full_bar + s, ph, 2u, p.bo_mma_full);
+              PROF_ADD(pw0);
+            }
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + s * stage_bytes);
             const uint32_t sb = sa + a_bytes;
@@ -485,6 +678,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         umma_commit(tfull_bar + buf);
+      }
+      if (prof) {
+        atomicAdd(&g_conv_prof[1], (unsigned long long)pw0);
+        atomicAdd(&g_conv_prof[2], (unsigned long long)pw1);
       }
     }
   } else {
@@ -502,27 +699,64 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
     uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - kEpiWarp0) * kEpiStageBytes;
     const int r = lg * 32 + lane;
+    long long pacc[6] = {0, 0, 0, 0, 0, 0};
+    const bool flat = p.ntaps == 1;  // 1x1: the tile is 128 * msub consecutive pixels of the flattened batch
+    int rh_[2], rw_[2];              // this lane's row of sub-tile 0 / 1 inside the CTA rectangle (tile-invariant)
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      const int R = sidx * p.sub_rows + r;
+      rh_[sidx] = R / p.TW;
+      rw_[sidx] = R - rh_[sidx] * p.TW;
+    }
     int acc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
-      const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
-      const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
-      const int th = t_in / p.tiles_w;
+      const int mt = fdiv(tile, p.fd_ns), n0 = (tile - mt * n_splits) * p.n_tile;
+      const int b = fdiv(mt, p.fd_tpi), t_in = mt - b * tiles_per_img;
+      const int th = fdiv(t_in, p.fd_tw);
       const int buf = acc & 1;
-      mbar_wait(tfull_bar + buf, (acc >> 1) & 1, 4u);
-      tc_fence_after();
-      for (int sidx = 0; sidx < p.msub; ++sidx) {
-        const int R = sidx * p.sub_rows + r;  // row of the whole CTA tile
-        const int rh = R / p.TW, rw = R - rh * p.TW;
-        const int h = th * p.TH + rh, w = (t_in - th * p.tiles_w) * p.TW + rw;
-        const bool valid = (r < p.sub_rows) && (h < p.tH) && (w < p.tW);
-        const int q = valid ? (b * p.tH + h) * p.tW + w : 0;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * p.msub + sidx) * acc_stride);
-        epi_drain(p, stage, lane, c_begin, c_end, t_addr, n0, valid, q, sidx == p.msub - 1 ? tempty_bar + buf : nullptr);
+      {
+        PROF_T0();
+        mbar_wait_bo(tfull_bar + buf, (acc >> 1) & 1, 4u, p.bo_epi);
+        PROF_ADD(pw0);
       }
+      tc_fence_after();
+      PROF_T0();
+#pragma unroll
+      for (int sidx = 0; sidx < 2; ++sidx) {
+        if (sidx >= p.msub) break;
+        const int h = th * p.TH + rh_[sidx], w = (t_in - th * p.tiles_w) * p.TW + rw_[sidx];
+        const bool valid = (r < p.sub_rows) && (h < p.tH) && (w < p.tW);
+        int qb = 0, rem = 0;
+        if (valid) {
+          if (flat) {
+            qb = fdiv(w, p.fd_hw);
+            rem = w - qb * p.img_HW;
+          } else {
+            qb = b;
+            rem = h * p.tW + w;
+          }
+        }
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * p.msub + sidx) * acc_stride);
+        epi_drain<MODE>(p, smem_u32(stage), smem_u32(sbias), lane, c_begin, c_end, t_addr, n0, valid, qb, rem,
+                        sidx == p.msub - 1 ? tempty_bar + buf : nullptr, pacc);
+      }
+      PROF_ADD(pw1);
+    }
+    if (prof && warp == kEpiWarp0 && lane == 0) {
+      atomicAdd(&g_conv_prof[3], (unsigned long long)pw0);
+      atomicAdd(&g_conv_prof[4], (unsigned long long)pw1);
+    }
+    if (prof && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) atomicAdd(&g_conv_prof[8 + i], (unsigned long long)pacc[i]);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (prof && threadIdx.x == 0) {
+    atomicAdd(&g_conv_prof[5], (unsigned long long)(clock64() - prof_start));
+    atomicAdd(&g_conv_prof[7], 1ull);
+  }
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -564,6 +798,7 @@ struct Conv3Extra {
   int b_bytes;     // weight region bytes
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(kConv2Threads, 1)
 conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvParams p, const Conv3Extra x, int n_splits, int total_tiles) {
@@ -591,6 +826,9 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int ngroups = 9 / x.b_group;  // weight boxes per 64-channel chunk
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * x.msub * acc_stride)) tmem_cols <<= 1;
+  const bool prof = (p.dbg & 8) != 0;
+  const long long prof_start = prof ? clock64() : 0;
+  long long pw0 = 0, pw1 = 0, pw2 = 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -602,6 +840,8 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
+  float* sbias = reinterpret_cast<float*>(stage_base + kEpiWarps * kEpiStageBytes);
+  epi_load_bias(p, sbias);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -616,31 +856,40 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int g = 0; g < ngroups; ++g)
             tma_load_3d(sB + (c * 9 + g * x.b_group) * tap_bytes, &tmB, ball_bar, c * 64, 0, g * x.b_group);
       }
-      int ia = 0;
+      int sa = -1;
+      uint32_t pa = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / n_splits;
-        const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
-        const int th = t_in / p.tiles_w;
+        const int mt = fdiv(tile, p.fd_ns);
+        const int b = fdiv(mt, p.fd_tpi), t_in = mt - b * tiles_per_img;
+        const int th = fdiv(t_in, p.fd_tw);
         const int h0 = th * 16 * x.msub, w0 = (t_in - th * p.tiles_w) * 8;
-        for (int c = 0; c < kchunks; ++c, ++ia) {
-          const int sa = ia % x.a_slots;
-          mbar_wait(a_empty + sa, ((ia / x.a_slots) & 1) ^ 1, 1u);
+        for (int c = 0; c < kchunks; ++c) {
+          if (++sa == x.a_slots) sa = 0;
+          if (sa == 0) pa ^= 1;
+          {
+            PROF_T0();
+            mbar_wait_bo(a_empty + sa, pa ^ 1, 1u, p.bo_prod);
+            PROF_ADD(pw0);
+          }
           mbar_expect_tx(a_full + sa, (uint32_t)(x.halo_rows * 128));
           tma_load_5d(sA + sa * x.a_bytes, &tmA, a_full + sa, p.a_base[0] + c * 64, w0 - 1, h0 - 1, b, 0);
         }
       }
+      if (prof) atomicAdd(&g_conv_prof[0], (unsigned long long)pw0);
     }
   } else if (warp < kProdWarps) {
     // ===================== TMA producers 1..3: streamed weight boxes, ring slot sb owned by warp 1 + sb % 3 =====================
     if (!x.b_stat && elect_one()) {
-      int ib = 0;
+      int sb = -1;
+      uint32_t pb = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
+        const int mt = fdiv(tile, p.fd_ns), n0 = (tile - mt * n_splits) * p.n_tile;
         for (int c = 0; c < kchunks; ++c) {
-          for (int g = 0; g < ngroups; ++g, ++ib) {
-            const int sb = ib % x.b_slots;
+          for (int g = 0; g < ngroups; ++g) {
+            if (++sb == x.b_slots) sb = 0;
+            if (sb == 0) pb ^= 1;
             if (1 + (sb % (kProdWarps - 1)) != warp) continue;  // a slot always belongs to the same producer
-            mbar_wait(b_empty + sb, ((ib / x.b_slots) & 1) ^ 1, 1u);
+            mbar_wait_bo(b_empty + sb, pb ^ 1, 1u, p.bo_prod);
             mbar_expect_tx(b_full + sb, (uint32_t)grp_bytes);
             tma_load_3d(sB + sb * grp_bytes, &tmB, b_full + sb, c * 64, n0, g * x.b_group);
           }
@@ -655,15 +904,25 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(ball_bar, 0, 2u);
         tc_fence_after();
       }
-      int ia = 0, ib = 0, acc = 0;
+      int sa = -1, sbn = -1, acc = 0;
+      uint32_t pa = 1, pb = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
         const int buf = acc & 1;
-        mbar_wait(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u);
+        {
+          PROF_T0();
+          mbar_wait_bo(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u, p.bo_mma_acc);
+          PROF_ADD(pw1);
+        }
         tc_fence_after();
         int first = 1;
-        for (int c = 0; c < kchunks; ++c, ++ia) {
-          const int sa = ia % x.a_slots;
-          mbar_wait(a_full + sa, (ia / x.a_slots) & 1, 2u);
+        for (int c = 0; c < kchunks; ++c) {
+          if (++sa == x.a_slots) sa = 0;
+          if (sa == 0) pa ^= 1;
+          {
+            PROF_T0();
+            mbar_wait_bo(a_full + sa, pa, 2u, p.bo_mma_full);
+            PROF_ADD(pw0);
+          }
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + sa * x.a_bytes);
           int ksteps = (p.Cin - c * 64) >> 4;
@@ -674,11 +933,16 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (x.b_stat) {
               g_base = smem_u32(sB + (c * 9 + g * x.b_group) * tap_bytes);
             } else {
-              sb = ib % x.b_slots;
-              mbar_wait(b_full + sb, (ib / x.b_slots) & 1, 2u);
+              if (++sbn == x.b_slots) sbn = 0;
+              if (sbn == 0) pb ^= 1;
+              sb = sbn;
+              {
+                PROF_T0();
+                mbar_wait_bo(b_full + sb, pb, 2u, p.bo_mma_full);
+                PROF_ADD(pw2);
+              }
               tc_fence_after();
               g_base = smem_u32(sB + sb * grp_bytes);
-              ++ib;
             }
             for (int u = 0; u < x.b_group; ++u) {
               const int t = g * x.b_group + u;
@@ -699,6 +963,11 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         umma_commit(tfull_bar + buf);
       }
+      if (prof) {
+        atomicAdd(&g_conv_prof[1], (unsigned long long)pw0);
+        atomicAdd(&g_conv_prof[2], (unsigned long long)pw1);
+        atomicAdd(&g_conv_prof[6], (unsigned long long)pw2);
+      }
     }
   } else {
     // ===================== epilogue =====================
@@ -709,26 +978,45 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
     uint8_t* stage = stage_base + (warp - kEpiWarp0) * kEpiStageBytes;
     const int r = lg * 32 + lane;
+    long long pacc[6] = {0, 0, 0, 0, 0, 0};
     int acc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
-      const int mt = tile / n_splits, n0 = (tile - mt * n_splits) * p.n_tile;
-      const int b = mt / tiles_per_img, t_in = mt - b * tiles_per_img;
-      const int th = t_in / p.tiles_w;
+      const int mt = fdiv(tile, p.fd_ns), n0 = (tile - mt * n_splits) * p.n_tile;
+      const int b = fdiv(mt, p.fd_tpi), t_in = mt - b * tiles_per_img;
+      const int th = fdiv(t_in, p.fd_tw);
       const int h0 = th * 16 * x.msub, w0 = (t_in - th * p.tiles_w) * 8;
       const int buf = acc & 1;
-      mbar_wait(tfull_bar + buf, (acc >> 1) & 1, 4u);
+      {
+        PROF_T0();
+        mbar_wait_bo(tfull_bar + buf, (acc >> 1) & 1, 4u, p.bo_epi);
+        PROF_ADD(pw0);
+      }
       tc_fence_after();
+      PROF_T0();
       for (int sidx = 0; sidx < x.msub; ++sidx) {
         const int h = h0 + sidx * 16 + (r >> 3), w = w0 + (r & 7);
         const bool valid = (h < p.tH) && (w < p.tW);
-        const int q = valid ? (b * p.tH + h) * p.tW + w : 0;
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * x.msub + sidx) * acc_stride);
-        epi_drain(p, stage, lane, c_begin, c_end, t_addr, n0, valid, q, sidx == x.msub - 1 ? tempty_bar + buf : nullptr);
+        epi_drain<MODE>(p, smem_u32(stage), smem_u32(sbias), lane, c_begin, c_end, t_addr, n0, valid, b,
+                        valid ? h * p.tW + w : 0, sidx == x.msub - 1 ? tempty_bar + buf : nullptr, pacc);
       }
+      PROF_ADD(pw1);
+    }
+    if (prof && warp == kEpiWarp0 && lane == 0) {
+      atomicAdd(&g_conv_prof[3], (unsigned long long)pw0);
+      atomicAdd(&g_conv_prof[4], (unsigned long long)pw1);
+    }
+    if (prof && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) atomicAdd(&g_conv_prof[8 + i], (unsigned long long)pacc[i]);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (prof && threadIdx.x == 0) {
+    atomicAdd(&g_conv_prof[5], (unsigned long long)(clock64() - prof_start));
+    atomicAdd(&g_conv_prof[7], 1ull);
+  }
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -747,9 +1035,10 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // The frame is read as aligned 32-bit words straight from HBM: 3 B per pixel instead of a 12 B/pixel fp32 tensor.
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemTH = 8, kStemTW = 16;
+constexpr int kStemMaxC0 = 128;
 constexpr int kStemRowWords = 27;  // 33 pixels x 3 B = 99 B plus up to 3 B of misalignment -> 26 words, +1 spare
 
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, 5)
 stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const __nv_bfloat16* __restrict__ wq,
                const __grid_constant__ ConvParams p, int tiles_per_img, int tiles_w, int total_tiles, int tiles_per_cta,
                int alias_stage) {
@@ -761,8 +1050,10 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
   uint8_t* sStage = alias_stage ? sA : reinterpret_cast<uint8_t*>(sIn + 17 * kStemRowWords + 4);  // A is dead once the MMAs retire
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float sbias[kStemMaxC0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int C0 = p.Cout;
+  epi_load_bias(p, sbias);
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)C0) tmem_cols <<= 1;
   if (tid == 0) {
@@ -845,9 +1136,9 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
       const int r = warp * 32 + lane;
       const int oh = oh0 + (r >> 4), ow = ow0 + (r & 15);
       const bool valid = oh < oH && ow < oW;
-      const int q = valid ? (b * oH + oh) * oW + ow : 0;
-      epi_drain(p, sStage + warp * (alias_stage ? 4096 : kEpiStageBytes), lane, 0, C0 >> 4,
-                tmem_base + ((uint32_t)(warp * 32) << 16), 0, valid, q, nullptr);
+      long long pacc[6] = {0, 0, 0, 0, 0, 0};
+      epi_drain<EPI_BF16>(p, smem_u32(sStage + warp * (alias_stage ? 4096 : kEpiStageBytes)), smem_u32(sbias), lane, 0, C0 >> 4,
+                tmem_base + ((uint32_t)(warp * 32) << 16), 0, valid, b, valid ? oh * oW + ow : 0, nullptr, pacc);
     }
     tc_fence_before();
     __syncthreads();  // TMEM, sA and sIn are reused by the next tile

@@ -545,7 +545,8 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       const int tiles_w = (ob.W + kStemTW - 1) / kStemTW, tiles_h = (ob.H + kStemTH - 1) / kStemTH;
       const int total = B * tiles_h * tiles_w, per_cta = 8;
       // the epilogue staging tile (32 rows x (min(2*C0,128)+16) B per warp) aliases the A tile when it fits in 4 KB per warp
-      const int alias = 32 * (std::min(2 * op.cout, 128) + 16) <= 4096 ? 1 : 0;
+      const int alias = 1;  // a pass stages 32 rows x (64 + 16) B per warp
+      if (op.cout > kStemMaxC0) return fail(YPB_ERR_ARG, "stem: too many output channels");
       const size_t smem = 1024 + 16384 + ((op.cout * 128 + 1023) & ~1023) + 17 * kStemRowWords * 4 + 16 +
                           (alias ? 0 : 4 * kEpiStageBytes);
       stem_tc_kernel<<<(total + per_cta - 1) / per_cta, 128, smem, st>>>(frames, e->H, e->W, B,
@@ -1152,6 +1153,65 @@ int ypb_conv2d_bf16(void* cuda_stream, const void* in, int B, int H, int W, int 
   if (!conv_plan_geometry(d, &L, &err)) return fail(YPB_ERR_ARG, err);
   if (!conv_bind(d, &L, &err)) return fail(YPB_ERR_CUDA, err);
   CUDA_TRY(conv_launch(L, reinterpret_cast<cudaStream_t>(cuda_stream), impl));
+  return YPB_OK;
+}
+
+// Diagnostics: time `iters` back-to-back launches of one conv (planned once) with CUDA events on `cuda_stream`.
+// dbg >= 0 overrides the YPB_DBG experiment mask of the launch (see ConvParams::dbg).
+int ypb_conv_bench(void* cuda_stream, const void* in, int B, int H, int W, int in_ctot, int in_c_off, int cin,
+                   const void* wg, const float* bias, int cout, int k, int stride, int act, const void* res, void* out,
+                   int out_ctot, int out_c_off, int out_fp32, int impl, int dbg, int iters, float* ms, char* desc,
+                   int desc_len) {
+  if (!ms || iters < 1) return fail(YPB_ERR_ARG, "bad argument");
+  ConvDesc d;
+  d.in = in; d.B = B; d.Hin = H; d.Win = W; d.in_ctot = in_ctot; d.in_c_off = in_c_off; d.cin = cin;
+  d.wg = wg; d.bias = bias; d.cout = cout; d.k = k; d.stride = stride; d.act = act;
+  d.out_mode = out_fp32 == 2 ? OUT_SHUFFLE2_BF16 : out_fp32 ? OUT_F32 : OUT_BF16;
+  const int oH = H / stride, oW = W / stride;
+  if (d.out_mode == OUT_SHUFFLE2_BF16) {
+    d.out = out; d.out_img_stride = 4LL * oH * oW * out_ctot; d.out_pix_stride = out_ctot; d.out_c_off = out_c_off;
+  } else {
+    d.out = out; d.out_img_stride = (long long)oH * oW * out_ctot; d.out_pix_stride = out_ctot; d.out_c_off = out_c_off;
+  }
+  if (res) { d.res = res; d.res_img_stride = d.out_img_stride; d.res_pix_stride = out_ctot; d.res_c_off = out_c_off; }
+  ConvLaunch L;
+  std::string err;
+  if (!conv_plan_geometry(d, &L, &err)) return fail(YPB_ERR_ARG, err);
+  if (!conv_bind(d, &L, &err)) return fail(YPB_ERR_CUDA, err);
+  if (dbg >= 0) { L.p.dbg = dbg; L.p1.dbg = dbg; }
+  if (desc && desc_len > 0) conv_describe(L, impl, desc, desc_len);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; ++i) CUDA_TRY(conv_launch(L, st, impl));
+  if (dbg >= 0 && (dbg & 8)) {
+    unsigned long long z[16] = {0};
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpyToSymbol(g_conv_prof, z, sizeof z));
+  }
+  CUDA_TRY(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) CUDA_TRY(conv_launch(L, st, impl));
+  CUDA_TRY(cudaEventRecord(e1, st));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
+  *ms /= (float)iters;
+  if (dbg >= 0 && (dbg & 8) && desc && desc_len > 0) {
+    unsigned long long z[16];
+    CUDA_TRY(cudaMemcpyFromSymbol(z, g_conv_prof, sizeof z));
+    const double n = z[7] ? (double)z[7] : 1.0, life = (double)z[5] / n;
+    const size_t len = strlen(desc);
+    snprintf(desc + len, desc_len - len,
+             " | per-CTA kcycles: life %.1f prod.wait_empty %.1f mma.wait_full %.1f mma.wait_tempty %.1f mma.wait_w %.1f "
+             "epi.wait_tfull %.1f epi.drain %.1f",
+             life / 1e3, z[0] / n / 1e3, z[1] / n / 1e3, z[2] / n / 1e3, z[6] / n / 1e3, z[3] / n / 1e3, z[4] / n / 1e3);
+    const double np = z[13] ? (double)z[13] : 1.0;
+    const size_t len2 = strlen(desc);
+    snprintf(desc + len2, desc_len - len2, " | cycles per epilogue pass: ld+wait %.0f release %.0f math %.0f stage %.0f writeout %.0f",
+             z[8] / np, z[9] / np, z[10] / np, z[11] / np, z[12] / np);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return YPB_OK;
 }
 

@@ -238,6 +238,7 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
+    cand = eng.candidate_counts().cpu().numpy()
     err = eng.device_error()
     if err or (is_seg and int(eng.mask_status[1].item())):
         raise SystemExit(f"bench.py: device error word {err:#x} / mask overflow {eng.mask_status.tolist()}")
@@ -333,7 +334,8 @@ def run_ours(args, wl):
                    "frame": f"{hw[1]}x{hw[0]}", "net_input": f"{W}x{H}", "imgsz": imgsz, "conf": CONF, "iou": IOU,
                    "retina_masks": True, "weights": "random-init, synthetic recipe (SURVEY.md 8d)",
                    "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph, "predict_micro_batch": yolo.micro_batch,
-                   "detections_per_step": n_det, "parallelism": f"frame-sharded replicas x{world}",
+                   "detections_per_step": n_det,
+                   "candidates_per_frame": {"mean": float(cand.mean()), "max": int(cand.max())}, "parallelism": f"frame-sharded replicas x{world}",
                    "l2": "each step streams >1 GB of activations through HBM (inputs+activations exceed the 126 MB L2)"},
         "p50_frame_latency_ms_b1": p50,
         "e2e": e2e, "gpu_launches": (eng.launches + (2 if is_seg else 0)) * args.steps,

@@ -118,6 +118,8 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
                  int32_t* status, const float* proto, int32_t* offsets_scratch);
 /* Byte offset and size of the proto buffer inside the bound workspace. */
 int ypb_proto_info(const ypb_engine* e, size_t* offset, size_t* bytes);
+/* Diagnostics: byte offset of the (B) int32 candidate counters of the selection stage inside the workspace. */
+int ypb_select_info(const ypb_engine* e, size_t* count_offset, int* cand_stride);
 
 /* Device-side error word (0 = ok); nonzero means a bounded pipeline wait inside a kernel gave up. */
 int ypb_device_error(ypb_engine* e, uint32_t* word);

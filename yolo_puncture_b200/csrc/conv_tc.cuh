@@ -1075,26 +1075,41 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
   const long long frame_bytes = (long long)H * W * 3, all_words = (frame_bytes * nB + 3) >> 2;
   const uint32_t* words = reinterpret_cast<const uint32_t*>(frames);  // cudaMalloc'd: at least 256-byte aligned
   uint32_t phase = 0;
-  const int t_begin = blockIdx.x * tiles_per_cta;
-  for (int tile = t_begin; tile < min(t_begin + tiles_per_cta, total_tiles); ++tile) {
+  const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, total_tiles);
+  // input patch of a tile: 17 rows; row r holds the aligned words covering bytes [g0, g0+99) of the frame row, g0 =
+  // byte offset of pixel (ih0+r, iw0); out-of-frame pixels are zeroed when the rows are converted below.
+  // The patch of tile t+1 is fetched into registers while tile t is converted, multiplied and stored.
+  constexpr int kPatchPerThread = (17 * kStemRowWords + 127) / 128;
+  uint32_t pre[kPatchPerThread];
+  auto fetch_patch = [&](int tile) {
     const int b = tile / tiles_per_img, t_in = tile - b * tiles_per_img;
     const int th = t_in / tiles_w;
-    const int oh0 = th * kStemTH, ow0 = (t_in - th * tiles_w) * kStemTW;
-    const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-    // input patch: 17 rows; row r holds the aligned words covering bytes [g0, g0+99) of the frame row, g0 = byte
-    // offset of pixel (ih0+r, iw0); out-of-frame pixels are zeroed when the rows are converted below
-    for (int i = tid; i < 17 * kStemRowWords; i += 128) {
+    const int ih0 = 2 * (th * kStemTH) - 1, iw0 = 2 * ((t_in - th * tiles_w) * kStemTW) - 1;
+#pragma unroll
+    for (int j = 0; j < kPatchPerThread; ++j) {
+      const int i = tid + 128 * j;
       const int r = i / kStemRowWords, wd = i - r * kStemRowWords;
       const int ih = ih0 + r;
       uint32_t v = 0;
-      if (ih >= 0 && ih < H) {
+      if (i < 17 * kStemRowWords && ih >= 0 && ih < H) {
         const long long g0 = (long long)b * frame_bytes + ((long long)ih * W + iw0) * 3;
         const long long wi = (g0 >> 2) + wd;  // arithmetic shift: floor, also for the (only) negative case g0 = -3
         if (wi >= 0 && wi < all_words) v = __ldg(words + wi);
       }
-      sIn[i] = v;
+      pre[j] = v;
     }
+  };
+  if (t_begin < t_end) fetch_patch(t_begin);
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int b = tile / tiles_per_img, t_in = tile - b * tiles_per_img;
+    const int th = t_in / tiles_w;
+    const int oh0 = th * kStemTH, ow0 = (t_in - th * tiles_w) * kStemTW;
+    const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+#pragma unroll
+    for (int j = 0; j < kPatchPerThread; ++j)
+      if (tid + 128 * j < 17 * kStemRowWords) sIn[tid + 128 * j] = pre[j];
     __syncthreads();
+    if (tile + 1 < t_end) fetch_patch(tile + 1);
     {  // im2col row of output pixel (ty, tx) = tid: k = (kh*3+kw)*3 + c_rgb, frame bytes are BGR
       const int ty = tid >> 4, tx = tid & 15;
       __nv_bfloat16 row[32];

@@ -164,7 +164,8 @@ constexpr int kNmsMaxDet = 300;
 //   det_lb  (B, max_det, 4)  the same boxes in letterboxed-input pixels (what non-retina masks crop with)
 //   keep    (B, max_det)     anchor index of each kept row
 //   coef    (B, max_det, nm) mask coefficients gathered from the head rows
-__global__ void __launch_bounds__(256)
+constexpr int kNmsThreads = 1024;
+__global__ void __launch_bounds__(kNmsThreads)
 nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict__ dbox, const int* __restrict__ dcls,
            unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_count, float iou_thr, int max_det,
            int max_nms, float max_wh, int e2e, const FrameXform* __restrict__ xf, float* __restrict__ det,
@@ -203,15 +204,17 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
     }
     if (threadIdx.x == 0) { s_nkept = nk; count[b] = nk; }
   } else {
-    // Greedy scan, 256 candidates (8 warps x 32 lanes) per round, in descending score order:
+    // Greedy scan, blockDim.x candidates (one per thread) per round, in descending score order:
     //  A. every thread tests its candidate against the boxes kept in earlier rounds (all warps in parallel);
-    //  B. warp 0..7 in turn resolves its own 32 candidates with ballots/shuffles (a live lane is kept and
-    //     suppresses the later lanes it overlaps), publishes the newly kept boxes, and the later warps test
+    //  B. the warps in turn resolve their own 32 candidates with ballots/shuffles (a live lane is kept and
+    //     suppresses the later lanes it overlaps), publish the newly kept boxes, and the later warps test
     //     their candidates against just those.  Equivalent to torchvision's sequential loop.
-    __shared__ int s_range[8][2];
+    // 1024 threads: an image with thousands of candidates needs few rounds (phase A costs nkept IoUs per round).
+    __shared__ int s_range[kNmsThreads / 32][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
     int nkept = 0;  // CTA-uniform
-    for (int i0 = 0; i0 < n && nkept < max_det; i0 += 256) {
+    for (int i0 = 0; i0 < n && nkept < max_det; i0 += blockDim.x) {
       const int i = i0 + threadIdx.x;
       bool alive = i < n;
       float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, area = 0.f, score = 0.f;
@@ -227,10 +230,12 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
         area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
       }
       for (int k = 0; k < nkept; ++k) {
+        if (!__any_sync(0xffffffffu, alive)) break;  // the whole warp is already suppressed (or past the end)
         if (alive && iou_tv(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area) > iou_thr)
           alive = false;
       }
-      for (int ws = 0; ws < 8; ++ws) {
+      const int nw_round = min(nwarps, (n - i0 + 31) >> 5);  // warps that hold candidates this round (CTA-uniform)
+      for (int ws = 0; ws < nw_round; ++ws) {
         if (warp == ws) {
           int nk = nkept;
           unsigned live = __ballot_sync(0xffffffffu, alive);

@@ -567,9 +567,15 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
     }
     case OP_SPPF: {
       const BufDesc& ib = e->bufs[op.in.buf];
-      const long long total = (long long)B * ib.H * ib.W * (op.in.C / 8);
-      sppf_pool_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-          reinterpret_cast<__nv_bfloat16*>(e->ws + ib.offset), B, ib.H, ib.W, op.in.C);
+      const size_t smem = (size_t)2 * ib.H * ib.W * 16;
+      if (smem > 200 * 1024) return fail(YPB_ERR_ARG, "sppf: feature map too large for the shared-memory pool kernel");
+      static size_t sppf_smem_set = 0;
+      if (smem > 48 * 1024 && smem > sppf_smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        sppf_smem_set = 200 * 1024;
+      }
+      sppf_pool_kernel<<<dim3(op.in.C / 8, B), 256, smem, st>>>(reinterpret_cast<__nv_bfloat16*>(e->ws + ib.offset), B, ib.H,
+                                                                ib.W, op.in.C);
       break;
     }
     case OP_DW: {
@@ -638,7 +644,7 @@ static int launch_select(ypb_engine* e, cudaStream_t st, const float* xform, con
                                                                               cand_count);
   }
   if (mid) CUDA_TRY(cudaEventRecord(mid, st));
-  nms_kernel<<<B, 256, 0, st>>>(head, g, dbox, dcls, keys, cand_count, prm->iou, prm->max_det, 30000,
+  nms_kernel<<<B, kNmsThreads, 0, st>>>(head, g, dbox, dcls, keys, cand_count, prm->iou, prm->max_det, 30000,
                                 prm->agnostic_nms ? 0.0f : 7680.0f, e->end2end ? 1 : 0,
                                 reinterpret_cast<const FrameXform*>(xform), det, det_lb, keep, coef, count);
   CUDA_TRY(cudaGetLastError());
@@ -1072,6 +1078,14 @@ int ypb_proto_info(const ypb_engine* e, size_t* offset, size_t* bytes) {
   return YPB_OK;
 }
 
+// Diagnostics: where the selection stage keeps its per-image candidate counters inside the workspace.
+int ypb_select_info(const ypb_engine* e, size_t* count_offset, int* cand_stride) {
+  if (!e || !e->planned || !count_offset || !cand_stride) return fail(YPB_ERR_ARG, "bad argument");
+  *count_offset = e->off_count;
+  *cand_stride = e->hg.cand_stride;
+  return YPB_OK;
+}
+
 int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int out_w, const float* det, const float* det_lb,
                  const float* coef, const int32_t* count, uint8_t* masks, int capacity, int32_t* status, const float* proto,
                  int32_t* offsets_scratch) {
@@ -1345,7 +1359,7 @@ int ypb_nms(void* cuda_stream, const float* boxes, const float* scores, const in
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(s);
   FrameXform* xf = reinterpret_cast<FrameXform*>(s + (size_t)B * cs * 8);
   nms_test_pack_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(boxes, scores, n_valid, B, N, cs, keys, xf);
-  nms_kernel<<<B, 256, 0, st>>>(nullptr, g, reinterpret_cast<const float4*>(boxes), cls, keys, n_valid, iou, max_det, 30000,
+  nms_kernel<<<B, kNmsThreads, 0, st>>>(nullptr, g, reinterpret_cast<const float4*>(boxes), cls, keys, n_valid, iou, max_det, 30000,
                                 agnostic ? 0.0f : 7680.0f, 0, xf, nullptr, nullptr, keep, nullptr, count);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;

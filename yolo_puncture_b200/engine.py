@@ -152,6 +152,13 @@ class Engine:
         self.det, self.det_lb, self.keep, self.coef, self.count = o.det, o.det_lb, o.keep, o.coef, o.count
         self._cur_out = o
 
+    def candidate_counts(self):
+        """Per-image candidate counts of the last infer() (diagnostics)."""
+        off, cs = C.c_size_t(), C.c_int()
+        check(self._lib.ypb_select_info(self._h, C.byref(off), C.byref(cs)))
+        start = self._ws_off + off.value
+        return self.ws[start:start + 4 * self.shape[0]].view(torch.int32)
+
     def proto_view(self):
         """The (B, H/4, W/4, 32) fp32 proto buffer of the last infer(), as a view of the workspace."""
         off, nbytes = C.c_size_t(), C.c_size_t()

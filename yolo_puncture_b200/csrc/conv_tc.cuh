@@ -651,10 +651,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           PROF_ADD(pw1);
         }
         tc_fence_after();
-        int first = 1;
+        uint32_t accf = 0;  // the first MMA of a tile overwrites the accumulators
         for (int c = 0; c < kchunks; ++c) {
           int ksteps = (p.Cin - c * 64) >> 4;
           if (ksteps > 4) ksteps = 4;
+          if (p.dbg & 4) ksteps = 0;
           for (int t = 0; t < p.ntaps; ++t) {
             if (++s == p.stages) s = 0;
             if (s == 0) ph ^= 1;
@@ -665,15 +666,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + s * stage_bytes);
-            const uint32_t sb = sa + a_bytes;
-            for (int sidx = 0; sidx < p.msub; ++sidx) {
+            const uint32_t b_lo = umma_desc_lo(sa + a_bytes);
+            constexpr uint32_t hi = umma_desc_hi(1024);
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx) {
+              if (sidx >= p.msub) break;
               const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.msub + sidx) * acc_stride);
-              const uint32_t sa_s = sa + (uint32_t)(sidx * p.sub_rows * 128);
-              for (int j = 0; j < ((p.dbg & 4) ? 0 : ksteps); ++j)
-                umma_bf16(d_tmem, umma_desc_sw128(sa_s + j * 32), umma_desc_sw128(sb + j * 32), idesc,
-                          (first && j == 0) ? 0u : 1u);
+              const uint32_t a_lo = umma_desc_lo(sa + (uint32_t)(sidx * p.sub_rows * 128));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j < ksteps) {
+                  umma_bf16_lohi(d_tmem, a_lo + 2 * j, hi, b_lo + 2 * j, hi, idesc, j == 0 ? accf : 1u);
+                }
+              }
             }
-            first = 0;
+            accf = 1;
             umma_commit(empty_bar + s);
           }
         }
@@ -914,7 +921,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           PROF_ADD(pw1);
         }
         tc_fence_after();
-        int first = 1;
+        uint32_t accf = 0;  // the first MMA of a tile overwrites the accumulators
         for (int c = 0; c < kchunks; ++c) {
           if (++sa == x.a_slots) sa = 0;
           if (sa == 0) pa ^= 1;
@@ -927,6 +934,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t a_base = smem_u32(sA + sa * x.a_bytes);
           int ksteps = (p.Cin - c * 64) >> 4;
           if (ksteps > 4) ksteps = 4;
+          if (p.dbg & 4) ksteps = 0;
           for (int g = 0; g < ngroups; ++g) {
             uint32_t g_base;
             int sb = 0;
@@ -947,15 +955,21 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int u = 0; u < x.b_group; ++u) {
               const int t = g * x.b_group + u;
               const int kh = t / 3, kw = t - kh * 3;
-              const uint32_t b_base = g_base + (uint32_t)(u * tap_bytes);
-              for (int sidx = 0; sidx < x.msub; ++sidx) {
-                const uint32_t a0 = a_base + (uint32_t)(((sidx * 16 + kh) * 10 + kw) * 128);
+              const uint32_t b_lo = umma_desc_lo(g_base + (uint32_t)(u * tap_bytes));
+#pragma unroll
+              for (int sidx = 0; sidx < 2; ++sidx) {
+                if (sidx >= x.msub) break;
+                const uint32_t a_lo = umma_desc_lo(a_base + (uint32_t)(((sidx * 16 + kh) * 10 + kw) * 128));
                 const uint32_t d_tmem = tmem_base + (uint32_t)((buf * x.msub + sidx) * acc_stride);
-                for (int j = 0; j < ((p.dbg & 4) ? 0 : ksteps); ++j)
-                  umma_bf16(d_tmem, umma_desc_sw128_sbo(a0 + j * 32, 1280), umma_desc_sw128(b_base + j * 32), idesc,
-                            (first && j == 0) ? 0u : 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (j < ksteps) {
+                    umma_bf16_lohi(d_tmem, a_lo + 2 * j, umma_desc_hi(1280), b_lo + 2 * j, umma_desc_hi(1024), idesc,
+                                   j == 0 ? accf : 1u);
+                  }
+                }
               }
-              first = 0;
+              accf = 1;
             }
             if (!x.b_stat) umma_commit(b_empty + sb);
           }

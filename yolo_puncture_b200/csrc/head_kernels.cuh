@@ -156,6 +156,18 @@ __device__ __forceinline__ float iou_tv(float ix1, float iy1, float ix2, float i
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
 }
 
+// iou_tv(...) > thr with an exact early-out: boxes that do not overlap have inter = 0, IoU = 0 (or NaN for two
+// zero-area boxes) and are never suppressed; with the per-class offset that is nearly every pair, and it skips the
+// IEEE division.
+__device__ __forceinline__ bool iou_gt(float ix1, float iy1, float ix2, float iy2, float iarea, float jx1, float jy1,
+                                       float jx2, float jy2, float jarea, float thr) {
+  const float xx1 = fmaxf(ix1, jx1), yy1 = fmaxf(iy1, jy1), xx2 = fminf(ix2, jx2), yy2 = fminf(iy2, jy2);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  if (!(w > 0.0f && h > 0.0f)) return thr < 0.0f;  // IoU is exactly 0 (or NaN): only a negative threshold is exceeded by 0
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter)) > thr;
+}
+
 constexpr int kNmsSmemKeys = 4096;
 constexpr int kNmsMaxDet = 300;
 
@@ -231,7 +243,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
       }
       for (int k = 0; k < nkept; ++k) {
         if (!__any_sync(0xffffffffu, alive)) break;  // the whole warp is already suppressed (or past the end)
-        if (alive && iou_tv(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area) > iou_thr)
+        if (alive && iou_gt(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area, iou_thr))
           alive = false;
       }
       const int nw_round = min(nwarps, (n - i0 + 31) >> 5);  // warps that hold candidates this round (CTA-uniform)
@@ -251,7 +263,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
               keep[(long long)b * max_det + nk] = anchor;
             }
             ++nk;
-            if (alive && lane > l && iou_tv(kx1, ky1, kx2, ky2, ka, x1, y1, x2, y2, area) > iou_thr) alive = false;
+            if (alive && lane > l && iou_gt(kx1, ky1, kx2, ky2, ka, x1, y1, x2, y2, area, iou_thr)) alive = false;
             live = __ballot_sync(0xffffffffu, alive) & ~((2u << l) - 1u);
           }
           if (lane == 0) { s_range[ws][0] = nkept; s_range[ws][1] = nk; }
@@ -260,7 +272,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
         const int kb = s_range[ws][0], ke = s_range[ws][1];
         if (warp > ws) {
           for (int k = kb; k < ke; ++k) {
-            if (alive && iou_tv(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area) > iou_thr)
+            if (alive && iou_gt(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area, iou_thr))
               alive = false;
           }
         }

@@ -245,30 +245,47 @@ def run_ours(args, wl):
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- e2e through the public API: host frames -> YOLO.predict -> boxes read back on the host ----
-    def e2e_step():
-        res = yolo.predict(frames, conf=CONF, iou=IOU, retina_masks=True, imgsz=imgsz, batch=B)
-        boxes = torch.cat([r.boxes.data for r in res]).cpu()
-        return res, boxes
+    # Headline arm: the frames sit in page-locked host memory (as the bench contract states; think of a capture /
+    # decode ring), so predict() copies them to the device from where they are.  Second arm: ordinary pageable numpy
+    # frames, which predict() first stages into its own pinned buffer with host threads.
+    pin = torch.empty((B, hw[0], hw[1], 3), dtype=torch.uint8).pin_memory()
+    pin_np = pin.numpy()
+    for i, f in enumerate(frames):
+        pin_np[i] = f
+    frames_pinned = [pin_np[i] for i in range(B)]
 
-    for _ in range(2):
-        e2e_step()
-    e2e_steps = max(3, min(args.steps, 10))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res, boxes = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = {"value": world * B * e2e_steps / e2e_s, "unit": "frames/s",
+    def run_e2e(frs):
+        def e2e_step():
+            res = yolo.predict(frs, conf=CONF, iou=IOU, retina_masks=True, imgsz=imgsz, batch=B)
+            boxes = torch.cat([r.boxes.data for r in res]).cpu()
+            return res, boxes
+
+        for _ in range(2):
+            e2e_step()
+        e2e_steps = max(3, min(args.steps, 10))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res, boxes = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        return world * B * e2e_steps / e2e_s, e2e_s / e2e_steps * 1e3, e2e_steps, boxes
+
+    v_pin, ms_pin, e2e_steps, boxes = run_e2e(frames_pinned)
+    v_page, ms_page, _, _ = run_e2e(frames)
+    e2e = {"value": v_pin, "unit": "frames/s",
            "h2d_bytes_per_step": B * H * W * 3 + B * 5 * 4, "d2h_bytes_per_step": B * 4 + int(boxes.numel()) * 4,
-           "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-           "note": "host cv2 letterbox + pinned H2D + engine + D2H of counts and boxes; masks stay on the device as in upstream Results"}
+           "steps": e2e_steps, "ms_per_step": ms_pin,
+           "pageable_frames": {"value": v_page, "ms_per_step": ms_page},
+           "note": "YOLO.predict() on host frames in pinned memory: H2D of the uint8 frames + engine + D2H of counts and "
+                   "boxes every step; masks stay on the device as in upstream Results.  pageable_frames = the same call on "
+                   "ordinary numpy frames (predict() stages them into pinned memory with host threads first)"}
 
     if rank != 0:
         if world > 1:

@@ -152,6 +152,10 @@ int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float*
             int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,
             int32_t* count /*(B)*/);
 size_t ypb_nms_scratch_bytes(int B, int N);
+/* Zero-staging path of predict(): is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / pinned torch
+   tensor)?  and: copy n such frames to consecutive device slots on `cuda_stream`, merging adjacent sources. */
+int ypb_host_is_pinned(const void* p, int* pinned);
+int ypb_h2d_frames(void* cuda_stream, void* dst_dev, const void* const* src, size_t bytes_each, int n);
 /* Host helper of the predict() pipeline: copy n frames into pinned staging memory with nthreads host threads. */
 int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads);
 /* Diagnostics: ceiling of the TMA operand-fetch path for an access pattern (csrc/tma_bench.cuh). */

@@ -9,6 +9,11 @@ mb = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 yolo = YOLO("yolov8s-seg", device=0)
 yolo.micro_batch = mb
 frames = [synth.synth_frame(i) for i in range(64)]
+if len(sys.argv) > 2 and sys.argv[2] == "pinned":
+    pin = torch.empty((64, 640, 640, 3), dtype=torch.uint8).pin_memory().numpy()
+    for i, f in enumerate(frames):
+        pin[i] = f
+    frames = [pin[i] for i in range(64)]
 for _ in range(3):
     yolo.predict(frames, conf=0.25, retina_masks=True, batch=64)
 torch.cuda.synchronize()
@@ -47,4 +52,5 @@ pr.enable()
 for _ in range(5):
     yolo.predict(frames, conf=0.25, retina_masks=True, batch=64)
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(30)
+pstats.Stats(pr).sort_stats("tottime").print_stats(14)

@@ -551,6 +551,16 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
 #undef EPI_MARK
 }
 
+// L2 prefetch of the residual row segment this lane's accumulator row will be added to (channels [n, n + ncols)).
+// Issued one tile ahead: the shortcut tensor was written several layers earlier and has left L2 by now, and a
+// DRAM-latency load inside the epilogue pass cannot be covered by the pass's own math.
+__device__ __forceinline__ void epi_prefetch_res(const ConvParams& p, bool valid, int qb, int rem, int n, int ncols) {
+  if (!valid) return;
+  const __nv_bfloat16* r = p.res + qb * p.res_img_stride + (long long)rem * p.res_pix_stride + p.res_c_off + n;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(r) & ~uintptr_t(127), a1 = reinterpret_cast<uintptr_t>(r + ncols) - 1;
+  for (uintptr_t a = a0; a <= a1; a += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+}
+
 // Cooperative copy of the (pre-scaled) bias into shared memory; call before the setup __syncthreads().
 __device__ __forceinline__ void epi_load_bias(const ConvParams& p, float* sbias) {
   const float sc = (p.act && p.out_mode != OUT_F32) ? 0.5f : 1.0f;
@@ -721,6 +731,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int b = fdiv(mt, p.fd_tpi), t_in = mt - b * tiles_per_img;
       const int th = fdiv(t_in, p.fd_tw);
       const int buf = acc & 1;
+      if (MODE == EPI_BF16_RES && tile + (int)gridDim.x < total_tiles && c_begin < c_end) {
+        const int tile2 = tile + gridDim.x;
+        const int mt2 = fdiv(tile2, p.fd_ns), n2 = (tile2 - mt2 * n_splits) * p.n_tile;
+        const int b2 = fdiv(mt2, p.fd_tpi), t2 = mt2 - b2 * tiles_per_img;
+        const int th2 = fdiv(t2, p.fd_tw);
+#pragma unroll
+        for (int sidx = 0; sidx < 2; ++sidx) {
+          if (sidx >= p.msub) break;
+          const int h = th2 * p.TH + rh_[sidx], w = (t2 - th2 * p.tiles_w) * p.TW + rw_[sidx];
+          const bool valid = (r < p.sub_rows) && (h < p.tH) && (w < p.tW);
+          int qb = b2, rem = h * p.tW + w;
+          if (flat) {
+            qb = fdiv(w, p.fd_hw);
+            rem = w - qb * p.img_HW;
+          }
+          epi_prefetch_res(p, valid, qb, rem, n2 + c_begin * 16, (c_end - c_begin) * 16);
+        }
+      }
       {
         PROF_T0();
         mbar_wait_bo(tfull_bar + buf, (acc >> 1) & 1, 4u, p.bo_epi);
@@ -1000,6 +1028,16 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int th = fdiv(t_in, p.fd_tw);
       const int h0 = th * 16 * x.msub, w0 = (t_in - th * p.tiles_w) * 8;
       const int buf = acc & 1;
+      if (MODE == EPI_BF16_RES && tile + (int)gridDim.x < total_tiles && c_begin < c_end) {
+        const int tile2 = tile + gridDim.x;
+        const int mt2 = fdiv(tile2, p.fd_ns), n2 = (tile2 - mt2 * n_splits) * p.n_tile;
+        const int b2 = fdiv(mt2, p.fd_tpi), t2 = mt2 - b2 * tiles_per_img;
+        const int th2 = fdiv(t2, p.fd_tw);
+        for (int sidx = 0; sidx < x.msub; ++sidx) {
+          const int h = th2 * 16 * x.msub + sidx * 16 + (r >> 3), w = (t2 - th2 * p.tiles_w) * 8 + (r & 7);
+          epi_prefetch_res(p, (h < p.tH) && (w < p.tW), b2, h * p.tW + w, n2 + c_begin * 16, (c_end - c_begin) * 16);
+        }
+      }
       {
         PROF_T0();
         mbar_wait_bo(tfull_bar + buf, (acc >> 1) & 1, 4u, p.bo_epi);

@@ -1328,6 +1328,36 @@ int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* byt
   return YPB_OK;
 }
 
+// Host helpers of the zero-staging path: frames that already live in page-locked memory (a capture / decode ring, a
+// pinned torch tensor) are copied to the device straight from where they are.
+int ypb_host_is_pinned(const void* p, int* pinned) {
+  if (!p || !pinned) return fail(YPB_ERR_ARG, "bad argument");
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *pinned = 0;
+    return YPB_OK;
+  }
+  *pinned = a.type == cudaMemoryTypeHost ? 1 : 0;
+  return YPB_OK;
+}
+
+// n frames of `bytes_each` bytes -> consecutive slots of dst_dev, one cudaMemcpyAsync per run of adjacent sources.
+int ypb_h2d_frames(void* cuda_stream, void* dst_dev, const void* const* src, size_t bytes_each, int n) {
+  if (!dst_dev || !src || n < 0) return fail(YPB_ERR_ARG, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  uint8_t* d = reinterpret_cast<uint8_t*>(dst_dev);
+  int i = 0;
+  while (i < n) {
+    int j = i + 1;
+    while (j < n && reinterpret_cast<const uint8_t*>(src[j]) == reinterpret_cast<const uint8_t*>(src[j - 1]) + bytes_each) ++j;
+    CUDA_TRY(cudaMemcpyAsync(d + (size_t)i * bytes_each, src[i], (size_t)(j - i) * bytes_each, cudaMemcpyHostToDevice, st));
+    i = j;
+  }
+  return YPB_OK;
+}
+
 size_t ypb_nms_scratch_bytes(int B, int N) {
   int cs = 1;
   while (cs < N) cs <<= 1;

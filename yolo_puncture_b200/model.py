@@ -273,6 +273,7 @@ class YOLO:
                 cmask = torch.from_numpy(words.view(np.int32)).to(self._device)
             direct = (shape[0], shape[1]) == (H, W)  # frames already have the network size: staging is a plain copy
             futs = None
+            pinned = False
             if direct:
                 frames_c = [f if f.flags["C_CONTIGUOUS"] else np.ascontiguousarray(f) for f in frames]
                 nbytes = H * W * 3
@@ -280,6 +281,14 @@ class YOLO:
                 src_ptrs = (ctypes.c_void_p * B)(*[f.ctypes.data for f in frames_c])
                 sizes = (ctypes.c_size_t * B)(*([nbytes] * B))
                 nthreads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+                # frames that already live in page-locked memory go to the device from where they are (no staging copy)
+                flag = ctypes.c_int(0)
+                pinned = True
+                for i in range(B):
+                    check(lib().ypb_host_is_pinned(src_ptrs[i], ctypes.byref(flag)))
+                    if not flag.value:
+                        pinned = False
+                        break
             else:
                 futs = [_pool().submit(letterbox_into, host[i], f, new_unpad, top, left) for i, f in enumerate(frames)]
             cs.wait_stream(main)
@@ -289,6 +298,17 @@ class YOLO:
 
             def enqueue_h2d(k):
                 lo, hi = k * mb, min((k + 1) * mb, B)
+                slot = k & 1
+                if pinned:
+                    with torch.cuda.stream(cs):
+                        if buf["in_free"][slot] is not None:
+                            cs.wait_event(buf["in_free"][slot])
+                        check(lib().ypb_h2d_frames(ctypes.c_void_p(cs.cuda_stream), ctypes.c_void_p(buf["dev"][slot].data_ptr()),
+                                                   ctypes.byref(src_ptrs, lo * ctypes.sizeof(ctypes.c_void_p)), nbytes, hi - lo))
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
+                    h2d_done.append(ev)
+                    return
                 if direct:  # native multi-threaded copy into pinned memory (ctypes drops the GIL)
                     vp = ctypes.sizeof(ctypes.c_void_p)
                     check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, lo * vp), ctypes.byref(src_ptrs, lo * vp),
@@ -296,7 +316,6 @@ class YOLO:
                 else:
                     for fu in futs[lo:hi]:
                         fu.result()
-                slot = k & 1
                 with torch.cuda.stream(cs):
                     if buf["in_free"][slot] is not None:
                         cs.wait_event(buf["in_free"][slot])

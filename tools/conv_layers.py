@@ -14,6 +14,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if "--prof" in sys.argv:  # wait-cycle accounting lives in the profiling build: python -m yolo_puncture_b200.build --prof
+    sys.argv.remove("--prof")
+    os.environ["YPB_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yolo_puncture_b200",
+                                         "libypb200_prof.so")
 from yolo_puncture_b200._lib import check, lib  # noqa: E402
 
 B = 64

@@ -84,6 +84,8 @@ def lib():
     global _LIB
     if _LIB is None:
         path = _build.ensure_built()
+        if os.environ.get("YPB_LIB"):  # diagnostics: e.g. the profiling build libypb200_prof.so (tools/conv_layers.py)
+            path = os.environ["YPB_LIB"]
         if not os.path.exists(path):
             raise YpbError(f"{path} missing: the CUDA extension is required, there is no fallback")
         handle = C.CDLL(path)

@@ -36,7 +36,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+LIB_PROF = os.path.join(HERE, "libypb200_prof.so")
+
+
+def build(force=False, verbose=False, prof=False):
+    """prof=True builds libypb200_prof.so: the same library with the per-role wait-cycle / epilogue-phase accounting
+    compiled in (-DYPB_PROF=1); tools/conv_layers.py loads it through YPB_LIB."""
+    if prof:
+        nvcc = _nvcc()
+        res = subprocess.run([nvcc, *NVCC_FLAGS, "-DYPB_PROF=1", "-o", LIB_PROF, os.path.join(CSRC, "ypb200.cu")],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        return LIB_PROF
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
@@ -58,4 +70,4 @@ def ensure_built():
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv))

@@ -214,7 +214,8 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   if (st2 > 8) st2 = 8;
   if (st2 < 2) st2 = 2;
   L->stages2 = st2;
-  L->smem2 = 1024 + st2 * stage2 + 256 + kEpiWarps * kEpiStageBytes + conv_bias_smem(d.cout);
+  const int epi_smem = kEpiWarps * epi_stage_bytes(d.out_mode == OUT_F32);
+  L->smem2 = 1024 + st2 * stage2 + 256 + epi_smem + conv_bias_smem(d.cout);
   if (L->smem2 < 120 * 1024) L->smem2 = 120 * 1024;
   p.out_mode = d.out_mode; p.act = d.act;
   p.dbg = getenv("YPB_DBG") ? atoi(getenv("YPB_DBG")) : 0;
@@ -228,7 +229,7 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
     // Operand bytes fetched from L2 per launch are what bounds these kernels (~7 TB/s L2->SM on B200): pick the
     // cheapest of {per-tap boxes, halo tiles with msub = 1 or 2, resident or streamed weights}.
     const int kch = (d.cin + 63) / 64;
-    const long avail = 227 * 1024 - 1024 - 512 - kEpiWarps * kEpiStageBytes - conv_bias_smem(d.cout);
+    const long avail = 227 * 1024 - 1024 - 512 - epi_smem - conv_bias_smem(d.cout);
     const long b_slot = (long)p.n_tile * 128, b_total = 9L * kch * b_slot;
     const double waste_taps = (double)L->total_tiles * p.msub * 128 - (double)d.B * oH * oW * splits;
     const double cost_taps = (double)L->total_tiles * k_iters * (p.msub * kATileBytes + b_slot) + waste_taps * 9.0 * kch * 64.0;
@@ -268,7 +269,7 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
           L->x3.msub = msub; L->x3.a_slots = (int)a_slots; L->x3.a_bytes = (int)a_bytes; L->x3.halo_rows = halo_rows;
           L->x3.b_slots = (int)b_slots; L->x3.b_group = b_group; L->x3.b_stat = stat; L->x3.b_bytes = (int)b_bytes;
           L->tiles_h3 = th3; L->tiles_w3 = tw3; L->total_tiles3 = (int)tiles3;
-          L->smem3 = (int)(1024 + a_slots * a_bytes + b_bytes + 512 + kEpiWarps * kEpiStageBytes + conv_bias_smem(d.cout));
+          L->smem3 = (int)(1024 + a_slots * a_bytes + b_bytes + 512 + epi_smem + conv_bias_smem(d.cout));
         }
       }
     }
@@ -359,7 +360,7 @@ static cudaError_t conv_launch_init() {
   if (e != cudaSuccess) return e;                                                                                 \
   e = cudaFuncSetAttribute(conv3_halo_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);     \
   if (e != cudaSuccess) return e;
-  YPB_SET_SMEM(EPI_BF16) YPB_SET_SMEM(EPI_BF16_RES) YPB_SET_SMEM(EPI_F32) YPB_SET_SMEM(EPI_SHUFFLE2)
+  YPB_SET_SMEM(0) YPB_SET_SMEM(1) YPB_SET_SMEM(2) YPB_SET_SMEM(3) YPB_SET_SMEM(4) YPB_SET_SMEM(5) YPB_SET_SMEM(6) YPB_SET_SMEM(7)
 #undef YPB_SET_SMEM
   int dev = 0;
   cudaGetDevice(&dev);
@@ -399,24 +400,25 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
     p3.tiles_h = L.tiles_h3; p3.tiles_w = L.tiles_w3;
     conv_set_fastdiv(p3, L.n_splits);
     const int grid3 = L.total_tiles3 < num_sms ? L.total_tiles3 : num_sms;
-    switch (epi_mode_of(p3.out_mode, p3.res != nullptr)) {
-      case EPI_BF16: conv3_halo_kernel<EPI_BF16><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
-      case EPI_BF16_RES: conv3_halo_kernel<EPI_BF16_RES><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
-      case EPI_F32: conv3_halo_kernel<EPI_F32><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
-      default: conv3_halo_kernel<EPI_SHUFFLE2><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
+#define YPB_HALO_CASE(MODE) \
+  case MODE: conv3_halo_kernel<MODE><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
+    switch (epi_mode_of(p3.out_mode, p3.res != nullptr, p3.act)) {
+      YPB_HALO_CASE(0) YPB_HALO_CASE(1) YPB_HALO_CASE(2) YPB_HALO_CASE(3) YPB_HALO_CASE(4) YPB_HALO_CASE(5) YPB_HALO_CASE(6)
+      YPB_HALO_CASE(7)
     }
+#undef YPB_HALO_CASE
     return cudaGetLastError();
   }
   ConvParams p2 = L.p;
   p2.stages = L.stages2;
   conv_set_fastdiv(p2, L.n_splits);
   const int grid = L.total_tiles < num_sms ? L.total_tiles : num_sms;
-  switch (epi_mode_of(p2.out_mode, p2.res != nullptr)) {
-    case EPI_BF16: conv_tc2_kernel<EPI_BF16><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
-    case EPI_BF16_RES: conv_tc2_kernel<EPI_BF16_RES><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
-    case EPI_F32: conv_tc2_kernel<EPI_F32><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
-    default: conv_tc2_kernel<EPI_SHUFFLE2><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
+#define YPB_TC2_CASE(MODE) \
+  case MODE: conv_tc2_kernel<MODE><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
+  switch (epi_mode_of(p2.out_mode, p2.res != nullptr, p2.act)) {
+    YPB_TC2_CASE(0) YPB_TC2_CASE(1) YPB_TC2_CASE(2) YPB_TC2_CASE(3) YPB_TC2_CASE(4) YPB_TC2_CASE(5) YPB_TC2_CASE(6) YPB_TC2_CASE(7)
   }
+#undef YPB_TC2_CASE
   return cudaGetLastError();
 }
 

@@ -129,6 +129,10 @@ __device__ __forceinline__ void conv_epilogue_store16(const ConvParams& p, int q
 // [0] producer-0 wait empty  [1] MMA wait full  [2] MMA wait tempty  [3] epilogue-warp-0 wait tfull
 // [4] epilogue-warp-0 drain  [5] CTA lifetime  [6] MMA wait weights (halo kernel)  [7] CTAs
 __device__ unsigned long long g_conv_prof[16];  // [8..13] epilogue pass phases (all epilogue warps): ld+wait, release, math, stage, write-out, passes
+#ifndef YPB_PROF
+#define YPB_PROF 0  // 1: build the wait-cycle / epilogue-phase accounting in (libypb200_prof.so, tools/conv_layers.py --dbg 8)
+#endif
+constexpr bool kProf = YPB_PROF != 0;
 #define PROF_T0() const long long _pt0 = prof ? clock64() : 0
 #define PROF_ADD(var) do { if (prof) var += clock64() - _pt0; } while (0)
 
@@ -271,12 +275,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Roles: warp 0 TMA producer, warp 1 MMA issuer (also owns TMEM), warps 2.. = kEpiWarps epilogue warps
 // (warp w reads TMEM lanes 32*(w%4)..+31; with 8 epilogue warps each lane group's columns are split in two).
 // ------------------------------------------------------------------------------------------------
-constexpr int kEpiWarps = 8;
+#ifndef YPB_EPI_WARPS
+#define YPB_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = YPB_EPI_WARPS;   // 4 lane groups x kEpiParts warps; each SM sub-partition hosts kEpiParts of them
+constexpr int kEpiParts = kEpiWarps / 4;
 constexpr int kProdWarps = 3;   // TMA producer warps: one thread sustains only ~1 box load per 0.35 us (tools/tma_bench.py)
 constexpr int kMmaWarp = kProdWarps;
 constexpr int kEpiWarp0 = kProdWarps + 1;
 constexpr int kConv2Threads = 32 * (kProdWarps + 1 + kEpiWarps);
-constexpr int kEpiStageBytes = 32 * (128 + 16);  // per-warp staging tile: 32 rows x (<=128 B + 16 B pad)
+constexpr int kEpiStageBytes = 32 * (128 + 16);  // per-warp staging tile of an fp32 pass: 32 rows x (128 B + 16 B pad)
+// per-warp staging bytes by output mode: a bf16 pass stages 32 rows x (64 B + 16 B pad)
+__host__ __device__ constexpr int epi_stage_bytes(bool f32) { return f32 ? 32 * (128 + 16) : 32 * (64 + 16); }
+// Which 128-row sub-tile and which 16-column chunks [cb, ce) of it epilogue part `part` drains (nch = n_tile / 16).
+// The kEpiParts warps of a TMEM lane group are spread over the msub sub-tiles first, then over column ranges
+// (multiples of 32 columns when there are enough of them).
+__host__ __device__ inline void epi_split(int msub, int nch, int part, int* sidx, int* cb, int* ce) {
+  const int pps = kEpiParts / msub < 1 ? 1 : kEpiParts / msub;  // parts per sub-tile
+  *sidx = part / pps;
+  const int q = part - *sidx * pps;
+  int per = (nch + pps - 1) / pps;
+  if (nch >= 2 * pps) per = (per + 1) & ~1;
+  *cb = q * per < nch ? q * per : nch;
+  *ce = *cb + per < nch ? *cb + per : nch;
+  if (*sidx >= msub) { *sidx = 0; *cb = *ce = 0; }  // more parts than work: idle
+}
 __host__ __device__ inline int conv_bias_smem(int cout) { return (cout * 4 + 15) & ~15; }
 
 __host__ __device__ inline int conv2_acc_stride(int n_tile) { return (n_tile + 31) & ~31; }
@@ -305,9 +328,12 @@ __host__ __device__ inline int conv2_smem_bytes(int n_tile, int stages) {
 // ~2500 cycles per 32x32 pass and bounded every layer with K <= 256, although TMEM reads (64 B/clk/SM) and the SFU
 // (16 SiLU/clk/SM) allow ~16 elements per clock.
 // ------------------------------------------------------------------------------------------------
-enum EpiMode : int { EPI_BF16 = 0, EPI_BF16_RES = 1, EPI_F32 = 2, EPI_SHUFFLE2 = 3 };
-__host__ __device__ inline int epi_mode_of(int out_mode, bool has_res) {
-  return out_mode == OUT_F32 ? EPI_F32 : out_mode == OUT_SHUFFLE2_BF16 ? EPI_SHUFFLE2 : has_res ? EPI_BF16_RES : EPI_BF16;
+// MODE = output layout (bits 0-1) | SiLU (bit 2): both are compile-time so that the pass is one straight-line stream and
+// the x/2 pre-scale of the SiLU is an immediate operand (the immediate form of FFMA issues at twice the rate).
+enum EpiMode : int { EPI_BF16 = 0, EPI_BF16_RES = 1, EPI_F32 = 2, EPI_SHUFFLE2 = 3, EPI_ACT = 4 };
+__host__ __device__ inline int epi_mode_of(int out_mode, bool has_res, int act) {
+  const int lay = out_mode == OUT_F32 ? EPI_F32 : out_mode == OUT_SHUFFLE2_BF16 ? EPI_SHUFFLE2 : has_res ? EPI_BF16_RES : EPI_BF16;
+  return lay | (act ? EPI_ACT : 0);
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -364,17 +390,17 @@ __device__ __forceinline__ void epi_row_deltas(int delta, int lane, int (&dl)[PP
 template <int NC, int MODE>
 __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32_t (&v)[32], uint32_t stage_sa, uint32_t sb_sa,
                                                int lane, int n, long long base, long long res_base,
-                                               const int (&dl)[MODE == EPI_F32 ? NC / 4 : NC / 8],
-                                               const int (&rl)[MODE == EPI_F32 ? NC / 4 : NC / 8], bool prof, long long& pt,
+                                               const int (&dl)[(MODE & 3) == EPI_F32 ? NC / 4 : NC / 8],
+                                               const int (&rl)[(MODE & 3) == EPI_F32 ? NC / 4 : NC / 8], bool prof, long long& pt,
                                                long long (&pacc)[6]) {
 #define EPI_MARK(k) do { if (prof) { const long long _n = clock64(); pacc[(k) - 8] += _n - pt; pt = _n; } } while (0)
-  constexpr bool F32 = MODE == EPI_F32;
+  constexpr int LAY = MODE & 3;
+  constexpr bool F32 = LAY == EPI_F32, ACT = (MODE & EPI_ACT) != 0;
   constexpr int PPR = F32 ? NC / 4 : NC / 8;  // 16-byte pieces per staged row
   constexpr int pitch = PPR * 16 + 16;
-  const float sc = (p.act && !F32) ? 0.5f : 1.0f;
   // residual: coalesced 16-byte loads, issued first so their latency hides behind the math
   uint4 rres[PPR];
-  if (MODE == EPI_BF16_RES) {
+  if (LAY == EPI_BF16_RES) {
 #pragma unroll
     for (int i = 0; i < PPR; ++i) {
       const int pc = (lane + 32 * i) % PPR;
@@ -386,12 +412,19 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
 #pragma unroll
   for (int i = 0; i < NC / 4; ++i) {
     const float4 b4 = lds128_ro(sb_sa + 16 * i);
-    y[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), sc, b4.x);
-    y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), sc, b4.y);
-    y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), sc, b4.z);
-    y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), sc, b4.w);
+    if (ACT && !F32) {  // h = x/2 (the bias copy is pre-halved)
+      y[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), 0.5f, b4.x);
+      y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), 0.5f, b4.y);
+      y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), 0.5f, b4.z);
+      y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), 0.5f, b4.w);
+    } else {
+      y[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+      y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+      y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+      y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+    }
   }
-  if (p.act && !(p.dbg & 1)) {
+  if (ACT && !(p.dbg & 1)) {
     if (!F32) {
 #pragma unroll
       for (int i = 0; i < NC; ++i) {  // y holds h = x/2: SiLU(x) = h + h*tanh(h)
@@ -441,7 +474,7 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
     } else {
       const int nn = n + pc * 8;
       long long coff = nn;
-      if (MODE == EPI_SHUFFLE2) {  // ConvTranspose2d(2,2): channel group g = (dy, dx) of the 2x2 output block
+      if (LAY == EPI_SHUFFLE2) {  // ConvTranspose2d(2,2): channel group g = (dy, dx) of the 2x2 output block
         const int cq = p.Cout >> 2;
         const int g = nn / cq, c = nn - g * cq;
         coff = ((long long)(g >> 1) * (2 * p.img_W) + (g & 1)) * p.out_pix_stride + c;
@@ -449,7 +482,7 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + base + coff;
 #pragma unroll
       for (int i = 0; i < PPR; ++i) {
-        if (MODE == EPI_BF16_RES) {
+        if (LAY == EPI_BF16_RES) {
           // y = bf16(act(...)) first, then bf16(y + res): the same two roundings as storing the conv output and
           // adding the shortcut afterwards (Bottleneck: x + cv2(cv1(x))).
           const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val[i]);
@@ -476,21 +509,22 @@ template <int MODE>
 __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa, uint32_t sbias_sa, int lane, int c_begin,
                                           int c_end, uint32_t t_addr, int n0, bool valid, int qb, int rem,
                                           uint64_t* release, long long (&pacc)[6]) {
-  constexpr bool F32 = MODE == EPI_F32;
+  constexpr int LAY = MODE & 3;
+  constexpr bool F32 = LAY == EPI_F32;
   constexpr int P32 = F32 ? 8 : 4, P16 = F32 ? 4 : 2;  // 16-byte pieces per staged row of a 32- / 16-column pass
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-  if (c_begin >= c_end || vmask == 0u) {  // nothing to read (n_tile == 16: second warp of the lane group; tile rows all padding)
+  if (c_begin >= c_end || vmask == 0u) {  // nothing to read (more warps than column chunks; tile rows all padding)
     __syncwarp();
     if (lane == 0 && release != nullptr) mbar_arrive(release);
     return;
   }
-  const bool prof = (p.dbg & 8) != 0 && lane == 0;
+  const bool prof = kProf && (p.dbg & 8) != 0 && lane == 0;
   long long pt = prof ? clock64() : 0;
 #define EPI_MARK(k) do { if (prof) { const long long _n = clock64(); pacc[(k) - 8] += _n - pt; pt = _n; } } while (0)
   // (qb, rem) = image and pixel-within-image of this lane's row; element offset of channel 0 of that row in the
   // output (pixel-shuffle: of sub-pixel (0,0))
   long long off_row;
-  if (MODE == EPI_SHUFFLE2) {
+  if (LAY == EPI_SHUFFLE2) {
     const int ph = fdiv(rem, p.fd_iw), pw = rem - ph * p.img_W;
     off_row = qb * p.out_img_stride + ((long long)(2 * ph) * (2 * p.img_W) + 2 * pw) * p.out_pix_stride + p.out_c_off;
   } else {
@@ -501,7 +535,7 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
   const int delta = valid ? (int)(off_row - base) : -1;
   long long res_base = 0;
   int rdelta = -1;
-  if (MODE == EPI_BF16_RES) {
+  if (LAY == EPI_BF16_RES) {
     const long long res_row = qb * p.res_img_stride + (long long)rem * p.res_pix_stride + p.res_c_off;
     res_base = __shfl_sync(0xffffffffu, res_row, src);
     rdelta = valid ? (int)(res_row - res_base) : -1;
@@ -509,43 +543,44 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
   const int col0 = c_begin * 16, ncols = (c_end - c_begin) * 16;
   const int n32 = ncols >> 5;
   const bool tail16 = (ncols & 31) != 0;
-  uint32_t v[32];
+  uint32_t va[32], vb[32];  // ping-pong accumulator registers: the tcgen05.ld of pass k+1 is in flight during pass k
   if (n32 > 0) {
     int dl[P32], rl[P32];
     epi_row_deltas<P32>(delta, lane, dl);
-    if (MODE == EPI_BF16_RES) epi_row_deltas<P32>(rdelta, lane, rl);
-    tmem_ldn<32>(t_addr + (uint32_t)col0, v);
-    for (int k = 0; k < n32; ++k) {
+    if (LAY == EPI_BF16_RES) epi_row_deltas<P32>(rdelta, lane, rl);
+    tmem_ldn<32>(t_addr + (uint32_t)col0, va);
+    auto pass32 = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int k) {
       const int col = col0 + 32 * k;
       tmem_ld_wait();
       EPI_MARK(8);
-      uint32_t w[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) w[i] = v[i];
       if (k + 1 < n32) {
-        tmem_ldn<32>(t_addr + (uint32_t)(col + 32), v);  // in flight during this pass's math, staging and write-out
+        tmem_ldn<32>(t_addr + (uint32_t)(col + 32), nxt);
       } else if (!tail16 && release != nullptr) {
         // last TMEM read of this tile has landed (tcgen05.wait::ld): hand the accumulator back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive(release);
       }
       EPI_MARK(9);
-      epi_store_pass<32, MODE>(p, w, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl,
+      epi_store_pass<32, MODE>(p, cur, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl,
                                prof, pt, pacc);
+    };
+    for (int k = 0; k < n32; k += 2) {
+      pass32(va, vb, k);
+      if (k + 1 < n32) pass32(vb, va, k + 1);
     }
   }
   if (tail16) {
     const int col = col0 + 32 * n32;
     int dl[P16], rl[P16];
     epi_row_deltas<P16>(delta, lane, dl);
-    if (MODE == EPI_BF16_RES) epi_row_deltas<P16>(rdelta, lane, rl);
-    tmem_ldn<16>(t_addr + (uint32_t)col, v);
+    if (LAY == EPI_BF16_RES) epi_row_deltas<P16>(rdelta, lane, rl);
+    tmem_ldn<16>(t_addr + (uint32_t)col, va);
     tmem_ld_wait();
     if (release != nullptr) {
       __syncwarp();
       if (lane == 0) mbar_arrive(release);
     }
-    epi_store_pass<16, MODE>(p, v, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl, prof,
+    epi_store_pass<16, MODE>(p, va, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl, prof,
                              pt, pacc);
   }
 #undef EPI_MARK
@@ -587,7 +622,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int acc_stride = conv2_acc_stride(p.n_tile);
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * p.msub * acc_stride)) tmem_cols <<= 1;
-  const bool prof = (p.dbg & 8) != 0;
+  const bool prof = kProf && (p.dbg & 8) != 0;
   const long long prof_start = prof ? clock64() : 0;
   long long pw0 = 0, pw1 = 0;
 
@@ -605,7 +640,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
-  float* sbias = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 256 + kEpiWarps * kEpiStageBytes);
+  constexpr int kStageB = epi_stage_bytes((MODE & 3) == EPI_F32);
+  float* sbias = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 256 + kEpiWarps * kStageB);
   epi_load_bias(p, sbias);
   tc_fence_before();
   __syncthreads();
@@ -710,44 +746,33 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // along the channel dimension, so every store instruction covers whole 128-byte lines of NHWC rows
     // (a thread-per-row store would touch 32 different lines per instruction).
     const int lg = warp & 3;
-    const int part = (warp - kEpiWarp0) >> 2;
-    const int nchunks = p.n_tile >> 4;
-    const int half = (nchunks + 1) >> 1;
-    const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
-    uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - kEpiWarp0) * kEpiStageBytes;
+    int sidx, c_begin, c_end;  // this warp's sub-tile and 16-column chunk range
+    epi_split(p.msub, p.n_tile >> 4, (warp - kEpiWarp0) >> 2, &sidx, &c_begin, &c_end);
+    uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - kEpiWarp0) * kStageB;
     const int r = lg * 32 + lane;
     long long pacc[6] = {0, 0, 0, 0, 0, 0};
     const bool flat = p.ntaps == 1;  // 1x1: the tile is 128 * msub consecutive pixels of the flattened batch
-    int rh_[2], rw_[2];              // this lane's row of sub-tile 0 / 1 inside the CTA rectangle (tile-invariant)
-#pragma unroll
-    for (int sidx = 0; sidx < 2; ++sidx) {
-      const int R = sidx * p.sub_rows + r;
-      rh_[sidx] = R / p.TW;
-      rw_[sidx] = R - rh_[sidx] * p.TW;
-    }
+    const int R = sidx * p.sub_rows + r;  // this lane's row inside the CTA rectangle (tile-invariant)
+    const int rh = R / p.TW, rw = R - rh * p.TW;
     int acc = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
       const int mt = fdiv(tile, p.fd_ns), n0 = (tile - mt * n_splits) * p.n_tile;
       const int b = fdiv(mt, p.fd_tpi), t_in = mt - b * tiles_per_img;
       const int th = fdiv(t_in, p.fd_tw);
       const int buf = acc & 1;
-      if (MODE == EPI_BF16_RES && tile + (int)gridDim.x < total_tiles && c_begin < c_end) {
+      if ((MODE & 3) == EPI_BF16_RES && tile + (int)gridDim.x < total_tiles && c_begin < c_end) {
         const int tile2 = tile + gridDim.x;
         const int mt2 = fdiv(tile2, p.fd_ns), n2 = (tile2 - mt2 * n_splits) * p.n_tile;
         const int b2 = fdiv(mt2, p.fd_tpi), t2 = mt2 - b2 * tiles_per_img;
         const int th2 = fdiv(t2, p.fd_tw);
-#pragma unroll
-        for (int sidx = 0; sidx < 2; ++sidx) {
-          if (sidx >= p.msub) break;
-          const int h = th2 * p.TH + rh_[sidx], w = (t2 - th2 * p.tiles_w) * p.TW + rw_[sidx];
-          const bool valid = (r < p.sub_rows) && (h < p.tH) && (w < p.tW);
-          int qb = b2, rem = h * p.tW + w;
-          if (flat) {
-            qb = fdiv(w, p.fd_hw);
-            rem = w - qb * p.img_HW;
-          }
-          epi_prefetch_res(p, valid, qb, rem, n2 + c_begin * 16, (c_end - c_begin) * 16);
+        const int h = th2 * p.TH + rh, w = (t2 - th2 * p.tiles_w) * p.TW + rw;
+        const bool valid = (r < p.sub_rows) && (h < p.tH) && (w < p.tW);
+        int qb = b2, rem = h * p.tW + w;
+        if (flat) {
+          qb = fdiv(w, p.fd_hw);
+          rem = w - qb * p.img_HW;
         }
+        epi_prefetch_res(p, valid, qb, rem, n2 + c_begin * 16, (c_end - c_begin) * 16);
       }
       {
         PROF_T0();
@@ -756,10 +781,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_after();
       PROF_T0();
-#pragma unroll
-      for (int sidx = 0; sidx < 2; ++sidx) {
-        if (sidx >= p.msub) break;
-        const int h = th * p.TH + rh_[sidx], w = (t_in - th * p.tiles_w) * p.TW + rw_[sidx];
+      {
+        const int h = th * p.TH + rh, w = (t_in - th * p.tiles_w) * p.TW + rw;
         const bool valid = (r < p.sub_rows) && (h < p.tH) && (w < p.tW);
         int qb = 0, rem = 0;
         if (valid) {
@@ -773,7 +796,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * p.msub + sidx) * acc_stride);
         epi_drain<MODE>(p, smem_u32(stage), smem_u32(sbias), lane, c_begin, c_end, t_addr, n0, valid, qb, rem,
-                        sidx == p.msub - 1 ? tempty_bar + buf : nullptr, pacc);
+                        tempty_bar + buf, pacc);
       }
       PROF_ADD(pw1);
     }
@@ -861,7 +884,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int ngroups = 9 / x.b_group;  // weight boxes per 64-channel chunk
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(2 * x.msub * acc_stride)) tmem_cols <<= 1;
-  const bool prof = (p.dbg & 8) != 0;
+  const bool prof = kProf && (p.dbg & 8) != 0;
   const long long prof_start = prof ? clock64() : 0;
   long long pw0 = 0, pw1 = 0, pw2 = 0;
 
@@ -875,7 +898,8 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
-  float* sbias = reinterpret_cast<float*>(stage_base + kEpiWarps * kEpiStageBytes);
+  constexpr int kStageB = epi_stage_bytes((MODE & 3) == EPI_F32);
+  float* sbias = reinterpret_cast<float*>(stage_base + kEpiWarps * kStageB);
   epi_load_bias(p, sbias);
   tc_fence_before();
   __syncthreads();
@@ -1014,11 +1038,9 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===================== epilogue =====================
     const int lg = warp & 3;
-    const int part = (warp - kEpiWarp0) >> 2;
-    const int nchunks = p.n_tile >> 4;
-    const int half = (nchunks + 1) >> 1;
-    const int c_begin = part == 0 ? 0 : half, c_end = part == 0 ? half : nchunks;
-    uint8_t* stage = stage_base + (warp - kEpiWarp0) * kEpiStageBytes;
+    int sidx, c_begin, c_end;  // this warp's sub-tile and 16-column chunk range
+    epi_split(x.msub, p.n_tile >> 4, (warp - kEpiWarp0) >> 2, &sidx, &c_begin, &c_end);
+    uint8_t* stage = stage_base + (warp - kEpiWarp0) * kStageB;
     const int r = lg * 32 + lane;
     long long pacc[6] = {0, 0, 0, 0, 0, 0};
     int acc = 0;
@@ -1028,15 +1050,13 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int th = fdiv(t_in, p.fd_tw);
       const int h0 = th * 16 * x.msub, w0 = (t_in - th * p.tiles_w) * 8;
       const int buf = acc & 1;
-      if (MODE == EPI_BF16_RES && tile + (int)gridDim.x < total_tiles && c_begin < c_end) {
+      if ((MODE & 3) == EPI_BF16_RES && tile + (int)gridDim.x < total_tiles && c_begin < c_end) {
         const int tile2 = tile + gridDim.x;
         const int mt2 = fdiv(tile2, p.fd_ns), n2 = (tile2 - mt2 * n_splits) * p.n_tile;
         const int b2 = fdiv(mt2, p.fd_tpi), t2 = mt2 - b2 * tiles_per_img;
         const int th2 = fdiv(t2, p.fd_tw);
-        for (int sidx = 0; sidx < x.msub; ++sidx) {
-          const int h = th2 * 16 * x.msub + sidx * 16 + (r >> 3), w = (t2 - th2 * p.tiles_w) * 8 + (r & 7);
-          epi_prefetch_res(p, (h < p.tH) && (w < p.tW), b2, h * p.tW + w, n2 + c_begin * 16, (c_end - c_begin) * 16);
-        }
+        const int h = th2 * 16 * x.msub + sidx * 16 + (r >> 3), w = (t2 - th2 * p.tiles_w) * 8 + (r & 7);
+        epi_prefetch_res(p, (h < p.tH) && (w < p.tW), b2, h * p.tW + w, n2 + c_begin * 16, (c_end - c_begin) * 16);
       }
       {
         PROF_T0();
@@ -1045,12 +1065,12 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_after();
       PROF_T0();
-      for (int sidx = 0; sidx < x.msub; ++sidx) {
+      {
         const int h = h0 + sidx * 16 + (r >> 3), w = w0 + (r & 7);
         const bool valid = (h < p.tH) && (w < p.tW);
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * x.msub + sidx) * acc_stride);
         epi_drain<MODE>(p, smem_u32(stage), smem_u32(sbias), lane, c_begin, c_end, t_addr, n0, valid, b,
-                        valid ? h * p.tW + w : 0, sidx == x.msub - 1 ? tempty_bar + buf : nullptr, pacc);
+                        valid ? h * p.tW + w : 0, tempty_bar + buf, pacc);
       }
       PROF_ADD(pw1);
     }
@@ -1204,7 +1224,7 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
       const int oh = oh0 + (r >> 4), ow = ow0 + (r & 15);
       const bool valid = oh < oH && ow < oW;
       long long pacc[6] = {0, 0, 0, 0, 0, 0};
-      epi_drain<EPI_BF16>(p, smem_u32(sStage + warp * (alias_stage ? 4096 : kEpiStageBytes)), smem_u32(sbias), lane, 0, C0 >> 4,
+      epi_drain<EPI_BF16 | EPI_ACT>(p, smem_u32(sStage + warp * (alias_stage ? 4096 : kEpiStageBytes)), smem_u32(sbias), lane, 0, C0 >> 4,
                 tmem_base + ((uint32_t)(warp * 32) << 16), 0, valid, b, valid ? oh * oW + ow : 0, nullptr, pacc);
     }
     tc_fence_before();

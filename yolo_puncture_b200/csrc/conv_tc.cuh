@@ -505,7 +505,7 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
 #undef EPI_MARK
 }
 
-template <int MODE>
+template <int MODE, bool PINGPONG = true>
 __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa, uint32_t sbias_sa, int lane, int c_begin,
                                           int c_end, uint32_t t_addr, int n0, bool valid, int qb, int rem,
                                           uint64_t* release, long long (&pacc)[6]) {
@@ -543,8 +543,25 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
   const int col0 = c_begin * 16, ncols = (c_end - c_begin) * 16;
   const int n32 = ncols >> 5;
   const bool tail16 = (ncols & 31) != 0;
-  uint32_t va[32], vb[32];  // ping-pong accumulator registers: the tcgen05.ld of pass k+1 is in flight during pass k
-  if (n32 > 0) {
+  uint32_t va[32];
+  if (!PINGPONG && n32 > 0) {  // register-lean variant (several CTAs per SM, e.g. the stem): one pass at a time
+    int dl[P32], rl[P32];
+    epi_row_deltas<P32>(delta, lane, dl);
+    if (LAY == EPI_BF16_RES) epi_row_deltas<P32>(rdelta, lane, rl);
+    for (int k = 0; k < n32; ++k) {
+      const int col = col0 + 32 * k;
+      tmem_ldn<32>(t_addr + (uint32_t)col, va);
+      tmem_ld_wait();
+      if (k + 1 == n32 && !tail16 && release != nullptr) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release);
+      }
+      epi_store_pass<32, MODE>(p, va, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl,
+                               prof, pt, pacc);
+    }
+  }
+  if (PINGPONG && n32 > 0) {
+    uint32_t vb[32];  // ping-pong accumulator registers: the tcgen05.ld of pass k+1 is in flight during pass k
     int dl[P32], rl[P32];
     epi_row_deltas<P32>(delta, lane, dl);
     if (LAY == EPI_BF16_RES) epi_row_deltas<P32>(rdelta, lane, rl);
@@ -1184,7 +1201,10 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
     if (tile + 1 < t_end) fetch_patch(tile + 1);
     {  // im2col row of output pixel (ty, tx) = tid: k = (kh*3+kw)*3 + c_rgb, frame bytes are BGR
       const int ty = tid >> 4, tx = tid & 15;
-      __nv_bfloat16 row[32];
+      // uint8 -> bf16 without the conversion pipe (I2F / F2F run on the 16-lane XU pipe next to the epilogue's tanh and
+      // bounded this kernel): 0x4B000000 | b is the float 2^23 + b, subtracting 2^23 leaves b exactly, and since
+      // b < 256 fits bf16's 8 significant bits the upper half of that float IS the bf16 value.
+      uint32_t fb[32];
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int r = 2 * ty + kh, ih = ih0 + r;
@@ -1196,13 +1216,18 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
           const int iw = iw0 + 2 * tx + kw;
           const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
           const uint8_t* px = rb + (2 * tx + kw) * 3;
-          row[(kh * 3 + kw) * 3 + 0] = __float2bfloat16_rn(in ? (float)px[2] : 0.f);
-          row[(kh * 3 + kw) * 3 + 1] = __float2bfloat16_rn(in ? (float)px[1] : 0.f);
-          row[(kh * 3 + kw) * 3 + 2] = __float2bfloat16_rn(in ? (float)px[0] : 0.f);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {  // frame bytes are BGR, k runs over RGB
+            const uint32_t bits = 0x4B000000u | (in ? (uint32_t)px[2 - c] : 0u);
+            fb[(kh * 3 + kw) * 3 + c] = __float_as_uint(__uint_as_float(bits) - 8388608.0f);
+          }
         }
       }
 #pragma unroll
-      for (int k = 27; k < 32; ++k) row[k] = __float2bfloat16_rn(0.f);
+      for (int k = 27; k < 32; ++k) fb[k] = 0u;
+      uint32_t row[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) row[k] = __byte_perm(fb[2 * k], fb[2 * k + 1], 0x7632);  // (hi16(a), hi16(b))
       const uint4* rv = reinterpret_cast<const uint4*>(row);
 #pragma unroll
       for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) << 4)) = rv[j & 3];
@@ -1224,7 +1249,7 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
       const int oh = oh0 + (r >> 4), ow = ow0 + (r & 15);
       const bool valid = oh < oH && ow < oW;
       long long pacc[6] = {0, 0, 0, 0, 0, 0};
-      epi_drain<EPI_BF16 | EPI_ACT>(p, smem_u32(sStage + warp * (alias_stage ? 4096 : kEpiStageBytes)), smem_u32(sbias), lane, 0, C0 >> 4,
+      epi_drain<EPI_BF16 | EPI_ACT, false>(p, smem_u32(sStage + warp * (alias_stage ? 4096 : kEpiStageBytes)), smem_u32(sbias), lane, 0, C0 >> 4,
                 tmem_base + ((uint32_t)(warp * 32) << 16), 0, valid, b, valid ? oh * oW + ow : 0, nullptr, pacc);
     }
     tc_fence_before();

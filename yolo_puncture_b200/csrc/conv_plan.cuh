@@ -369,6 +369,21 @@ static cudaError_t conv_launch_init() {
   return cudaSuccess;
 }
 
+// Launch of a persistent conv kernel with programmatic stream serialization (PDL): its prologue (barrier init, TMEM
+// allocation, bias copy) overlaps the tail of the previous kernel in the stream / captured graph.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("YPB_NO_PDL") != nullptr;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int impl) {
   if (impl == 1) {
     const long long total = (long long)L.sg.nB * L.sg.oH * L.sg.oW * (L.p.Cout / 16);
@@ -400,26 +415,28 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
     p3.tiles_h = L.tiles_h3; p3.tiles_w = L.tiles_w3;
     conv_set_fastdiv(p3, L.n_splits);
     const int grid3 = L.total_tiles3 < num_sms ? L.total_tiles3 : num_sms;
+    cudaError_t le = cudaSuccess;
 #define YPB_HALO_CASE(MODE) \
-  case MODE: conv3_halo_kernel<MODE><<<grid3, kConv2Threads, L.smem3, stream>>>(L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
+  case MODE: le = launch_pdl(conv3_halo_kernel<MODE>, grid3, kConv2Threads, L.smem3, stream, L.tmHalo3, L.tmB3, p3, L.x3, L.n_splits, L.total_tiles3); break;
     switch (epi_mode_of(p3.out_mode, p3.res != nullptr, p3.act)) {
       YPB_HALO_CASE(0) YPB_HALO_CASE(1) YPB_HALO_CASE(2) YPB_HALO_CASE(3) YPB_HALO_CASE(4) YPB_HALO_CASE(5) YPB_HALO_CASE(6)
       YPB_HALO_CASE(7)
     }
 #undef YPB_HALO_CASE
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
   }
   ConvParams p2 = L.p;
   p2.stages = L.stages2;
   conv_set_fastdiv(p2, L.n_splits);
   const int grid = L.total_tiles < num_sms ? L.total_tiles : num_sms;
+  cudaError_t le = cudaSuccess;
 #define YPB_TC2_CASE(MODE) \
-  case MODE: conv_tc2_kernel<MODE><<<grid, kConv2Threads, L.smem2, stream>>>(L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
+  case MODE: le = launch_pdl(conv_tc2_kernel<MODE>, grid, kConv2Threads, L.smem2, stream, L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
   switch (epi_mode_of(p2.out_mode, p2.res != nullptr, p2.act)) {
     YPB_TC2_CASE(0) YPB_TC2_CASE(1) YPB_TC2_CASE(2) YPB_TC2_CASE(3) YPB_TC2_CASE(4) YPB_TC2_CASE(5) YPB_TC2_CASE(6) YPB_TC2_CASE(7)
   }
 #undef YPB_TC2_CASE
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace ypb

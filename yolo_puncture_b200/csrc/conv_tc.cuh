@@ -664,6 +664,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only launch constants (weights' bias, tensor maps) and on-chip state: it overlaps the
+  // tail of the previous kernel; activations are read / written only after the predecessor has fully completed
+  pdl_trigger();
+  pdl_wait();
 
   if (warp < kProdWarps) {
     // ===================== TMA producers: warp w owns the ring stages s with s % kProdWarps == w =====================
@@ -922,6 +926,8 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // see conv_tc2_kernel
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer 0: halo tiles (and the resident weights, once) =====================

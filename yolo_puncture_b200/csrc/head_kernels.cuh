@@ -103,6 +103,98 @@ decode_filter_kernel(const float* __restrict__ head, HeadGeom g, int nB, float c
       ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)a);
 }
 
+// Same contract as decode_filter_kernel for nc % 4 == 0: a warp scans EIGHT anchors at a time, four lanes per anchor,
+// each lane streaming its share of the class logits with independent 16-byte loads (the one-warp-per-anchor version
+// has three dependent-latency loads in flight per warp and reaches ~1 TB/s); the rare candidates (score > conf) are
+// then decoded one after the other by the whole warp with exactly the arithmetic of decode_filter_kernel.
+__global__ void __launch_bounds__(256)
+decode_filter8_kernel(const float* __restrict__ head, HeadGeom g, int nB, float conf, int xyxy_direct,
+                      const unsigned* __restrict__ cls_mask, float4* __restrict__ dbox, int* __restrict__ dcls,
+                      unsigned long long* __restrict__ cand_keys, int* __restrict__ cand_count) {
+  const int lane = threadIdx.x & 31, grp = lane >> 2, sub = lane & 3;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = (long long)nB * g.A;
+  const long long a0 = warp_id * 8;
+  if (a0 >= total) return;
+  const long long mine = a0 + grp;
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  if (mine < total) {
+    const float4* cl = reinterpret_cast<const float4*>(head + mine * g.no + 64);
+    const int n4 = g.nc >> 2;
+    for (int c4 = sub; c4 < n4; c4 += 4) {
+      const float4 v = __ldg(cl + c4);
+      const int c = c4 * 4;
+      if (v.x > best) { best = v.x; bidx = c; }
+      if (v.y > best) { best = v.y; bidx = c + 1; }
+      if (v.z > best) { best = v.z; bidx = c + 2; }
+      if (v.w > best) { best = v.w; bidx = c + 3; }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {  // first index wins ties, like torch.max
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+  }
+  const float score = sigmoid_f(best);
+  bool cand = (mine < total) && (score > conf);
+  // predict(classes=[...]): upstream filters on the arg-max class after the confidence test
+  if (cand && !xyxy_direct && cls_mask != nullptr && !((cls_mask[bidx >> 5] >> (bidx & 31)) & 1u)) cand = false;
+  unsigned todo = __ballot_sync(0xffffffffu, cand && sub == 0);
+  while (todo != 0u) {  // warp-uniform
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const long long wid = a0 + (src >> 2);
+    const float c_score = __shfl_sync(0xffffffffu, score, src);
+    const int c_idx = __shfl_sync(0xffffffffu, bidx, src);
+    const int b = (int)(wid / g.A), a = (int)(wid - (long long)b * g.A);
+    const float* row = head + wid * g.no;
+    // ---- DFL: softmax over 16 bins per side, expectation; lane l holds side l/16 (and +2) bin l%16 ----
+    float d[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const float x = row[half * 32 + lane];
+      float m = x;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float e = expf(x - m);
+      float s = e, ws = e * (float)(lane & 15);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ws += __shfl_xor_sync(0xffffffffu, ws, o);
+      }
+      d[half] = __fdiv_rn(ws, s);
+    }
+    const float dl = __shfl_sync(0xffffffffu, d[0], 0), dt = __shfl_sync(0xffffffffu, d[0], 16);
+    const float dr = __shfl_sync(0xffffffffu, d[1], 0), db = __shfl_sync(0xffffffffu, d[1], 16);
+    if (lane == 0) {
+      int lvl = 0;
+      if (a >= g.lvl_start[1]) lvl = 1;
+      if (a >= g.lvl_start[2]) lvl = 2;
+      const int local = a - g.lvl_start[lvl];
+      const int iy = local / g.lvl_w[lvl], ix = local - iy * g.lvl_w[lvl];
+      const float ax = (float)ix + 0.5f, ay = (float)iy + 0.5f, st = g.lvl_stride[lvl];
+      const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt), x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
+      float4 box;
+      if (xyxy_direct) {
+        box = make_float4(__fmul_rn(x1, st), __fmul_rn(y1, st), __fmul_rn(x2, st), __fmul_rn(y2, st));
+      } else {
+        const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.0f), st), cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.0f), st);
+        const float w = __fmul_rn(__fsub_rn(x2, x1), st), h = __fmul_rn(__fsub_rn(y2, y1), st);
+        const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+        box = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+      }
+      dbox[wid] = box;
+      dcls[wid] = c_idx;
+      const int slot = atomicAdd(cand_count + b, 1);
+      cand_keys[(long long)b * g.cand_stride + slot] =
+          ((unsigned long long)__float_as_uint(c_score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)a);
+    }
+  }
+}
+
 // End-to-end (YOLOv10, NMS-free) heads: every (anchor, class) pair with score > conf is a candidate of the
 // top-k; key = score_bits << 32 | ~(anchor*nc + class).  Runs after decode_filter_kernel(xyxy_direct=1), which
 // has already written the xyxy box of every anchor whose best class passes conf.  One warp per anchor.

@@ -1121,8 +1121,17 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
   const int bands = (g.out_h + kMaskTile - 1) / kMaskTile;
   dim3 grid(bands, capacity);
   if (capacity > 65535) return fail(YPB_ERR_ARG, "masks: capacity > 65535");
-  mask_decode_kernel<<<grid, 256, 0, st>>>(proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb, offsets,
-                                           e->B, capacity, g, masks);
+  // dynamic smem = the band's logit window: rows needed by 64 output rows x every column of the un-padded proto window
+  const int band_rows = std::min(g.ch, (int)(kMaskTile * g.scale_h) + 3);
+  const size_t band_smem = (size_t)band_rows * g.cw * sizeof(float);
+  if (band_smem > 160 * 1024) return fail(YPB_ERR_ARG, "masks: proto window too large for the band buffer");
+  static size_t mask_smem_set = 0;
+  if (band_smem > 30 * 1024 && band_smem > mask_smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(mask_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    mask_smem_set = 160 * 1024;
+  }
+  mask_decode_kernel<<<grid, 256, band_smem, st>>>(proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb,
+                                                  offsets, e->B, capacity, g, masks);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;
 }

@@ -96,6 +96,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsign
   return false;
 }
 
+// Bounded wait that parks the thread in the hardware (mbarrier.try_wait suspends until the phase flips or a time
+// limit passes).  Slower to react than polling, but it consumes no issue slots: right when other resident CTAs have
+// work for the SM sub-partition (the stem kernel), wrong for a warp-specialised role that owns its sub-partition.
+__device__ __forceinline__ bool mbar_wait_blocking(uint64_t* bar, uint32_t parity, unsigned int err_code) {
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    if (mbar_try_wait(bar, parity)) return true;
+  }
+  atomicOr(&g_dev_error, err_code);
+  return false;
+}
+
 // Same, with a back-off between polls (ns = 0: tight polling).  Idle pollers share the SM's memory-instruction
 // queue with the epilogue warps' LDS/STS/SHFL: see the measurements quoted at the call sites in conv_tc.cuh.
 __device__ __forceinline__ bool mbar_wait_bo(uint64_t* bar, uint32_t parity, unsigned int err_code, unsigned int ns) {

@@ -1177,8 +1177,8 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
   constexpr int kPatchPerThread = (17 * kStemRowWords + 127) / 128;
   uint32_t pre[kPatchPerThread];
   auto fetch_patch = [&](int tile) {
-    const int b = tile / tiles_per_img, t_in = tile - b * tiles_per_img;
-    const int th = t_in / tiles_w;
+    const int b = fdiv(tile, p.fd_tpi), t_in = tile - b * tiles_per_img;
+    const int th = fdiv(t_in, p.fd_tw);
     const int ih0 = 2 * (th * kStemTH) - 1, iw0 = 2 * ((t_in - th * tiles_w) * kStemTW) - 1;
 #pragma unroll
     for (int j = 0; j < kPatchPerThread; ++j) {
@@ -1196,8 +1196,8 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
   };
   if (t_begin < t_end) fetch_patch(t_begin);
   for (int tile = t_begin; tile < t_end; ++tile) {
-    const int b = tile / tiles_per_img, t_in = tile - b * tiles_per_img;
-    const int th = t_in / tiles_w;
+    const int b = fdiv(tile, p.fd_tpi), t_in = tile - b * tiles_per_img;
+    const int th = fdiv(t_in, p.fd_tw);
     const int oh0 = th * kStemTH, ow0 = (t_in - th * tiles_w) * kStemTW;
     const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
 #pragma unroll
@@ -1211,16 +1211,22 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
       // bounded this kernel): 0x4B000000 | b is the float 2^23 + b, subtracting 2^23 leaves b exactly, and since
       // b < 256 fits bf16's 8 significant bits the upper half of that float IS the bf16 value.
       uint32_t fb[32];
+      bool col_ok[3];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = iw0 + 2 * tx + kw;
+        col_ok[kw] = iw >= 0 && iw < W;
+      }
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int r = 2 * ty + kh, ih = ih0 + r;
         const long long g0 = (long long)b * frame_bytes + ((long long)ih * W + iw0) * 3;
         const int shift = (int)(g0 & 3);  // bytes between the first loaded word and pixel (ih, iw0)
         const uint8_t* rb = reinterpret_cast<const uint8_t*>(sIn + r * kStemRowWords) + shift;
+        const bool row_ok = ih >= 0 && ih < H;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int iw = iw0 + 2 * tx + kw;
-          const bool in = ih >= 0 && ih < H && iw >= 0 && iw < W;
+          const bool in = row_ok && col_ok[kw];
           const uint8_t* px = rb + (2 * tx + kw) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {  // frame bytes are BGR, k runs over RGB
@@ -1247,7 +1253,7 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
         umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sA) + j * 32), umma_desc_sw128(smem_u32(sB) + j * 32), idesc, j ? 1u : 0u);
       umma_commit(&bar);
     }
-    mbar_wait(&bar, phase, 16u);
+    mbar_wait_blocking(&bar, phase, 16u);  // several CTAs share the SM: a parked warp leaves its issue slots to them
     phase ^= 1;
     tc_fence_after();
     {

@@ -543,6 +543,8 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       sp.out = e->ws + ob.offset; sp.out_img_stride = (long long)ob.H * ob.W * ob.C; sp.out_pix_stride = ob.C;
       sp.out_c_off = op.out.c_off; sp.bias = reinterpret_cast<const float*>(wa + op.b_off);
       const int tiles_w = (ob.W + kStemTW - 1) / kStemTW, tiles_h = (ob.H + kStemTH - 1) / kStemTH;
+      sp.tiles_w = tiles_w; sp.tiles_h = tiles_h;
+      conv_set_fastdiv(sp, 1);
       const int total = B * tiles_h * tiles_w, per_cta = 8;
       // the epilogue staging tile (32 rows x (min(2*C0,128)+16) B per warp) aliases the A tile when it fits in 4 KB per warp
       const int alias = 1;  // a pass stages 32 rows x (64 + 16) B per warp

@@ -315,11 +315,30 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
     mask_ms = mask_ev0.elapsed_time(mask_ev1)
     mask_bytes = n_det * hw[0] * hw[1] + B * (H // 4) * (W // 4) * 32 * 4
-    roofline = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all %d launches of a step)" % n_conv,
+    # DRAM traffic of the conv launches from the committed ncu capture of the same workload (tools/ncu_traffic.sh)
+    traffic, traffic_note = None, "no ncu capture committed for this workload"
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            nt = json.load(f)
+        if nt.get("workload") == args.workload and nt.get("conv_launches") == n_conv:
+            traffic = nt["conv_dram_bytes_per_step"] / n_conv
+            traffic_note = (f"ncu dram__bytes_read+write.sum over the {n_conv} conv launches of one step = "
+                            f"{nt['conv_dram_bytes_per_step'] / 1e9:.2f} GB vs {conv_by / 1e9:.2f} GB algorithmic "
+                            f"(in + out + weights of every launch); conv share of the step under ncu "
+                            f"{100 * nt['conv_share_of_step_under_ncu']:.1f} %")
+    except OSError:
+        pass
+    conv_ops = [(m, o) for m, o in zip(prof, ops) if o[1] == 1]
+    top_ms, top_op = max(conv_ops, key=lambda t: t[0])
+    roofline = {"kernel": "conv_tc2_kernel / conv3_halo_kernel (tcgen05 implicit-GEMM convs: all %d launches of a step)" % n_conv,
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"] + ", sustained",
+                "frac": achieved / peaks["tf_sustained"], "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": peaks["source"] + ", sustained",
                 "flops_per_step": conv_fl, "avg_launch_ms": conv_ms / n_conv, "conv_ms_per_step": conv_ms,
                 "conv_algorithmic_gbs": conv_by / (conv_ms * 1e-3) / 1e9,
+                "algorithmic_bytes_per_launch": conv_by / n_conv,
+                "longest_launch": {"op": top_op[0], "ms": float(top_ms), "tflops": top_op[2] / (top_ms * 1e-3) / 1e12,
+                                   "frac_of_sustained_peak": top_op[2] / (top_ms * 1e-3) / 1e12 / peaks["tf_sustained"]},
                 "step_breakdown_ms": {
                     "stem": float(sum(m for m, o in zip(prof, ops) if o[1] == 0)), "conv_tc": float(conv_ms),
                     "upsample+sppf": float(sum(m for m, o in zip(prof, ops) if o[1] in (2, 3))),

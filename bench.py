@@ -34,6 +34,9 @@ WORKLOADS = {
     "yolov8m-seg-1080p-b16": ("yolov8m-seg", 16, (1080, 1920), 1280),
     "yolov8x-seg-640-b32": ("yolov8x-seg", 32, (640, 640), 640),
     "yolov10n-640-b32": ("yolov10n", 32, (640, 640), 640),
+    "yolo11n-seg-640-b64": ("yolo11n-seg", 64, (640, 640), 640),
+    "yolo11s-seg-640-b64": ("yolo11s-seg", 64, (640, 640), 640),
+    "yolo11x-seg-640-b32": ("yolo11x-seg", 32, (640, 640), 640),
 }
 DEFAULT_WORKLOAD = "yolov8s-seg-640-b64"
 CONF, IOU = 0.25, 0.7

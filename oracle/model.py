@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .modules import (
-    C2f, C2fCIB, Concat, Conv, Detect, PSA, RepVGGDW, SCDown, SPPF, Segment, v10Detect,
+    C2f, C2fCIB, C2PSA, C3k2, Concat, Conv, Detect, PSA, RepVGGDW, SCDown, SPPF, Segment, v10Detect,
 )
 
 # (depth, width, max_channels)
@@ -45,10 +45,28 @@ _V10N = [
     ([16, 19, 22], 1, "v10Detect", ["nc"]),
 ]
 
+# UPSTREAM cfg/models/11/yolo11-seg.yaml; parse_model forces c3k=True for the m/l/x scales and builds
+# the head with the non-legacy (depthwise) class branch
+_V11_SCALES = {"n": (0.50, 0.25, 1024), "s": (0.50, 0.50, 1024), "m": (0.50, 1.00, 512),
+               "l": (1.00, 1.00, 512), "x": (1.00, 1.50, 512)}
+_V11_SEG = [
+    (-1, 1, "Conv", [64, 3, 2]), (-1, 1, "Conv", [128, 3, 2]), (-1, 2, "C3k2", [256, False, 0.25]),
+    (-1, 1, "Conv", [256, 3, 2]), (-1, 2, "C3k2", [512, False, 0.25]), (-1, 1, "Conv", [512, 3, 2]),
+    (-1, 2, "C3k2", [512, True]), (-1, 1, "Conv", [1024, 3, 2]), (-1, 2, "C3k2", [1024, True]),
+    (-1, 1, "SPPF", [1024, 5]), (-1, 2, "C2PSA", [1024]),
+    (-1, 1, "Upsample", [None, 2, "nearest"]), ([-1, 6], 1, "Concat", [1]), (-1, 2, "C3k2", [512, False]),
+    (-1, 1, "Upsample", [None, 2, "nearest"]), ([-1, 4], 1, "Concat", [1]), (-1, 2, "C3k2", [256, False]),
+    (-1, 1, "Conv", [256, 3, 2]), ([-1, 13], 1, "Concat", [1]), (-1, 2, "C3k2", [512, False]),
+    (-1, 1, "Conv", [512, 3, 2]), ([-1, 10], 1, "Concat", [1]), (-1, 2, "C3k2", [1024, True]),
+    ([16, 19, 22], 1, "Segment", ["nc", 32, 256]),
+]
+
 MODEL_SPECS = {f"yolov8{s}-seg": (_V8_SEG, _V8_SCALES[s]) for s in "nsmlx"}
 MODEL_SPECS["yolov10n"] = (_V10N, _V10_SCALES["n"])
+MODEL_SPECS.update({f"yolo11{s}-seg": (_V11_SEG, _V11_SCALES[s]) for s in "nsmlx"})
 
-_MODULES = {"Conv": Conv, "C2f": C2f, "SPPF": SPPF, "SCDown": SCDown, "PSA": PSA, "C2fCIB": C2fCIB}
+_MODULES = {"Conv": Conv, "C2f": C2f, "SPPF": SPPF, "SCDown": SCDown, "PSA": PSA, "C2fCIB": C2fCIB, "C3k2": C3k2,
+            "C2PSA": C2PSA}
 
 
 def make_divisible(x, divisor):
@@ -64,6 +82,7 @@ class OracleModel(nn.Module):
         self.name, self.nc = name, nc
         self.task = "segment" if name.endswith("-seg") else "detect"
         ch = [3]
+        legacy = True  # v8 full-conv class branch; C3k2 models (YOLO11) use the depthwise one
         layers, self.froms, save = [], [], set()
         for i, (f, n, m, args) in enumerate(rows):
             args = [nc if a == "nc" else a for a in args]
@@ -72,8 +91,14 @@ class OracleModel(nn.Module):
                 c1, c2 = ch[f], args[0]
                 c2 = make_divisible(min(c2, max_ch) * width, 8)
                 a = [c1, c2, *args[1:]]
-                if m in ("C2f", "C2fCIB"):
+                if m in ("C2f", "C2fCIB", "C3k2", "C2PSA"):
                     a.insert(2, n)
+                if m == "C3k2":
+                    legacy = False
+                    if len(a) < 4:
+                        a.append(False)
+                    if name[len("yolo11")] in "mlx":
+                        a[3] = True
                 mod = _MODULES[m](*a)
             elif m == "Upsample":
                 mod, c2 = nn.Upsample(None, args[1], args[2]), ch[f]
@@ -81,7 +106,7 @@ class OracleModel(nn.Module):
                 mod, c2 = Concat(args[0]), sum(ch[x] for x in f)
             elif m == "Segment":
                 npr = make_divisible(min(args[2], max_ch) * width, 8)
-                mod, c2 = Segment(args[0], args[1], npr, [ch[x] for x in f]), None
+                mod, c2 = Segment(args[0], args[1], npr, [ch[x] for x in f], legacy=legacy), None
             elif m == "v10Detect":
                 mod, c2 = v10Detect(args[0], [ch[x] for x in f]), None
             else:

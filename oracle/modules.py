@@ -275,6 +275,67 @@ class C2fCIB(C2f):
 
 
 # ------------------------------------------------------------------------------------------------
+# YOLO11 blocks (UPSTREAM block.py::C3k / C3k2 / PSABlock / C2PSA)
+# ------------------------------------------------------------------------------------------------
+class C3k(nn.Module):
+    """C3 with n Bottleneck(c_, c_, k=(k,k), e=1.0): cv3(cat(m(cv1(x)), cv2(x)))."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5, k=3):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, k=(k, k), e=1.0) for _ in range(n)))
+
+    def forward(self, x):
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+
+
+class C3k2(C2f):
+    """C2f whose inner blocks are C3k(c, c, 2) (c3k=True) or Bottleneck(c, c) with the default e=0.5."""
+
+    def __init__(self, c1, c2, n=1, c3k=False, e=0.5, g=1, shortcut=True):
+        super().__init__(c1, c2, n, shortcut, g, e)
+        self.m = nn.ModuleList(
+            C3k(self.c, self.c, 2, shortcut, g) if c3k else Bottleneck(self.c, self.c, shortcut, g) for _ in range(n)
+        )
+
+
+class PSABlock(nn.Module):
+    def __init__(self, c, attn_ratio=0.5, num_heads=4, shortcut=True):
+        super().__init__()
+        self.attn = Attention(c, attn_ratio=attn_ratio, num_heads=num_heads)
+        self.ffn = nn.Sequential(Conv(c, c * 2, 1), Conv(c * 2, c, 1, act=False))
+        self.add = shortcut
+        self.emu = None
+
+    def forward(self, x):
+        x = x + self.attn(x) if self.add else self.attn(x)
+        if self.emu == "bf16":
+            x = _r16(x)
+        x = x + self.ffn(x) if self.add else self.ffn(x)
+        if self.emu == "bf16":
+            x = _r16(x)
+        return x
+
+
+class C2PSA(nn.Module):
+    def __init__(self, c1, c2, n=1, e=0.5):
+        super().__init__()
+        assert c1 == c2
+        self.c = int(c1 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
+        self.cv2 = Conv(2 * self.c, c1, 1)
+        self.m = nn.Sequential(*(PSABlock(self.c, attn_ratio=0.5, num_heads=self.c // 64) for _ in range(n)))
+
+    def forward(self, x):
+        a, b = self.cv1(x).split((self.c, self.c), dim=1)
+        b = self.m(b)
+        return self.cv2(torch.cat((a, b), 1))
+
+
+# ------------------------------------------------------------------------------------------------
 # Heads (SURVEY.md A.3)
 # ------------------------------------------------------------------------------------------------
 def make_anchors(feats, strides, grid_cell_offset=0.5):

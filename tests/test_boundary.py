@@ -14,7 +14,7 @@ from yolo_puncture_b200 import YOLO, _lib
 from yolo_puncture_b200.engine import Engine, YpbError
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SEG = [f"yolov8{s}-seg" for s in "nsmlx"] + ["yolov10n"]
+SEG = [f"yolov8{s}-seg" for s in "nsmlx"] + ["yolov10n"] + [f"yolo11{s}-seg" for s in "nsmlx"]
 
 
 def test_library_exports_every_declared_symbol():

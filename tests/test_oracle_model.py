@@ -6,7 +6,11 @@ import torch
 from oracle.model import build_model, conv_flops, count_parameters
 
 PARAMS = {"yolov8n-seg": 3409968, "yolov8s-seg": 11821056, "yolov8m-seg": 27285968,
-          "yolov8l-seg": 45997728, "yolov8x-seg": 71827888, "yolov10n": 2775520}
+          "yolov8l-seg": 45997728, "yolov8x-seg": 71827888, "yolov10n": 2775520,
+          # YOLO11-seg: upstream's model summaries / model-zoo table give 2,876,848 parameters for
+          # yolo11n-seg and 10.1 / 22.4 / 27.6 / 62.1 M for s / m / l / x
+          "yolo11n-seg": 2876848, "yolo11s-seg": 10113248, "yolo11m-seg": 22420896, "yolo11l-seg": 27678368,
+          "yolo11x-seg": 62142656}
 
 
 @pytest.mark.parametrize("name,total", sorted(PARAMS.items()))
@@ -58,3 +62,21 @@ def test_v10_head_output():
         y, _ = m(torch.rand(2, 3, 640, 640))
     assert y.shape == (2, 300, 6)
     assert bool((y[:, :-1, 4] >= y[:, 1:, 4]).all())  # descending scores
+
+
+def test_yolo11_seg_shapes_and_fuse_equivalence():
+    torch.manual_seed(0)
+    m = build_model("yolo11n-seg")
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.1)
+    x = torch.rand(1, 3, 640, 640)
+    with torch.no_grad():
+        y, (maps, mc, proto) = m(x)
+        assert y.shape == (1, 116, 8400) and proto.shape == (1, 32, 160, 160) and mc.shape == (1, 32, 8400)
+        m.fuse()
+        y2, (_, _, proto2) = m(x)
+    assert (y - y2).abs().max() < 1e-3 and (proto - proto2).abs().max() < 1e-4

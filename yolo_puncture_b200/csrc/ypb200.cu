@@ -64,13 +64,17 @@ struct View { int buf = -1, c_off = 0, C = 0; };
 
 enum OpKind { OP_STEM, OP_CONV, OP_UPSAMPLE, OP_SPPF, OP_DW, OP_ATTN };
 enum SrcKind { SRC_CONV_BN = 0, SRC_CONV_BIAS = 1, SRC_CONVT = 2 };
-struct ConvSrc { std::string mod; int kind; int cout; };
+// slot > cout: the source's output channels are padded with zero weights / zero bias up to `slot` channels of the op's
+// output (SiLU(0) = 0, so the padded channels of the activation stay zero): lets a layer with fewer than 16 channels
+// (yolo11n's 8-channel bottleneck) run on the tensor-core kernels, whose channel counts are multiples of 16
+struct ConvSrc { std::string mod; int kind; int cout; int slot = 0; int width() const { return slot > cout ? slot : cout; } };
 
 struct Op {
   OpKind kind = OP_CONV;
   std::string name;
   std::vector<ConvSrc> srcs;
   int cin = 0, cout = 0, k = 1, s = 1, act = 1, out_mode = OUT_BF16;
+  int cin_real = 0;  // > 0: the module's real input channels (< cin: the rest of the input slice is zero padding)
   View in, out, res;
   int head_lvl = -1, head_coff = 0;
   size_t w_off = 0, b_off = 0;  // byte offsets in the weight arena
@@ -159,16 +163,18 @@ struct ypb_engine {
 
   // Conv(+BN)+SiLU, possibly several modules fused along Cout (they must share input, k, s).
   void conv(const std::vector<std::string>& mods, const std::vector<int>& couts, View in, View out, int k, int s,
-            bool act = true, View res = View()) {
+            bool act = true, View res = View(), int cin_real = 0, int slot = 0) {
     Op op;
     op.kind = OP_CONV; op.name = mods[0];
     op.cin = in.C; op.k = k; op.s = s; op.act = act ? 1 : 0; op.in = in; op.out = out; op.res = res;
+    op.cin_real = cin_real;
     int tot = 0;
     for (size_t i = 0; i < mods.size(); ++i) {
       ConvSrc src{mods[i], SRC_CONV_BN, couts[i]};
-      add_conv_weights(src, in.C, k);
+      src.slot = slot;
+      add_conv_weights(src, cin_real > 0 ? cin_real : in.C, k);
       op.srcs.push_back(src);
-      tot += couts[i];
+      tot += src.width();
     }
     op.cout = tot;
     ops.push_back(op);
@@ -235,11 +241,25 @@ struct ypb_engine {
   }
   // UPSTREAM block.py::PSA (+ Attention), heads = c/64, key_dim 32, head_dim 64
   void psa(const std::string& mod, View in, View out, int lvl) {
-    const int c = in.C / 2, nh = c / 64;
-    const int P = new_buf(mod + ".ab", lvl, 2 * c), Q = new_buf(mod + ".qkv", lvl, 2 * c), PE = new_buf(mod + ".pe", lvl, c);
-    const int AO = new_buf(mod + ".ao", lvl, c), F = new_buf(mod + ".ffn", lvl, 2 * c);
+    const int c = in.C / 2;
+    const int P = new_buf(mod + ".ab", lvl, 2 * c);
     conv1(mod + ".cv1", in, whole(P), 1, 1);
-    const View b = slice(P, c, c);
+    psa_block(mod, slice(P, c, c), lvl);
+    conv1(mod + ".cv2", whole(P), out, 1, 1);
+  }
+  // UPSTREAM block.py::C2PSA: PSA with n PSABlocks named m.{j}
+  void c2psa(const std::string& mod, View in, View out, int n, int lvl) {
+    const int c = in.C / 2;
+    const int P = new_buf(mod + ".ab", lvl, 2 * c);
+    conv1(mod + ".cv1", in, whole(P), 1, 1);
+    for (int j = 0; j < n; ++j) psa_block(mod + ".m." + std::to_string(j), slice(P, c, c), lvl);
+    conv1(mod + ".cv2", whole(P), out, 1, 1);
+  }
+  // b = b + attn(b); b = b + ffn(b), in place on the channel slice b (PSA body / PSABlock)
+  void psa_block(const std::string& mod, View b, int lvl) {
+    const int c = b.C, nh = c / 64;
+    const int Q = new_buf(mod + ".qkv", lvl, 2 * c), PE = new_buf(mod + ".pe", lvl, c);
+    const int AO = new_buf(mod + ".ao", lvl, c), F = new_buf(mod + ".ffn", lvl, 2 * c);
     conv_noact(mod + ".attn.qkv", b, whole(Q));
     {  // pe: depthwise 3x3 over v (the v channels of each head are a strided subset of the qkv buffer)
       Op op;
@@ -258,7 +278,37 @@ struct ypb_engine {
     conv_noact(mod + ".attn.proj", whole(AO), b, b);          // b = b + attn(b), in place
     conv1(mod + ".ffn.0", b, whole(F), 1, 1);
     conv_noact(mod + ".ffn.1", whole(F), b, b);               // b = b + ffn(b), in place
-    conv1(mod + ".cv2", whole(P), out, 1, 1);
+  }
+  static int pad16(int c) { return (c + 15) & ~15; }
+  // UPSTREAM block.py::Bottleneck(c, c, shortcut, k=(3,3), e): t = cv1(x) (c_ = c*e channels), out = [x +] cv2(t)
+  void bottleneck(const std::string& mod, View x, View out, bool shortcut, int c_mid, int lvl) {
+    const int cp = pad16(c_mid);
+    const int t = new_buf(mod + ".t", lvl, cp);
+    conv({mod + ".cv1"}, {c_mid}, x, whole(t), 3, 1, true, View(), 0, cp);
+    conv({mod + ".cv2"}, {out.C}, whole(t), out, 3, 1, true, shortcut ? x : View(), cp != c_mid ? c_mid : 0, 0);
+  }
+  // UPSTREAM block.py::C3k(c, c, n, shortcut, e=0.5): cv3(cat(m(cv1(x)), cv2(x))), m = n x Bottleneck(c_, c_, e=1.0).
+  // cv1 and cv2 read the same input: one GEMM writes [a | b]; the bottleneck chain updates a in place.
+  void c3k(const std::string& mod, View x, View out, int n, bool shortcut, int lvl) {
+    const int c_ = x.C / 2;
+    const int Z = new_buf(mod + ".ab", lvl, 2 * c_);
+    conv({mod + ".cv1", mod + ".cv2"}, {c_, c_}, x, whole(Z), 1, 1);
+    const View a = slice(Z, 0, c_);
+    for (int j = 0; j < n; ++j) bottleneck(mod + ".m." + std::to_string(j), a, a, shortcut, c_, lvl);
+    conv1(mod + ".cv3", whole(Z), out, 1, 1);
+  }
+  // UPSTREAM block.py::C3k2(c1, c2, n, c3k, e, shortcut=True): C2f whose blocks are C3k(c, c, 2) or Bottleneck(c, c, e=0.5)
+  void c3k2(const std::string& mod, View in, View out, int n, bool use_c3k, double e, int lvl) {
+    const int c = (int)(out.C * e);
+    const int Y = new_buf(mod + ".cat", lvl, (2 + n) * c);
+    conv1(mod + ".cv1", in, slice(Y, 0, 2 * c), 1, 1);
+    for (int j = 0; j < n; ++j) {
+      const View x = slice(Y, (1 + j) * c, c), y = slice(Y, (2 + j) * c, c);
+      const std::string mj = mod + ".m." + std::to_string(j);
+      if (use_c3k) c3k(mj, x, y, 2, true, lvl);
+      else bottleneck(mj, x, y, true, c / 2, lvl);
+    }
+    conv1(mod + ".cv2", whole(Y), out, 1, 1);
   }
   // UPSTREAM block.py::C2fCIB with CIB(c, c, shortcut, e=1.0, lk)
   void c2fcib(const std::string& mod, View in, View out, int n, bool shortcut, bool lk, int lvl) {
@@ -489,6 +539,123 @@ static bool build_v10n(ypb_engine& e) {
   return true;
 }
 
+// UPSTREAM cfg/models/11/yolo11-seg.yaml: the app's default weights are yolo11{n,x}-seg
+// (reference yolo_seg/app.py:216-223, yolo_with_deva.py:226).  Same skeleton as yolov10n (C2PSA at layer 10, head at
+// 23); C3k2 blocks, non-legacy (depthwise) class branch, Segment head.
+static bool build_v11seg(ypb_engine& e, char scale) {
+  double d, w; int mc;
+  switch (scale) {
+    case 'n': d = 0.50; w = 0.25; mc = 1024; break;
+    case 's': d = 0.50; w = 0.50; mc = 1024; break;
+    case 'm': d = 0.50; w = 1.00; mc = 512; break;
+    case 'l': d = 1.00; w = 1.00; mc = 512; break;
+    case 'x': d = 1.00; w = 1.50; mc = 512; break;
+    default: return false;
+  }
+  auto ch = [&](int c) { return make_div8(std::min(c, mc) * w); };
+  const int n2 = std::max((int)std::lround(2 * d), 1);
+  const bool big = scale == 'm' || scale == 'l' || scale == 'x';  // parse_model forces c3k=True for m/l/x
+  const int c64 = ch(64), c128 = ch(128), c256 = ch(256), c512 = ch(512), c1024 = ch(1024);
+  e.nm = 32;
+  const std::string M = "model.";
+  const int x0 = e.new_buf("model.0", 1, c64), x1 = e.new_buf("model.1", 2, c128), x2 = e.new_buf("model.2", 2, c256);
+  const int x3 = e.new_buf("model.3", 3, c256);
+  const int cat15 = e.new_buf("model.15", 3, c512 + c512);    // [up(13) | 4]
+  const int x5 = e.new_buf("model.5", 4, c512);
+  const int cat12 = e.new_buf("model.12", 4, c1024 + c512);   // [up(10) | 6]
+  const int x7 = e.new_buf("model.7", 5, c1024), x8 = e.new_buf("model.8", 5, c1024), x9 = e.new_buf("model.9", 5, c1024);
+  const int cat21 = e.new_buf("model.21", 5, c512 + c1024);   // [20 | 10]
+  const int cat18 = e.new_buf("model.18", 4, c256 + c512);    // [17 | 13]
+  const int x16 = e.new_buf("model.16", 3, c256), x19 = e.new_buf("model.19", 4, c512), x22 = e.new_buf("model.22", 5, c1024);
+  const View v4 = e.slice(cat15, c512, c512), v6 = e.slice(cat12, c1024, c512), v10 = e.slice(cat21, c512, c1024);
+  const View v13 = e.slice(cat18, c256, c512), v17 = e.slice(cat18, 0, c256), v20 = e.slice(cat21, 0, c512);
+  {
+    Op op;
+    op.kind = OP_STEM; op.name = "model.0"; op.cin = 3; op.cout = c64; op.k = 3; op.s = 2; op.out = e.whole(x0);
+    ConvSrc src{"model.0", SRC_CONV_BN, c64};
+    e.add_conv_weights(src, 3, 3);
+    op.srcs.push_back(src);
+    e.ops.push_back(op);
+  }
+  e.conv1(M + "1", e.whole(x0), e.whole(x1), 3, 2);
+  e.c3k2(M + "2", e.whole(x1), e.whole(x2), n2, big, 0.25, 2);       // C3k2(256, False, 0.25)
+  e.conv1(M + "3", e.whole(x2), e.whole(x3), 3, 2);
+  e.c3k2(M + "4", e.whole(x3), v4, n2, big, 0.25, 3);                // C3k2(512, False, 0.25)
+  e.conv1(M + "5", v4, e.whole(x5), 3, 2);
+  e.c3k2(M + "6", e.whole(x5), v6, n2, true, 0.5, 4);                // C3k2(512, True)
+  e.conv1(M + "7", v6, e.whole(x7), 3, 2);
+  e.c3k2(M + "8", e.whole(x7), e.whole(x8), n2, true, 0.5, 5);       // C3k2(1024, True)
+  e.sppf(M + "9", e.whole(x8), e.whole(x9), 5);
+  e.c2psa(M + "10", e.whole(x9), v10, n2, 5);
+  e.upsample(v10, e.slice(cat12, 0, c1024));
+  e.c3k2(M + "13", e.whole(cat12), v13, n2, big, 0.5, 4);            // C3k2(512, False)
+  e.upsample(v13, e.slice(cat15, 0, c512));
+  e.c3k2(M + "16", e.whole(cat15), e.whole(x16), n2, big, 0.5, 3);   // C3k2(256, False) -> P3
+  e.conv1(M + "17", e.whole(x16), v17, 3, 2);
+  e.c3k2(M + "19", e.whole(cat18), e.whole(x19), n2, big, 0.5, 4);   // C3k2(512, False) -> P4
+  e.conv1(M + "20", e.whole(x19), v20, 3, 2);
+  e.c3k2(M + "22", e.whole(cat21), e.whole(x22), n2, true, 0.5, 5);  // C3k2(1024, True) -> P5
+  e.name_view("model.0", e.whole(x0)); e.name_view("model.1", e.whole(x1)); e.name_view("model.2", e.whole(x2));
+  e.name_view("model.3", e.whole(x3)); e.name_view("model.4", v4); e.name_view("model.5", e.whole(x5));
+  e.name_view("model.6", v6); e.name_view("model.7", e.whole(x7)); e.name_view("model.8", e.whole(x8));
+  e.name_view("model.9", e.whole(x9)); e.name_view("model.10", v10); e.name_view("model.12", e.whole(cat12));
+  e.name_view("model.13", v13); e.name_view("model.15", e.whole(cat15)); e.name_view("model.16", e.whole(x16));
+  e.name_view("model.17", v17); e.name_view("model.18", e.whole(cat18)); e.name_view("model.19", e.whole(x19));
+  e.name_view("model.20", v20); e.name_view("model.21", e.whole(cat21)); e.name_view("model.22", e.whole(x22));
+
+  // Segment head (module 23): cv2 / cv4 as in yolov8-seg, cv3 = the depthwise class branch of UPSTREAM Detect(legacy=False)
+  const std::string Hd = "model.23.";
+  const int chs[3] = {c256, c512, c1024};
+  const View P[3] = {e.whole(x16), e.whole(x19), e.whole(x22)};
+  const int hc2 = std::max(std::max(16, chs[0] / 4), 64), hc3 = std::max(chs[0], std::min(e.nc, 100));
+  const int hc4 = std::max(chs[0] / 4, e.nm);
+  for (int i = 0; i < 3; ++i) {
+    e.feat[i] = P[i];
+    const std::string si = std::to_string(i);
+    const int lvl = 3 + i, x = chs[i];
+    // the first 3x3 conv of the box and coefficient branches reads the same P_i: one fused GEMM, N = hc2 + hc4
+    const int f0 = e.new_buf(Hd + "lvl" + si + ".s0", lvl, hc2 + hc4);
+    e.conv({Hd + "cv2." + si + ".0", Hd + "cv4." + si + ".0"}, {hc2, hc4}, P[i], e.whole(f0), 3, 1);
+    const int t2 = e.new_buf(Hd + "cv2." + si + ".t", lvl, hc2), t4 = e.new_buf(Hd + "cv4." + si + ".t", lvl, hc4);
+    e.conv1(Hd + "cv2." + si + ".1", e.slice(f0, 0, hc2), e.whole(t2), 3, 1);
+    e.conv1(Hd + "cv4." + si + ".1", e.slice(f0, hc2, hc4), e.whole(t4), 3, 1);
+    const std::string b3 = Hd + "cv3." + si + ".";
+    const int u0 = e.new_buf(b3 + "u0", lvl, x), u1 = e.new_buf(b3 + "u1", lvl, hc3), u2 = e.new_buf(b3 + "u2", lvl, hc3);
+    const int u3 = e.new_buf(b3 + "u3", lvl, hc3);
+    e.dwconv({b3 + "0.0"}, {3}, P[i], e.whole(u0), 3, 1, true);
+    e.conv1(b3 + "0.1", e.whole(u0), e.whole(u1), 1, 1);
+    e.dwconv({b3 + "1.0"}, {3}, e.whole(u1), e.whole(u2), 3, 1, true);
+    e.conv1(b3 + "1.1", e.whole(u2), e.whole(u3), 1, 1);
+    e.head_out(Hd + "cv2." + si + ".2", e.whole(t2), 64, i, 0);
+    e.head_out(b3 + "2", e.whole(u3), e.nc, i, 64);
+    e.head_out(Hd + "cv4." + si + ".2", e.whole(t4), e.nm, i, 64 + e.nc);
+  }
+  e.add_weight(Hd + "dfl.conv.weight", {1, 16, 1, 1}, false);
+  // Proto (UPSTREAM block.py::Proto)
+  const int npr = ch(256);
+  const int p1 = e.new_buf(Hd + "proto.cv1", 3, npr), p2 = e.new_buf(Hd + "proto.upsample", 2, npr);
+  const int p3 = e.new_buf(Hd + "proto.cv2", 2, npr), pr = e.new_buf("proto", 2, e.nm, 1);
+  e.conv1(Hd + "proto.cv1", P[0], e.whole(p1), 3, 1);
+  {
+    Op op;
+    op.kind = OP_CONV; op.name = Hd + "proto.upsample";
+    op.cin = npr; op.cout = 4 * npr; op.k = 1; op.s = 1; op.act = 0; op.out_mode = OUT_SHUFFLE2_BF16;
+    op.in = e.whole(p1); op.out = e.whole(p2);
+    ConvSrc src{Hd + "proto.upsample", SRC_CONVT, npr};
+    e.add_conv_weights(src, npr, 2);
+    op.srcs.push_back(src);
+    e.ops.push_back(op);
+  }
+  e.conv1(Hd + "proto.cv2", e.whole(p2), e.whole(p3), 3, 1);
+  {
+    e.conv1(Hd + "proto.cv3", e.whole(p3), e.whole(pr), 1, 1);
+    e.ops.back().out_mode = OUT_F32;
+  }
+  e.proto_buf = pr;
+  e.name_view("proto", e.whole(pr));
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // weights: BN fold + repack
 // ------------------------------------------------------------------------------------------------
@@ -685,6 +852,7 @@ int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out) {
   const std::string s = model_spec;
   if (s.size() == 11 && s.rfind("yolov8", 0) == 0 && s.substr(7) == "-seg") ok = build_v8seg(*e, s[6]);
   if (s == "yolov10n") ok = build_v10n(*e);
+  if (s.size() == 11 && s.rfind("yolo11", 0) == 0 && s.substr(7) == "-seg") ok = build_v11seg(*e, s[6]);
   if (!ok) {
     delete e;
     return fail(YPB_ERR_ARG, "unknown model spec '" + s + "'");
@@ -800,13 +968,14 @@ int ypb_finalize_weights(ypb_engine* e, int device) {
       } else {
         uint16_t* wg = reinterpret_cast<uint16_t*>(host.data() + op.w_off);
         const int kk = op.k * op.k;
+        const int cr = op.cin_real > 0 ? op.cin_real : op.cin;  // padded input / output channels keep zero weights
         for (int co = 0; co < s.cout; ++co)
-          for (int ci = 0; ci < op.cin; ++ci)
+          for (int ci = 0; ci < cr; ++ci)
             for (int t = 0; t < kk; ++t)
-              wg[((size_t)t * op.cout + n_off + co) * op.cin + ci] = f32_to_bf16(w[((size_t)co * op.cin + ci) * kk + t]);
+              wg[((size_t)t * op.cout + n_off + co) * op.cin + ci] = f32_to_bf16(w[((size_t)co * cr + ci) * kk + t]);
         for (int co = 0; co < s.cout; ++co) bias[n_off + co] = b[co];
       }
-      n_off += s.cout;
+      n_off += s.width();
     }
   }
   CUDA_TRY(cudaSetDevice(device));

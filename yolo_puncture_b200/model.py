@@ -25,7 +25,7 @@ from .engine import MAX_DET, Engine, YpbError
 from .results import Results
 from .synth import synth_state_dict
 
-KNOWN_SPECS = tuple(f"yolov8{s}-seg" for s in "nsmlx") + ("yolov10n",)
+KNOWN_SPECS = tuple(f"yolov8{s}-seg" for s in "nsmlx") + ("yolov10n",) + tuple(f"yolo11{s}-seg" for s in "nsmlx")
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -282,10 +282,23 @@ def run_ours(args, wl):
 
     v_pin, ms_pin, e2e_steps, boxes = run_e2e(frames_pinned)
     v_page, ms_page, _, _ = run_e2e(frames)
+    handoff = None
+    if is_seg:  # index-mask hand-off to the tracker (reference yolo_with_deva.py:54-88) on one step's Results
+        from yolo_puncture_b200 import index_masks
+        res_h = yolo.predict(frames_pinned, conf=CONF, iou=IOU, retina_masks=True, imgsz=imgsz, batch=B)
+        index_masks(res_h)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            out_h = index_masks(res_h, suppress_small_mask=True, min_area=100)
+        torch.cuda.synchronize()
+        handoff = {"ms_per_step": (time.perf_counter() - t0) / 5 * 1e3, "frames": B,
+                   "kept_objects": sum(len(i) for _, i in out_h),
+                   "note": "index_masks(): int64 (H0,W0) id map + (id, score, class) list per frame, 3 launches per batch"}
     e2e = {"value": v_pin, "unit": "frames/s",
            "h2d_bytes_per_step": B * H * W * 3 + B * 5 * 4, "d2h_bytes_per_step": B * 4 + int(boxes.numel()) * 4,
            "steps": e2e_steps, "ms_per_step": ms_pin,
-           "pageable_frames": {"value": v_page, "ms_per_step": ms_page},
+           "pageable_frames": {"value": v_page, "ms_per_step": ms_page}, "index_mask_handoff": handoff,
            "note": "YOLO.predict() on host frames in pinned memory: H2D of the uint8 frames + engine + D2H of counts and "
                    "boxes every step; masks stay on the device as in upstream Results.  pageable_frames = the same call on "
                    "ordinary numpy frames (predict() stages them into pinned memory with host threads first)"}

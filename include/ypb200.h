@@ -152,6 +152,13 @@ int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float*
             int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,
             int32_t* count /*(B)*/);
 size_t ypb_nms_scratch_bytes(int B, int N);
+/* Index-mask hand-off to the tracker (replaces the per-detection loop of reference yolo_seg/yolo_with_deva.py:54-88).
+   masks: (n_total, H, W) uint8 {0,1} in detection order, frame b owning rows [offsets[b], offsets[b+1]) (offsets on the
+   device).  area (n_total) receives the pixel count of every mask, ids (n_total) the 1-based id of every kept detection
+   inside its frame (0 = suppressed: area < min_area; min_area < 0 keeps everything), index_map (B, H, W) int64 the id
+   of the LAST kept detection covering each pixel, else 0.  All device pointers, caller's stream. */
+int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int H, int W,
+                    int min_area, int32_t* area, int32_t* ids, int64_t* index_map);
 /* Zero-staging path of predict(): is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / pinned torch
    tensor)?  and: copy n such frames to consecutive device slots on `cuda_stream`, merging adjacent sources. */
 int ypb_host_is_pinned(const void* p, int* pinned);

@@ -1,0 +1,24 @@
+"""Oracle of the index-mask hand-off (test infrastructure; see oracle/__init__.py).
+
+Restates reference yolo_seg/yolo_with_deva.py:54-88 (`auto_segment`, masks already at frame size): torch CPU, the same
+loop, `.sum()` filter and boolean scatter as the reference."""
+
+import torch
+
+
+def auto_segment_index_mask(masks, conf, cls, suppress_small_mask=True, min_area=100):
+    """masks: (n, H, W) float {0,1} or None; conf, cls: (n,).  Returns (int64 (H, W) index mask, list of (id, score, category_id))."""
+    if masks is None or len(masks) == 0:
+        return None, []
+    h, w = masks.shape[1:]
+    output_mask = torch.zeros((h, w), dtype=torch.int64)
+    segments_info = []
+    curr_id = 1
+    for i in range(len(masks)):
+        mask = masks[i].float()
+        if suppress_small_mask and mask.sum() < min_area:
+            continue
+        output_mask[mask > 0.5] = curr_id
+        segments_info.append((curr_id, float(conf[i]), int(cls[i])))
+        curr_id += 1
+    return output_mask, segments_info

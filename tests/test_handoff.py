@@ -1,0 +1,86 @@
+"""Index-mask hand-off (reference yolo_seg/yolo_with_deva.py:54-88): oracle micro-case on the CPU,
+kernel vs oracle on the GPU (random masks and real predict() output) — integer output, bit-exact."""
+import pytest
+import torch
+
+from oracle.handoff import auto_segment_index_mask
+
+
+def test_oracle_overwrite_order_and_small_mask_suppression():
+    m = torch.zeros(3, 20, 20)
+    m[0, 0:15, 0:15] = 1       # 225 px  -> id 1
+    m[1, 2:5, 2:5] = 1         # 9 px    -> suppressed (< 100), id not consumed
+    m[2, 5:18, 5:18] = 1       # 169 px  -> id 2, overwrites the overlap with detection 0
+    out, info = auto_segment_index_mask(m, torch.tensor([0.9, 0.8, 0.7]), torch.tensor([3.0, 4.0, 5.0]), True, 100)
+    assert [i[0] for i in info] == [1, 2] and [i[2] for i in info] == [3, 5]
+    assert out[0, 0] == 1 and out[3, 3] == 1 and out[10, 10] == 2 and out[19, 19] == 0
+    out2, info2 = auto_segment_index_mask(m, torch.tensor([0.9, 0.8, 0.7]), torch.tensor([3.0, 4.0, 5.0]), False, 100)
+    assert [i[0] for i in info2] == [1, 2, 3] and out2[3, 3] == 2 and out2[10, 10] == 3
+
+
+class _FakeBoxes:
+    def __init__(self, conf, cls):
+        self.conf, self.cls, self.data = conf, cls, conf
+
+
+class _FakeMasks:
+    def __init__(self, raw):
+        self.raw = raw
+
+
+class _FakeResults:
+    def __init__(self, raw, conf, cls, shape):
+        self.masks = _FakeMasks(raw) if raw is not None else None
+        self.boxes = _FakeBoxes(conf, cls)
+        self.orig_shape = shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W", [(640, 640), (1080, 1920), (37, 53)])
+@pytest.mark.parametrize("suppress", [True, False])
+def test_index_masks_kernel_matches_oracle_on_random_masks(H, W, suppress):
+    from yolo_puncture_b200 import index_masks
+    g = torch.Generator().manual_seed(H * 7 + W)
+    counts = [5, 0, 1, 17]
+    res, refs = [], []
+    for n in counts:
+        if n == 0:
+            res.append(_FakeResults(None, torch.zeros(0), torch.zeros(0), (H, W)))
+            refs.append((None, []))
+            continue
+        m = torch.zeros(n, H, W, dtype=torch.uint8)
+        for i in range(n):  # rectangles of very different areas, some tiny
+            y0, x0 = int(torch.randint(0, H - 2, (1,), generator=g)), int(torch.randint(0, W - 2, (1,), generator=g))
+            hh, ww = int(torch.randint(1, max(2, H // 2), (1,), generator=g)), int(torch.randint(1, max(2, W // 2), (1,), generator=g))
+            if i % 3 == 0:
+                hh, ww = min(hh, 6), min(ww, 9)
+            m[i, y0:y0 + hh, x0:x0 + ww] = 1
+        conf, cls = torch.rand(n, generator=g), torch.randint(0, 80, (n,), generator=g).float()
+        res.append(_FakeResults(m.cuda(), conf.cuda(), cls.cuda(), (H, W)))
+        refs.append(auto_segment_index_mask(m.float(), conf, cls, suppress, 100))
+    out = index_masks(res, suppress_small_mask=suppress, min_area=100)
+    for (imap, info), (rmap, rinfo) in zip(out, refs):
+        if rmap is None:
+            assert int(imap.abs().sum()) == 0 and info == []
+            continue
+        assert torch.equal(imap.cpu(), rmap)
+        assert [(d["id"], d["category_id"]) for d in info] == [(i[0], i[2]) for i in rinfo]
+        assert all(abs(d["score"] - i[1]) < 1e-6 for d, i in zip(info, rinfo))
+
+
+@pytest.mark.gpu
+def test_index_masks_on_predict_output():
+    from yolo_puncture_b200 import YOLO, index_masks, synth
+    yolo = YOLO("yolov8n-seg", device=0)
+    frames = synth.synth_frames(6)
+    res = yolo.predict(frames, conf=0.25, retina_masks=True)
+    out = index_masks(res, suppress_small_mask=True, min_area=100)
+    assert len(out) == len(frames)
+    for r, (imap, info) in zip(res, out):
+        assert imap.shape == (640, 640) and imap.dtype == torch.int64
+        if r.masks is None:
+            assert info == [] and int(imap.max()) == 0
+            continue
+        rmap, rinfo = auto_segment_index_mask(r.masks.data.cpu(), r.boxes.conf.cpu(), r.boxes.cls.cpu(), True, 100)
+        assert torch.equal(imap.cpu(), rmap)
+        assert [(d["id"], d["category_id"]) for d in info] == [(i[0], i[2]) for i in rinfo]

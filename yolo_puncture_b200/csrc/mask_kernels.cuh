@@ -204,4 +204,80 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Index-mask hand-off.  Replaces the per-detection Python loop of reference
+// yolo_seg/yolo_with_deva.py:54-88 (`auto_segment`): for the detections of a frame in order, skip those whose mask
+// area is below a threshold (`suppress_small_mask`), give the others ids 1, 2, ... and paint `output_mask[mask > 0.5] = id`
+// (later detections overwrite earlier ones).  Three launches for a whole batch of frames instead of a `.sum()` host
+// sync and a boolean scatter per detection.
+// ------------------------------------------------------------------------------------------------
+// area[i] += number of set pixels in a slice of mask i.  grid (slices, N), 256 threads, 16 bytes per thread per step.
+__global__ void __launch_bounds__(256)
+mask_area_kernel(const uint8_t* __restrict__ masks, long long hw, int* __restrict__ area) {
+  const uint8_t* m = masks + (long long)blockIdx.y * hw;
+  const long long per = (((hw + gridDim.x - 1) / gridDim.x) + 15) & ~15LL;  // slices start on 16-byte boundaries of the mask
+  const long long lo = (long long)blockIdx.x * per, hi = min(lo + per, hw);
+  unsigned sum = 0;
+  long long i = lo + threadIdx.x * 16LL;
+  if ((reinterpret_cast<uintptr_t>(m + lo) & 15) == 0) {
+    for (; i + 16 <= hi; i += 256 * 16) {
+      const uint4 v = *reinterpret_cast<const uint4*>(m + i);
+      // bytes are 0/1: a multiply by 0x01010101 sums the four bytes of a word into its top byte
+      sum += ((v.x * 0x01010101u) >> 24) + ((v.y * 0x01010101u) >> 24) + ((v.z * 0x01010101u) >> 24) + ((v.w * 0x01010101u) >> 24);
+    }
+    // tail of the slice (fewer than 16 bytes left for this thread's last step)
+    for (long long j = i; j < hi && j < i + 16; ++j) sum += m[j];
+  } else {
+    for (long long j = lo + threadIdx.x; j < hi; j += 256) sum += m[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0 && sum) atomicAdd(area + blockIdx.y, (int)sum);
+}
+
+// ids[i] = running 1-based id of detection i inside its frame, 0 when suppressed (area < min_area; min_area < 0 keeps all)
+__global__ void mask_ids_kernel(const int* __restrict__ offsets, int nB, const int* __restrict__ area, int min_area,
+                                int* __restrict__ ids) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nB) return;
+  int cur = 0;
+  for (int i = offsets[b]; i < offsets[b + 1]; ++i) ids[i] = (min_area < 0 || area[i] >= min_area) ? ++cur : 0;
+}
+
+// index_map[b][p] = id of the LAST kept detection of frame b whose mask covers pixel p, else 0.  8 pixels per thread.
+__global__ void __launch_bounds__(256)
+index_paint_kernel(const uint8_t* __restrict__ masks, const int* __restrict__ offsets, const int* __restrict__ ids, long long hw,
+                   long long* __restrict__ index_map) {
+  const int b = blockIdx.y;
+  const long long p0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 8;
+  if (p0 >= hw) return;
+  const int lo = offsets[b], hi = offsets[b + 1];
+  long long out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool vec = p0 + 8 <= hw && ((hw & 7) == 0);
+  for (int i = lo; i < hi; ++i) {
+    const int id = ids[i];
+    if (id == 0) continue;
+    const uint8_t* m = masks + (long long)i * hw + p0;
+    if (vec) {
+      const uint2 v = *reinterpret_cast<const uint2*>(m);
+      if ((v.x | v.y) == 0u) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((v.x >> (8 * j)) & 0xffu) out[j] = id;
+        if ((v.y >> (8 * j)) & 0xffu) out[4 + j] = id;
+      }
+    } else {
+      for (int j = 0; j < 8 && p0 + j < hw; ++j)
+        if (m[j]) out[j] = id;
+    }
+  }
+  long long* o = index_map + (long long)b * hw + p0;
+  if (vec) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) *reinterpret_cast<longlong2*>(o + j) = make_longlong2(out[j], out[j + 1]);
+  } else {
+    for (int j = 0; j < 8 && p0 + j < hw; ++j) o[j] = out[j];
+  }
+}
+
 }  // namespace ypb

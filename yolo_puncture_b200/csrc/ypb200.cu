@@ -1514,6 +1514,26 @@ int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* byt
   return YPB_OK;
 }
 
+// Index-mask hand-off to the tracker (reference yolo_seg/yolo_with_deva.py:54-88), see mask_kernels.cuh.
+int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int H, int W,
+                    int min_area, int32_t* area, int32_t* ids, int64_t* index_map) {
+  if (!offsets || !index_map || B < 1 || H < 1 || W < 1 || n_total < 0 || (n_total > 0 && (!masks || !area || !ids)))
+    return fail(YPB_ERR_ARG, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const long long hw = (long long)H * W;
+  if (n_total > 0) {
+    if (n_total > 65535 || B > 65535) return fail(YPB_ERR_ARG, "index_masks: more than 65535 masks / frames per call");
+    CUDA_TRY(cudaMemsetAsync(area, 0, (size_t)n_total * 4, st));
+    const int slices = (int)std::max(1LL, std::min(64LL, hw / (256 * 16)));
+    mask_area_kernel<<<dim3(slices, n_total), 256, 0, st>>>(masks, hw, area);
+    mask_ids_kernel<<<(B + 127) / 128, 128, 0, st>>>(offsets, B, area, min_area, ids);
+  }
+  index_paint_kernel<<<dim3((unsigned)((hw + 2047) / 2048), B), 256, 0, st>>>(masks, offsets, ids, hw,
+                                                                             reinterpret_cast<long long*>(index_map));
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
 // Host helpers of the zero-staging path: frames that already live in page-locked memory (a capture / decode ring, a
 // pinned torch tensor) are copied to the device straight from where they are.
 int ypb_host_is_pinned(const void* p, int* pinned) {

@@ -1,0 +1,72 @@
+"""Index-mask hand-off to the tracker.
+
+Drop-in for the per-detection loop of reference yolo_seg/yolo_with_deva.py:54-88 (`auto_segment`): from the `Results` of
+`YOLO.predict(..., retina_masks=True)` build, per frame, the int64 (H, W) index mask DEVA consumes (pixel = 1-based id of
+the last kept detection covering it, 0 = background) and the `(id, score, category_id)` list — three kernel launches
+for a whole batch of frames (`ypb_index_masks`) instead of a `.sum()` host sync and a boolean scatter per detection.
+"""
+
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib
+
+
+def index_masks(results, suppress_small_mask=True, min_area=100):
+    """results: list of `Results` (masks at frame size, i.e. predict(retina_masks=True)).
+    Returns a list of (index_mask int64 (H, W) device tensor, segments_info list of dicts {id, score, category_id}),
+    one per frame, with the reference's semantics: detections in order; `mask.sum() < min_area` ones are skipped when
+    suppress_small_mask; kept ones get ids 1, 2, ...; later detections overwrite earlier ones."""
+    results = list(results)
+    if not results:
+        return []
+    raws, counts = [], []
+    dev = None
+    for r in results:
+        m = r.masks.raw if r.masks is not None else None
+        if m is not None:
+            if not torch.is_tensor(m) or not m.is_cuda or m.dtype != torch.uint8:
+                raise ValueError("index_masks needs the device-resident uint8 masks of YOLO.predict()")
+            if tuple(m.shape[1:]) != tuple(r.orig_shape):
+                raise ValueError("index_masks needs masks at frame size: call predict(retina_masks=True) on unresized frames")
+            dev = m.device
+        raws.append(m)
+        counts.append(0 if m is None else int(m.shape[0]))
+    shapes = {tuple(r.orig_shape) for r in results}
+    if len(shapes) != 1:
+        raise ValueError("index_masks: all frames of a call must have one size")
+    H, W = shapes.pop()
+    if dev is None:  # no detection in any frame
+        ref = results[0].boxes.data if results[0].boxes is not None and torch.is_tensor(results[0].boxes.data) else None
+        dev = ref.device if ref is not None and ref.is_cuda else torch.device("cuda")
+        return [(torch.zeros((H, W), dtype=torch.int64, device=dev), []) for _ in results]
+    B, n_total = len(results), sum(counts)
+    # masks of one predict() call are consecutive slices of one buffer: use it in place, otherwise gather once
+    present = [m for m in raws if m is not None]
+    contiguous = all(m.is_contiguous() for m in present) and all(
+        b.data_ptr() == a.data_ptr() + a.numel() for a, b in zip(present, present[1:]))
+    base = present[0] if contiguous else torch.cat(present)
+    offsets = torch.zeros(B + 1, dtype=torch.int32)
+    offsets[1:] = torch.tensor(counts, dtype=torch.int32).cumsum(0)
+    with torch.cuda.device(dev):
+        offs_d = offsets.to(dev, non_blocking=True)
+        area = torch.empty(n_total, dtype=torch.int32, device=dev)
+        ids = torch.empty(n_total, dtype=torch.int32, device=dev)
+        index_map = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        check(lib().ypb_index_masks(C.c_void_p(st), C.c_void_p(base.data_ptr()), C.c_void_p(offs_d.data_ptr()), B, n_total, H, W,
+                                    int(min_area) if suppress_small_mask else -1, C.c_void_p(area.data_ptr()),
+                                    C.c_void_p(ids.data_ptr()), C.c_void_p(index_map.data_ptr())))
+        ids_h = ids.cpu().tolist()  # the one host sync of the hand-off
+    out, k = [], 0
+    for b, r in enumerate(results):
+        info = []
+        if counts[b]:
+            conf, cls = r.boxes.conf.cpu().tolist(), r.boxes.cls.cpu().tolist()
+            for i in range(counts[b]):
+                if ids_h[k + i]:
+                    info.append({"id": ids_h[k + i], "score": float(conf[i]), "category_id": int(cls[i])})
+        k += counts[b]
+        out.append((index_map[b], info))
+    return out

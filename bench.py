@@ -296,7 +296,7 @@ def run_ours(args, wl):
                    "kept_objects": sum(len(i) for _, i in out_h),
                    "note": "index_masks(): int64 (H0,W0) id map + (id, score, class) list per frame, 3 launches per batch"}
     e2e = {"value": v_pin, "unit": "frames/s",
-           "h2d_bytes_per_step": B * H * W * 3 + B * 5 * 4, "d2h_bytes_per_step": B * 4 + int(boxes.numel()) * 4,
+           "h2d_bytes_per_step": B * hw[0] * hw[1] * 3 + B * 5 * 4,  # raw frames (LetterBox runs on the device) "d2h_bytes_per_step": B * 4 + int(boxes.numel()) * 4,
            "steps": e2e_steps, "ms_per_step": ms_pin,
            "pageable_frames": {"value": v_page, "ms_per_step": ms_page}, "index_mask_handoff": handoff,
            "note": "YOLO.predict() on host frames in pinned memory: H2D of the uint8 frames + engine + D2H of counts and "

@@ -152,6 +152,13 @@ int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float*
             int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,
             int32_t* count /*(B)*/);
 size_t ypb_nms_scratch_bytes(int B, int N);
+/* LetterBox on the device (UPSTREAM data/augment.py::LetterBox for frames at least as large as the network input):
+   src (B,H0,W0,3) uint8 -> dst (B,H,W,3): cv2.INTER_LINEAR resize to (new_h,new_w) pasted at (top,left), rest = pad_value.
+   xofs/yofs (new_w / new_h int32 source indices) and xa/ya (2 int16 11-bit coefficients per output column / row) are
+   built by the caller exactly as OpenCV builds them (model.py::cv2_linear_tables); device pointers, caller's stream. */
+int ypb_letterbox_u8(void* cuda_stream, const uint8_t* src, int B, int H0, int W0, uint8_t* dst, int H, int W, int new_w,
+                     int new_h, int top, int left, const int32_t* xofs, const int16_t* xa, const int32_t* yofs,
+                     const int16_t* ya, int pad_value);
 /* Index-mask hand-off to the tracker (replaces the per-detection loop of reference yolo_seg/yolo_with_deva.py:54-88).
    masks: (n_total, H, W) uint8 {0,1} in detection order, frame b owning rows [offsets[b], offsets[b+1]) (offsets on the
    device).  area (n_total) receives the pixel count of every mask, ids (n_total) the 1-based id of every kept detection

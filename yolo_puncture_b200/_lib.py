@@ -66,6 +66,8 @@ SIGNATURES = {
                         c_void_p, c_void_p]),
     "ypb_nms_scratch_bytes": (c_size_t, [c_int, c_int]),
     "ypb_stage_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
+    "ypb_letterbox_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "ypb_index_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ypb_host_is_pinned": (c_int, [c_void_p, C.POINTER(c_int)]),
     "ypb_h2d_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int]),

@@ -143,4 +143,42 @@ sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int nB, int h, int w, int c) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// LetterBox on the device: raw uint8 BGR frames -> resized (cv2.INTER_LINEAR) and 114-padded
+// network input.  Replaces the host cv2.resize + copyMakeBorder of UPSTREAM data/augment.py::LetterBox for the
+// down-scaling case (video frames larger than the network size), bit for bit: OpenCV's 8-bit bilinear resize is
+// fixed-point — 11-bit coefficients (tables built on the host exactly as cv2 builds them), horizontal pass in int32,
+// vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2.  One thread per output pixel (3 channels).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+letterbox_u8_kernel(const uint8_t* __restrict__ src, int nB, int H0, int W0, uint8_t* __restrict__ dst, int H, int W, int new_w,
+                    int new_h, int top, int left, const int* __restrict__ xofs, const short* __restrict__ xa,
+                    const int* __restrict__ yofs, const short* __restrict__ ya, int pad) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)H * W;
+  if (idx >= per * nB) return;
+  const int b = (int)(idx / per);
+  const int rem = (int)(idx - (long long)b * per);
+  const int y = rem / W, x = rem - y * W;
+  uint8_t* o = dst + idx * 3;
+  const int ry = y - top, rx = x - left;
+  if (ry < 0 || ry >= new_h || rx < 0 || rx >= new_w) {
+    o[0] = o[1] = o[2] = (uint8_t)pad;
+    return;
+  }
+  const int x0 = xofs[rx], x1 = min(x0 + 1, W0 - 1), y0 = yofs[ry], y1 = min(y0 + 1, H0 - 1);
+  const int a0 = xa[2 * rx], a1 = xa[2 * rx + 1], b0 = ya[2 * ry], b1 = ya[2 * ry + 1];
+  const uint8_t* f = src + (long long)b * H0 * W0 * 3;
+  const uint8_t* r0 = f + (long long)y0 * W0 * 3;
+  const uint8_t* r1 = f + (long long)y1 * W0 * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = r0[x0 * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+    const int h1 = r1[x0 * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+    int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    o[c] = (uint8_t)v;
+  }
+}
+
 }  // namespace ypb

@@ -1514,6 +1514,20 @@ int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* byt
   return YPB_OK;
 }
 
+// LetterBox on the device (misc_kernels.cuh): all pointers device, tables built by the caller as cv2 builds them.
+int ypb_letterbox_u8(void* cuda_stream, const uint8_t* src, int B, int H0, int W0, uint8_t* dst, int H, int W, int new_w,
+                     int new_h, int top, int left, const int32_t* xofs, const int16_t* xa, const int32_t* yofs,
+                     const int16_t* ya, int pad_value) {
+  if (!src || !dst || !xofs || !xa || !yofs || !ya || B < 1 || H0 < 1 || W0 < 1 || H < 1 || W < 1 || new_w < 1 || new_h < 1 ||
+      top < 0 || left < 0 || top + new_h > H || left + new_w > W)
+    return fail(YPB_ERR_ARG, "bad argument");
+  const long long total = (long long)B * H * W;
+  letterbox_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+      src, B, H0, W0, dst, H, W, new_w, new_h, top, left, xofs, xa, yofs, ya, pad_value);
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
 // Index-mask hand-off to the tracker (reference yolo_seg/yolo_with_deva.py:54-88), see mask_kernels.cuh.
 int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int H, int W,
                     int min_area, int32_t* area, int32_t* ids, int64_t* index_map) {

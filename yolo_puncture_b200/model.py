@@ -60,6 +60,24 @@ def letterbox_into(dst, img, new_unpad, top, left):
     dst[top:top + h, left:left + w] = img
 
 
+def cv2_linear_tables(src_n, dst_n):
+    """Source index and 11-bit fixed-point coefficient pair of every output column (or row) of OpenCV's 8-bit
+    INTER_LINEAR resize, built the way cv2 builds them (resize.cpp): scale = 1/(dst/src) in double,
+    f = float((d+0.5)*scale - 0.5), s = floor(f), f -= s, clamped at both borders, coefficients
+    saturate_cast<short>((1-f, f) * 2048).  Bit-exact against cv2.resize when down-scaling (tests/test_letterbox.py)."""
+    scale = 1.0 / (dst_n / src_n)
+    d = np.arange(dst_n, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int32)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    lo, hi = s < 0, s >= src_n - 1
+    f[lo | hi] = 0.0
+    s[lo] = 0
+    s[hi] = src_n - 1
+    coef = np.stack([np.rint((np.float32(1.0) - f) * np.float32(2048.0)), np.rint(f * np.float32(2048.0))], 1).astype(np.int16)
+    return s, coef
+
+
 _POOL = None
 
 
@@ -159,6 +177,7 @@ class YOLO:
         self._staging = {}
         self.overrides = {}
         self.micro_batch = 32  # frames per engine pass inside predict(); H2D of pass k+1 overlaps compute of pass k
+        self.device_letterbox = True  # resize + pad on the GPU when the frame is at least as large as the network input
         if device is not None:
             self._set_device(device)
 
@@ -243,6 +262,24 @@ class YOLO:
             }}
         return self._staging[key]
 
+    def _letterbox_buffers(self, buf, B, mb, shape, new_unpad, need_host=True):
+        """Raw-frame staging and the cv2 coefficient tables of the device LetterBox for one source shape."""
+        key = (B, mb, tuple(shape[:2]), tuple(new_unpad))
+        lb = buf.get("letterbox")
+        if lb is not None and lb["key"] == key and need_host and lb["raw_host"] is None:
+            lb["raw_host"] = torch.empty((B, shape[0], shape[1], 3), dtype=torch.uint8).pin_memory()
+        if lb is None or lb["key"] != key:
+            xofs, xa = cv2_linear_tables(shape[1], new_unpad[0])
+            yofs, ya = cv2_linear_tables(shape[0], new_unpad[1])
+            dev = self._device
+            lb = {"key": key,
+                  "raw_host": torch.empty((B, shape[0], shape[1], 3), dtype=torch.uint8).pin_memory() if need_host else None,
+                  "raw_dev": [torch.empty((mb, shape[0], shape[1], 3), dtype=torch.uint8, device=dev) for _ in range(2)],
+                  "xofs": torch.from_numpy(xofs).to(dev), "xa": torch.from_numpy(xa).to(dev),
+                  "yofs": torch.from_numpy(yofs).to(dev), "ya": torch.from_numpy(ya).to(dev)}
+            buf["letterbox"] = lb
+        return lb
+
     def _predict_batch(self, frames, shape, imgsz, auto, conf, iou, retina, max_det, classes, agnostic):
         """One group of same-shape frames.  The group runs as micro-batches of `mb` frames through one static engine
         plan: frames are letterboxed into pinned memory by host threads, each micro-batch's H2D copy is issued on a
@@ -274,10 +311,12 @@ class YOLO:
             direct = (shape[0], shape[1]) == (H, W)  # frames already have the network size: staging is a plain copy
             futs = None
             pinned = False
-            if direct:
+            # LetterBox on the device when it is a down-scale (bit-exact with cv2 there): the raw frames are uploaded
+            # and resized + padded by one kernel instead of cv2.resize on host threads
+            dev_lb = (not direct) and self.device_letterbox and new_unpad[0] <= shape[1] and new_unpad[1] <= shape[0]
+            if direct or dev_lb:
                 frames_c = [f if f.flags["C_CONTIGUOUS"] else np.ascontiguousarray(f) for f in frames]
-                nbytes = H * W * 3
-                dst_ptrs = (ctypes.c_void_p * B)(*[buf["host"][i].data_ptr() for i in range(B)])
+                nbytes = shape[0] * shape[1] * 3  # == H * W * 3 when direct
                 src_ptrs = (ctypes.c_void_p * B)(*[f.ctypes.data for f in frames_c])
                 sizes = (ctypes.c_size_t * B)(*([nbytes] * B))
                 nthreads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
@@ -289,6 +328,11 @@ class YOLO:
                     if not flag.value:
                         pinned = False
                         break
+                if dev_lb:
+                    lb = self._letterbox_buffers(buf, B, mb, shape, new_unpad, need_host=not pinned)
+                if not pinned:
+                    stage_host = lb["raw_host"] if dev_lb else buf["host"]
+                    dst_ptrs = (ctypes.c_void_p * B)(*[stage_host[i].data_ptr() for i in range(B)])
             else:
                 futs = [_pool().submit(letterbox_into, host[i], f, new_unpad, top, left) for i, f in enumerate(frames)]
             cs.wait_stream(main)
@@ -299,27 +343,28 @@ class YOLO:
             def enqueue_h2d(k):
                 lo, hi = k * mb, min((k + 1) * mb, B)
                 slot = k & 1
-                if pinned:
-                    with torch.cuda.stream(cs):
-                        if buf["in_free"][slot] is not None:
-                            cs.wait_event(buf["in_free"][slot])
-                        check(lib().ypb_h2d_frames(ctypes.c_void_p(cs.cuda_stream), ctypes.c_void_p(buf["dev"][slot].data_ptr()),
-                                                   ctypes.byref(src_ptrs, lo * ctypes.sizeof(ctypes.c_void_p)), nbytes, hi - lo))
-                        ev = torch.cuda.Event()
-                        ev.record(cs)
-                    h2d_done.append(ev)
-                    return
-                if direct:  # native multi-threaded copy into pinned memory (ctypes drops the GIL)
-                    vp = ctypes.sizeof(ctypes.c_void_p)
+                vp = ctypes.sizeof(ctypes.c_void_p)
+                if (direct or dev_lb) and not pinned:  # native multi-threaded copy into pinned memory (ctypes drops the GIL)
                     check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, lo * vp), ctypes.byref(src_ptrs, lo * vp),
                                                  ctypes.byref(sizes, lo * ctypes.sizeof(ctypes.c_size_t)), hi - lo, nthreads))
-                else:
+                elif not (direct or dev_lb):
                     for fu in futs[lo:hi]:
                         fu.result()
                 with torch.cuda.stream(cs):
                     if buf["in_free"][slot] is not None:
                         cs.wait_event(buf["in_free"][slot])
-                    buf["dev"][slot][: hi - lo].copy_(buf["host"][lo:hi], non_blocking=True)
+                    target = lb["raw_dev"][slot] if dev_lb else buf["dev"][slot]
+                    if pinned:  # frames already live in page-locked memory: copy from where they are
+                        check(lib().ypb_h2d_frames(ctypes.c_void_p(cs.cuda_stream), ctypes.c_void_p(target.data_ptr()),
+                                                   ctypes.byref(src_ptrs, lo * vp), nbytes, hi - lo))
+                    else:
+                        target[: hi - lo].copy_((lb["raw_host"] if dev_lb else buf["host"])[lo:hi], non_blocking=True)
+                    if dev_lb:
+                        check(lib().ypb_letterbox_u8(
+                            ctypes.c_void_p(cs.cuda_stream), ctypes.c_void_p(target.data_ptr()), hi - lo, shape[0], shape[1],
+                            ctypes.c_void_p(buf["dev"][slot].data_ptr()), H, W, new_unpad[0], new_unpad[1], top, left,
+                            ctypes.c_void_p(lb["xofs"].data_ptr()), ctypes.c_void_p(lb["xa"].data_ptr()),
+                            ctypes.c_void_p(lb["yofs"].data_ptr()), ctypes.c_void_p(lb["ya"].data_ptr()), 114))
                     ev = torch.cuda.Event()
                     ev.record(cs)
                 h2d_done.append(ev)

@@ -152,6 +152,10 @@ int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float*
             int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,
             int32_t* count /*(B)*/);
 size_t ypb_nms_scratch_bytes(int B, int N);
+/* Needle length on the device (replaces D2H of the mask + cv2.findContours + cv2.minAreaRect of reference
+   yolo_seg/app.py:97-105, utils/mask_tools.py:12-22): for every (H,W) uint8 {0,1} mask the long side of its
+   minimum-area bounding rectangle and long / max(short, 1).  row_extents: scratch of n*H*2 int32.  Device pointers. */
+int ypb_mask_min_rect(void* cuda_stream, const uint8_t* masks, int n, int H, int W, int32_t* row_extents, float* out);
 /* LetterBox on the device (UPSTREAM data/augment.py::LetterBox for frames at least as large as the network input):
    src (B,H0,W0,3) uint8 -> dst (B,H,W,3): cv2.INTER_LINEAR resize to (new_h,new_w) pasted at (top,left), rest = pad_value.
    xofs/yofs (new_w / new_h int32 source indices) and xa/ya (2 int16 11-bit coefficients per output column / row) are

@@ -22,3 +22,24 @@ def auto_segment_index_mask(masks, conf, cls, suppress_small_mask=True, min_area
         segments_info.append((curr_id, float(conf[i]), int(cls[i])))
         curr_id += 1
     return output_mask, segments_info
+
+
+def coord_min_rect_len(mask):
+    """Reference yolo_seg/app.py:101-102 + utils/mask_tools.py:12-22 for one (H, W) {0,1} mask: external contours
+    (cv2.findContours, as `Masks.xy` does), int32 points, cv2.minAreaRect -> (long side, long / max(short, 1))."""
+    import cv2
+    import numpy as np
+    m = np.ascontiguousarray(np.asarray(mask).astype(np.uint8))
+    c = cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[0]
+    if not c:
+        return 0.0, 0.0
+    pts = np.concatenate([p.reshape(-1, 2) for p in c]).astype(np.float32)
+    points = np.array(pts, dtype=np.int32).reshape((-1, 2))
+    if len(points) < 3:
+        return 0.0, 0.0
+    (_, (width, height), _) = cv2.minAreaRect(points)
+    length = max(width, height)
+    width = min(height, width)
+    if width == 0:
+        width = 1
+    return float(length), float(length / width)

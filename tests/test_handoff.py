@@ -3,7 +3,7 @@ kernel vs oracle on the GPU (random masks and real predict() output) — integer
 import pytest
 import torch
 
-from oracle.handoff import auto_segment_index_mask
+from oracle.handoff import auto_segment_index_mask, coord_min_rect_len
 
 
 def test_oracle_overwrite_order_and_small_mask_suppression():
@@ -84,3 +84,68 @@ def test_index_masks_on_predict_output():
         rmap, rinfo = auto_segment_index_mask(r.masks.data.cpu(), r.boxes.conf.cpu(), r.boxes.cls.cpu(), True, 100)
         assert torch.equal(imap.cpu(), rmap)
         assert [(d["id"], d["category_id"]) for d in info] == [(i[0], i[2]) for i in rinfo]
+
+
+def _shape_masks(H, W):
+    """Rotated rectangles, an ellipse, two separate blobs, an L shape: masks whose minimum-area rectangle is unambiguous."""
+    import cv2
+    import numpy as np
+    ms = []
+    for (cx, cy, w, h, ang) in [(300, 200, 220, 40, 17.0), (150, 400, 90, 60, -33.0), (400, 420, 300, 12, 71.0), (320, 320, 50, 50, 45.0)]:
+        m = np.zeros((H, W), np.uint8)
+        box = cv2.boxPoints(((cx, cy), (w, h), ang)).astype(np.int32)
+        cv2.fillPoly(m, [box], 1)
+        ms.append(m)
+    m = np.zeros((H, W), np.uint8)
+    cv2.ellipse(m, (250, 300), (120, 35), 28.0, 0, 360, 1, -1)
+    ms.append(m)
+    m = np.zeros((H, W), np.uint8)
+    cv2.circle(m, (100, 100), 30, 1, -1)
+    cv2.circle(m, (400, 180), 22, 1, -1)
+    ms.append(m)
+    m = np.zeros((H, W), np.uint8)
+    m[100:400, 100:140] = 1
+    m[360:400, 100:300] = 1
+    ms.append(m)
+    return np.stack(ms)
+
+
+def test_oracle_min_rect_len_of_an_axis_aligned_bar():
+    import numpy as np
+    m = np.zeros((100, 100), np.uint8)
+    m[10:20, 5:85] = 1  # 80 x 10 pixels -> pixel-centre extents 79 x 9
+    length, ratio = coord_min_rect_len(m)
+    assert abs(length - 79.0) < 1e-3 and abs(ratio - 79.0 / 9.0) < 1e-3
+
+
+@pytest.mark.gpu
+def test_min_rect_len_matches_cv2_on_shapes():
+    from yolo_puncture_b200 import min_rect_len
+    ms = _shape_masks(480, 640)
+    got = min_rect_len(torch.from_numpy(ms).cuda()).cpu()
+    for i, m in enumerate(ms):
+        length, ratio = coord_min_rect_len(m)
+        assert abs(float(got[i, 0]) - length) <= 2e-2 + 1e-4 * length, (i, float(got[i, 0]), length)
+        assert abs(float(got[i, 1]) - ratio) <= 1e-2 * ratio, (i, float(got[i, 1]), ratio)
+
+
+@pytest.mark.gpu
+def test_min_rect_len_on_predict_output():
+    from yolo_puncture_b200 import YOLO, min_rect_len, synth
+    yolo = YOLO("yolov8n-seg", device=0)
+    res = yolo.predict(synth.synth_frames(4), conf=0.25, retina_masks=True)
+    checked = 0
+    for r in res:
+        if r.masks is None:
+            continue
+        got = min_rect_len(r.masks).cpu()
+        m = r.masks.raw.cpu().numpy()
+        for i in range(len(m)):
+            if int(m[i].sum()) < 50:
+                continue
+            length, ratio = coord_min_rect_len(m[i])
+            # the minimum-area rectangle can be ambiguous (two orientations of nearly equal area): compare areas,
+            # and the length when the areas pin the same rectangle
+            assert abs(float(got[i, 0]) - length) <= 0.05 + 2e-3 * length, (i, float(got[i, 0]), length)
+            checked += 1
+    assert checked > 0

@@ -280,4 +280,108 @@ index_paint_kernel(const uint8_t* __restrict__ masks, const int* __restrict__ of
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Needle length on the device.  The reference measures the needle as the long side of
+// cv2.minAreaRect of the best detection's contour polygon (reference yolo_seg/app.py:97-105 ->
+// utils/mask_tools.py:12-22 `get_coord_min_rect_len`), which costs a D2H copy of the full mask plus cv2.findContours
+// per frame.  The minimum-area rectangle of the contour equals that of the convex hull of the mask's set pixels, and
+// every hull vertex is the first or last set pixel of its row, so:
+//   mask_row_extents_kernel : one warp per (mask, row) -> (xmin, xmax) of the set pixels of that row;
+//   mask_min_rect_kernel    : one CTA per mask -> convex hull of the <= 2H extent points (monotone chain, integer
+//                             cross products) and, for every hull edge in parallel, the bounding rectangle aligned
+//                             with it; the smallest area wins (what rotating calipers enumerates).
+// Output per mask: (length = long side, ratio = long / max(short, 1)), the reference's return values.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+mask_row_extents_kernel(const uint8_t* __restrict__ masks, int H, int W, int2* __restrict__ ext) {
+  const int lane = threadIdx.x & 31;
+  const int y = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (y >= H) return;
+  const uint8_t* row = masks + ((long long)blockIdx.y * H + y) * W;
+  int lo = 1 << 30, hi = -1;
+  for (int x = lane; x < W; x += 32) {
+    if (row[x]) {
+      lo = min(lo, x);
+      hi = max(hi, x);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) ext[(long long)blockIdx.y * H + y] = make_int2(lo, hi);
+}
+
+constexpr int kRectMaxPts = 2 * 2304;  // rows of the largest supported frame (2304) x 2
+
+__global__ void __launch_bounds__(256)
+mask_min_rect_kernel(const int2* __restrict__ ext, int H, float* __restrict__ out /*(n,2)*/) {
+  __shared__ short2 s_pts[kRectMaxPts];
+  __shared__ short2 s_hull[kRectMaxPts + 2];
+  __shared__ int s_n, s_h;
+  __shared__ float s_best[256], s_w[256], s_hh[256];
+  const int2* e = ext + (long long)blockIdx.x * H;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int y = 0; y < H; ++y) {  // points sorted by (y, x)
+      const int2 v = e[y];
+      if (v.y < 0) continue;
+      s_pts[n++] = make_short2((short)v.x, (short)y);
+      if (v.y != v.x) s_pts[n++] = make_short2((short)v.y, (short)y);
+    }
+    s_n = n;
+    // Andrew's monotone chain (y-major order): integer cross products, collinear points dropped
+    int k = 0;
+    auto cross = [](short2 o, short2 a, short2 b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); };
+    for (int i = 0; i < n; ++i) {
+      while (k >= 2 && cross(s_hull[k - 2], s_hull[k - 1], s_pts[i]) <= 0) --k;
+      s_hull[k++] = s_pts[i];
+    }
+    for (int i = n - 2, t = k + 1; i >= 0; --i) {
+      while (k >= t && cross(s_hull[k - 2], s_hull[k - 1], s_pts[i]) <= 0) --k;
+      s_hull[k++] = s_pts[i];
+    }
+    s_h = n > 1 ? k - 1 : n;  // the last point repeats the first
+  }
+  __syncthreads();
+  const int h = s_h;
+  float best = 3.0e38f, bw = 0.f, bh = 0.f;
+  if (h >= 3) {
+    for (int i = threadIdx.x; i < h; i += 256) {
+      const short2 a = s_hull[i], b = s_hull[(i + 1) % h];
+      const float ex = (float)(b.x - a.x), ey = (float)(b.y - a.y);
+      const float inv = rsqrtf(ex * ex + ey * ey);
+      const float ux = ex * inv, uy = ey * inv;
+      float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
+      for (int j = 0; j < h; ++j) {
+        const float px = (float)s_hull[j].x, py = (float)s_hull[j].y;
+        const float pu = px * ux + py * uy, pv = py * ux - px * uy;
+        umin = fminf(umin, pu); umax = fmaxf(umax, pu);
+        vmin = fminf(vmin, pv); vmax = fmaxf(vmax, pv);
+      }
+      const float w = umax - umin, hh = vmax - vmin;
+      if (w * hh < best) { best = w * hh; bw = w; bh = hh; }
+    }
+  }
+  s_best[threadIdx.x] = best; s_w[threadIdx.x] = bw; s_hh[threadIdx.x] = bh;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float length = 0.f, ratio = 0.f;
+    if (h >= 3) {
+      int arg = 0;
+      for (int i = 1; i < 256; ++i) if (s_best[i] < s_best[arg]) arg = i;
+      const float lo = fminf(s_w[arg], s_hh[arg]);
+      length = fmaxf(s_w[arg], s_hh[arg]);
+      ratio = length / (lo == 0.f ? 1.f : lo);
+    } else if (h == 2) {  // all set pixels on one line: a degenerate rectangle of zero width
+      const float dx = (float)(s_hull[1].x - s_hull[0].x), dy = (float)(s_hull[1].y - s_hull[0].y);
+      length = sqrtf(dx * dx + dy * dy);
+      ratio = length;
+    }
+    out[2 * blockIdx.x] = length;
+    out[2 * blockIdx.x + 1] = ratio;
+  }
+}
+
 }  // namespace ypb

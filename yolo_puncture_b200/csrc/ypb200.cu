@@ -1514,6 +1514,20 @@ int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* byt
   return YPB_OK;
 }
 
+// Needle length on the device: minimum-area rectangle of every mask (mask_kernels.cuh).
+int ypb_mask_min_rect(void* cuda_stream, const uint8_t* masks, int n, int H, int W, int32_t* row_extents /*(n,H,2)*/,
+                      float* out /*(n,2): length, length/width*/) {
+  if (n < 0 || H < 1 || W < 1 || (n > 0 && (!masks || !row_extents || !out))) return fail(YPB_ERR_ARG, "bad argument");
+  if (2 * H > kRectMaxPts || W > 32767) return fail(YPB_ERR_ARG, "mask_min_rect: frame larger than 2304 rows / 32767 columns");
+  if (n == 0) return YPB_OK;
+  if (n > 65535) return fail(YPB_ERR_ARG, "mask_min_rect: more than 65535 masks per call");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  mask_row_extents_kernel<<<dim3((H + 3) / 4, n), 128, 0, st>>>(masks, H, W, reinterpret_cast<int2*>(row_extents));
+  mask_min_rect_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const int2*>(row_extents), H, out);
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
 // LetterBox on the device (misc_kernels.cuh): all pointers device, tables built by the caller as cv2 builds them.
 int ypb_letterbox_u8(void* cuda_stream, const uint8_t* src, int B, int H0, int W0, uint8_t* dst, int H, int W, int new_w,
                      int new_h, int top, int left, const int32_t* xofs, const int16_t* xa, const int32_t* yofs,

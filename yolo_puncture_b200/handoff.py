@@ -70,3 +70,22 @@ def index_masks(results, suppress_small_mask=True, min_area=100):
         k += counts[b]
         out.append((index_map[b], info))
     return out
+
+
+def min_rect_len(masks):
+    """Device replacement of reference utils/mask_tools.py:12-22 `get_coord_min_rect_len(masks.xy[i])` for every mask of
+    a `Masks` object (or an (n, H, W) uint8 CUDA tensor): returns an (n, 2) float32 device tensor of
+    (length = long side of the minimum-area rectangle, length / max(short side, 1)) without copying the masks to the
+    host or running cv2.findContours (consumer: yolo_seg/app.py:97-105)."""
+    m = masks.raw if hasattr(masks, "raw") else masks
+    if not torch.is_tensor(m) or not m.is_cuda or m.dtype != torch.uint8 or m.dim() != 3:
+        raise ValueError("min_rect_len needs device-resident (n, H, W) uint8 masks")
+    m = m.contiguous()
+    n, H, W = m.shape
+    with torch.cuda.device(m.device):
+        out = torch.empty((n, 2), dtype=torch.float32, device=m.device)
+        ext = torch.empty((max(n, 1), H, 2), dtype=torch.int32, device=m.device)
+        st = torch.cuda.current_stream(m.device).cuda_stream
+        check(lib().ypb_mask_min_rect(C.c_void_p(st), C.c_void_p(m.data_ptr()), n, H, W, C.c_void_p(ext.data_ptr()),
+                                      C.c_void_p(out.data_ptr())))
+    return out

@@ -20,7 +20,8 @@ def test_oracle_overwrite_order_and_small_mask_suppression():
 
 class _FakeBoxes:
     def __init__(self, conf, cls):
-        self.conf, self.cls, self.data = conf, cls, conf
+        self.conf, self.cls = conf, cls
+        self.data = torch.cat([torch.zeros(len(conf), 4, device=conf.device), conf[:, None], cls[:, None]], 1)
 
 
 class _FakeMasks:

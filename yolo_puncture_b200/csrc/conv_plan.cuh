@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -234,10 +236,25 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
     const double waste_taps = (double)L->total_tiles * p.msub * 128 - (double)d.B * oH * oW * splits;
     const double cost_taps = (double)L->total_tiles * k_iters * (p.msub * kATileBytes + b_slot) + waste_taps * 9.0 * kch * 64.0;
     double best = cost_taps;
+    // Sub-tiles per CTA tile: measured (tools/conv_layers.py with YPB_HALO_MSUB=1/2, B200) a tile costs about
+    // (msub + 0.7) sub-tile times - the hand-offs and the pipeline refill of a tile are worth ~0.7 of a 128-row
+    // sub-tile - and a CTA runs ceil(tiles / SMs) of them, so two stacked sub-tiles win unless their padded rows cost
+    // more than that (a 40-row map tiled 32 rows high wastes 37 % of its MMAs; 16-row tiles win there by 9 %).
+    int msub_pick = 0;
+    {
+      double tbest = 1e30;
+      for (int msub = 2; msub >= 1; --msub) {
+        if (2 * msub * conv2_acc_stride(p.n_tile) > 512) continue;
+        const long tiles3 = (long)d.B * ((oH + 16 * msub - 1) / (16 * msub)) * ((oW + 7) / 8) * splits;
+        const double t = std::ceil(tiles3 / 148.0) * (msub + 0.7);
+        if (t < tbest) { tbest = t; msub_pick = msub; }
+      }
+    }
     const int force_msub = getenv("YPB_HALO_MSUB") ? atoi(getenv("YPB_HALO_MSUB")) : 0;
     for (int msub = 1; msub <= 2; ++msub) {
       if (2 * msub * conv2_acc_stride(p.n_tile) > 512) continue;
       if (force_msub && msub != force_msub && 2 * force_msub * conv2_acc_stride(p.n_tile) <= 512) continue;
+      if (!force_msub && !getenv("YPB_PLAN_BYTES") && msub_pick && msub != msub_pick) continue;
       const int halo_rows = (16 * msub + 2) * 10;
       const long a_bytes = ((long)halo_rows * 128 + 1023) & ~1023L;
       const int th3 = (oH + 16 * msub - 1) / (16 * msub), tw3 = (oW + 7) / 8;

@@ -58,15 +58,12 @@ def index_masks(results, suppress_small_mask=True, min_area=100):
         check(lib().ypb_index_masks(C.c_void_p(st), C.c_void_p(base.data_ptr()), C.c_void_p(offs_d.data_ptr()), B, n_total, H, W,
                                     int(min_area) if suppress_small_mask else -1, C.c_void_p(area.data_ptr()),
                                     C.c_void_p(ids.data_ptr()), C.c_void_p(index_map.data_ptr())))
-        ids_h = ids.cpu().tolist()  # the one host sync of the hand-off
+        # one device-to-host copy for the whole batch: ids next to (conf, cls) of every detection
+        meta = torch.cat([r.boxes.data[:, 4:6].to(dev, torch.float32) for r, c in zip(results, counts) if c])
+        packed = torch.cat([ids.to(torch.float32)[:, None], meta], 1).cpu().tolist()  # the one host sync of the hand-off
     out, k = [], 0
-    for b, r in enumerate(results):
-        info = []
-        if counts[b]:
-            conf, cls = r.boxes.conf.cpu().tolist(), r.boxes.cls.cpu().tolist()
-            for i in range(counts[b]):
-                if ids_h[k + i]:
-                    info.append({"id": ids_h[k + i], "score": float(conf[i]), "category_id": int(cls[i])})
+    for b in range(B):
+        info = [{"id": int(i), "score": float(sc), "category_id": int(cl)} for i, sc, cl in packed[k:k + counts[b]] if i]
         k += counts[b]
         out.append((index_map[b], info))
     return out

@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 # metric is quoted on "YOLO-seg 640^2" and configs[2] is its single-GPU YOLO-seg configuration.
 WORKLOADS = {
     "yolov8s-seg-640-b64": ("yolov8s-seg", 64, (640, 640), 640),
+    "yolov8s-seg-640-b32": ("yolov8s-seg", 32, (640, 640), 640),
+    "yolov8s-seg-640-b16": ("yolov8s-seg", 16, (640, 640), 640),
     "yolov8n-seg-640-b1": ("yolov8n-seg", 1, (640, 640), 640),
     "yolov8n-seg-640-b64": ("yolov8n-seg", 64, (640, 640), 640),
     "yolov8m-seg-1080p-b16": ("yolov8m-seg", 16, (1080, 1920), 1280),

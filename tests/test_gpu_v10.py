@@ -40,7 +40,8 @@ def test_v10_layers_track_bf16_emulating_oracle(v10):
     assert float((got - raw).abs().mean() / raw.abs().mean()) < 0.03
 
 
-@pytest.mark.parametrize("conf,max_det,classes", [(0.25, 300, None), (0.5, 300, None), (0.25, 10, None), (0.25, 300, [0, 7, 22, 44])])
+@pytest.mark.parametrize("conf,max_det,classes", [(0.25, 300, None), (0.5, 300, None), (0.25, 10, None), (0.25, 300, [0, 7, 22, 44]),
+                                                  (0.15, 300, None), (0.15, 50, None)])  # low conf: > 4096 pairs -> select-then-sort path
 def test_v10_topk_selection_strict_on_engine_tensors(v10, conf, max_det, classes):
     net, yolo, frames, oops = v10["net"], v10["yolo"], v10["frames"], v10["oops"]
     res = yolo.predict(frames, conf=conf, max_det=max_det, classes=classes)

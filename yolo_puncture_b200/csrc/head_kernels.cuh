@@ -119,6 +119,8 @@ decode_filter8_kernel(const float* __restrict__ head, HeadGeom g, int nB, float 
   const long long mine = a0 + grp;
   float best = -INFINITY;
   int bidx = 0x7fffffff;
+  // sigmoid(x) > conf  =>  x > logit(conf); a margin keeps the exact float comparison on sigmoid_f authoritative
+  const float pair_logit_lo = (conf > 0.f && conf < 1.f) ? __logf(conf / (1.0f - conf)) - 0.05f : -INFINITY;
   if (mine < total) {
     const float4* cl = reinterpret_cast<const float4*>(head + mine * g.no + 64);
     const int n4 = g.nc >> 2;
@@ -129,6 +131,26 @@ decode_filter8_kernel(const float* __restrict__ head, HeadGeom g, int nB, float 
       if (v.y > best) { best = v.y; bidx = c + 1; }
       if (v.z > best) { best = v.z; bidx = c + 2; }
       if (v.w > best) { best = v.w; bidx = c + 3; }
+      if (xyxy_direct) {
+        // end-to-end heads: every (anchor, class) pair with score > conf is a top-k candidate (what
+        // pair_candidates_kernel does in a second pass over the head); logits far below the threshold skip the sigmoid
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!(vv[u] > pair_logit_lo)) continue;
+          const float sc = sigmoid_f(vv[u]);
+          if (!(sc > conf)) continue;
+          const int cc = c + u;
+          if (cls_mask != nullptr && !((cls_mask[cc >> 5] >> (cc & 31)) & 1u)) continue;
+          const int bimg = (int)(mine / g.A), an = (int)(mine - (long long)bimg * g.A);
+          const int slot = atomicAdd(cand_count + bimg, 1);
+          if (slot < g.cand_stride)
+            cand_keys[(long long)bimg * g.cand_stride + slot] =
+                ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(an * g.nc + cc));
+          else
+            atomicOr(&g_dev_error, 0x100u);  // candidate list overflow (conf far below any sensible value)
+        }
+      }
     }
   }
 #pragma unroll
@@ -188,9 +210,11 @@ decode_filter8_kernel(const float* __restrict__ head, HeadGeom g, int nB, float 
       }
       dbox[wid] = box;
       dcls[wid] = c_idx;
-      const int slot = atomicAdd(cand_count + b, 1);
-      cand_keys[(long long)b * g.cand_stride + slot] =
-          ((unsigned long long)__float_as_uint(c_score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)a);
+      if (!xyxy_direct) {  // v8 / 11: one candidate per anchor (end-to-end heads pushed their (anchor, class) pairs above)
+        const int slot = atomicAdd(cand_count + b, 1);
+        cand_keys[(long long)b * g.cand_stride + slot] =
+            ((unsigned long long)__float_as_uint(c_score) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)a);
+      }
     }
   }
 }
@@ -285,7 +309,63 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
   int n_pow2 = 1;
   while (n_pow2 < n) n_pow2 <<= 1;
   unsigned long long* keys;
-  if (n_pow2 <= kNmsSmemKeys) {
+  __shared__ int s_sel[2];
+  bool selected = false;
+  if (e2e && n_pow2 > kNmsSmemKeys) {
+    // End-to-end top-k over more pairs than the shared-memory sort holds: only the best max_det matter, so select
+    // them first.  Histogram of the scores (float bits are monotonic for positive floats) over 4096 bins, the bin
+    // where the count from the top reaches max_det, then every key at or above that bin is compacted into shared
+    // memory and sorted there (exactly the keys a full sort would put first, in the same order).
+    int* hist = reinterpret_cast<int*>(s_keys);
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) hist[i] = 0;
+    unsigned lo_bits = 0xffffffffu, hi_bits = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned sb = (unsigned)(gk[i] >> 32);
+      lo_bits = min(lo_bits, sb);
+      hi_bits = max(hi_bits, sb);
+    }
+    __shared__ unsigned s_lo, s_hi;
+    if (threadIdx.x == 0) { s_lo = 0xffffffffu; s_hi = 0u; }
+    __syncthreads();
+    atomicMin(&s_lo, lo_bits);
+    atomicMax(&s_hi, hi_bits);
+    __syncthreads();
+    const unsigned base = s_lo;
+    int shift = 0;
+    while (((s_hi - base) >> shift) >= 4096u) ++shift;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[((unsigned)(gk[i] >> 32) - base) >> shift], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0, t = 4095;
+      for (; t > 0; --t) {
+        acc += hist[t];
+        if (acc >= max_det) break;
+      }
+      if (t == 0) acc += hist[0];
+      s_sel[0] = t;
+      s_sel[1] = acc;  // keys in bins >= t
+    }
+    __syncthreads();
+    const int tbin = s_sel[0], nsel = s_sel[1];
+    __syncthreads();  // everyone has read the histogram results: its memory is reused for the keys
+    if (nsel <= kNmsSmemKeys) {
+      if (threadIdx.x == 0) s_sel[0] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = gk[i];
+        if ((int)((((unsigned)(k >> 32)) - base) >> shift) >= tbin) s_keys[atomicAdd(&s_sel[0], 1)] = k;
+      }
+      __syncthreads();
+      n = nsel;
+      n_pow2 = 1;
+      while (n_pow2 < n) n_pow2 <<= 1;
+      for (int i = n + threadIdx.x; i < n_pow2; i += blockDim.x) s_keys[i] = 0ull;
+      selected = true;
+    }
+  }
+  if (selected) {
+    keys = s_keys;
+  } else if (n_pow2 <= kNmsSmemKeys) {
     keys = s_keys;
     for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = i < n ? gk[i] : 0ull;
   } else {  // rare: sort in place in global memory (cand_stride = next_pow2(A) leaves room for the padding)

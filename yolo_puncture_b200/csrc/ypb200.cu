@@ -805,15 +805,17 @@ static int launch_select(ypb_engine* e, cudaStream_t st, const float* xform, con
   int* dcls = reinterpret_cast<int*>(e->ws + e->off_dcls);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(e->ws + e->off_keys);
   const long long warps = (long long)B * g.A;
+  bool pairs_done = false;
   if (g.nc % 4 == 0 && g.no % 4 == 0 && g.nc >= 16) {
     const long long w8 = (warps + 7) / 8;
     decode_filter8_kernel<<<(unsigned)((w8 * 32 + 255) / 256), 256, 0, st>>>(head, g, B, prm->conf, e->end2end ? 1 : 0,
                                                                             prm->class_mask, dbox, dcls, keys, cand_count);
+    pairs_done = true;  // end-to-end heads: the (anchor, class) pairs were pushed in the same pass
   } else {
     decode_filter_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(head, g, B, prm->conf, e->end2end ? 1 : 0,
                                                                               prm->class_mask, dbox, dcls, keys, cand_count);
   }
-  if (e->end2end) {  // NMS-free head: candidates are (anchor, class) pairs; rebuild the key list from scratch
+  if (e->end2end && !pairs_done) {  // NMS-free head: candidates are (anchor, class) pairs; rebuild the key list from scratch
     CUDA_TRY(cudaMemsetAsync(cand_count, 0, (size_t)B * 4, st));
     pair_candidates_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(head, g, B, prm->conf, prm->class_mask, keys,
                                                                               cand_count);

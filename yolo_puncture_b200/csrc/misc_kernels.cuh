@@ -1,75 +1,11 @@
-// Bandwidth-bound layer kernels around the tensor-core convs: fused preprocess + stem conv,
-// nearest 2x upsample into a concat slice, SPPF chained max-pools.
-// UPSTREAM sites replaced: engine/predictor.py::preprocess (BGR->RGB, /255) + model.0 Conv,
-// nn.Upsample(2,'nearest') + Concat, block.py::SPPF's three MaxPool2d(5,1,2)  (SURVEY.md §2.2).
+// Bandwidth-bound layer kernels around the tensor-core convs: nearest 2x upsample into a concat slice, SPPF chained
+// max-pools, LetterBox on the device.  (The stem lives in conv_tc.cuh: stem_tc_kernel.)
+// UPSTREAM sites replaced: nn.Upsample(2,'nearest') + Concat, block.py::SPPF's three MaxPool2d(5,1,2),
+// data/augment.py::LetterBox  (SURVEY.md §2.2, §8f).
 #pragma once
 #include "common.cuh"
 
 namespace ypb {
-
-// ------------------------------------------------------------------------------------------------
-// Stem: uint8 BGR HWC letterboxed frame -> RGB/255 -> Conv3x3 s2 p1 (+folded BN) -> SiLU -> bf16 NHWC.
-// The frame is read as bytes straight from HBM (3 B/pixel instead of a 12 B/pixel fp32 CHW tensor),
-// K = 27 is too thin for the tensor pipe so this one runs on the FMA pipe in fp32.
-// Weights: wk[(kh*3+kw)*3 + c_rgb][C0] fp32, bias[C0].
-// ------------------------------------------------------------------------------------------------
-constexpr int kStemTile = 16;  // 16x16 output pixels per CTA, 256 threads
-
-__global__ void __launch_bounds__(256)
-stem_conv_kernel(const uint8_t* __restrict__ frames, int H, int W, const float* __restrict__ wk,
-                 const float* __restrict__ bias, int C0, __nv_bfloat16* __restrict__ out, int out_ctot) {
-  extern __shared__ float stem_smem[];
-  const int IT = 2 * kStemTile + 1;               // 33 input rows/cols per tile
-  float* s_in = stem_smem;                        // [IT][IT][3] RGB/255
-  float* s_w = s_in + IT * IT * 3;                // [27][C0]
-  float* s_b = s_w + 27 * C0;                     // [C0]
-  const int oH = H >> 1, oW = W >> 1;
-  const int b = blockIdx.z;
-  const int oh0 = blockIdx.y * kStemTile, ow0 = blockIdx.x * kStemTile;
-  const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-  const uint8_t* img = frames + (size_t)b * H * W * 3;
-  for (int i = threadIdx.x; i < IT * IT; i += 256) {
-    const int r = i / IT, c = i - r * IT;
-    const int ih = ih0 + r, iw = iw0 + c;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-      const uint8_t* px = img + ((size_t)ih * W + iw) * 3;
-      v2 = __fdiv_rn((float)px[0], 255.f);  // B -> channel 2
-      v1 = __fdiv_rn((float)px[1], 255.f);
-      v0 = __fdiv_rn((float)px[2], 255.f);  // R -> channel 0
-    }
-    s_in[i * 3 + 0] = v0;
-    s_in[i * 3 + 1] = v1;
-    s_in[i * 3 + 2] = v2;
-  }
-  for (int i = threadIdx.x; i < 27 * C0; i += 256) s_w[i] = wk[i];
-  for (int i = threadIdx.x; i < C0; i += 256) s_b[i] = bias[i];
-  __syncthreads();
-  const int ty = threadIdx.x / kStemTile, tx = threadIdx.x - ty * kStemTile;
-  const int oh = oh0 + ty, ow = ow0 + tx;
-  if (oh >= oH || ow >= oW) return;
-  float x[27];
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) x[(kh * 3 + kw) * 3 + c] = s_in[((2 * ty + kh) * IT + 2 * tx + kw) * 3 + c];
-  __nv_bfloat16* o = out + ((size_t)(b * oH + oh) * oW + ow) * out_ctot;
-  for (int n0 = 0; n0 < C0; n0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = s_b[n0 + j];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[k], s_w[k * C0 + n0 + j], acc[j]);
-    }
-    uint4 s = make_uint4(pack_bf16x2(silu_f(acc[0]), silu_f(acc[1])), pack_bf16x2(silu_f(acc[2]), silu_f(acc[3])),
-                         pack_bf16x2(silu_f(acc[4]), silu_f(acc[5])), pack_bf16x2(silu_f(acc[6]), silu_f(acc[7])));
-    *reinterpret_cast<uint4*>(o + n0) = s;
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Nearest 2x upsample of a channel slice into a channel slice of the (2h, 2w) concat buffer.

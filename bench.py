@@ -139,6 +139,40 @@ def cpu_baseline(model, hw, imgsz, budget_s=12.0):
                       f"(letterbox+forward+NMS+retina masks), median {med * 1e3:.1f} ms"}
 
 
+def torch_gpu_comparator(model, H, W, B, dev, iters=10):
+    """SURVEY.md 8d's same-box GPU comparator: the oracle module itself under torch.cuda, bf16, channels_last (cuDNN /
+    cuBLAS kernels chosen by torch), forward pass only (no NMS, no masks), frames already resident and preprocessed.
+    A reported baseline like cpu_baseline; never on the product path."""
+    import torch
+    from oracle.model import build_model
+    from yolo_puncture_b200.synth import synth_state_dict
+    try:
+        net = build_model(model)
+        net.load_state_dict(synth_state_dict([(k, v.shape) for k, v in net.state_dict().items()], model))
+        net = net.fuse().to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        net.stride = net.stride.to(dev)
+        head = net.model[-1]
+        head.stride = head.stride.to(dev)
+        x = torch.rand((B, 3, H, W), device=dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        torch.backends.cudnn.benchmark = True
+        with torch.no_grad():
+            for _ in range(3):
+                net(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                net(x)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        return {"value": B / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "batch": B,
+                "kind": "oracle module under torch.cuda bf16 channels_last (library kernels), forward pass only: "
+                        "no preprocessing, NMS or masks"}
+    except Exception as ex:  # a comparator must never break the bench line
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's CPU predict path (oracle port; the real package is not installable
     here), all host threads, each step = a bounded 2-frame sample of the workload."""
@@ -380,6 +414,7 @@ def run_ours(args, wl):
     p50 = float(np.median(lat))
 
     base = cpu_baseline(model, hw, imgsz) if world == 1 and not args.no_cpu_baseline else None
+    gpu_lib = torch_gpu_comparator(model, H, W, B, dev) if world == 1 and not args.no_cpu_baseline else None
     line = {
         "metric": "frames/sec YOLO-seg inference (per-frame detector hot path)", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -398,6 +433,8 @@ def run_ours(args, wl):
     }
     if base is not None:
         line["cpu_baseline"] = base
+    if gpu_lib is not None:
+        line["gpu_library_baseline"] = gpu_lib
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

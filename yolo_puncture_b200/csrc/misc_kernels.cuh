@@ -9,24 +9,29 @@ namespace ypb {
 
 // ------------------------------------------------------------------------------------------------
 // Nearest 2x upsample of a channel slice into a channel slice of the (2h, 2w) concat buffer.
-// One thread per (output pixel, 8-channel vector).
+// One thread per (input pixel, 8-channel vector): one load, the 2x2 block of stores.
 // ------------------------------------------------------------------------------------------------
-__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int in_ctot, int in_c_off,
-                                  __nv_bfloat16* __restrict__ out, int out_ctot, int out_c_off, int nB, int h, int w,
-                                  int C) {
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int in_ctot, int in_c_off, __nv_bfloat16* __restrict__ out, int out_ctot,
+                  int out_c_off, int nB, int h, int w, int C) {
+  // one thread per (INPUT pixel, 8-channel vector): one 16-byte load, four 16-byte stores (the 2x2 output block)
   const int vec = C >> 3;
-  const long long total = (long long)nB * 4 * h * w * vec;
+  const long long total = (long long)nB * h * w * vec;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int v = (int)(idx % vec);
   long long pix = idx / vec;
-  const int ow = (int)(pix % (2 * w));
-  pix /= (2 * w);
-  const int oh = (int)(pix % (2 * h));
-  const int b = (int)(pix / (2 * h));
-  const uint4 val = *reinterpret_cast<const uint4*>(in + (((long long)b * h + (oh >> 1)) * w + (ow >> 1)) * in_ctot +
-                                                    in_c_off + v * 8);
-  *reinterpret_cast<uint4*>(out + (((long long)b * 2 * h + oh) * (2 * w) + ow) * out_ctot + out_c_off + v * 8) = val;
+  const int x = (int)(pix % w);
+  pix /= w;
+  const int y = (int)(pix % h);
+  const int b = (int)(pix / h);
+  const uint4 val = *reinterpret_cast<const uint4*>(in + (((long long)b * h + y) * w + x) * in_ctot + in_c_off + v * 8);
+  __nv_bfloat16* o = out + (((long long)b * 2 * h + 2 * y) * (2 * w) + 2 * x) * out_ctot + out_c_off + v * 8;
+  const long long row = (long long)2 * w * out_ctot;
+  *reinterpret_cast<uint4*>(o) = val;
+  *reinterpret_cast<uint4*>(o + out_ctot) = val;
+  *reinterpret_cast<uint4*>(o + row) = val;
+  *reinterpret_cast<uint4*>(o + row + out_ctot) = val;
 }
 
 // ------------------------------------------------------------------------------------------------

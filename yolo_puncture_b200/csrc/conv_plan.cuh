@@ -50,6 +50,7 @@ struct ConvLaunch {
   int n_splits = 1, total_tiles = 0, stages2 = 2, smem2 = 0;  // persistent-kernel launch shape
   ConvSimtGeom sg;
   CUtensorMap tmA, tmB;
+  CUtensorMap tmO;  // output map of the TMA-store epilogue (1x1 convs), valid when p.tma_out != 0
   dim3 grid;
   int smem = 0;
   double flops = 0;
@@ -72,16 +73,21 @@ static PFN_tmapEncodeTiled tmap_encoder() {
   return fn;
 }
 
+static bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void* base, int rank,
+                       const cuuint64_t* dims, const cuuint64_t* strides_bytes /*rank-1*/, const cuuint32_t* box, std::string* err);
 static bool encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
                             const cuuint64_t* strides_bytes /*rank-1*/, const cuuint32_t* box, std::string* err) {
+  return encode_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, base, rank, dims, strides_bytes, box, err);
+}
+static bool encode_map(CUtensorMap* m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void* base, int rank,
+                       const cuuint64_t* dims, const cuuint64_t* strides_bytes /*rank-1*/, const cuuint32_t* box, std::string* err) {
   PFN_tmapEncodeTiled enc = tmap_encoder();
   if (!enc) {
     *err = "cuTensorMapEncodeTiled unavailable (no CUDA driver)";
     return false;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -217,7 +223,8 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
   if (st2 < 2) st2 = 2;
   L->stages2 = st2;
   const int epi_smem = kEpiWarps * epi_stage_bytes(d.out_mode == OUT_F32);
-  L->smem2 = 1024 + st2 * stage2 + 256 + epi_smem + conv_bias_smem(d.cout);
+  const int epi_smem2 = kEpiWarps * epi_stage_bytes(d.out_mode == OUT_F32, d.k == 1) + 1024;  // conv_tc2: 1 KB-aligned tiles
+  L->smem2 = 1024 + st2 * stage2 + 256 + epi_smem2 + conv_bias_smem(d.cout);
   if (L->smem2 < 120 * 1024) L->smem2 = 120 * 1024;
   p.out_mode = d.out_mode; p.act = d.act;
   p.dbg = getenv("YPB_DBG") ? atoi(getenv("YPB_DBG")) : 0;
@@ -344,6 +351,28 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
     cuuint32_t hb[5] = {64, 10, 18, 1, 1};
     L->halo_ok = encode_bf16_map(&L->tmHalo, d.in, 5, dims, str, hb, err);
   }
+  // TMA-store epilogue for 1x1 convs without residual: warp tiles of 32 pixels x 32 channels.  The output strides
+  // come from the planned geometry (bind-time descriptors carry pointers only).
+  p.tma_out = 0;
+  if (d.k == 1 && d.res == nullptr && (d.out_mode == OUT_BF16 || d.out_mode == OUT_F32) && !getenv("YPB_NO_TMA_STORE")) {
+    const bool f32 = d.out_mode == OUT_F32;
+    const int elt = f32 ? 4 : 2;
+    const long long hw = (long long)L->oH * L->oW;
+    const long long pix = p.out_pix_stride, img = p.out_img_stride;
+    const bool contiguous = img == hw * pix;
+    const uint8_t* obase = reinterpret_cast<const uint8_t*>(d.out) + (long long)p.out_c_off * elt;
+    const bool aligned = pix > 0 && img > 0 && (reinterpret_cast<uintptr_t>(obase) & 15) == 0 && (pix * elt) % 16 == 0 && (img * elt) % 16 == 0;
+    if (aligned && (contiguous || hw % 32 == 0)) {
+      cuuint64_t od[3] = {(cuuint64_t)d.cout, (cuuint64_t)(contiguous ? hw * d.B : hw), (cuuint64_t)d.B};
+      cuuint64_t os[2] = {(cuuint64_t)(pix * elt), (cuuint64_t)(img * elt)};
+      cuuint32_t ob[3] = {32, 32, 1};
+      const int rank = contiguous ? 2 : 3;
+      if (!encode_map(&L->tmO, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                      f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, obase, rank, od, os, ob, err))
+        return false;
+      p.tma_out = rank;
+    }
+  }
   cuuint64_t wd[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.cout, (cuuint64_t)(d.k * d.k)};
   cuuint64_t ws[2] = {(cuuint64_t)d.cin * 2, (cuuint64_t)d.cin * 2 * d.cout};
   cuuint32_t wb[3] = {64, (cuuint32_t)p.n_tile, 1};
@@ -448,7 +477,7 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
   const int grid = L.total_tiles < num_sms ? L.total_tiles : num_sms;
   cudaError_t le = cudaSuccess;
 #define YPB_TC2_CASE(MODE) \
-  case MODE: le = launch_pdl(conv_tc2_kernel<MODE>, grid, kConv2Threads, L.smem2, stream, L.tmA, L.tmB, p2, L.n_splits, L.total_tiles); break;
+  case MODE: le = launch_pdl(conv_tc2_kernel<MODE>, grid, kConv2Threads, L.smem2, stream, L.tmA, L.tmB, p2.tma_out ? L.tmO : L.tmB, p2, L.n_splits, L.total_tiles); break;
   switch (epi_mode_of(p2.out_mode, p2.res != nullptr, p2.act)) {
     YPB_TC2_CASE(0) YPB_TC2_CASE(1) YPB_TC2_CASE(2) YPB_TC2_CASE(3) YPB_TC2_CASE(4) YPB_TC2_CASE(5) YPB_TC2_CASE(6) YPB_TC2_CASE(7)
   }

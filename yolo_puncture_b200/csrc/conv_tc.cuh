@@ -56,6 +56,7 @@ struct ConvParams {
   // exact division by launch constants as multiply-high + shift (x < 2^31): a runtime integer division is a ~150-cycle
   // dependent chain, and the per-tile index math of a warp-specialised role has no other warps to hide behind
   uint32_t fd_ns[2], fd_tpi[2], fd_tw[2], fd_hw[2], fd_iw[2];  // n_splits, tiles per image, tiles_w, img_HW, img_W
+  int tma_out;  // 0: coalesced manual stores; 2 / 3: 32x32 warp tiles leave through a 2-D / 3-D TMA store map (1x1 convs)
   int bo_prod, bo_mma_acc, bo_mma_full, bo_epi;  // poll back-off (ns) of the four kinds of mbarrier waits (YPB_BO=a,b,c,d)
   int dbg;  // YPB_DBG experiments (0 in production): 1 = no bias/SiLU math, 2 = no output stores, 4 = no MMA issue
 };
@@ -290,7 +291,10 @@ constexpr int kMmaWarp = kEpiWarps + kProdWarps;
 constexpr int kConv2Threads = 32 * (kProdWarps + 1 + kEpiWarps);
 constexpr int kEpiStageBytes = 32 * (128 + 16);  // per-warp staging tile of an fp32 pass: 32 rows x (128 B + 16 B pad)
 // per-warp staging bytes by output mode: a bf16 pass stages 32 rows x (64 B + 16 B pad)
-__host__ __device__ constexpr int epi_stage_bytes(bool f32) { return f32 ? 32 * (128 + 16) : 32 * (64 + 16); }
+// (flat = 1x1 conv: room for two dense, swizzled 32-row tiles, the double buffer of the TMA-store path)
+__host__ __device__ constexpr int epi_stage_bytes(bool f32, bool flat = false) {
+  return flat ? (f32 ? 2 * 32 * 128 : 2 * 32 * 64) : (f32 ? 32 * (128 + 16) : 32 * (64 + 16));
+}
 // Which 128-row sub-tile and which 16-column chunks [cb, ce) of it epilogue part `part` drains (nch = n_tile / 16).
 // The kEpiParts warps of a TMEM lane group are spread over the msub sub-tiles first, then over column ranges
 // (multiples of 32 columns when there are enough of them).
@@ -396,7 +400,8 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
                                                int lane, int n, long long base, long long res_base,
                                                const int (&dl)[(MODE & 3) == EPI_F32 ? NC / 4 : NC / 8],
                                                const int (&rl)[(MODE & 3) == EPI_F32 ? NC / 4 : NC / 8], bool prof, long long& pt,
-                                               long long (&pacc)[6]) {
+                                               long long (&pacc)[6], const CUtensorMap* tmO = nullptr, int tma_mode = 0,
+                                               int tq = 0, int tb = 0, int tbuf = 0) {
 #define EPI_MARK(k) do { if (prof) { const long long _n = clock64(); pacc[(k) - 8] += _n - pt; pt = _n; } } while (0)
   constexpr int LAY = MODE & 3;
   constexpr bool F32 = LAY == EPI_F32, ACT = (MODE & EPI_ACT) != 0;
@@ -448,6 +453,40 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
     if (acc == 123.456f) pt += 1;
   }
   EPI_MARK(10);
+  if (NC == 32 && (LAY == EPI_BF16 || LAY == EPI_F32) && tma_mode != 0) {
+    // TMA-store path (1x1 convs): the warp's 32 rows x 32 columns go to one of two dense staging tiles in the TMA
+    // swizzle (64-byte rows: SWIZZLE_64B, 128-byte rows: SWIZZLE_128B - also what keeps the 16-byte row-per-lane
+    // writes conflict-free), then ONE bulk tensor store writes them out; rows past the end of the tensor are clipped
+    // by the TMA unit.  The other tile may still be draining: wait only for the store that last read this one.
+    constexpr int ROWB = F32 ? 128 : 64;
+    const uint32_t tile = stage_sa + (uint32_t)tbuf * (32 * ROWB);
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+    const uint32_t row = tile + lane * ROWB;
+    const int sw = F32 ? (lane & 7) : ((lane >> 1) & 3);
+    if (!F32) {
+#pragma unroll
+      for (int i = 0; i < PPR; ++i)
+        sts128(row + ((i ^ sw) << 4), pack_bf16x2(y[8 * i], y[8 * i + 1]), pack_bf16x2(y[8 * i + 2], y[8 * i + 3]),
+               pack_bf16x2(y[8 * i + 4], y[8 * i + 5]), pack_bf16x2(y[8 * i + 6], y[8 * i + 7]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < PPR; ++i)
+        sts128(row + ((i ^ sw) << 4), __float_as_uint(y[4 * i]), __float_as_uint(y[4 * i + 1]), __float_as_uint(y[4 * i + 2]),
+               __float_as_uint(y[4 * i + 3]));
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    EPI_MARK(11);
+    if (lane == 0 && !(p.dbg & 2)) {
+      if (tma_mode == 2) tma_store_2d(tmO, tile, n, tq);
+      else tma_store_3d(tmO, tile, n, tq, tb);
+      bulk_commit();
+    }
+    EPI_MARK(12);
+    if (prof) pacc[5] += 1;
+    return;
+  }
   const uint32_t my = stage_sa + lane * pitch;
   if (!F32) {
 #pragma unroll
@@ -512,7 +551,8 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
 template <int MODE, bool PINGPONG = true>
 __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa, uint32_t sbias_sa, int lane, int c_begin,
                                           int c_end, uint32_t t_addr, int n0, bool valid, int qb, int rem,
-                                          uint64_t* release, long long (&pacc)[6]) {
+                                          uint64_t* release, long long (&pacc)[6], const CUtensorMap* tmO = nullptr,
+                                          int tma_mode = 0, int tq = 0, int tb = 0, int* tbuf = nullptr) {
   constexpr int LAY = MODE & 3;
   constexpr bool F32 = LAY == EPI_F32;
   constexpr int P32 = F32 ? 8 : 4, P16 = F32 ? 4 : 2;  // 16-byte pieces per staged row of a 32- / 16-column pass
@@ -582,8 +622,13 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
         if (lane == 0) mbar_arrive(release);
       }
       EPI_MARK(9);
+      int tb_idx = 0;
+      if (tma_mode != 0) {
+        tb_idx = *tbuf;
+        *tbuf ^= 1;
+      }
       epi_store_pass<32, MODE>(p, cur, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl,
-                               prof, pt, pacc);
+                               prof, pt, pacc, tmO, tma_mode, tq, tb, tb_idx);
     };
     for (int k = 0; k < n32; k += 2) {
       pass32(va, vb, k);
@@ -600,6 +645,10 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
     if (release != nullptr) {
       __syncwarp();
       if (lane == 0) mbar_arrive(release);
+    }
+    if (tma_mode != 0) {  // the manual pass reuses the staging memory the bulk stores read from
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
     }
     epi_store_pass<16, MODE>(p, va, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl, prof,
                              pt, pacc);
@@ -626,7 +675,7 @@ __device__ __forceinline__ void epi_load_bias(const ConvParams& p, float* sbias)
 template <int MODE>
 __global__ void __launch_bounds__(kConv2Threads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ ConvParams p, int n_splits, int total_tiles) {
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvParams p, int n_splits, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int a_bytes = p.msub * kATileBytes;
@@ -650,6 +699,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == kProdWarp0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out != 0) tma_prefetch_desc(&tmO);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
@@ -661,8 +711,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, tmem_cols);
-  constexpr int kStageB = epi_stage_bytes((MODE & 3) == EPI_F32);
-  float* sbias = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 256 + kEpiWarps * kStageB);
+  const int kStageB = epi_stage_bytes((MODE & 3) == EPI_F32, p.ntaps == 1);
+  // epilogue staging tiles start on a 1 KB boundary (TMA-store swizzle atoms)
+  uint8_t* stage0 = smem + ((p.stages * stage_bytes + 256 + 1023) & ~1023);
+  float* sbias = reinterpret_cast<float*>(stage0 + kEpiWarps * kStageB);
   epi_load_bias(p, sbias);
   tc_fence_before();
   __syncthreads();
@@ -774,7 +826,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int lg = warp & 3;
     int sidx, c_begin, c_end;  // this warp's sub-tile and 16-column chunk range
     epi_split(p.msub, p.n_tile >> 4, (warp - kEpiWarp0) >> 2, &sidx, &c_begin, &c_end);
-    uint8_t* stage = smem + p.stages * stage_bytes + 256 + (warp - kEpiWarp0) * kStageB;
+    uint8_t* stage = stage0 + (warp - kEpiWarp0) * kStageB;
+    int tbuf = 0;  // which of the two TMA-store staging tiles the next pass uses
     const int r = lg * 32 + lane;
     long long pacc[6] = {0, 0, 0, 0, 0, 0};
     const bool flat = p.ntaps == 1;  // 1x1: the tile is 128 * msub consecutive pixels of the flattened batch
@@ -821,11 +874,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * p.msub + sidx) * acc_stride);
+        int tq = 0, tb = 0;
+        if (p.tma_out != 0) {  // flat tiles only: pixel index of this warp's first row
+          tq = t_in * p.TW + sidx * p.sub_rows + lg * 32;
+          if (p.tma_out == 3) {
+            tb = fdiv(tq, p.fd_hw);
+            tq -= tb * p.img_HW;
+          }
+        }
         epi_drain<MODE>(p, smem_u32(stage), smem_u32(sbias), lane, c_begin, c_end, t_addr, n0, valid, qb, rem,
-                        tempty_bar + buf, pacc);
+                        tempty_bar + buf, pacc, &tmO, p.tma_out, tq, tb, &tbuf);
       }
       PROF_ADD(pw1);
     }
+    if (p.tma_out != 0 && lane == 0) bulk_wait_all();  // the bulk stores read this CTA's shared memory until they complete
     if (prof && warp == kEpiWarp0 && lane == 0) {
       atomicAdd(&g_conv_prof[3], (unsigned long long)pw0);
       atomicAdd(&g_conv_prof[4], (unsigned long long)pw1);

@@ -118,6 +118,19 @@ __device__ __forceinline__ bool mbar_wait_bo(uint64_t* bar, uint32_t parity, uns
   return false;
 }
 
+// Whole-warp wait: every lane polls and the loop leaves when all of them have seen the phase complete.  The exit
+// condition is a vote, i.e. warp-uniform as far as ptxas can tell, which keeps the loops AROUND the wait (and the
+// descriptor arithmetic in them) on the uniform datapath: the MMA warp runs its tile / tap loops converged and
+// elects a lane only for the tcgen05 instructions themselves.
+__device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity, unsigned int err_code, unsigned int ns) {
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    if (__all_sync(0xffffffffu, mbar_test_wait(bar, parity))) return true;
+    if (ns) __nanosleep(ns);
+  }
+  atomicOr(&g_dev_error, err_code);
+  return false;
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor)
 // ------------------------------------------------------------------------------------------------

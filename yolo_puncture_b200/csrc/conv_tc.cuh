@@ -686,7 +686,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle makes the warp index provably warp-uniform: role branches become uniform branches and the role
+  // bodies may keep their loop state on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int kchunks = (p.Cin + 63) >> 6;
   const int acc_stride = conv2_acc_stride(p.n_tile);
@@ -763,19 +765,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (accumulation order: chunk-major, tap-minor, like conv3_halo_kernel) =====================
-    if (elect_one()) {
+    // The whole warp runs the loops converged (uniform-datapath address arithmetic); one elected lane - always the
+    // same one for a full member mask - issues the tcgen05 instructions.  With the loops inside a single-lane region
+    // ptxas computed every descriptor in vector registers and moved it over with R2UR: ~100 issue cycles per MMA,
+    // more than the 64 cycles an M=128, N<=128 MMA takes.
+    {
       const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+      const int msub = p.msub;
+      const uint32_t sub_bytes = (uint32_t)(p.sub_rows * 128);
       int s = -1, acc = 0;
       uint32_t ph = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc) {
         const int buf = acc & 1;
         {
           PROF_T0();
-          mbar_wait_bo(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u, p.bo_mma_acc);  // epilogue has drained this accumulator
+          mbar_wait_warp(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u, p.bo_mma_acc);  // epilogue has drained this accumulator
           PROF_ADD(pw1);
         }
         tc_fence_after();
         uint32_t accf = 0;  // the first MMA of a tile overwrites the accumulators
+        const uint32_t d_tmem0 = tmem_base + (uint32_t)(buf * msub * acc_stride);
         for (int c = 0; c < kchunks; ++c) {
           int ksteps = (p.Cin - c * 64) >> 4;
           if (ksteps > 4) ksteps = 4;
@@ -785,32 +794,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (s == 0) ph ^= 1;
             {
               PROF_T0();
-              mbar_wait_bo(full_bar + s, ph, 2u, p.bo_mma_full);
+              mbar_wait_warp(full_bar + s, ph, 2u, p.bo_mma_full);
               PROF_ADD(pw0);
             }
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + s * stage_bytes);
             const uint32_t b_lo = umma_desc_lo(sa + a_bytes);
+            const uint32_t a_lo0 = umma_desc_lo(sa), a_lo1 = umma_desc_lo(sa + sub_bytes);
             constexpr uint32_t hi = umma_desc_hi(1024);
+            if (elect_one()) {
 #pragma unroll
-            for (int sidx = 0; sidx < 2; ++sidx) {
-              if (sidx >= p.msub) break;
-              const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.msub + sidx) * acc_stride);
-              const uint32_t a_lo = umma_desc_lo(sa + (uint32_t)(sidx * p.sub_rows * 128));
+              for (int j = 0; j < 4; ++j)
+                if (j < ksteps) umma_bf16_lohi(d_tmem0, a_lo0 + 2 * j, hi, b_lo + 2 * j, hi, idesc, j == 0 ? accf : 1u);
+              if (msub > 1) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (j < ksteps) {
-                  umma_bf16_lohi(d_tmem, a_lo + 2 * j, hi, b_lo + 2 * j, hi, idesc, j == 0 ? accf : 1u);
-                }
+                for (int j = 0; j < 4; ++j)
+                  if (j < ksteps)
+                    umma_bf16_lohi(d_tmem0 + (uint32_t)acc_stride, a_lo1 + 2 * j, hi, b_lo + 2 * j, hi, idesc, j == 0 ? accf : 1u);
               }
+              umma_commit(empty_bar + s);
             }
             accf = 1;
-            umma_commit(empty_bar + s);
           }
         }
-        umma_commit(tfull_bar + buf);
+        if (elect_one()) umma_commit(tfull_bar + buf);
       }
-      if (prof) {
+      if (prof && elect_one()) {
         atomicAdd(&g_conv_prof[1], (unsigned long long)pw0);
         atomicAdd(&g_conv_prof[2], (unsigned long long)pw1);
       }
@@ -963,7 +972,9 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 37);
   uint8_t* stage_base = reinterpret_cast<uint8_t*>(bars) + 512;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle makes the warp index provably warp-uniform: role branches become uniform branches and the role
+  // bodies may keep their loop state on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int kchunks = (p.Cin + 63) >> 6;
   const int acc_stride = conv2_acc_stride(p.n_tile);
@@ -974,7 +985,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   while (tmem_cols < (uint32_t)(2 * x.msub * acc_stride)) tmem_cols <<= 1;
   const bool prof = kProf && (p.dbg & 8) != 0;
   const long long prof_start = prof ? clock64() : 0;
-  long long pw0 = 0, pw1 = 0, pw2 = 0;
+  long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0;
 
   if (warp == kProdWarp0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -997,10 +1008,14 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   pdl_wait();
 
   const int pw = warp - kProdWarp0;  // producer index
-  if (pw == 0) {
+  if (pw == 0 || (x.b_stat && pw > 0 && pw < kProdWarps)) {
     // ===================== TMA producer 0: halo tiles (and the resident weights, once) =====================
+    // With resident weights the other producer warps have nothing to stream and share the halo loads: slot sa
+    // belongs to producer sa % a_prods (a thread's bulk loads complete one after the other; several threads
+    // keep several boxes in flight, tools/tma_bench.py).
+    const int a_prods = x.b_stat ? kProdWarps : 1;
     if (elect_one()) {
-      if (x.b_stat) {
+      if (x.b_stat && pw == 0) {
         mbar_expect_tx(ball_bar, (uint32_t)(9 * kchunks * tap_bytes));
         for (int c = 0; c < kchunks; ++c)
           for (int g = 0; g < ngroups; ++g)
@@ -1016,6 +1031,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c = 0; c < kchunks; ++c) {
           if (++sa == x.a_slots) sa = 0;
           if (sa == 0) pa ^= 1;
+          if (sa % a_prods != pw) continue;
           {
             PROF_T0();
             mbar_wait_bo(a_empty + sa, pa ^ 1, 1u, p.bo_prod);
@@ -1025,7 +1041,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_load_5d(sA + sa * x.a_bytes, &tmA, a_full + sa, p.a_base[0] + c * 64, w0 - 1, h0 - 1, b, 0);
         }
       }
-      if (prof) atomicAdd(&g_conv_prof[0], (unsigned long long)pw0);
+      if (prof && pw == 0) atomicAdd(&g_conv_prof[0], (unsigned long long)pw0);
     }
   } else if (pw > 0 && pw < kProdWarps) {
     // ===================== TMA producers 1..3: streamed weight boxes, ring slot sb owned by warp 1 + sb % 3 =====================
@@ -1047,11 +1063,13 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues: see conv_tc2_kernel) =====================
+    {
       const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
-      if (x.b_stat) {
-        mbar_wait(ball_bar, 0, 2u);
+      const int msub = x.msub, b_group = x.b_group;
+      const bool b_stat = x.b_stat != 0;
+      if (b_stat) {
+        mbar_wait_warp(ball_bar, 0, 2u, 0);
         tc_fence_after();
       }
       int sa = -1, sbn = -1, acc = 0;
@@ -1060,67 +1078,83 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int buf = acc & 1;
         {
           PROF_T0();
-          mbar_wait_bo(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u, p.bo_mma_acc);
+          mbar_wait_warp(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u, p.bo_mma_acc);
           PROF_ADD(pw1);
         }
         tc_fence_after();
         uint32_t accf = 0;  // the first MMA of a tile overwrites the accumulators
+        const uint32_t d_tmem0 = tmem_base + (uint32_t)(buf * msub * acc_stride);
         for (int c = 0; c < kchunks; ++c) {
           if (++sa == x.a_slots) sa = 0;
           if (sa == 0) pa ^= 1;
           {
             PROF_T0();
-            mbar_wait_bo(a_full + sa, pa, 2u, p.bo_mma_full);
+            mbar_wait_warp(a_full + sa, pa, 2u, p.bo_mma_full);
             PROF_ADD(pw0);
           }
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + sa * x.a_bytes);
           int ksteps = (p.Cin - c * 64) >> 4;
           if (ksteps > 4) ksteps = 4;
           if (p.dbg & 4) ksteps = 0;
+          const long long _ti0 = prof ? clock64() : 0;
+          // tap (kh, kw) of sub-tile s: the halo buffer seen from row (16 s + kh) * 10 + kw on
+          uint32_t a_lo = umma_desc_lo(smem_u32(sA + sa * x.a_bytes));  // advanced tap by tap (16-byte units)
+          int kw = 0;
           for (int g = 0; g < ngroups; ++g) {
-            uint32_t g_base;
+            uint32_t b_lo;
             int sb = 0;
-            if (x.b_stat) {
-              g_base = smem_u32(sB + (c * 9 + g * x.b_group) * tap_bytes);
+            if (b_stat) {
+              b_lo = umma_desc_lo(smem_u32(sB + (c * 9 + g * b_group) * tap_bytes));
             } else {
               if (++sbn == x.b_slots) sbn = 0;
               if (sbn == 0) pb ^= 1;
               sb = sbn;
               {
                 PROF_T0();
-                mbar_wait_bo(b_full + sb, pb, 2u, p.bo_mma_full);
+                mbar_wait_warp(b_full + sb, pb, 2u, p.bo_mma_full);
                 PROF_ADD(pw2);
               }
               tc_fence_after();
-              g_base = smem_u32(sB + sb * grp_bytes);
+              b_lo = umma_desc_lo(smem_u32(sB + sb * grp_bytes));
             }
-            for (int u = 0; u < x.b_group; ++u) {
-              const int t = g * x.b_group + u;
-              const int kh = t / 3, kw = t - kh * 3;
-              const uint32_t b_lo = umma_desc_lo(g_base + (uint32_t)(u * tap_bytes));
+            for (int u = 0; u < b_group; ++u) {
+              if (elect_one()) {
 #pragma unroll
-              for (int sidx = 0; sidx < 2; ++sidx) {
-                if (sidx >= x.msub) break;
-                const uint32_t a_lo = umma_desc_lo(a_base + (uint32_t)(((sidx * 16 + kh) * 10 + kw) * 128));
-                const uint32_t d_tmem = tmem_base + (uint32_t)((buf * x.msub + sidx) * acc_stride);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (j < ksteps) {
-                    umma_bf16_lohi(d_tmem, a_lo + 2 * j, umma_desc_hi(1280), b_lo + 2 * j, umma_desc_hi(1024), idesc,
+                for (int j = 0; j < 4; ++j)
+                  if (j < ksteps)
+                    umma_bf16_lohi(d_tmem0, a_lo + 2 * j, umma_desc_hi(1280), b_lo + 2 * j, umma_desc_hi(1024), idesc,
                                    j == 0 ? accf : 1u);
-                  }
+                if (msub > 1) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (j < ksteps)
+                      umma_bf16_lohi(d_tmem0 + (uint32_t)acc_stride, a_lo + (16 * 10 * 128 >> 4) + 2 * j, umma_desc_hi(1280),
+                                     b_lo + 2 * j, umma_desc_hi(1024), idesc, j == 0 ? accf : 1u);
                 }
               }
               accf = 1;
+              b_lo += (uint32_t)(tap_bytes >> 4);
+              a_lo += 128 >> 4;                    // next kw
+              if (++kw == 3) {                     // next kh: down one halo row (10 pixels), back three columns
+                kw = 0;
+                a_lo += (7 * 128) >> 4;
+              }
             }
-            if (!x.b_stat) umma_commit(b_empty + sb);
+            if (!b_stat && elect_one()) umma_commit(b_empty + sb);
           }
-          umma_commit(a_empty + sa);
+          const long long _ti1 = prof ? clock64() : 0;
+          if (elect_one()) umma_commit(a_empty + sa);
+          if (prof) { pw4 += _ti1 - _ti0; pw3 += clock64() - _ti1; }
         }
-        umma_commit(tfull_bar + buf);
+        {
+          PROF_T0();
+          if (elect_one()) umma_commit(tfull_bar + buf);
+          PROF_ADD(pw3);
+        }
       }
-      if (prof) {
+      if (prof && elect_one()) {
+        atomicAdd(&g_conv_prof[14], (unsigned long long)pw3);
+        atomicAdd(&g_conv_prof[15], (unsigned long long)pw4);
         atomicAdd(&g_conv_prof[1], (unsigned long long)pw0);
         atomicAdd(&g_conv_prof[2], (unsigned long long)pw1);
         atomicAdd(&g_conv_prof[6], (unsigned long long)pw2);

@@ -23,9 +23,13 @@ tma_bench_kernel(const __grid_constant__ CUtensorMap tm2d, const __grid_constant
   // the stages s with s % pairs == pair; p.H (mode 0/1) = rows per box (128 or 256; stage = rows*128 bytes).
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int box_rows = (p.mode == 2 || p.H == 0) ? 128 : p.H;
-  const int stage_bytes = box_rows * 128;
-  const int pairs = (p.mode == 2 || p.W == 0) ? 1 : p.W;
+  // mode 4: halo boxes {64 ch, 10, R} of a (C_tot, W, H, B) map, one per tile of 8 x (R-2) pixels, tiles strided
+  // over the CTAs like conv3_halo_kernel does; rows_total = C_tot | R << 16 | producers << 24.
+  const int halo_R = (p.rows_total >> 16) & 0xff;
+  const int box_rows = p.mode == 4 ? halo_R * 10 : (p.mode == 2 || p.H == 0) ? 128 : p.H;
+  const int tx_bytes = box_rows * 128;
+  const int stage_bytes = (tx_bytes + 1023) & ~1023;
+  const int pairs = p.mode == 4 ? ((p.rows_total >> 24) & 0xf) : (p.mode == 2 || p.W == 0) ? 1 : p.W;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   if (threadIdx.x == 0) {
@@ -40,10 +44,15 @@ tma_bench_kernel(const __grid_constant__ CUtensorMap tm2d, const __grid_constant
     for (int it = warp; it < p.iters; it += pairs) {
       const int s = it % p.stages;
       mbar_wait(empty_bar + s, ((it / p.stages) & 1) ^ 1, 0x1000u);
-      const int variant = p.mode == 2 ? 0 : p.B;  // 0: expect_tx then copy, 1: relaxed expect_tx, 2: copy then expect_tx
-      if (variant == 0) mbar_expect_tx(full_bar + s, stage_bytes);
-      if (variant == 1) mbar_expect_tx_relaxed(full_bar + s, stage_bytes);
-      if (p.mode == 2) {
+      const int variant = (p.mode == 2 || p.mode == 4) ? 0 : p.B;  // 0: expect_tx then copy, 1: relaxed expect_tx, 2: copy then expect_tx
+      if (variant == 0) mbar_expect_tx(full_bar + s, tx_bytes);
+      if (variant == 1) mbar_expect_tx_relaxed(full_bar + s, tx_bytes);
+      if (p.mode == 4) {
+        const int tw = p.W / 8, th = (p.H + halo_R - 3) / (halo_R - 2);
+        const int tile = (blockIdx.x + it * gridDim.x) % (tw * th * p.B);
+        const int b = tile / (tw * th), r = tile % (tw * th);
+        tma_load_5d(smem + s * stage_bytes, &tm5d, full_bar + s, 0, (r % tw) * 8 - 1, (r / tw) * (halo_R - 2) - 1, b, 0);
+      } else if (p.mode == 2) {
         const int tile = (blockIdx.x + (it / 9) * gridDim.x) % (tiles_w * tiles_h * p.B);
         const int t = it % 9;
         const int b = tile / (tiles_w * tiles_h), r = tile % (tiles_w * tiles_h);
@@ -55,7 +64,7 @@ tma_bench_kernel(const __grid_constant__ CUtensorMap tm2d, const __grid_constant
         const long long row = p.mode == 1 ? 0 : ((long long)(blockIdx.x + (long long)it * gridDim.x) * box_rows) % p.rows_total;
         tma_load_5d(smem + s * stage_bytes, &tm2d, full_bar + s, 0, (int)row, 0, 0, 0);
       }
-      if (variant == 2) mbar_expect_tx(full_bar + s, stage_bytes);
+      if (variant == 2) mbar_expect_tx(full_bar + s, tx_bytes);
     }
   } else if (warp >= 4 && warp < 4 + pairs) {  // consumers
     for (int it = warp - 4; it < p.iters; it += pairs) {

@@ -1405,8 +1405,9 @@ int ypb_conv_bench(void* cuda_stream, const void* in, int B, int H, int W, int i
     const size_t len = strlen(desc);
     snprintf(desc + len, desc_len - len,
              " | per-CTA kcycles: life %.1f prod.wait_empty %.1f mma.wait_full %.1f mma.wait_tempty %.1f mma.wait_w %.1f "
-             "epi.wait_tfull %.1f epi.drain %.1f",
-             life / 1e3, z[0] / n / 1e3, z[1] / n / 1e3, z[2] / n / 1e3, z[6] / n / 1e3, z[3] / n / 1e3, z[4] / n / 1e3);
+             "epi.wait_tfull %.1f epi.drain %.1f mma.issue %.1f mma.commit %.1f",
+             life / 1e3, z[0] / n / 1e3, z[1] / n / 1e3, z[2] / n / 1e3, z[6] / n / 1e3, z[3] / n / 1e3, z[4] / n / 1e3,
+             z[15] / n / 1e3, z[14] / n / 1e3);
     const double np = z[13] ? (double)z[13] : 1.0;
     const size_t len2 = strlen(desc);
     snprintf(desc + len2, desc_len - len2, " | cycles per epilogue pass: ld+wait %.0f release %.0f math %.0f stage %.0f writeout %.0f",
@@ -1429,7 +1430,14 @@ int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, i
     cuuint32_t box[5] = {64, (cuuint32_t)((mode != 2 && H == 256) ? 256 : 128), 1, 1, 1};
     if (!encode_bf16_map(&m2, buf, 5, dims, str, box, &err)) return fail(YPB_ERR_CUDA, err);
   }
-  if (mode == 3) {
+  const int halo_R = (rows >> 16) & 0xff, halo_C = rows & 0xffff;
+  if (mode == 4) {
+    if (halo_R < 3 || halo_C < 8) return fail(YPB_ERR_ARG, "mode 4: rows = C_tot | R << 16 | producers << 24");
+    cuuint64_t dims[5] = {(cuuint64_t)halo_C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 1};
+    cuuint64_t str[4] = {(cuuint64_t)halo_C * 2, (cuuint64_t)halo_C * 2 * W, (cuuint64_t)halo_C * 2 * W * H, (cuuint64_t)halo_C * 2 * W * H * B};
+    cuuint32_t box[5] = {64, 10, (cuuint32_t)halo_R, 1, 1};
+    if (!encode_bf16_map(&m5, buf, 5, dims, str, box, &err)) return fail(YPB_ERR_CUDA, err);
+  } else if (mode == 3) {
     cuuint64_t dims[2] = {64, (cuuint64_t)rows};
     cuuint64_t str[1] = {128};
     cuuint32_t box[2] = {64, (cuuint32_t)(H == 256 ? 256 : 128)};
@@ -1443,7 +1451,7 @@ int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, i
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int stage_b = (mode != 2 && H == 256) ? 32768 : 16384;
+  const int stage_b = mode == 4 ? ((halo_R * 10 * 128 + 1023) & ~1023) : (mode != 2 && H == 256) ? 32768 : 16384;
   const int smem = stages * stage_b + 1024 + 256;
   if (smem > 227 * 1024) return fail(YPB_ERR_ARG, "too many stages");
   CUDA_TRY(cudaFuncSetAttribute(tma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -232,6 +232,27 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
       : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// KS consecutive K=16 steps of one 128 x N tile (descriptor start addresses advance by 32 bytes = 2 units per step).
+// ksteps is dispatched to the straight-line KS = 4 / 2 forms: predicating each MMA on `j < ksteps` costs a handful of
+// uniform moves per instruction (ptxas gives every predicated MMA its own operand registers).
+template <int KS>
+__device__ __forceinline__ void umma_bf16_ksteps(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accf) {
+#pragma unroll
+  for (int j = 0; j < KS; ++j) umma_bf16_lohi(d_tmem, a_lo + 2 * j, a_hi, b_lo + 2 * j, b_hi, idesc, j == 0 ? accf : 1u);
+}
+__device__ __forceinline__ void umma_bf16_ksteps_n(int ksteps, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                   uint32_t b_hi, uint32_t idesc, uint32_t accf) {
+  if (ksteps == 4) {
+    umma_bf16_ksteps<4>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accf);
+  } else if (ksteps == 2) {
+    umma_bf16_ksteps<2>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accf);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (j < ksteps) umma_bf16_lohi(d_tmem, a_lo + 2 * j, a_hi, b_lo + 2 * j, b_hi, idesc, j == 0 ? accf : 1u);
+  }
+}
 // low / high words of a K-major SWIZZLE_128B descriptor (see umma_desc_sw128): start>>4 | LBO=1<<16 ; SBO>>4 | v1 | layout 2
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
 __host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }

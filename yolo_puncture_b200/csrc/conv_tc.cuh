@@ -803,15 +803,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t a_lo0 = umma_desc_lo(sa), a_lo1 = umma_desc_lo(sa + sub_bytes);
             constexpr uint32_t hi = umma_desc_hi(1024);
             if (elect_one()) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j < ksteps) umma_bf16_lohi(d_tmem0, a_lo0 + 2 * j, hi, b_lo + 2 * j, hi, idesc, j == 0 ? accf : 1u);
-              if (msub > 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j < ksteps)
-                    umma_bf16_lohi(d_tmem0 + (uint32_t)acc_stride, a_lo1 + 2 * j, hi, b_lo + 2 * j, hi, idesc, j == 0 ? accf : 1u);
-              }
+              umma_bf16_ksteps_n(ksteps, d_tmem0, a_lo0, hi, b_lo, hi, idesc, accf);
+              if (msub > 1) umma_bf16_ksteps_n(ksteps, d_tmem0 + (uint32_t)acc_stride, a_lo1, hi, b_lo, hi, idesc, accf);
               umma_commit(empty_bar + s);
             }
             accf = 1;
@@ -1119,18 +1112,10 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             for (int u = 0; u < b_group; ++u) {
               if (elect_one()) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j < ksteps)
-                    umma_bf16_lohi(d_tmem0, a_lo + 2 * j, umma_desc_hi(1280), b_lo + 2 * j, umma_desc_hi(1024), idesc,
-                                   j == 0 ? accf : 1u);
-                if (msub > 1) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (j < ksteps)
-                      umma_bf16_lohi(d_tmem0 + (uint32_t)acc_stride, a_lo + (16 * 10 * 128 >> 4) + 2 * j, umma_desc_hi(1280),
-                                     b_lo + 2 * j, umma_desc_hi(1024), idesc, j == 0 ? accf : 1u);
-                }
+                umma_bf16_ksteps_n(ksteps, d_tmem0, a_lo, umma_desc_hi(1280), b_lo, umma_desc_hi(1024), idesc, accf);
+                if (msub > 1)
+                  umma_bf16_ksteps_n(ksteps, d_tmem0 + (uint32_t)acc_stride, a_lo + (16 * 10 * 128 >> 4), umma_desc_hi(1280), b_lo,
+                                     umma_desc_hi(1024), idesc, accf);
               }
               accf = 1;
               b_lo += (uint32_t)(tap_bytes >> 4);

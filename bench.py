@@ -433,7 +433,7 @@ def run_ours(args, wl):
         "config": {"workload": args.workload, "model": model, "batch_per_gpu": B, "global_batch": world * B,
                    "frame": f"{hw[1]}x{hw[0]}", "net_input": f"{W}x{H}", "imgsz": imgsz, "conf": CONF, "iou": IOU,
                    "retina_masks": True, "weights": "random-init, synthetic recipe (SURVEY.md 8d)",
-                   "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph, "predict_micro_batch": yolo.micro_batch,
+                   "conv_impl": args.conv_impl, "cuda_graph": not args.no_graph, "predict_passes": [hi - lo for (_, lo, hi, _, _) in yolo._schedule(B)],
                    "detections_per_step": n_det,
                    "candidates_per_frame": {"mean": float(cand.mean()), "max": int(cand.max())}, "parallelism": f"frame-sharded replicas x{world}",
                    "l2": "each step streams >1 GB of activations through HBM (inputs+activations exceed the 126 MB L2)"},

@@ -173,6 +173,7 @@ int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offs
 /* Zero-staging path of predict(): is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / pinned torch
    tensor)?  and: copy n such frames to consecutive device slots on `cuda_stream`, merging adjacent sources. */
 int ypb_host_is_pinned(const void* p, int* pinned);
+int ypb_hosts_are_pinned(const void* const* ptrs, int n, int* all_pinned);  /* the same for n pointers: 1 iff all are */
 int ypb_h2d_frames(void* cuda_stream, void* dst_dev, const void* const* src, size_t bytes_each, int n);
 /* Host helper of the predict() pipeline: copy n frames into pinned staging memory with nthreads host threads. */
 int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads);

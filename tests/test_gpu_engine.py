@@ -207,6 +207,38 @@ def test_predict_api_sources_order_and_batch_invariance(nseg):
     assert set(sp) == {"preprocess", "inference", "postprocess"} and all(v >= 0 for v in sp.values())
 
 
+def test_pass_schedule_invariance(nseg):
+    """predict() splits a large group into a 16-frame head pass (second engine plan) + the rest; any schedule must
+    give the results of one frame at a time, bit for bit, pinned or pageable frames alike."""
+    from yolo_puncture_b200 import synth
+    yolo = nseg["yolo"]
+    frames = synth.synth_frames(40)
+    assert [hi - lo for (_, lo, hi, _, _) in yolo._schedule(40)] == [16, 24]
+    auto = yolo.predict(frames, conf=0.25, retina_masks=True, batch=64)
+    pin = torch.empty((40, 640, 640, 3), dtype=torch.uint8).pin_memory()
+    for i, f in enumerate(frames):
+        pin[i] = torch.from_numpy(f)
+    auto_pin = yolo.predict([pin[i].numpy() for i in range(40)], conf=0.25, retina_masks=True, batch=64)
+    try:
+        yolo.micro_batch = 7  # uniform passes with a ragged tail
+        assert [hi - lo for (_, lo, hi, _, _) in yolo._schedule(40)] == [7, 7, 7, 7, 7, 5]
+        uni = yolo.predict(frames, conf=0.25, retina_masks=True, batch=64)
+    finally:
+        yolo.micro_batch = None
+    n = 0
+    for i in (0, 15, 16, 39):
+        one = yolo.predict(frames[i], conf=0.25, retina_masks=True)[0]
+        for r in (auto[i], auto_pin[i], uni[i]):
+            assert torch.equal(one.boxes.data, r.boxes.data)
+            assert (one.masks is None) == (r.masks is None)
+            if one.masks is not None:
+                assert torch.equal(one.masks.raw, r.masks.raw)
+        n += len(one.boxes)
+    for a, b, c in zip(auto, auto_pin, uni):
+        assert torch.equal(a.boxes.data, b.boxes.data) and torch.equal(a.boxes.data, c.boxes.data)
+    assert n > 0
+
+
 @pytest.mark.parametrize("name", ["yolov8s-seg", "yolov8m-seg"])
 def test_other_scales_strict(name):
     from oracle import ops as oops

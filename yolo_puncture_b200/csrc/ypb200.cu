@@ -1587,6 +1587,19 @@ int ypb_host_is_pinned(const void* p, int* pinned) {
   return YPB_OK;
 }
 
+int ypb_hosts_are_pinned(const void* const* ptrs, int n, int* all_pinned) {
+  if (!ptrs || !all_pinned || n < 0) return fail(YPB_ERR_ARG, "bad argument");
+  *all_pinned = 1;
+  for (int i = 0; i < n && *all_pinned; ++i) {
+    int one = 0;
+    if (ptrs[i] == nullptr) return fail(YPB_ERR_ARG, "null frame pointer");
+    const int rc = ypb_host_is_pinned(ptrs[i], &one);
+    if (rc != YPB_OK) return rc;
+    if (!one) *all_pinned = 0;
+  }
+  return YPB_OK;
+}
+
 // n frames of `bytes_each` bytes -> consecutive slots of dst_dev, one cudaMemcpyAsync per run of adjacent sources.
 int ypb_h2d_frames(void* cuda_stream, void* dst_dev, const void* const* src, size_t bytes_each, int n) {
   if (!dst_dev || !src || n < 0) return fail(YPB_ERR_ARG, "bad argument");

@@ -172,11 +172,18 @@ class YOLO:
         if state_dict is None:
             state_dict = synth_state_dict([(n, s) for n, s, _ in self.engine.weight_specs()], spec, seed, nc=self.nc)
         self.engine.load_state_dict(state_dict)
+        self._state_dict = state_dict  # kept for the head-pass engine (second plan size), built on first use
+        self._head_engine = None
         self._device = None
         self._device_token = torch.zeros(1)
         self._staging = {}
         self.overrides = {}
-        self.micro_batch = 32  # frames per engine pass inside predict(); H2D of pass k+1 overlaps compute of pass k
+        # Frames per engine pass inside predict().  None: automatic schedule - up to 32 frames run as one pass; larger
+        # groups start with a HEAD pass of 16 frames so the engine starts after a quarter of the first upload, and the
+        # rest follows in passes of up to 48 (fixed per-pass cost ~0.5 ms on yolov8s-seg: fewer, larger passes win).
+        # An int forces uniform passes of that size.  H2D of pass k+1 always overlaps compute of pass k.
+        self.micro_batch = None
+        self.head_pass = 16
         self.device_letterbox = True  # resize + pad on the GPU when the frame is at least as large as the network input
         if device is not None:
             self._set_device(device)
@@ -202,6 +209,8 @@ class YOLO:
         if not torch.cuda.is_available():
             raise YpbError("no CUDA device available: the B200 engine has no CPU fallback")
         self.engine.finalize(d)
+        if self._head_engine is not None:
+            self._head_engine.finalize(d)
         self._device = d
         self._device_token = torch.zeros(1, device=d)
         self._staging = {}
@@ -250,20 +259,47 @@ class YOLO:
                     results[i] = r
         return iter(results) if stream else results
 
-    def _buffers(self, B, mb, H, W):
-        key = (B, mb, H, W)
+    def _head(self):
+        """Second engine instance (same weights) so that two pass sizes stay planned side by side."""
+        if self._head_engine is None:
+            e = Engine(self.spec, self.nc)
+            e.load_state_dict(self._state_dict)
+            e.finalize(self._device)
+            self._head_engine = e
+        return self._head_engine
+
+    def _schedule(self, B, pinned=True):
+        """[(engine, lo, hi, capacity, slot)]: the engine passes of a group of B frames (slot = input / output set).
+        Frames in pageable memory are staged into pinned memory by host threads first (~0.1 ms per 640x640 frame, slower
+        than the engine consumes them): there uniform passes of 32 measured best."""
+        if self.micro_batch or not pinned:
+            mb = min(B, int(self.micro_batch or 32))
+            return [(self.engine, lo, min(lo + mb, B), mb, k & 1) for k, lo in enumerate(range(0, B, mb))]
+        if B <= 32 or B - self.head_pass < self.head_pass:
+            return [(self.engine, 0, B, B, 0)]
+        passes = [(self._head(), 0, self.head_pass, self.head_pass, 0)]
+        rest = B - self.head_pass
+        n = (rest + 47) // 48
+        mb = (rest + n - 1) // n
+        for k, lo in enumerate(range(self.head_pass, B, mb)):
+            passes.append((self.engine, lo, min(lo + mb, B), mb, (k + 1) & 1))
+        return passes
+
+    def _buffers(self, B, caps, H, W):
+        key = (B, caps, H, W)
         if key not in self._staging:
             self._staging = {key: {
                 "host": torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory(),
-                "dev": [torch.empty((mb, H, W, 3), dtype=torch.uint8, device=self._device) for _ in range(2)],
-                "xf_dev": torch.empty((mb, 5), dtype=torch.float32, device=self._device),
+                "dev": [torch.empty((c, H, W, 3), dtype=torch.uint8, device=self._device) for c in caps],
+                "xf_dev": torch.empty((max(caps), 5), dtype=torch.float32, device=self._device),
                 "copy_stream": torch.cuda.Stream(device=self._device),
                 "in_free": [None, None],
             }}
         return self._staging[key]
 
-    def _letterbox_buffers(self, buf, B, mb, shape, new_unpad, need_host=True):
+    def _letterbox_buffers(self, buf, B, caps, shape, new_unpad, need_host=True):
         """Raw-frame staging and the cv2 coefficient tables of the device LetterBox for one source shape."""
+        mb = caps
         key = (B, mb, tuple(shape[:2]), tuple(new_unpad))
         lb = buf.get("letterbox")
         if lb is not None and lb["key"] == key and need_host and lb["raw_host"] is None:
@@ -274,46 +310,31 @@ class YOLO:
             dev = self._device
             lb = {"key": key,
                   "raw_host": torch.empty((B, shape[0], shape[1], 3), dtype=torch.uint8).pin_memory() if need_host else None,
-                  "raw_dev": [torch.empty((mb, shape[0], shape[1], 3), dtype=torch.uint8, device=dev) for _ in range(2)],
+                  "raw_dev": [torch.empty((c, shape[0], shape[1], 3), dtype=torch.uint8, device=dev) for c in caps],
                   "xofs": torch.from_numpy(xofs).to(dev), "xa": torch.from_numpy(xa).to(dev),
                   "yofs": torch.from_numpy(yofs).to(dev), "ya": torch.from_numpy(ya).to(dev)}
             buf["letterbox"] = lb
         return lb
 
     def _predict_batch(self, frames, shape, imgsz, auto, conf, iou, retina, max_det, classes, agnostic):
-        """One group of same-shape frames.  The group runs as micro-batches of `mb` frames through one static engine
-        plan: frames are letterboxed into pinned memory by host threads, each micro-batch's H2D copy is issued on a
-        copy stream as soon as its frames are staged, and it overlaps the engine pass of the previous micro-batch."""
-        eng = self.engine
+        """One group of same-shape frames.  The group runs as the engine passes of `_schedule()` through static engine
+        plans: frames are letterboxed into pinned memory by host threads, each pass's H2D copy is issued on a copy
+        stream as soon as its frames are staged, and it overlaps the engine pass before it."""
         B = len(frames)
         t0 = time.perf_counter()
         new_unpad, top, bottom, left, right = letterbox_geometry(shape, imgsz, auto)
         H, W = new_unpad[1] + top + bottom, new_unpad[0] + left + right
         if H % 32 or W % 32:
             raise YpbError(f"letterboxed size {H}x{W} is not a multiple of 32 (imgsz={imgsz})")
-        mb = B if B <= self.micro_batch else self.micro_batch
-        n_mb = (B + mb - 1) // mb
         seg = self.task == "segment"
         mh, mw = (shape[0], shape[1]) if retina else (H, W)
         with torch.cuda.device(self._device):
-            eng.plan(mb, H, W)
-            buf = self._buffers(B, mb, H, W)
-            host = buf["host"].numpy()
-            main = torch.cuda.current_stream(self._device)
-            cs = buf["copy_stream"]
-            buf["xf_dev"].copy_(torch.tensor([box_xform((H, W), shape)] * mb, dtype=torch.float32))
-            cmask = None
-            if classes is not None:
-                words = np.zeros(((self.nc + 31) // 32,), np.uint32)
-                for c in classes:
-                    words[int(c) >> 5] |= np.uint32(1) << np.uint32(int(c) & 31)
-                cmask = torch.from_numpy(words.view(np.int32)).to(self._device)
             direct = (shape[0], shape[1]) == (H, W)  # frames already have the network size: staging is a plain copy
-            futs = None
-            pinned = False
             # LetterBox on the device when it is a down-scale (bit-exact with cv2 there): the raw frames are uploaded
             # and resized + padded by one kernel instead of cv2.resize on host threads
             dev_lb = (not direct) and self.device_letterbox and new_unpad[0] <= shape[1] and new_unpad[1] <= shape[0]
+            futs = None
+            pinned = False
             if direct or dev_lb:
                 frames_c = [f if f.flags["C_CONTIGUOUS"] else np.ascontiguousarray(f) for f in frames]
                 nbytes = shape[0] * shape[1] * 3  # == H * W * 3 when direct
@@ -322,14 +343,30 @@ class YOLO:
                 nthreads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
                 # frames that already live in page-locked memory go to the device from where they are (no staging copy)
                 flag = ctypes.c_int(0)
-                pinned = True
-                for i in range(B):
-                    check(lib().ypb_host_is_pinned(src_ptrs[i], ctypes.byref(flag)))
-                    if not flag.value:
-                        pinned = False
-                        break
+                check(lib().ypb_hosts_are_pinned(src_ptrs, B, ctypes.byref(flag)))
+                pinned = bool(flag.value)
+            passes = self._schedule(B, pinned)
+            n_mb = len(passes)
+            caps = tuple(max([c for (_, _, _, c, sl) in passes if sl == slot] or [1]) for slot in range(2))
+            for (e, _, _, cap, _) in passes:
+                e.plan(cap, H, W)
+            buf = self._buffers(B, caps, H, W)
+            host = buf["host"].numpy()
+            main = torch.cuda.current_stream(self._device)
+            cs = buf["copy_stream"]
+            xf_key = ((H, W), tuple(shape[:2]))
+            if buf.get("xf_key") != xf_key:  # same geometry as the last call: the device copy is still valid
+                buf["xf_dev"].copy_(torch.tensor([box_xform((H, W), shape)] * max(caps), dtype=torch.float32))
+                buf["xf_key"] = xf_key
+            cmask = None
+            if classes is not None:
+                words = np.zeros(((self.nc + 31) // 32,), np.uint32)
+                for c in classes:
+                    words[int(c) >> 5] |= np.uint32(1) << np.uint32(int(c) & 31)
+                cmask = torch.from_numpy(words.view(np.int32)).to(self._device)
+            if direct or dev_lb:
                 if dev_lb:
-                    lb = self._letterbox_buffers(buf, B, mb, shape, new_unpad, need_host=not pinned)
+                    lb = self._letterbox_buffers(buf, B, caps, shape, new_unpad, need_host=not pinned)
                 if not pinned:
                     stage_host = lb["raw_host"] if dev_lb else buf["host"]
                     dst_ptrs = (ctypes.c_void_p * B)(*[stage_host[i].data_ptr() for i in range(B)])
@@ -341,8 +378,7 @@ class YOLO:
             dets, cnts, mask_parts = [], [], []
 
             def enqueue_h2d(k):
-                lo, hi = k * mb, min((k + 1) * mb, B)
-                slot = k & 1
+                _, lo, hi, _, slot = passes[k]
                 vp = ctypes.sizeof(ctypes.c_void_p)
                 if (direct or dev_lb) and not pinned:  # native multi-threaded copy into pinned memory (ctypes drops the GIL)
                     check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, lo * vp), ctypes.byref(src_ptrs, lo * vp),
@@ -375,25 +411,24 @@ class YOLO:
             protos = buf.setdefault("proto_copy", [None, None])
 
             def launch(k):
-                lo, hi = k * mb, min((k + 1) * mb, B)
-                slot = k & 1
+                eng, lo, hi, cap, slot = passes[k]
                 main.wait_event(h2d_done[k])
                 eng.use_outputs(slot)
-                eng.infer(buf["dev"][slot], buf["xf_dev"], conf, iou, max_det, agnostic, cmask)
+                eng.infer(buf["dev"][slot][:cap], buf["xf_dev"][:cap], conf, iou, max_det, agnostic, cmask)
                 fr = torch.cuda.Event()
                 fr.record(main)
                 buf["in_free"][slot] = fr
-                if hi - lo < mb:
-                    eng.count[hi - lo:].zero_()  # padded tail of the last micro-batch
+                if hi - lo < cap:
+                    eng.count[hi - lo:].zero_()  # padded tail of the last pass
                 if seg:
                     pv = eng.proto_view()
-                    if protos[slot] is None or protos[slot].numel() != pv.numel():
-                        protos[slot] = torch.empty_like(pv)
-                    protos[slot].copy_(pv, non_blocking=True)
+                    if protos[k & 1] is None or protos[k & 1].numel() != pv.numel():
+                        protos[k & 1] = torch.empty_like(pv)
+                    protos[k & 1].copy_(pv, non_blocking=True)
 
             def finish(k):
-                lo, hi = k * mb, min((k + 1) * mb, B)
-                o = eng.out_sets[k & 1]
+                eng, lo, hi, cap, slot = passes[k]
+                o = eng.out_sets[slot]
                 counts = o.count[: hi - lo].cpu()  # stream-ordered D2H: the host sync of this pass
                 n_k = int(counts.sum())
                 cnts.append(counts)
@@ -413,16 +448,15 @@ class YOLO:
                 if k > 0:
                     finish(k - 1)
             finish(n_mb - 1)
-            eng.use_outputs((n_mb - 1) & 1)
             t2 = time.perf_counter()
-            err = eng.device_error()
+            err = self.engine.device_error()
             if err:
                 raise YpbError(f"device pipeline error word 0x{err:x}")
             t3 = time.perf_counter()
         speed = {"preprocess": (t1 - t0) * 1e3 / B, "inference": (t2 - t1) * 1e3 / B, "postprocess": (t3 - t2) * 1e3 / B}
         out = []
         for k in range(n_mb):
-            lo, hi = k * mb, min((k + 1) * mb, B)
+            _, lo, hi, _, _ = passes[k]
             counts, det, masks, off = cnts[k].tolist(), dets[k], mask_parts[k], 0
             for j in range(hi - lo):
                 n = counts[j]

@@ -1297,27 +1297,37 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
       // uint8 -> bf16 without the conversion pipe (I2F / F2F run on the 16-lane XU pipe next to the epilogue's tanh and
       // bounded this kernel): 0x4B000000 | b is the float 2^23 + b, subtracting 2^23 leaves b exactly, and since
       // b < 256 fits bf16's 8 significant bits the upper half of that float IS the bf16 value.
+      // The 9 bytes of a kernel row (3 pixels x BGR) come out of three aligned shared-memory words: two funnel
+      // shifts line them up, one PRMT per byte drops it into the float pattern (explicit shared-space loads; the
+      // byte-pointer version compiled to 27 generic loads with 64-bit address arithmetic each).
       uint32_t fb[32];
-      bool col_ok[3];
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int iw = iw0 + 2 * tx + kw;
-        col_ok[kw] = iw >= 0 && iw < W;
-      }
+      // the only out-of-frame COLUMN is iw = -1 (kw = 0 of the first pixel of a left-edge tile): W is even, so the
+      // right edge never overhangs; out-of-frame ROWS were zero-filled when the patch was fetched
+      const bool left_pad = iw0 < 0 && tx == 0;
+      const uint32_t sIn_sa = smem_u32(sIn);
+      // low two bits of the byte offset of pixel (ih, iw0) in the frame buffer (what fetch_patch aligned the row on)
+      const uint32_t g_lo = (uint32_t)b * (uint32_t)(frame_bytes & 3) + (uint32_t)iw0 * 3u;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const int r = 2 * ty + kh, ih = ih0 + r;
-        const long long g0 = (long long)b * frame_bytes + ((long long)ih * W + iw0) * 3;
-        const int shift = (int)(g0 & 3);  // bytes between the first loaded word and pixel (ih, iw0)
-        const uint8_t* rb = reinterpret_cast<const uint8_t*>(sIn + r * kStemRowWords) + shift;
-        const bool row_ok = ih >= 0 && ih < H;
+        const int r = 2 * ty + kh;
+        const uint32_t shift = (g_lo + (uint32_t)(ih0 + r) * (uint32_t)((W * 3) & 3)) & 3u;
+        const uint32_t off = shift + 6u * (uint32_t)tx;
+        const uint32_t wa = sIn_sa + (uint32_t)(r * kStemRowWords) * 4u + (off & ~3u);
+        uint32_t w0, w1, w2;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(wa));
+        asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(w1) : "r"(wa));
+        asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(w2) : "r"(wa));
+        const uint32_t sh = (off & 3u) * 8u;
+        uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
+        const uint32_t a2 = w2 >> sh;
+        if (left_pad) a0 &= 0xFF000000u;  // pixel iw = -1: its three bytes read as zero
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const bool in = row_ok && col_ok[kw];
-          const uint8_t* px = rb + (2 * tx + kw) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {  // frame bytes are BGR, k runs over RGB
-            const uint32_t bits = 0x4B000000u | (in ? (uint32_t)px[2 - c] : 0u);
+            const int i = kw * 3 + (2 - c);  // byte of the 9-byte run
+            const uint32_t src = i < 4 ? a0 : (i < 8 ? a1 : a2);
+            const uint32_t bits = __byte_perm(src, 0x4B000000u, 0x7440 | (i & 3));
             fb[(kh * 3 + kw) * 3 + c] = __float_as_uint(__uint_as_float(bits) - 8388608.0f);
           }
         }
@@ -1327,9 +1337,11 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
       uint32_t row[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) row[k] = __byte_perm(fb[2 * k], fb[2 * k + 1], 0x7632);  // (hi16(a), hi16(b))
-      const uint4* rv = reinterpret_cast<const uint4*>(row);
+      const uint32_t sA_row = smem_u32(sA) + (uint32_t)tid * 128u;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) << 4)) = rv[j & 3];
+      for (int j = 0; j < 8; ++j)
+        sts128(sA_row + (uint32_t)((j ^ (tid & 7)) << 4), row[4 * (j & 3)], row[4 * (j & 3) + 1], row[4 * (j & 3) + 2],
+               row[4 * (j & 3) + 3]);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();

@@ -180,6 +180,7 @@ int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* byt
 /* Diagnostics: ceiling of the TMA operand-fetch path for an access pattern (csrc/tma_bench.cuh). */
 int ypb_mma_bench(void* buf, int rows, int n, int iters, int shifted, int tma_iters, float* ms);
 int ypb_latency_probe(long long* out_dev /* 8 x int64, device */);
+int ypb_debug_prof(unsigned long long* out16, int reset);  /* profiling build: device-side cycle counters */
 int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, int H, int B, float* ms, double* bytes);
 
 #ifdef __cplusplus

@@ -42,7 +42,7 @@ def random_case(B, N, seed, nclass=80, tie_levels=None, spread=600.0):
 
 
 @pytest.mark.parametrize("N,nclass,ties", [(1, 80, None), (37, 3, 64), (300, 80, None), (1000, 2, 512), (5000, 4, None),
-                                           (8400, 1, 4096)])
+                                           (8400, 1, 4096), (2500, 300, 256), (3000, 16, None)])
 @pytest.mark.parametrize("agnostic", [False, True])
 def test_nms_bit_exact_vs_torchvision(N, nclass, ties, agnostic):
     B = 3
@@ -54,6 +54,29 @@ def test_nms_bit_exact_vs_torchvision(N, nclass, ties, agnostic):
         ref = ref_keep(boxes[b, :n], scores[b, :n], cls[b, :n], 0.7, 300, agnostic)
         assert int(count[b]) == len(ref)
         assert keep[b, :len(ref)].tolist() == ref.tolist()
+
+
+def test_nms_class_buckets_and_window_fallback():
+    """The class-aware scan chains kept boxes per (class & 127) bucket and only runs while every coordinate sits in a
+    window narrower than the class offset; dense same-class clusters, bucket collisions (classes 5 / 133 / 261) and
+    coordinates outside the window (plain scan) must all keep exactly what torchvision keeps."""
+    g = torch.Generator().manual_seed(11)
+    N = 2400
+    ctr = torch.rand(1, N, 2, generator=g) * 120 + 200           # one dense cluster
+    wh = torch.rand(1, N, 2, generator=g) * 60 + 40
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], -1)
+    scores = torch.rand(1, N, generator=g) * 0.7 + 0.25
+    cls = torch.tensor([5, 133, 261], dtype=torch.int32)[torch.randint(0, 3, (1, N), generator=g)]
+    nv = torch.tensor([N], dtype=torch.int32)
+    for iou in (0.7, 0.3):
+        keep, count = run(boxes, scores, cls, nv, iou=iou)
+        ref = ref_keep(boxes[0], scores[0], cls[0], iou, 300, False)
+        assert int(count[0]) == len(ref) and keep[0, :len(ref)].tolist() == ref.tolist()
+    far = boxes.clone()
+    far[0, ::7] += 6000.0                                         # outside the window: the plain scan takes over
+    keep, count = run(far, scores, cls, nv)
+    ref = ref_keep(far[0], scores[0], cls[0], 0.7, 300, False)
+    assert int(count[0]) == len(ref) and keep[0, :len(ref)].tolist() == ref.tolist()
 
 
 def test_nms_golden_fixture():

@@ -310,6 +310,8 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
   while (n_pow2 < n) n_pow2 <<= 1;
   unsigned long long* keys;
   __shared__ int s_sel[2];
+  __shared__ int s_path;  // profiling build: 1 class-aware scan, 2 plain scan, 0 end-to-end top-k
+  if (kProf && threadIdx.x == 0) s_path = 0;
   bool selected = false;
   if (e2e && n_pow2 > kNmsSmemKeys) {
     // End-to-end top-k over more pairs than the shared-memory sort holds: only the best max_det matter, so select
@@ -372,7 +374,9 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
     keys = gk;
     for (int i = n + threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = 0ull;
   }
+  const long long _np0 = kProf ? clock64() : 0;
   bitonic_sort_desc(keys, n_pow2);
+  const long long _np1 = kProf ? clock64() : 0;
   if (n > max_nms) n = max_nms;
 
   __shared__ int s_cls[kNmsMaxDet];
@@ -398,7 +402,100 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     int nkept = 0;  // CTA-uniform
-    for (int i0 = 0; i0 < n && nkept < max_det; i0 += blockDim.x) {
+    // Class-aware fast path.  With the per-class offset (cls * max_wh) boxes of different classes cannot overlap as
+    // long as every coordinate lies in a window narrower than max_wh: then a candidate only has to be tested against
+    // kept boxes of ITS class.  Kept boxes are chained per class bucket (s_head / s_next, newest first), the in-warp
+    // resolution uses match.any on the class id, and the greedy order inside a warp is recovered with a ballot fixed
+    // point.  Same decisions as the plain scan below (IoU is symmetric bit for bit: max/min, a*b, a+b commute) -
+    // an image with thousands of same-class-sparse candidates drops from O(candidates x kept) IoU tests to a few
+    // per candidate.  Class-agnostic NMS (max_wh = 0) and out-of-window coordinates take the plain scan.
+    __shared__ int s_head[128];
+    __shared__ short s_next[kNmsMaxDet];
+    __shared__ float s_wbox[32][5];
+    bool in_window = true;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int anchor = (int)(0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull));
+      const float4 bx = dbox[(long long)b * g.A + anchor];
+      in_window = in_window && bx.x > -2000.f && bx.y > -2000.f && bx.z < 5000.f && bx.w < 5000.f && bx.x <= bx.z && bx.y <= bx.w;
+    }
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_head[i] = -1;
+    const bool class_sep = __syncthreads_and(in_window) && max_wh >= 7680.0f && max_det <= kNmsMaxDet && iou_thr >= 0.0f;
+    if (kProf && threadIdx.x == 0) s_path = class_sep ? 1 : 2;
+    for (int i0 = 0; class_sep && i0 < n && nkept < max_det; i0 += blockDim.x) {
+      const int i = i0 + threadIdx.x;
+      bool alive = i < n;
+      float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, area = 0.f, score = 0.f;
+      int anchor = 0, cls = -1 - lane;  // dead lanes: distinct pseudo classes, never matched
+      if (alive) {
+        const unsigned long long key = keys[i];
+        anchor = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+        score = __uint_as_float((unsigned)(key >> 32));
+        const float4 bx = dbox[(long long)b * g.A + anchor];
+        cls = dcls[(long long)b * g.A + anchor];
+        const float off = __fmul_rn((float)cls, max_wh);
+        x1 = __fadd_rn(bx.x, off); y1 = __fadd_rn(bx.y, off); x2 = __fadd_rn(bx.z, off); y2 = __fadd_rn(bx.w, off);
+        area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+      }
+      const int bkt = cls & 127;
+      // A. kept boxes of earlier rounds, this class only
+      if (alive) {
+        for (int k = s_head[bkt]; k >= 0; k = s_next[k]) {
+          if (s_cls[k] == cls && iou_gt(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area, iou_thr)) {
+            alive = false;
+            break;
+          }
+        }
+      }
+      const int nw_round = min(nwarps, (n - i0 + 31) >> 5);  // warps that hold candidates this round (CTA-uniform)
+      for (int ws = 0; ws < nw_round; ++ws) {
+        if (warp == ws) {
+          // B. this warp's 32 candidates among themselves
+          s_wbox[lane][0] = x1; s_wbox[lane][1] = y1; s_wbox[lane][2] = x2; s_wbox[lane][3] = y2; s_wbox[lane][4] = area;
+          __syncwarp();
+          unsigned cand = __match_any_sync(0xffffffffu, cls) & ((1u << lane) - 1u);  // earlier lanes of my class
+          unsigned sup = 0u;  // those that overlap me beyond the threshold
+          while (alive && cand != 0u) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            if (iou_gt(s_wbox[j][0], s_wbox[j][1], s_wbox[j][2], s_wbox[j][3], s_wbox[j][4], x1, y1, x2, y2, area, iou_thr)) sup |= 1u << j;
+          }
+          // greedy order: lane i is kept iff it is alive and no KEPT earlier lane suppresses it; iterating
+          // K <- {alive, sup & K == 0} from K = alive fixes lane t after t+1 steps, and stops at the (unique) solution
+          unsigned K = __ballot_sync(0xffffffffu, alive);
+          for (;;) {
+            const unsigned Kn = __ballot_sync(0xffffffffu, alive && (sup & K) == 0u);
+            if (Kn == K) break;
+            K = Kn;
+          }
+          const int rank = __popc(K & ((1u << lane) - 1u));
+          const int room = max_det - nkept;
+          const bool kept_here = ((K >> lane) & 1u) != 0u && rank < room;
+          if (kept_here) {
+            const int idx = nkept + rank;
+            s_kept[idx][0] = x1; s_kept[idx][1] = y1; s_kept[idx][2] = x2; s_kept[idx][3] = y2; s_kept[idx][4] = area;
+            s_score[idx] = score;
+            s_cls[idx] = cls;
+            keep[(long long)b * max_det + idx] = anchor;
+            s_next[idx] = (short)atomicExch(&s_head[bkt], idx);  // newest first
+          }
+          if (lane == 0) { s_range[ws][0] = nkept; s_range[ws][1] = nkept + min(__popc(K), room); }
+        }
+        __syncthreads();
+        const int kb = s_range[ws][0], ke = s_range[ws][1];
+        if (warp > ws && alive) {  // C. later candidates against the boxes this warp just kept (front of the chain)
+          for (int k = s_head[bkt]; k >= kb; k = s_next[k]) {
+            if (s_cls[k] == cls && iou_gt(s_kept[k][0], s_kept[k][1], s_kept[k][2], s_kept[k][3], s_kept[k][4], x1, y1, x2, y2, area, iou_thr)) {
+              alive = false;
+              break;
+            }
+          }
+        }
+        nkept = ke;
+        if (nkept >= max_det) break;  // CTA-uniform
+      }
+      __syncthreads();  // s_range / s_wbox are rewritten next round
+    }
+    for (int i0 = 0; !class_sep && i0 < n && nkept < max_det; i0 += blockDim.x) {
       const int i = i0 + threadIdx.x;
       bool alive = i < n;
       float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, area = 0.f, score = 0.f;
@@ -456,6 +553,15 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
     if (threadIdx.x == 0) { s_nkept = nkept; count[b] = nkept; }
   }
   __syncthreads();
+  if (kProf && threadIdx.x == 0) {  // slowest image of the launch: [0] candidates, [1] sort, [2] greedy scan cycles, [3] kept
+    const long long _np2 = clock64();
+    if (atomicMax(&g_conv_prof[2], (unsigned long long)(_np2 - _np1)) < (unsigned long long)(_np2 - _np1)) {
+      g_conv_prof[0] = (unsigned long long)n;
+      g_conv_prof[1] = (unsigned long long)(_np1 - _np0);
+      g_conv_prof[3] = (unsigned long long)s_nkept;
+      g_conv_prof[4] = (unsigned long long)s_path;
+    }
+  }
   const int nk = s_nkept;
   const FrameXform t = xf[b];
   for (int i = threadIdx.x; i < nk; i += blockDim.x) {

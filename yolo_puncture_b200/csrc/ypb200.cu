@@ -1418,6 +1418,18 @@ int ypb_conv_bench(void* cuda_stream, const void* in, int B, int H, int W, int i
   return YPB_OK;
 }
 
+// Diagnostics (profiling build): read and optionally clear the 16 device-side cycle counters.
+int ypb_debug_prof(unsigned long long* out16, int reset) {
+  if (!out16) return fail(YPB_ERR_ARG, "bad argument");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out16, g_conv_prof, 16 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(g_conv_prof, z, sizeof z));
+  }
+  return YPB_OK;
+}
+
 // Diagnostics: operand-fetch ceiling of the TMA path (see tma_bench.cuh).  buf: device, >= rows*128 bytes (mode 0/1)
 // or B*H*W*128 bytes (mode 2).  Returns elapsed milliseconds in *ms and bytes moved in *bytes.
 int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, int H, int B, float* ms, double* bytes) {

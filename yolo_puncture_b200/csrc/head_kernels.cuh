@@ -452,7 +452,8 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
           // B. this warp's 32 candidates among themselves
           s_wbox[lane][0] = x1; s_wbox[lane][1] = y1; s_wbox[lane][2] = x2; s_wbox[lane][3] = y2; s_wbox[lane][4] = area;
           __syncwarp();
-          unsigned cand = __match_any_sync(0xffffffffu, cls) & ((1u << lane) - 1u);  // earlier lanes of my class
+          const unsigned alive_in = __ballot_sync(0xffffffffu, alive);
+          unsigned cand = __match_any_sync(0xffffffffu, cls) & ((1u << lane) - 1u) & alive_in;  // live earlier lanes of my class
           unsigned sup = 0u;  // those that overlap me beyond the threshold
           while (alive && cand != 0u) {
             const int j = __ffs(cand) - 1;
@@ -461,7 +462,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
           }
           // greedy order: lane i is kept iff it is alive and no KEPT earlier lane suppresses it; iterating
           // K <- {alive, sup & K == 0} from K = alive fixes lane t after t+1 steps, and stops at the (unique) solution
-          unsigned K = __ballot_sync(0xffffffffu, alive);
+          unsigned K = alive_in;
           for (;;) {
             const unsigned Kn = __ballot_sync(0xffffffffu, alive && (sup & K) == 0u);
             if (Kn == K) break;

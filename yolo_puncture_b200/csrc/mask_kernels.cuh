@@ -179,6 +179,12 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
     }
     __syncthreads();
     if (oy >= g.out_h) continue;
+    // this thread's 16 pixels lie outside the box (rows above / below it inside the band, columns left / right of it
+    // inside the tile): zeros without touching the interpolation
+    if (vec_ok && ox0 + 16 <= g.out_w && (!row_in || (g.retina && ((float)(ox0 + 16) <= bx1 || (float)ox0 >= bx2)))) {
+      *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
     const float4* t0 = reinterpret_cast<const float4*>(s_hrow + (y0 - sy_lo) * kMaskTile + tcol);
     const float4* t1 = reinterpret_cast<const float4*>(s_hrow + (y1 - sy_lo) * kMaskTile + tcol);
     uint32_t packed[4] = {0, 0, 0, 0};

@@ -37,6 +37,9 @@ CASES = [
     (13, 80, 80, 64, 0, 64, 128, 1, 1, 1, True, 192, 64, False),    # same, odd tile count, residual, output slice
     (8, 160, 160, 32, 0, 32, 64, 3, 2, 1, False, 64, 0, False),     # stride 2 with two stacked sub-tiles per CTA tile
     (20, 80, 80, 64, 0, 64, 128, 3, 2, 1, False, 128, 0, False),    # stride 2, 40x40 output, 120-row sub-tiles
+    (3, 46, 74, 32, 0, 32, 64, 3, 2, 1, False, 96, 32, False),      # stride-2 halo (Cin 32): ragged 23x37 output, output slice
+    (2, 64, 64, 32, 0, 32, 32, 3, 2, 1, False, 32, 0, False),       # stride-2 halo, n_tile 32
+    (5, 32, 48, 32, 0, 32, 48, 3, 2, 0, False, 48, 0, True),        # stride-2 halo, no activation, fp32 rows
 ]
 
 

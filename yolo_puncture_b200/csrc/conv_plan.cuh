@@ -137,6 +137,21 @@ static long pick_tile_msub(int H, int W, int msub, int* TH_sub, int* TW) {
 }
 
 // Geometry only (no pointers, no driver calls): usable on a box without a GPU.
+static void conv3_set_taps(Conv3Extra* x, bool s2) {
+  x->s2 = s2 ? 1 : 0;
+  for (int t = 0; t < 9; ++t) {
+    const int kh = t / 3, kw = t % 3;
+    if (!s2) {
+      x->tap_off[t] = ((kh * 10 + kw) * 128) >> 4;
+    } else {
+      const int r = kh > 0, ph = kh != 1, wq = kw > 0, half = kw != 1;
+      x->tap_off[t] = ((((r * 2 + ph) * 10 + wq) * 128) + half * 64) >> 4;
+    }
+  }
+  x->sub_off = (s2 ? 16 * 2 * 10 * 128 : 16 * 10 * 128) >> 4;
+  x->a_hi = umma_desc_hi(s2 ? 2560 : 1280);
+}
+
 static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   ConvParams& p = L->p;
   memset(&p, 0, sizeof p);
@@ -294,8 +309,31 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
           L->x3.b_slots = (int)b_slots; L->x3.b_group = b_group; L->x3.b_stat = stat; L->x3.b_bytes = (int)b_bytes;
           L->tiles_h3 = th3; L->tiles_w3 = tw3; L->total_tiles3 = (int)tiles3;
           L->smem3 = (int)(1024 + a_slots * a_bytes + b_bytes + 512 + epi_smem + conv_bias_smem(d.cout));
+          conv3_set_taps(&L->x3, false);
         }
       }
+    }
+  }
+  if (d.k == 3 && d.stride == 2 && d.cin == 32 && d.in_ctot == 32 && d.in_c_off == 0 && splits == 1 && !getenv("YPB_NO_HALO") &&
+      !getenv("YPB_NO_HALO_S2")) {
+    // Stride 2 with 32 input channels (the layer after the stem): a pixel PAIR is one 128-byte row of the
+    // (2C, W/2, 2, H/2, B) view, so the halo trick carries over with a parity-split box {64, 10, 2, 17} per 8 x 16
+    // output tile and resident weights: L2 -> smem traffic drops ~3x against nine per-tap boxes plus per-tile weight
+    // boxes, which is what bounded this layer (1.4 GB per launch at 640x640, B = 64).
+    const long avail = 227 * 1024 - 1024 - 512 - epi_smem - conv_bias_smem(d.cout);
+    const long b_total = 9L * p.n_tile * 128;
+    const int halo_rows = 17 * 2 * 10;
+    const long a_bytes = ((long)halo_rows * 128 + 1023) & ~1023L;
+    long a_slots = (avail - b_total) / a_bytes;
+    if (a_slots > 4) a_slots = 4;
+    if (b_total <= 96 * 1024 && a_slots >= 2 && 2 * conv2_acc_stride(p.n_tile) <= 512) {
+      const int th3 = (oH + 15) / 16, tw3 = (oW + 7) / 8;
+      L->use_halo = true;
+      L->x3.msub = 1; L->x3.a_slots = (int)a_slots; L->x3.a_bytes = (int)a_bytes; L->x3.halo_rows = halo_rows;
+      L->x3.b_slots = 0; L->x3.b_group = 3; L->x3.b_stat = 1; L->x3.b_bytes = (int)b_total;
+      L->tiles_h3 = th3; L->tiles_w3 = tw3; L->total_tiles3 = d.B * th3 * tw3;
+      L->smem3 = (int)(1024 + a_slots * a_bytes + b_total + 512 + epi_smem + conv_bias_smem(d.cout));
+      conv3_set_taps(&L->x3, true);
     }
   }
   ConvSimtGeom& g = L->sg;
@@ -344,6 +382,7 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   }
   if (L->use_halo) {
     cuuint32_t hb[5] = {64, 10, (cuuint32_t)(16 * L->x3.msub + 2), 1, 1};
+    if (L->x3.s2) { hb[2] = 2; hb[3] = (cuuint32_t)(16 * L->x3.msub + 1); }
     if (!encode_bf16_map(&L->tmHalo3, d.in, 5, dims, str, hb, err)) return false;
   }
   L->halo_ok = false;
@@ -387,7 +426,7 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
 // One-line description of the launch the planner chose (diagnostics).
 static void conv_describe(const ConvLaunch& L, int impl, char* out, int n) {
   if (L.use_halo && impl == 0)
-    snprintf(out, n, "halo msub=%d a_slots=%d b_stat=%d b_slots=%d b_group=%d n_tile=%d splits=%d tiles=%d smem=%d", L.x3.msub,
+    snprintf(out, n, "halo%s msub=%d a_slots=%d b_stat=%d b_slots=%d b_group=%d n_tile=%d splits=%d tiles=%d smem=%d", L.x3.s2 ? "-s2" : "", L.x3.msub,
              L.x3.a_slots, L.x3.b_stat, L.x3.b_slots, L.x3.b_group, L.p.n_tile, L.n_splits, L.total_tiles3, L.smem3);
   else
     snprintf(out, n, "tc2 msub=%d tile=%dx%d stages=%d n_tile=%d splits=%d tiles=%d smem=%d", L.p.msub, L.p.TH, L.p.TW,

@@ -944,12 +944,49 @@ struct Conv3Extra {
   int b_group;     // taps per weight box / ring slot: 3 (one kernel row) or 1
   int b_stat;      // 1: all weights resident in smem
   int b_bytes;     // weight region bytes
+  // A-operand addressing of the nine taps inside the halo buffer, in descriptor units (16 bytes):
+  //   stride 1: box {64 ch, 10, 16 msub + 2}; tap (kh, kw) starts (kh*10 + kw) rows in, 8-pixel groups 1280 B apart
+  //   stride 2 (Cin = 32, `s2`): the input is viewed as (2C = 64, W/2, 2, H/2, B) - a row of the view is a PAIR of
+  //     input columns, [even column's 32 channels | odd column's 32 channels] - and the box is {64, 10, 2, 16 msub + 1}:
+  //     tap (kh, kw) reads row-pair r = (kh > 0), row parity (kh != 1), column pair (kw > 0) and the channel half
+  //     (kw != 1) as a 64-byte K offset; output rows are 2 x 10 x 128 B apart
+  int s2;
+  int tap_off[9];
+  int sub_off;     // second sub-tile (16 output rows further down)
+  uint32_t a_hi;   // high descriptor word of A: SBO = 1280 (stride 1) or 2560 (stride 2)
 };
+
+// All nine taps of one 64-channel chunk against resident weights, straight-line: 9 x KS (x 2 sub-tiles) MMAs whose
+// descriptors are the chunk's base words plus launch constants.  Called by the elected lane.
+template <int KS, bool TWO>
+__device__ __forceinline__ void halo_issue_taps(const Conv3Extra& x, uint32_t d_tmem0, uint32_t acc_stride, uint32_t a_lo0,
+                                                uint32_t a_hi, uint32_t b_lo0, uint32_t tap_units, uint32_t idesc, uint32_t accf) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const uint32_t a_lo = a_lo0 + (uint32_t)x.tap_off[t], b_lo = b_lo0 + (uint32_t)t * tap_units;
+    umma_bf16_ksteps<KS>(d_tmem0, a_lo, a_hi, b_lo, umma_desc_hi(1024), idesc, t == 0 ? accf : 1u);
+    if (TWO)
+      umma_bf16_ksteps<KS>(d_tmem0 + acc_stride, a_lo + (uint32_t)x.sub_off, a_hi, b_lo, umma_desc_hi(1024), idesc,
+                           t == 0 ? accf : 1u);
+  }
+}
+
+// One kernel row (three taps, stride 1) against one streamed weight box, straight-line.  Called by the elected lane.
+template <int KS, bool TWO>
+__device__ __forceinline__ void halo_issue_row(uint32_t d_tmem0, uint32_t acc_stride, uint32_t a_lo, uint32_t sub_off, uint32_t a_hi,
+                                               uint32_t b_lo, uint32_t tap_units, uint32_t idesc, uint32_t accf) {
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const uint32_t a = a_lo + (uint32_t)(u * (128 >> 4)), bq = b_lo + (uint32_t)u * tap_units;
+    umma_bf16_ksteps<KS>(d_tmem0, a, a_hi, bq, umma_desc_hi(1024), idesc, u == 0 ? accf : 1u);
+    if (TWO) umma_bf16_ksteps<KS>(d_tmem0 + acc_stride, a + sub_off, a_hi, bq, umma_desc_hi(1024), idesc, u == 0 ? accf : 1u);
+  }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kConv2Threads, 1)
 conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ ConvParams p, const Conv3Extra x, int n_splits, int total_tiles) {
+                  const __grid_constant__ ConvParams p, const __grid_constant__ Conv3Extra x, int n_splits, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -1031,7 +1068,8 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             PROF_ADD(pw0);
           }
           mbar_expect_tx(a_full + sa, (uint32_t)(x.halo_rows * 128));
-          tma_load_5d(sA + sa * x.a_bytes, &tmA, a_full + sa, p.a_base[0] + c * 64, w0 - 1, h0 - 1, b, 0);
+          if (x.s2) tma_load_5d(sA + sa * x.a_bytes, &tmA, a_full + sa, 0, w0 - 1, 0, h0 - 1, b);
+          else tma_load_5d(sA + sa * x.a_bytes, &tmA, a_full + sa, p.a_base[0] + c * 64, w0 - 1, h0 - 1, b, 0);
         }
       }
       if (prof && pw == 0) atomicAdd(&g_conv_prof[0], (unsigned long long)pw0);
@@ -1090,8 +1128,27 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (ksteps > 4) ksteps = 4;
           if (p.dbg & 4) ksteps = 0;
           const long long _ti0 = prof ? clock64() : 0;
-          // tap (kh, kw) of sub-tile s: the halo buffer seen from row (16 s + kh) * 10 + kw on
-          uint32_t a_lo = umma_desc_lo(smem_u32(sA + sa * x.a_bytes));  // advanced tap by tap (16-byte units)
+          // tap t of sub-tile s: the halo buffer seen from tap_off[t] (+ s * sub_off) on
+          const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA + sa * x.a_bytes));
+          const uint32_t a_hi = x.a_hi;
+          if (b_stat && (ksteps == 4 || ksteps == 2)) {
+            // resident weights: one elected region issues the whole chunk (the per-tap loop below costs ~100 issue
+            // cycles per tap, more than the two 64-cycle MMAs of a tap of a 32-channel layer)
+            const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB + c * 9 * tap_bytes)), tu = (uint32_t)(tap_bytes >> 4);
+            if (elect_one()) {
+              if (ksteps == 4) {
+                if (msub > 1) halo_issue_taps<4, true>(x, d_tmem0, (uint32_t)acc_stride, a_lo0, a_hi, b_lo0, tu, idesc, accf);
+                else halo_issue_taps<4, false>(x, d_tmem0, (uint32_t)acc_stride, a_lo0, a_hi, b_lo0, tu, idesc, accf);
+              } else {
+                if (msub > 1) halo_issue_taps<2, true>(x, d_tmem0, (uint32_t)acc_stride, a_lo0, a_hi, b_lo0, tu, idesc, accf);
+                else halo_issue_taps<2, false>(x, d_tmem0, (uint32_t)acc_stride, a_lo0, a_hi, b_lo0, tu, idesc, accf);
+              }
+            }
+            accf = 1;
+          } else {
+          // streamed weights (stride 1 only) or an odd K-step count: tap by tap, the A window advanced incrementally
+          // (+1 pixel per kw, +1 halo row - 10 pixels - per kh)
+          uint32_t a_lo = a_lo0;
           int kw = 0;
           for (int g = 0; g < ngroups; ++g) {
             uint32_t b_lo;
@@ -1110,22 +1167,43 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tc_fence_after();
               b_lo = umma_desc_lo(smem_u32(sB + sb * grp_bytes));
             }
+            if (b_group == 3 && ksteps == 4) {  // a whole kernel row per weight box: 12 / 24 MMAs back to back
+              if (elect_one()) {
+                if (msub > 1)
+                  halo_issue_row<4, true>(d_tmem0, (uint32_t)acc_stride, a_lo, (uint32_t)x.sub_off, a_hi, b_lo,
+                                          (uint32_t)(tap_bytes >> 4), idesc, accf);
+                else
+                  halo_issue_row<4, false>(d_tmem0, (uint32_t)acc_stride, a_lo, (uint32_t)x.sub_off, a_hi, b_lo,
+                                           (uint32_t)(tap_bytes >> 4), idesc, accf);
+              }
+              accf = 1;
+              a_lo += (10 * 128) >> 4;  // next kernel row
+            } else if (b_group == 1 && ksteps == 4 && msub == 1) {  // one tap per weight box (wide N): four MMAs
+              if (elect_one()) umma_bf16_ksteps<4>(d_tmem0, a_lo, a_hi, b_lo, umma_desc_hi(1024), idesc, accf);
+              accf = 1;
+              a_lo += 128 >> 4;
+              if (++kw == 3) {
+                kw = 0;
+                a_lo += (7 * 128) >> 4;
+              }
+            } else
             for (int u = 0; u < b_group; ++u) {
               if (elect_one()) {
-                umma_bf16_ksteps_n(ksteps, d_tmem0, a_lo, umma_desc_hi(1280), b_lo, umma_desc_hi(1024), idesc, accf);
+                umma_bf16_ksteps_n(ksteps, d_tmem0, a_lo, a_hi, b_lo, umma_desc_hi(1024), idesc, accf);
                 if (msub > 1)
-                  umma_bf16_ksteps_n(ksteps, d_tmem0 + (uint32_t)acc_stride, a_lo + (16 * 10 * 128 >> 4), umma_desc_hi(1280), b_lo,
+                  umma_bf16_ksteps_n(ksteps, d_tmem0 + (uint32_t)acc_stride, a_lo + (uint32_t)x.sub_off, a_hi, b_lo,
                                      umma_desc_hi(1024), idesc, accf);
               }
               accf = 1;
               b_lo += (uint32_t)(tap_bytes >> 4);
-              a_lo += 128 >> 4;                    // next kw
-              if (++kw == 3) {                     // next kh: down one halo row (10 pixels), back three columns
+              a_lo += 128 >> 4;
+              if (++kw == 3) {
                 kw = 0;
                 a_lo += (7 * 128) >> 4;
               }
             }
             if (!b_stat && elect_one()) umma_commit(b_empty + sb);
+          }
           }
           const long long _ti1 = prof ? clock64() : 0;
           if (elect_one()) umma_commit(a_empty + sa);

@@ -124,8 +124,20 @@ decode_filter8_kernel(const float* __restrict__ head, HeadGeom g, int nB, float 
   if (mine < total) {
     const float4* cl = reinterpret_cast<const float4*>(head + mine * g.no + 64);
     const int n4 = g.nc >> 2;
-    for (int c4 = sub; c4 < n4; c4 += 4) {
-      const float4 v = __ldg(cl + c4);
+    // eight independent 16-byte loads per lane in flight (nc <= 128: the whole row in one batch), then the scan in
+    // ascending class order: the kernel is latency-bound on these loads (ncu: 21 warps per issue on long scoreboard)
+    for (int base = 0; base < n4; base += 32) {
+    float4 vq[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c4 = base + sub + 4 * u;
+      vq[u] = c4 < n4 ? __ldg(cl + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u8 = 0; u8 < 8; ++u8) {
+      const int c4 = base + sub + 4 * u8;
+      if (c4 >= n4) break;
+      const float4 v = vq[u8];
       const int c = c4 * 4;
       if (v.x > best) { best = v.x; bidx = c; }
       if (v.y > best) { best = v.y; bidx = c + 1; }
@@ -151,6 +163,7 @@ decode_filter8_kernel(const float* __restrict__ head, HeadGeom g, int nB, float 
             atomicOr(&g_dev_error, 0x100u);  // candidate list overflow (conf far below any sensible value)
         }
       }
+    }
     }
   }
 #pragma unroll

@@ -14,17 +14,15 @@ namespace ypb {
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int in_ctot, int in_c_off, __nv_bfloat16* __restrict__ out, int out_ctot,
                   int out_c_off, int nB, int h, int w, int C) {
-  // one thread per (INPUT pixel, 8-channel vector): one 16-byte load, four 16-byte stores (the 2x2 output block)
+  // one thread per (INPUT pixel, 8-channel vector): one 16-byte load, four 16-byte stores (the 2x2 output block).
+  // grid.y = (image, input row), grid.x covers the w * C/8 vectors of that row: one 32-bit division per thread
+  // (the flat-index version spent most of its instructions on three 64-bit div/mod pairs).
   const int vec = C >> 3;
-  const long long total = (long long)nB * h * w * vec;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int v = (int)(idx % vec);
-  long long pix = idx / vec;
-  const int x = (int)(pix % w);
-  pix /= w;
-  const int y = (int)(pix % h);
-  const int b = (int)(pix / h);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * vec) return;
+  const int x = i / vec, v = i - x * vec;
+  const int b = blockIdx.y / h, y = blockIdx.y - b * h;
+  (void)nB;
   const uint4 val = *reinterpret_cast<const uint4*>(in + (((long long)b * h + y) * w + x) * in_ctot + in_c_off + v * 8);
   __nv_bfloat16* o = out + (((long long)b * 2 * h + 2 * y) * (2 * w) + 2 * x) * out_ctot + out_c_off + v * 8;
   const long long row = (long long)2 * w * out_ctot;

@@ -728,8 +728,9 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       break;
     case OP_UPSAMPLE: {
       const BufDesc &ib = e->bufs[op.in.buf], &ob = e->bufs[op.out.buf];
-      const long long total = (long long)B * ib.H * ib.W * (op.in.C / 8);
-      upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      const int row_vecs = ib.W * (op.in.C / 8);
+      if ((long long)B * ib.H > 65535) return fail(YPB_ERR_ARG, "upsample: batch x rows exceeds the grid limit");
+      upsample2x_kernel<<<dim3((unsigned)((row_vecs + 255) / 256), (unsigned)(B * ib.H)), 256, 0, st>>>(
           reinterpret_cast<const __nv_bfloat16*>(e->ws + ib.offset), ib.C, op.in.c_off,
           reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C, op.out.c_off, B, ib.H, ib.W, op.in.C);
       break;

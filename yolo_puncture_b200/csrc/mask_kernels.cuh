@@ -50,12 +50,14 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   const int slot = blockIdx.y;
   const int total = offsets[nB];
   if (slot >= total || slot >= capacity) return;
-  int lo = 0, hi = nB;  // slot -> (image, detection)
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (offsets[mid] <= slot) lo = mid; else hi = mid;
+  // slot -> (image, detection): the image is the last one whose offset is <= slot.  Every warp counts those with
+  // its lanes side by side (one L2 round trip; a binary search is log2(B) dependent ones before the CTA can start)
+  int below = 0;
+  for (int i0 = 0; i0 < nB; i0 += 32) {
+    const int i = i0 + (threadIdx.x & 31);
+    below += __popc(__ballot_sync(0xffffffffu, i < nB && offsets[i] <= slot));
   }
-  const int b = lo, di = slot - offsets[lo];
+  const int b = below - 1, di = slot - offsets[b];
   const int ty0 = blockIdx.x * kMaskTile;
 
   float bx1, by1, bx2, by2;

@@ -17,7 +17,10 @@ What pins this restatement instead (tests/test_oracle_*.py):
   * conv FLOPs of yolov10n's one-to-one path = 6.70 G (reference README.md:48 "6.7G"),
   * output shapes, NMS / top-k / letterbox / scale_boxes / crop_mask known-answer micro-cases,
   * torchvision.ops.nms as the arithmetic backend of NMS so library semantics are inherited,
-  * optional cross-check against a real `ultralytics` install when one is importable.
+  * hand-derived known-answer vectors for DFL + dist2bbox, process_mask_native / process_mask and the class-offset
+    NMS (tests/test_oracle_known_answers.py: expected values worked out on paper, not produced by this package),
+  * a cross-check against a real `ultralytics` install wherever one is importable
+    (tests/test_oracle_vs_ultralytics.py, pytest.importorskip; skipped in the build container).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this package, and only as the checker or the timed CPU baseline.  The product path

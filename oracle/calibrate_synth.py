@@ -5,7 +5,7 @@ variance of its pre-BatchNorm output on synthetic frame 0 (two scalars per layer
 statistics are centred the way trained ones are), and (ii) the per-level class-bias shift that puts
 the 98th percentile of the per-anchor max class logit at logit(0.25).
 
-    python -m oracle.calibrate_synth [model ...]
+    python -m oracle.calibrate_synth [--recipe=damped] [model ...]
 """
 
 import json
@@ -21,7 +21,7 @@ from .modules import Conv
 
 
 @torch.no_grad()
-def calibrate(name, seed=0, pct=0.98, conf=0.25):
+def calibrate(name, seed=0, pct=0.98, conf=0.25, recipe="default"):
     net = build_model(name)
     specs = [(k, v.shape) for k, v in net.state_dict().items()]
     mod_names = {id(m): n for n, m in net.named_modules()}
@@ -34,15 +34,15 @@ def calibrate(name, seed=0, pct=0.98, conf=0.25):
         bn[mname] = [mu, max(v, 1e-12)]
         part = synth.synth_state_dict(
             [(f"{mname}.bn.{leaf}", self.bn.weight.shape) for leaf in ("weight", "bias", "running_mean", "running_var")],
-            name, seed, calib={"bn": bn})
+            name, seed, calib={"bn": bn}, recipe=recipe)
         self.bn.weight.copy_(part[f"{mname}.bn.weight"])
         self.bn.bias.copy_(part[f"{mname}.bn.bias"])
         self.bn.running_mean.copy_(part[f"{mname}.bn.running_mean"])
         self.bn.running_var.copy_(part[f"{mname}.bn.running_var"])
         return self.act(self.bn(y))
 
-    net.load_state_dict(synth.synth_state_dict(specs, name, seed, calib={}))
-    im = ops.preprocess([synth.synth_frame(0)], 640)
+    net.load_state_dict(synth.synth_state_dict(specs, name, seed, calib={}, recipe=recipe))
+    im = ops.preprocess([synth.synth_frame(0, structured=synth.RECIPES[recipe]["structured"])], 640)
     orig = Conv.forward
     Conv.forward = conv_forward
     try:
@@ -51,7 +51,7 @@ def calibrate(name, seed=0, pct=0.98, conf=0.25):
         Conv.forward = orig
     # class-bias shift per level, on the calibrated net
     calib = {"bn": bn, "cls_shift": [0.0, 0.0, 0.0]}
-    net.load_state_dict(synth.synth_state_dict(specs, name, seed, calib=calib))
+    net.load_state_dict(synth.synth_state_dict(specs, name, seed, calib=calib, recipe=recipe))
     feats = net.features(im, upto=len(net.model) - 1)
     head = net.model[-1]
     maps = head.head_maps([feats[j] for j in net.froms[-1]])
@@ -62,15 +62,33 @@ def calibrate(name, seed=0, pct=0.98, conf=0.25):
         q = torch.quantile(amax, pct).item()
         shifts.append(target - q)
     calib["cls_shift"] = shifts
+    if synth.RECIPES[recipe]["bias_proto"] and hasattr(head, "proto"):
+        # coefficient of the constant prototype, per level: mean mask logit = 2.5 x its spatial standard deviation
+        net.load_state_dict(synth.synth_state_dict(specs, name, seed, calib=calib, recipe=recipe))
+        xs = [feats[j] for j in net.froms[-1]]
+        proto = head.proto(xs[0])[0]                                   # (32, mh, mw); channel 0 is the constant plane
+        p0 = float(proto[0].mean())
+        coef0 = []
+        for i, x in enumerate(xs):
+            mc = head.cv4[i](x)[0].flatten(1)                          # (32, h*w)
+            mc = mc[:, :: max(1, mc.shape[1] // 128)]
+            lg = torch.einsum("ka,khw->ahw", mc[1:], proto[1:])
+            m, s = float(lg.mean()), float(lg.std((1, 2)).mean())
+            coef0.append((2.5 * s - m) / p0)
+        calib["coef0_bias"] = coef0
     return calib
 
 
 def main(argv):
+    recipe = "default"
+    if argv and argv[0].startswith("--recipe="):
+        recipe, argv = argv[0].split("=", 1)[1], argv[1:]
     names = argv or list(MODEL_SPECS)
     table = synth.load_calibration()
     for n in names:
-        table[f"{n}:0"] = calibrate(n)
-        print(n, "layers", len(table[f"{n}:0"]["bn"]), "cls_shift", table[f"{n}:0"]["cls_shift"])
+        key = f"{n}:0" if recipe == "default" else f"{n}:0:{recipe}"
+        table[key] = calibrate(n, recipe=recipe)
+        print(key, "layers", len(table[key]["bn"]), "cls_shift", table[key]["cls_shift"], table[key].get("coef0_bias"))
     with open(synth._CALIB_PATH, "w") as f:
         json.dump(table, f, separators=(",", ":"))
 

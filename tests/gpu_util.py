@@ -40,12 +40,12 @@ def describe_mismatch(got, ref, rtol, atol, max_items=12):
     return "\n".join(lines)
 
 
-def oracle_with_synth(name, emulate):
+def oracle_with_synth(name, emulate, recipe="default"):
     """(oracle net fused [+bf16 emulation], state_dict) with the deterministic synthetic weights."""
     from oracle.model import build_model
     from yolo_puncture_b200 import synth
     net = build_model(name)
-    sd = synth.synth_state_dict([(k, v.shape) for k, v in net.state_dict().items()], name)
+    sd = synth.synth_state_dict([(k, v.shape) for k, v in net.state_dict().items()], name, recipe=recipe)
     net.load_state_dict(sd)
     net.fuse()
     if emulate:
@@ -83,3 +83,34 @@ def box_iou_matrix(a, b):
     aa = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
     ab = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
     return inter / (aa[:, None] + ab[None] - inter).clamp(min=1e-9)
+
+
+def drift_stats(ref, got):
+    """Match detections of `got` to the reference `ref` (lists of Results) by class and IoU > 0.9.
+    Returns (match rate, per-match max box-coordinate error in px, per-match mask IoU, reference detections)."""
+    tot, matched, errs, ious = 0, 0, [], []
+    for r, g in zip(ref, got):
+        if len(r) == 0:
+            continue
+        rb = torch.as_tensor(r.boxes.data).cpu()
+        gb = torch.as_tensor(g.boxes.data).cpu()
+        tot += len(rb)
+        if len(gb) == 0:
+            continue
+        m = box_iou_matrix(rb[:, :4], gb[:, :4]) * (rb[:, 5:6] == gb[None, :, 5]).float()
+        best, j = m.max(1)
+        ok = best > 0.9
+        matched += int(ok.sum())
+        errs += (rb[ok, :4] - gb[j[ok], :4]).abs().max(1).values.tolist()
+        if r.masks is not None and g.masks is not None:
+            ious += mask_iou(torch.as_tensor(r.masks.data).cpu()[ok], torch.as_tensor(g.masks.data).cpu()[j[ok]]).tolist()
+    return matched / max(tot, 1), errs, ious, tot
+
+
+def ulp_report(got, ref):
+    """Elementwise |got - ref| in units of the bf16 ulp of the reference value: (max, p99.9, mean, share > 1 ulp)."""
+    got, ref = got.float().flatten(), ref.float().flatten()
+    ulp = torch.exp2(torch.floor(torch.log2(ref.abs().clamp(min=2.0 ** -20))) - 7)
+    e = (got - ref).abs() / ulp
+    k = max(1, int(e.numel() * 0.999))
+    return float(e.max()), float(e.kthvalue(k).values), float(e.mean()), float((e > 1).float().mean())

@@ -40,7 +40,7 @@ def test_v10_layers_track_bf16_emulating_oracle(v10):
     assert float((got - raw).abs().mean() / raw.abs().mean()) < 0.03
 
 
-@pytest.mark.parametrize("conf,max_det,classes", [(0.25, 300, None), (0.5, 300, None), (0.25, 10, None), (0.25, 300, [0, 7, 22, 44]),
+@pytest.mark.parametrize("conf,max_det,classes", [(0.25, 300, None), (0.5, 300, None), (0.25, 10, None), (0.25, 300, [0, 7, 22, 44]), (0.25, 10, [0, 7, 22, 44]), (0.15, 300, [3, 5]),
                                                   (0.15, 300, None), (0.15, 50, None)])  # low conf: > 4096 pairs -> select-then-sort path
 def test_v10_topk_selection_strict_on_engine_tensors(v10, conf, max_det, classes):
     net, yolo, frames, oops = v10["net"], v10["yolo"], v10["frames"], v10["oops"]
@@ -54,12 +54,9 @@ def test_v10_topk_selection_strict_on_engine_tensors(v10, conf, max_det, classes
     head = net.model[-1]
     with torch.no_grad():
         y = head._inference(maps)                                   # (B, 4+nc, A) xyxy + sigmoid scores
-        if classes is not None:                                     # the engine filters classes before the top-k
-            keep_c = torch.zeros(nc, dtype=torch.bool)
-            keep_c[classes] = True
-            y[:, 4:][:, ~keep_c] = 0.0
-        sel = head.postprocess(y.permute(0, 2, 1), min(max_det, 300), nc)  # (B, k, 6) descending score
-    dets = oops.non_max_suppression(sel, conf, 0.7, max_det=max_det, end2end=True)
+        sel = head.postprocess(y.permute(0, 2, 1), head.max_det, nc)       # (B, 300, 6) descending score
+    # upstream order: top-k -> conf -> [:max_det] -> classes (oracle/ops.py, end2end branch); nothing is bent here
+    dets = oops.non_max_suppression(sel, conf, 0.7, classes=classes, max_det=max_det, end2end=True)
     for b in range(B):
         d = dets[b]
         n = len(res[b])

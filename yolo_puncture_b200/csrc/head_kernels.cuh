@@ -152,8 +152,7 @@ decode_filter8_kernel(const float* __restrict__ head, HeadGeom g, int nB, float 
           if (!(vv[u] > pair_logit_lo)) continue;
           const float sc = sigmoid_f(vv[u]);
           if (!(sc > conf)) continue;
-          const int cc = c + u;
-          if (cls_mask != nullptr && !((cls_mask[cc >> 5] >> (cc & 31)) & 1u)) continue;
+          const int cc = c + u;  // predict(classes=[...]) filters AFTER the top-k / conf / max_det cut (nms_kernel, e2e)
           const int bimg = (int)(mine / g.A), an = (int)(mine - (long long)bimg * g.A);
           const int slot = atomicAdd(cand_count + bimg, 1);
           if (slot < g.cand_stride)
@@ -246,7 +245,7 @@ pair_candidates_kernel(const float* __restrict__ head, HeadGeom g, int nB, float
   for (int c = lane; c < g.nc; c += 32) {
     const float score = sigmoid_f(row[64 + c]);
     if (!(score > conf)) continue;
-    if (cls_mask != nullptr && !((cls_mask[c >> 5] >> (c & 31)) & 1u)) continue;
+    (void)cls_mask;  // predict(classes=[...]) filters AFTER the top-k / conf / max_det cut (nms_kernel, e2e)
     const int slot = atomicAdd(cand_count + b, 1);
     if (slot < g.cand_stride)
       cand_keys[(long long)b * g.cand_stride + slot] =
@@ -309,8 +308,9 @@ constexpr int kNmsThreads = 1024;
 __global__ void __launch_bounds__(kNmsThreads)
 nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict__ dbox, const int* __restrict__ dcls,
            unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_count, float iou_thr, int max_det,
-           int max_nms, float max_wh, int e2e, const FrameXform* __restrict__ xf, float* __restrict__ det,
-           float* __restrict__ det_lb, int* __restrict__ keep, float* __restrict__ coef, int* __restrict__ count) {
+           int max_nms, float max_wh, int e2e, const unsigned* __restrict__ cls_mask, const FrameXform* __restrict__ xf,
+           float* __restrict__ det, float* __restrict__ det_lb, int* __restrict__ keep, float* __restrict__ coef,
+           int* __restrict__ count) {
   __shared__ unsigned long long s_keys[kNmsSmemKeys];
   __shared__ float s_kept[kNmsMaxDet][5];  // offset box + area
   __shared__ float s_score[kNmsMaxDet];
@@ -394,16 +394,36 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
 
   __shared__ int s_cls[kNmsMaxDet];
   if (e2e) {
-    // UPSTREAM Detect.postprocess + `pred[pred[:, 4] > conf][:max_det]`: the top-max_det pairs by score, no suppression
+    // UPSTREAM Detect.postprocess + `pred[pred[:, 4] > conf][:max_det]`: the top-max_det pairs by score, no suppression;
+    // predict(classes=[...]) is applied to THOSE rows afterwards (ops.non_max_suppression, end2end branch), so a
+    // filtered class frees no slot for a lower-scoring pair.  Order-preserving compaction (max_det <= blockDim.x).
     const int nk = n < max_det ? n : max_det;
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-      const unsigned long long key = keys[i];
+    __shared__ int s_wcnt[kNmsThreads / 32];
+    const int i = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long key = 0ull;
+    int cls = 0;
+    bool take = false;
+    if (i < nk) {
+      key = keys[i];
       const unsigned pair = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
-      s_score[i] = __uint_as_float((unsigned)(key >> 32));
-      s_cls[i] = (int)(pair % (unsigned)g.nc);
-      keep[(long long)b * max_det + i] = (int)(pair / (unsigned)g.nc);
+      cls = (int)(pair % (unsigned)g.nc);
+      take = cls_mask == nullptr || ((cls_mask[cls >> 5] >> (cls & 31)) & 1u) != 0u;
     }
-    if (threadIdx.x == 0) { s_nkept = nk; count[b] = nk; }
+    const unsigned tk = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) s_wcnt[warp] = __popc(tk);
+    __syncthreads();
+    int pos = __popc(tk & ((1u << lane) - 1u)), total = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      if (w < warp) pos += s_wcnt[w];
+      total += s_wcnt[w];
+    }
+    if (take) {
+      const unsigned pair = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+      s_score[pos] = __uint_as_float((unsigned)(key >> 32));
+      s_cls[pos] = cls;
+      keep[(long long)b * max_det + pos] = (int)(pair / (unsigned)g.nc);
+    }
+    if (threadIdx.x == 0) { s_nkept = total; count[b] = total; }
   } else {
     // Greedy scan, blockDim.x candidates (one per thread) per round, in descending score order:
     //  A. every thread tests its candidate against the boxes kept in earlier rounds (all warps in parallel);

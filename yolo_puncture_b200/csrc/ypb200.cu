@@ -823,7 +823,7 @@ static int launch_select(ypb_engine* e, cudaStream_t st, const float* xform, con
   }
   if (mid) CUDA_TRY(cudaEventRecord(mid, st));
   nms_kernel<<<B, kNmsThreads, 0, st>>>(head, g, dbox, dcls, keys, cand_count, prm->iou, prm->max_det, 30000,
-                                prm->agnostic_nms ? 0.0f : 7680.0f, e->end2end ? 1 : 0,
+                                prm->agnostic_nms ? 0.0f : 7680.0f, e->end2end ? 1 : 0, e->end2end ? prm->class_mask : nullptr,
                                 reinterpret_cast<const FrameXform*>(xform), det, det_lb, keep, coef, count);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;
@@ -1660,7 +1660,7 @@ int ypb_nms(void* cuda_stream, const float* boxes, const float* scores, const in
   FrameXform* xf = reinterpret_cast<FrameXform*>(s + (size_t)B * cs * 8);
   nms_test_pack_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(boxes, scores, n_valid, B, N, cs, keys, xf);
   nms_kernel<<<B, kNmsThreads, 0, st>>>(nullptr, g, reinterpret_cast<const float4*>(boxes), cls, keys, n_valid, iou, max_det, 30000,
-                                agnostic ? 0.0f : 7680.0f, 0, xf, nullptr, nullptr, keep, nullptr, count);
+                                agnostic ? 0.0f : 7680.0f, 0, nullptr, xf, nullptr, nullptr, keep, nullptr, count);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;
 }

@@ -23,6 +23,26 @@ _CALIB_PATH = os.path.join(os.path.dirname(__file__), "synth_calibration.json")
 # measured once on frame 0 by oracle/calibrate_synth.py and committed in synth_calibration.json).
 
 
+# Weight recipes.  "default": SURVEY.md 8d.  "damped": the same tensors with every BatchNorm gain scaled by `gamma`
+# (pre-activations stay in SiLU's near-linear range, so a rounding perturbation is not amplified faster than the signal
+# itself from layer to layer: a random-init net at full gain sits in the chaotic phase, a trained one does not), see
+# tools/recipe_probe.py and DESIGN.md section 4.
+# "damped" also gives the head the decisiveness of a trained one, without which no bf16 pipeline can meet a 1e-2 px /
+# IoU 0.99 bar against fp32 (a logit error of 0.3 % moves a flat DFL expectation by ~1 px):
+#   * DFL prior: the box branch's final bias is a peak -dfl_alpha*(k - k0)^2 per side (k0 per level and side below), so
+#     the softmax over the 16 bins is as peaked as a trained model's; bin k0+1 keeps a prior mass of DFL_P1 so that the
+#     expectation sits ~0.002 bin above k0 and the features move it (box edges then stay clear of integer pixel
+#     coordinates, where a 1e-4 px difference would flip a whole row of the cropped mask);
+#   * bias prototype: proto channel 0 is the constant plane SiLU(2) (BN gain 0, beta 2), its coefficient is a per-level
+#     constant calibrated so that the mean mask logit sits 2.5 sigma above zero (masks fill most of their box; few pixels
+#     have a logit within rounding noise of the threshold), like the saturated mask logits of a trained Proto head.
+RECIPES = {"default": {"gamma": 1.0, "dfl_alpha": 0.0, "bias_proto": False, "structured": True},
+           "damped": {"gamma": 0.5, "dfl_alpha": 8.0, "bias_proto": True, "structured": False}}
+DFL_K0 = [[3, 4, 5, 4], [4, 3, 4, 5], [2, 3, 3, 2]]  # [level][side l,t,r,b], in bins (x stride = pixels)
+BIAS_PROTO_BETA = 2.0
+DFL_P1 = 0.002
+
+
 def _gen(name, seed):
     g = torch.Generator()
     g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
@@ -40,7 +60,7 @@ def load_calibration():
     return {}
 
 
-def synth_state_dict(specs, model_name, seed=0, calib=None, nc=80):
+def synth_state_dict(specs, model_name, seed=0, calib=None, nc=80, recipe="default"):
     """specs: iterable of (name, shape).  Returns {name: fp32 tensor} following the recipe:
     conv weights U(+-sqrt(3/fan_in)); BN gamma~U(.5,1.5), beta~N(0,.1), running_mean = mu_l +
     N(0,.1)*sqrt(v_l), running_var = v_l*U(.5,1.5) with (mu_l, v_l) the layer's calibrated pre-BN
@@ -48,7 +68,9 @@ def synth_state_dict(specs, model_name, seed=0, calib=None, nc=80):
     calibrated shift (so a few hundred candidates per frame pass conf=0.25); mask-coefficient final
     bias ~N(0,1).  calib: {"bn": {conv_module_name: [mu, v]}, "cls_shift": [s0, s1, s2]}."""
     if calib is None:
-        calib = load_calibration().get(f"{model_name}:{seed}", {})
+        key = f"{model_name}:{seed}" if recipe == "default" else f"{model_name}:{seed}:{recipe}"
+        calib = load_calibration().get(key, {})
+    rp = RECIPES[recipe]
     cls_bias_shift = calib.get("cls_shift", [0.0, 0.0, 0.0])
     bn_stats = calib.get("bn", {})
     strides = [8.0, 16.0, 32.0]
@@ -68,7 +90,7 @@ def synth_state_dict(specs, model_name, seed=0, calib=None, nc=80):
         if is_bn:
             mu_l, v_l = bn_stats.get(name[: name.index(".bn.")], (0.0, 1.0))
             if leaf == "weight":
-                t = _uniform(shape, 0.5, 1.5, g)
+                t = _uniform(shape, 0.5, 1.5, g) * rp["gamma"]
             elif leaf == "bias":
                 t = torch.randn(shape, generator=g) * 0.1
             elif leaf == "running_mean":
@@ -77,6 +99,8 @@ def synth_state_dict(specs, model_name, seed=0, calib=None, nc=80):
                 t = _uniform(shape, 0.5, 1.5, g) * v_l
             else:
                 raise ValueError(name)
+            if rp["bias_proto"] and ".proto.cv3.bn." in name and leaf in ("weight", "bias"):
+                t[0] = 0.0 if leaf == "weight" else BIAS_PROTO_BETA
             sd[name] = t
             continue
         if leaf == "weight":
@@ -85,18 +109,33 @@ def synth_state_dict(specs, model_name, seed=0, calib=None, nc=80):
             else:
                 fan_in = shape[1] * shape[2] * shape[3]
             b = math.sqrt(3.0 / fan_in)
-            sd[name] = _uniform(shape, -b, b, g)
+            t = _uniform(shape, -b, b, g)
+            if rp["bias_proto"] and "cv4" in parts and parts[-2] == "2":
+                t[0] = 0.0  # the bias prototype's coefficient is the calibrated constant alone
+            sd[name] = t
             continue
         if leaf == "bias":
             # final 1x1 convs of the head branches and the ConvTranspose
             branch = next((p for p in parts if p in ("cv2", "cv3", "cv4", "one2one_cv2", "one2one_cv3", "upsample")), None)
             if branch in ("cv2", "one2one_cv2"):
                 t = torch.full(shape, 1.0)
+                if rp["dfl_alpha"] > 0:
+                    lvl = int(parts[parts.index(branch) + 1])
+                    k = torch.arange(16, dtype=torch.float32)
+                    sides = []
+                    for k0 in DFL_K0[lvl]:
+                        side = -rp["dfl_alpha"] * (k - k0) ** 2
+                        side[k0 + 1] = math.log(DFL_P1)
+                        sides.append(side)
+                    t = torch.cat(sides)
             elif branch in ("cv3", "one2one_cv3"):
                 lvl = int(parts[parts.index(branch) + 1])
                 t = torch.full(shape, math.log(5 / nc / (640 / strides[lvl]) ** 2) + float(cls_bias_shift[lvl]))
             elif branch == "cv4":
                 t = torch.randn(shape, generator=g)
+                if rp["bias_proto"]:
+                    lvl = int(parts[parts.index(branch) + 1])
+                    t[0] = float(calib.get("coef0_bias", [0.0, 0.0, 0.0])[lvl])
             else:
                 t = torch.randn(shape, generator=g) * 0.1
             sd[name] = t

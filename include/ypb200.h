@@ -41,10 +41,11 @@ typedef enum {
 
 /* ---- library ---------------------------------------------------------------------------- */
 int ypb_version(void);
+int ypb_is_diag_build(void); /* 0 for libypb200.so; 1 for libypb200_diag.so (debugging twins + micro-benchmarks built in) */
 const char* ypb_last_error(void);
 
 /* ---- engine lifetime: replaces YOLO(path) + AutoBackend(fuse=True) ----------------------- */
-/* model_spec: "yolov8{n,s,m,l,x}-seg" | "yolov10n"; nc = number of classes. */
+/* model_spec: "yolov8{n,s,m,l,x}-seg" | "yolov10n" | "yolo11{n,s,m,l,x}-seg"; nc = number of classes. */
 int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out);
 void ypb_engine_destroy(ypb_engine* e);
 
@@ -130,8 +131,9 @@ int ypb_device_error(ypb_engine* e, uint32_t* word);
 int ypb_view_count(const ypb_engine* e);
 int ypb_view_info(const ypb_engine* e, int index, const char** name, size_t* offset, int* H, int* W, int* Ctot,
                   int* c_off, int* C, int* dtype);
-/* 0: persistent tcgen05 tensor-core convs (default, the product path); 1: CUDA-core debugging twin (tests only);
- * 2: first-generation one-tile-per-CTA tcgen05 kernel (kept for A/B measurements). */
+/* 0: persistent tcgen05 tensor-core convs (the product path, the only implementation in libypb200.so).  1 (CUDA-core
+ * twin), 2 (first-generation one-tile-per-CTA tcgen05 kernel) and 3 (halo experiment) exist only in libypb200_diag.so
+ * (include/ypb200_diag.h); the product library rejects them. */
 int ypb_set_conv_impl(ypb_engine* e, int impl);
 /* ypb_infer() replays a CUDA graph captured on first use of an argument set (default on); 0 = plain launches. */
 int ypb_set_graph(ypb_engine* e, int on);
@@ -141,12 +143,6 @@ int ypb_conv2d_bf16(void* cuda_stream, const void* in_nhwc_bf16, int B, int H, i
                     int cin, const void* w_gemm_bf16 /*[k*k][cout][cin]*/, const float* bias, int cout, int k,
                     int stride, int act, const void* res_nhwc_bf16 /*nullable, same layout as out*/, void* out,
                     int out_ctot, int out_c_off, int out_fp32, int impl);
-/* Diagnostics: average milliseconds of `iters` back-to-back launches of one conv (out_mode 0 bf16, 1 fp32, 2 pixel-shuffle
-   bf16); dbg >= 0 overrides the experiment mask; desc receives a description of the launch the planner chose. */
-int ypb_conv_bench(void* cuda_stream, const void* in_nhwc_bf16, int B, int H, int W, int in_ctot, int in_c_off, int cin,
-                   const void* w_gemm_bf16, const float* bias, int cout, int k, int stride, int act,
-                   const void* res_nhwc_bf16, void* out, int out_ctot, int out_c_off, int out_mode, int impl, int dbg,
-                   int iters, float* ms, char* desc, int desc_len);
 int ypb_nms(void* cuda_stream, const float* boxes_xyxy /*(B,N,4)*/, const float* scores /*(B,N)*/,
             const int32_t* cls /*(B,N)*/, const int32_t* n_valid /*(B)*/, int B, int N, float iou, int max_det,
             int agnostic, void* scratch /* >= B*nextpow2(N)*8 + B*4 bytes */, int32_t* keep /*(B,max_det)*/,
@@ -177,12 +173,6 @@ int ypb_hosts_are_pinned(const void* const* ptrs, int n, int* all_pinned);  /* t
 int ypb_h2d_frames(void* cuda_stream, void* dst_dev, const void* const* src, size_t bytes_each, int n);
 /* Host helper of the predict() pipeline: copy n frames into pinned staging memory with nthreads host threads. */
 int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads);
-/* Diagnostics: ceiling of the TMA operand-fetch path for an access pattern (csrc/tma_bench.cuh). */
-int ypb_mma_bench(void* buf, int rows, int n, int iters, int shifted, int tma_iters, float* ms);
-int ypb_latency_probe(long long* out_dev /* 8 x int64, device */);
-int ypb_debug_prof(unsigned long long* out16, int reset);  /* profiling build: device-side cycle counters */
-int ypb_tma_bench(void* buf, int mode, int stages, int iters, int rows, int W, int H, int B, float* ms, double* bytes);
-
 #ifdef __cplusplus
 }
 #endif

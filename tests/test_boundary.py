@@ -17,15 +17,45 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SEG = [f"yolov8{s}-seg" for s in "nsmlx"] + ["yolov10n"] + [f"yolo11{s}-seg" for s in "nsmlx"]
 
 
+def _declared(header_name):
+    header = open(os.path.join(ROOT, "include", header_name)).read()
+    return set(re.findall(r"\b(ypb_[a-z0-9_]+)\s*\(", header))
+
+
 def test_library_exports_every_declared_symbol():
-    header = open(os.path.join(ROOT, "include", "ypb200.h")).read()
-    declared = set(re.findall(r"\b(ypb_[a-z0-9_]+)\s*\(", header))
+    declared = _declared("ypb200.h")
     assert len(declared) >= 20
     handle = ctypes.CDLL(_lib._build.ensure_built())
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in ypb200.h but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes prototypes out of sync with the header"
     assert _lib.lib().ypb_version() == 100
+
+
+def test_product_library_carries_no_diagnostics():
+    """Debugging twins and micro-benchmarks live in libypb200_diag.so (include/ypb200_diag.h), not in the product."""
+    diag = _declared("ypb200_diag.h") - _declared("ypb200.h")
+    assert diag == set(_lib.DIAG_SIGNATURES) and len(diag) >= 5
+    handle = ctypes.CDLL(_lib._build.ensure_built())
+    if os.environ.get("YPB_LIB"):
+        pytest.skip("YPB_LIB override in effect")
+    assert handle.ypb_is_diag_build() == 0
+    for name in diag:
+        assert not hasattr(handle, name), f"{name} is a diagnostic but the product library exports it"
+    import subprocess
+    syms = subprocess.run(["cuobjdump", "-elf", _lib._build.LIB], capture_output=True, text=True).stdout
+    for twin in ("conv_simt_kernel", "conv_halo_test_kernel", "tma_bench_kernel", "mma_bench_kernel", "latency_probe_kernel"):
+        assert twin not in syms, f"{twin} compiled into the product library"
+    e = Engine("yolov8n-seg")
+    with pytest.raises(YpbError, match="libypb200_diag"):
+        e.set_conv_impl(2)
+
+
+def test_diag_library_exports_its_header():
+    handle = ctypes.CDLL(_lib._build.build(diag=True))
+    assert handle.ypb_is_diag_build() == 1
+    for name in _declared("ypb200_diag.h") | _declared("ypb200.h"):
+        assert hasattr(handle, name), f"{name} missing from libypb200_diag.so"
 
 
 @pytest.mark.parametrize("name", SEG)

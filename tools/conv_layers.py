@@ -18,7 +18,7 @@ if "--prof" in sys.argv:  # wait-cycle accounting lives in the profiling build: 
     sys.argv.remove("--prof")
     os.environ["YPB_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yolo_puncture_b200",
                                          "libypb200_prof.so")
-from yolo_puncture_b200._lib import check, lib  # noqa: E402
+from yolo_puncture_b200._lib import check, diag_lib, lib  # noqa: E402
 
 B = 64
 # name, Hin, Win, in_ctot, in_c_off, cin, cout, k, stride, res, out_mode(0 bf16,1 f32,2 shuffle), out_ctot, act
@@ -100,7 +100,7 @@ def main():
         ms_l, desc = [], C.create_string_buffer(640)
         for d in dbgs:
             ms = C.c_float()
-            check(lib().ypb_conv_bench(C.c_void_p(st), C.c_void_p(x.data_ptr()), nb, H, W, ictot, ioff, cin,
+            check(diag_lib().ypb_conv_bench(C.c_void_p(st), C.c_void_p(x.data_ptr()), nb, H, W, ictot, ioff, cin,
                                        C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()), cout, k, s, act,
                                        C.c_void_p(r.data_ptr()) if res else None, C.c_void_p(out.data_ptr()), octot, 0, omode,
                                        a.impl, d, a.iters, C.byref(ms), desc, 640))

@@ -6,12 +6,12 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from yolo_puncture_b200._lib import check, lib  # noqa: E402
+from yolo_puncture_b200._lib import check, diag_lib, lib  # noqa: E402
 
 
 def run(buf, mode, stages, iters, rows=0, W=0, H=0, B=0):
     ms, by = C.c_float(), C.c_double()
-    check(lib().ypb_tma_bench(C.c_void_p(buf.data_ptr()), mode, stages, iters, rows, W, H, B, C.byref(ms), C.byref(by)))
+    check(diag_lib().ypb_tma_bench(C.c_void_p(buf.data_ptr()), mode, stages, iters, rows, W, H, B, C.byref(ms), C.byref(by)))
     return by.value / (ms.value * 1e-3) / 1e9, ms.value
 
 

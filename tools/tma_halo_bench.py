@@ -11,12 +11,12 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from yolo_puncture_b200._lib import check, lib  # noqa: E402
+from yolo_puncture_b200._lib import check, diag_lib, lib  # noqa: E402
 
 
 def run(buf, ctot, R, prods, stages, iters, W, H, B):
     ms, by = C.c_float(), C.c_double()
-    check(lib().ypb_tma_bench(C.c_void_p(buf.data_ptr()), 4, stages, iters, ctot | (R << 16) | (prods << 24), W, H, B,
+    check(diag_lib().ypb_tma_bench(C.c_void_p(buf.data_ptr()), 4, stages, iters, ctot | (R << 16) | (prods << 24), W, H, B,
                               C.byref(ms), C.byref(by)))
     return ms.value, by.value
 

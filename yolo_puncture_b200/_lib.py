@@ -59,9 +59,6 @@ SIGNATURES = {
     "ypb_set_graph": (c_int, [c_void_p, c_int]),
     "ypb_conv2d_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
-    "ypb_conv_bench": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
-                               c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                               C.POINTER(c_float), C.c_char_p, c_int]),
     "ypb_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p,
                         c_void_p, c_void_p]),
     "ypb_nms_scratch_bytes": (c_size_t, [c_int, c_int]),
@@ -70,10 +67,18 @@ SIGNATURES = {
     "ypb_letterbox_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "ypb_index_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "ypb_debug_prof": (c_int, [c_void_p, c_int]),
     "ypb_host_is_pinned": (c_int, [c_void_p, C.POINTER(c_int)]),
     "ypb_hosts_are_pinned": (c_int, [c_void_p, c_int, C.POINTER(c_int)]),
     "ypb_h2d_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+    "ypb_is_diag_build": (c_int, []),
+}
+
+# include/ypb200_diag.h: exported by libypb200_diag.so only (debugging twins, micro-benchmarks)
+DIAG_SIGNATURES = {
+    "ypb_conv_bench": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                               c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                               C.POINTER(c_float), C.c_char_p, c_int]),
+    "ypb_debug_prof": (c_int, [c_void_p, c_int]),
     "ypb_mma_bench": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float)]),
     "ypb_latency_probe": (c_int, [c_void_p]),
     "ypb_tma_bench": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(c_float),
@@ -83,6 +88,12 @@ SIGNATURES = {
 
 class YpbError(RuntimeError):
     pass
+
+
+def _attach(handle, table):
+    for name, (res, args) in table.items():
+        fn = getattr(handle, name)
+        fn.restype, fn.argtypes = res, args
 
 
 def lib():
@@ -95,11 +106,29 @@ def lib():
         if not os.path.exists(path):
             raise YpbError(f"{path} missing: the CUDA extension is required, there is no fallback")
         handle = C.CDLL(path)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(handle, name)
-            fn.restype, fn.argtypes = res, args
+        _attach(handle, SIGNATURES)
+        if handle.ypb_is_diag_build():
+            _attach(handle, DIAG_SIGNATURES)
         _LIB = handle
     return _LIB
+
+
+_DIAG = None
+
+
+def diag_lib():
+    """libypb200_diag.so: the product translation unit plus debugging twins and micro-benchmarks (built on demand,
+    in-tree).  Tests of the twins and the tools/ scripts use it; the product path never does."""
+    global _DIAG
+    if _DIAG is None:
+        if lib().ypb_is_diag_build():
+            _DIAG = lib()
+        else:
+            handle = C.CDLL(_build.build(diag=True))
+            _attach(handle, SIGNATURES)
+            _attach(handle, DIAG_SIGNATURES)
+            _DIAG = handle
+    return _DIAG
 
 
 def check(rc):

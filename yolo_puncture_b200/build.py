@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libypb200.so")
 SOURCES = ["ypb200.cu", "common.cuh", "conv_tc.cuh", "conv_plan.cuh", "head_kernels.cuh", "mask_kernels.cuh",
-           "misc_kernels.cuh"]
+           "misc_kernels.cuh", "v10_kernels.cuh"]  # + tma_bench.cuh in the diagnostics build
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
@@ -32,28 +32,43 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "ypb200.h")]
+    deps = [os.path.join(CSRC, s) for s in os.listdir(CSRC) if s != "tma_bench.cuh"] + [os.path.join(ROOT, "include", "ypb200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
 LIB_PROF = os.path.join(HERE, "libypb200_prof.so")
+LIB_DIAG = os.path.join(HERE, "libypb200_diag.so")
 
 
-def build(force=False, verbose=False, prof=False):
-    """prof=True builds libypb200_prof.so: the same library with the per-role wait-cycle / epilogue-phase accounting
+def _stale(path):
+    if not os.path.exists(path):
+        return True
+    t = os.path.getmtime(path)
+    deps = [os.path.join(CSRC, s) for s in os.listdir(CSRC)] + [os.path.join(ROOT, "include", h) for h in ("ypb200.h", "ypb200_diag.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False, prof=False, diag=False):
+    """Product library: libypb200.so (the product kernels and the C ABI of include/ypb200.h, nothing else).
+    diag=True builds libypb200_diag.so: the same translation unit with -DYPB_DIAG=1, i.e. plus the debugging twins of
+    the conv kernel and the micro-benchmarks of include/ypb200_diag.h (tests/test_gpu_conv.py twins, tools/).
+    prof=True builds libypb200_prof.so: the diagnostics build with the per-role wait-cycle / epilogue-phase accounting
     compiled in (-DYPB_PROF=1); tools/conv_layers.py loads it through YPB_LIB."""
-    if prof:
-        nvcc = _nvcc()
-        res = subprocess.run([nvcc, *NVCC_FLAGS, "-DYPB_PROF=1", "-o", LIB_PROF, os.path.join(CSRC, "ypb200.cu")],
-                             capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-        return LIB_PROF
-    if not force and not needs_build():
-        return LIB
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libypb200.so")
+    if prof or diag:
+        out = LIB_PROF if prof else LIB_DIAG
+        if not force and not _stale(out):
+            return out
+        flags = ["-DYPB_DIAG=1"] + (["-DYPB_PROF=1"] if prof else [])
+        res = subprocess.run([nvcc, *NVCC_FLAGS, *flags, "-o", out, os.path.join(CSRC, "ypb200.cu")],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        return out
+    if not force and not needs_build():
+        return LIB
     cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "ypb200.cu")]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
@@ -70,4 +85,4 @@ def ensure_built():
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv, diag="--diag" in sys.argv))

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "conv_tc.cuh"
@@ -48,7 +49,9 @@ struct ConvLaunch {
   CUtensorMap tmA1;
   dim3 grid1;
   int n_splits = 1, total_tiles = 0, stages2 = 2, smem2 = 0;  // persistent-kernel launch shape
+#if YPB_DIAG
   ConvSimtGeom sg;
+#endif
   CUtensorMap tmA, tmB;
   CUtensorMap tmO;  // output map of the TMA-store epilogue (1x1 convs), valid when p.tma_out != 0
   dim3 grid;
@@ -336,10 +339,12 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
       conv3_set_taps(&L->x3, true);
     }
   }
+#if YPB_DIAG
   ConvSimtGeom& g = L->sg;
   memset(&g, 0, sizeof g);
   g.in_H = d.Hin; g.in_W = d.Win; g.in_ctot = d.in_ctot; g.in_c_off = d.in_c_off;
   g.k = d.k; g.stride = d.stride; g.pad = d.k / 2; g.oH = oH; g.oW = oW; g.nB = d.B;
+#endif
   {  // p1 = p with the one-tile-per-CTA geometry saved above
     const ConvParams g1 = L->p1;
     L->p1 = p;
@@ -354,8 +359,10 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
   ConvParams& p = L->p;
   p.out = d.out; p.bias = d.bias; p.res = reinterpret_cast<const __nv_bfloat16*>(d.res);
   L->p1.out = d.out; L->p1.bias = d.bias; L->p1.res = p.res;
+#if YPB_DIAG
   L->sg.in = reinterpret_cast<const __nv_bfloat16*>(d.in);
   L->sg.wg = reinterpret_cast<const __nv_bfloat16*>(d.wg);
+#endif
   const cuuint64_t C = (cuuint64_t)d.in_ctot;
   cuuint64_t dims[5], str[4];
   cuuint32_t box[5];
@@ -433,13 +440,38 @@ static void conv_describe(const ConvLaunch& L, int impl, char* out, int n) {
              L.stages2, L.p.n_tile, L.n_splits, L.total_tiles, L.smem2);
 }
 
-static int g_num_sms = 148;
-// One-time function attributes (must not happen inside a stream capture).
+// Per-device launch state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are properties of ONE
+// device: a process that drives several GPUs (YOLO.to('cuda:1'), one host thread per GPU) needs them per ordinal.
+struct DeviceState {
+  bool conv_attrs = false, halo_test_attr = false;
+  size_t sppf_smem = 0, mask_smem = 0;
+  int num_sms = 148;
+};
+static std::mutex g_dev_mutex;
+static DeviceState g_dev_state[64];
+static DeviceState& device_state() {  // of the CURRENT device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_dev_state[dev & 63];
+}
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: a C-ABI entry
+// point must not change the calling thread's current device behind the host application's back.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (device < 0 || cudaGetDevice(&prev) != cudaSuccess) return;
+    if (prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// One-time function attributes of the current device (must not happen inside a stream capture).
 static cudaError_t conv_launch_init() {
-  static bool done = false;
-  if (done) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  DeviceState& ds = device_state();
+  if (ds.conv_attrs) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
 #define YPB_SET_SMEM(MODE)                                                                                        \
   e = cudaFuncSetAttribute(conv_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);       \
   if (e != cudaSuccess) return e;                                                                                 \
@@ -449,8 +481,8 @@ static cudaError_t conv_launch_init() {
 #undef YPB_SET_SMEM
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  done = true;
+  cudaDeviceGetAttribute(&ds.num_sms, cudaDevAttrMultiProcessorCount, dev);
+  ds.conv_attrs = true;
   return cudaSuccess;
 }
 
@@ -470,20 +502,32 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int
 }
 
 static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int impl) {
+#if YPB_DIAG
   if (impl == 1) {
     const long long total = (long long)L.sg.nB * L.sg.oH * L.sg.oW * (L.p.Cout / 16);
     conv_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(L.sg, L.p);
     return cudaGetLastError();
   }
+#else
+  if (impl != 0) return cudaErrorNotSupported;  // the debugging twins live in libypb200_diag.so
+#endif
   {
     cudaError_t e = conv_launch_init();
     if (e != cudaSuccess) return e;
   }
-  const int num_sms = g_num_sms;
+  const int num_sms = device_state().num_sms;
+#if YPB_DIAG
   if (impl == 3) {  // halo-reuse experiment (3x3 stride 1, Cout <= 128): 16x8 tiles
     if (!L.halo_ok) return cudaErrorInvalidValue;
-    static bool set3 = false;
-    if (!set3) { cudaFuncSetAttribute(conv_halo_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); set3 = true; }
+    {
+      std::lock_guard<std::mutex> lock(g_dev_mutex);
+      DeviceState& ds = device_state();
+      if (!ds.halo_test_attr) {
+        cudaFuncSetAttribute(conv_halo_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        ds.halo_test_attr = true;
+      }
+    }
     ConvParams p3 = L.p1;
     p3.tiles_h = (p3.tH + 15) / 16; p3.tiles_w = (p3.tW + 7) / 8;
     const int grid3 = p3.tB * p3.tiles_h * p3.tiles_w;
@@ -492,9 +536,19 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
     return cudaGetLastError();
   }
   if (impl == 2) {  // first-generation kernel: one tile per CTA (kept for A/B measurements)
+    {
+      std::lock_guard<std::mutex> lock(g_dev_mutex);
+      DeviceState& ds = device_state();
+      if (!ds.halo_test_attr) {
+        cudaFuncSetAttribute(conv_halo_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        ds.halo_test_attr = true;
+      }
+    }
     conv_tc_kernel<<<L.grid1, kConvThreads, L.smem, stream>>>(L.tmA1, L.tmB, L.p1);
     return cudaGetLastError();
   }
+#endif
   if (L.use_halo && impl == 0) {
     ConvParams p3 = L.p;
     p3.tiles_h = L.tiles_h3; p3.tiles_w = L.tiles_w3;

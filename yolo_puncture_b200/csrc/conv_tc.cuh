@@ -23,6 +23,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef YPB_DIAG
+#define YPB_DIAG 0  // 1: also build the debugging twins and micro-benchmarks (libypb200_diag.so; never in the product library)
+#endif
+
 namespace ypb {
 
 enum ConvOutMode : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_SHUFFLE2_BF16 = 2 };
@@ -79,6 +83,7 @@ __host__ inline void conv_set_fastdiv(ConvParams& p, int n_splits) {
   fastdiv_make((uint32_t)p.img_W, p.fd_iw);
 }
 
+#if YPB_DIAG
 // Store 16 consecutive output channels [n, n+16) of output pixel q. v = raw accumulators.
 __device__ __forceinline__ void conv_epilogue_store16(const ConvParams& p, int q, int n, const float (&acc)[16]) {
   float y[16];
@@ -125,6 +130,7 @@ __device__ __forceinline__ void conv_epilogue_store16(const ConvParams& p, int q
   *reinterpret_cast<uint4*>(o) = s0;
   *reinterpret_cast<uint4*>(o + 8) = s1;
 }
+#endif  // YPB_DIAG
 
 // YPB_DBG bit 8: per-role wait-cycle accounting (summed over CTAs; read back by ypb_conv_bench).
 // [0] producer-0 wait empty  [1] MMA wait full  [2] MMA wait tempty  [3] epilogue-warp-0 wait tfull
@@ -145,6 +151,7 @@ __host__ __device__ inline int conv_smem_bytes(int n_tile, int stages) {
   return 1024 /*align slack*/ + stages * conv_stage_bytes(n_tile) + 256 /*barriers*/;
 }
 
+#if YPB_DIAG  // first-generation kernel: one tile per CTA (libypb200_diag.so only, A/B measurements)
 __global__ void __launch_bounds__(kConvThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvParams p) {
@@ -264,6 +271,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_dealloc(tmem_base, tmem_cols);
   }
 }
+#endif  // YPB_DIAG
 
 // ------------------------------------------------------------------------------------------------
 // Persistent, warp-specialised version (the product path).  One CTA per SM loops over output tiles:
@@ -1453,6 +1461,7 @@ stem_tc_kernel(const uint8_t* __restrict__ frames, int H, int W, int nB, const _
   }
 }
 
+#if YPB_DIAG
 // ------------------------------------------------------------------------------------------------
 // EXPERIMENT (impl 3): 3x3 stride-1 conv whose nine taps all read ONE halo tile in shared memory.
 // Tile = 16 rows x 8 cols of output; the halo box {64 ch, 10, 18} (180 rows of 128 B, SWIZZLE_128B) is loaded
@@ -1584,5 +1593,6 @@ __global__ void conv_simt_kernel(const ConvSimtGeom g, const ConvParams p) {
   }
   conv_epilogue_store16(p, q, ng * 16, acc);
 }
+#endif  // YPB_DIAG
 
 }  // namespace ypb

@@ -29,7 +29,10 @@
 #include "mask_kernels.cuh"
 #include "misc_kernels.cuh"
 #include "v10_kernels.cuh"
+#if YPB_DIAG
+#include "../../include/ypb200_diag.h"
 #include "tma_bench.cuh"
+#endif
 
 using namespace ypb;
 
@@ -739,10 +742,13 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       const BufDesc& ib = e->bufs[op.in.buf];
       const size_t smem = (size_t)2 * ib.H * ib.W * 16;
       if (smem > 200 * 1024) return fail(YPB_ERR_ARG, "sppf: feature map too large for the shared-memory pool kernel");
-      static size_t sppf_smem_set = 0;
-      if (smem > 48 * 1024 && smem > sppf_smem_set) {
-        CUDA_TRY(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        sppf_smem_set = 200 * 1024;
+      if (smem > 48 * 1024) {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        DeviceState& ds = device_state();
+        if (smem > ds.sppf_smem) {
+          CUDA_TRY(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          ds.sppf_smem = 200 * 1024;
+        }
       }
       sppf_pool_kernel<<<dim3(op.in.C / 8, B), 256, smem, st>>>(reinterpret_cast<__nv_bfloat16*>(e->ws + ib.offset), B, ib.H,
                                                                 ib.W, op.in.C);
@@ -844,6 +850,7 @@ static int check_infer_args(ypb_engine* e, const uint8_t* frames, const float* x
 extern "C" {
 
 int ypb_version(void) { return 100; }
+int ypb_is_diag_build(void) { return YPB_DIAG ? 1 : 0; }
 const char* ypb_last_error(void) { return g_last_error.c_str(); }
 
 int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out) {
@@ -866,9 +873,12 @@ int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out) {
 
 void ypb_engine_destroy(ypb_engine* e) {
   if (!e) return;
-  e->drop_graph();
-  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
-  if (e->w_arena) cudaFree(e->w_arena);
+  {
+    DeviceGuard guard(e->device);
+    e->drop_graph();
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    if (e->w_arena) cudaFree(e->w_arena);
+  }
   delete e;
 }
 
@@ -892,7 +902,10 @@ int ypb_load_weight(ypb_engine* e, const char* name, const float* data, int64_t 
   if (numel != w.numel()) return fail(YPB_ERR_ARG, std::string("size mismatch for '") + name + "'");
   if (w.used) w.data.assign(data, data + numel);
   w.loaded = true;
+  // the device copy is stale from here on: ypb_infer() must fail until finalize + bind have been redone
   e->finalized = false;
+  e->bound = false;
+  e->drop_graph();
   return YPB_OK;
 }
 
@@ -981,7 +994,11 @@ int ypb_finalize_weights(ypb_engine* e, int device) {
       n_off += s.width();
     }
   }
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);  // the caller's current device is restored on return
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return fail(YPB_ERR_CUDA, "cannot select CUDA device " + std::to_string(device));
+  }
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(YPB_ERR_CUDA, "device is not sm_100 (Blackwell B200); there is no fallback path");
@@ -1080,7 +1097,7 @@ int ypb_bind_workspace(ypb_engine* e, void* workspace, size_t bytes) {
   if (!e->planned || !e->finalized) return fail(YPB_ERR_STATE, "bind: finalize weights and plan first");
   if (bytes < e->ws_bytes) return fail(YPB_ERR_ARG, "workspace too small");
   if ((uintptr_t)workspace & 1023) return fail(YPB_ERR_ARG, "workspace must be 1024-byte aligned");
-  CUDA_TRY(cudaSetDevice(e->device));
+  DeviceGuard guard(e->device);
   e->ws = reinterpret_cast<uint8_t*>(workspace);
   const uint8_t* wa = reinterpret_cast<const uint8_t*>(e->w_arena);
   const HeadGeom& g = e->hg;
@@ -1115,6 +1132,9 @@ double ypb_conv_flops(const ypb_engine* e) { return e ? e->flops : 0.0; }
 
 int ypb_set_conv_impl(ypb_engine* e, int impl) {
   if (!e || impl < 0 || impl > 3) return fail(YPB_ERR_ARG, "bad argument");
+#if !YPB_DIAG
+  if (impl != 0) return fail(YPB_ERR_ARG, "conv impl 1-3 are debugging twins: load libypb200_diag.so (include/ypb200_diag.h)");
+#endif
   e->conv_impl = impl;
   e->drop_graph();
   return YPB_OK;
@@ -1142,6 +1162,7 @@ int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const flo
   int rc0 = check_infer_args(e, frames, xform, prm, det, det_lb, keep, coef, count);
   if (rc0) return rc0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  DeviceGuard guard(e->device);
   if (!e->use_graph) return enqueue_infer(e, st, frames, xform, prm, det, det_lb, keep, coef, count);
   ypb_engine::GraphKey key;
   memset(&key, 0, sizeof key);
@@ -1225,6 +1246,7 @@ int ypb_infer_profile(ypb_engine* e, void* cuda_stream, const uint8_t* frames, c
   const int n = (int)e->ops.size();
   if (!op_ms || capacity < n + 2) return fail(YPB_ERR_ARG, "op_ms too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  DeviceGuard guard(e->device);
   std::vector<cudaEvent_t> ev(n + 3);
   for (auto& x : ev) CUDA_TRY(cudaEventCreate(&x));
   CUDA_TRY(cudaEventRecord(ev[0], st));
@@ -1271,7 +1293,9 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
                  int32_t* offsets_scratch) {
   if (!e || !det || !det_lb || !coef || !count || !masks || !status || capacity < 1) return fail(YPB_ERR_ARG, "bad argument");
   if (!e->bound || e->nm == 0 || e->proto_buf < 0) return fail(YPB_ERR_STATE, "masks: not a bound -seg engine");
+  if (e->nm != 32) return fail(YPB_ERR_ARG, "masks: the decode kernel is built for 32 mask coefficients");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  DeviceGuard guard(e->device);
   const BufDesc& pb = e->bufs[e->proto_buf];
   MaskGeom g{};
   g.mh = pb.H; g.mw = pb.W; g.nm = e->nm; g.max_det = kNmsMaxDet; g.retina = retina ? 1 : 0;
@@ -1299,10 +1323,13 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
   const int band_rows = std::min(g.ch, (int)(kMaskTile * g.scale_h) + 3);
   const size_t band_smem = (size_t)band_rows * g.cw * sizeof(float);
   if (band_smem > 160 * 1024) return fail(YPB_ERR_ARG, "masks: proto window too large for the band buffer");
-  static size_t mask_smem_set = 0;
-  if (band_smem > 30 * 1024 && band_smem > mask_smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(mask_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    mask_smem_set = 160 * 1024;
+  if (band_smem > 30 * 1024) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceState& ds = device_state();
+    if (band_smem > ds.mask_smem) {
+      CUDA_TRY(cudaFuncSetAttribute(mask_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      ds.mask_smem = 160 * 1024;
+    }
   }
   mask_decode_kernel<<<grid, 256, band_smem, st>>>(proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb,
                                                   offsets, e->B, capacity, g, masks);
@@ -1353,12 +1380,16 @@ int ypb_conv2d_bf16(void* cuda_stream, const void* in, int B, int H, int W, int 
   if (res) { d.res = res; d.res_img_stride = d.out_img_stride; d.res_pix_stride = out_ctot; d.res_c_off = out_c_off; }
   ConvLaunch L;
   std::string err;
+#if !YPB_DIAG
+  if (impl != 0) return fail(YPB_ERR_ARG, "conv impl 1-3 are debugging twins: load libypb200_diag.so (include/ypb200_diag.h)");
+#endif
   if (!conv_plan_geometry(d, &L, &err)) return fail(YPB_ERR_ARG, err);
   if (!conv_bind(d, &L, &err)) return fail(YPB_ERR_CUDA, err);
   CUDA_TRY(conv_launch(L, reinterpret_cast<cudaStream_t>(cuda_stream), impl));
   return YPB_OK;
 }
 
+#if YPB_DIAG  // ---- diagnostics and micro-benchmarks: libypb200_diag.so only (include/ypb200_diag.h) ----
 // Diagnostics: time `iters` back-to-back launches of one conv (planned once) with CUDA events on `cuda_stream`.
 // dbg >= 0 overrides the YPB_DBG experiment mask of the launch (see ConvParams::dbg).
 int ypb_conv_bench(void* cuda_stream, const void* in, int B, int H, int W, int in_ctot, int in_c_off, int cin,
@@ -1519,6 +1550,7 @@ int ypb_latency_probe(long long* out_dev) {
   CUDA_TRY(cudaDeviceSynchronize());
   return YPB_OK;
 }
+#endif  // YPB_DIAG
 
 // Host-side helper: copy n frames into the pinned staging buffer with `nthreads` host threads (the Python caller
 // releases the GIL for the duration of the call).  Frame staging is the host stage of the predict() pipeline.

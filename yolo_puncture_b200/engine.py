@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from ._lib import InferParams, YpbError, check, lib
+from ._lib import InferParams, YpbError, check, diag_lib, lib
 
 MAX_DET = 300
 
@@ -222,7 +222,8 @@ def conv2d_bf16(x, w_gemm, bias, k, stride, act, cin=None, in_c_off=0, res=None,
     if out is None:
         out = torch.zeros((B, oH, oW, cout), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
     st = torch.cuda.current_stream(x.device).cuda_stream
-    check(lib().ypb_conv2d_bf16(C.c_void_p(st), _ptr(x), B, H, W, ctot, in_c_off, cin, _ptr(w_gemm), _ptr(bias), cout, k,
+    handle = lib() if impl == 0 else diag_lib()  # impl 1-3: debugging twins, libypb200_diag.so only
+    check(handle.ypb_conv2d_bf16(C.c_void_p(st), _ptr(x), B, H, W, ctot, in_c_off, cin, _ptr(w_gemm), _ptr(bias), cout, k,
                                 stride, int(act), _ptr(res), _ptr(out), out.shape[3], out_c_off, int(out_fp32), impl))
     return out
 

@@ -94,10 +94,17 @@ class Masks(BaseTensor):
 
     @property
     def data(self):
+        """float32 view of the masks, converted ONCE and cached: the reference loop `masks.data[i]` per detection
+        (yolo_seg/yolo_with_deva.py:61-83) must not convert the whole (n,H,W) tensor on every access."""
         d = self._data
-        if isinstance(d, np.ndarray):
-            return d if d.dtype == np.float32 else d.astype(np.float32)
-        return d if d.dtype == torch.float32 else d.to(torch.float32)
+        f = getattr(self, "_f32", None)
+        if f is None:
+            if isinstance(d, np.ndarray):
+                f = d if d.dtype == np.float32 else d.astype(np.float32)
+            else:
+                f = d if d.dtype == torch.float32 else d.to(torch.float32)
+            self._f32 = f
+        return f
 
     @property
     def raw(self):

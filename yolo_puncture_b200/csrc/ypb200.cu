@@ -128,6 +128,16 @@ struct ypb_engine {
   std::vector<GraphEntry> graphs;  // small LRU cache: callers alternate between a few input buffers
   unsigned long long graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
+  // Branch-parallel capture: the layer ops form a DAG (proto branch, the three head levels and the rest of the neck
+  // only meet at decode); each op is pinned to one of a few capture streams so that independent chains become parallel
+  // branches of the CUDA graph and fill each other's tail waves / launch gaps.  Built once per topology.
+  struct OpSched { int stream = 0; std::vector<int> waits; bool record = false; };
+  std::vector<OpSched> sched;
+  int n_streams = 1;
+  bool branch_parallel = true;
+  cudaStream_t side_streams[8] = {};
+  std::vector<cudaEvent_t> op_events;
+  void build_schedule(int max_streams);
   void drop_graph() {
     for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     graphs.clear();
@@ -344,6 +354,18 @@ struct ypb_engine {
 // ------------------------------------------------------------------------------------------------
 static int make_div8(double x) { return (int)(std::ceil(x / 8.0) * 8); }
 
+// Zero channels to append to a fused conv's N so that it splits into equal tiles of a multiple of 16 channels, each
+// <= 256 wide and at least 128 wide (see conv_plan_geometry's split rule).  0 when N already splits well.
+static int fused_n_pad(int n) {
+  for (int pad = 0; pad <= 64; pad += 16) {
+    const int t = n + pad;
+    if (t <= 256) return pad;
+    const int splits = (t + 255) / 256;
+    if (t % (16 * splits) == 0) return pad;
+  }
+  return 0;
+}
+
 static bool build_v8seg(ypb_engine& e, char scale) {
   double d, w; int mc;
   switch (scale) {
@@ -412,22 +434,7 @@ static bool build_v8seg(ypb_engine& e, char scale) {
   const View P[3] = {e.whole(x15), e.whole(x18), e.whole(x21)};
   const int hc2 = std::max(std::max(16, chs[0] / 4), 64), hc3 = std::max(chs[0], std::min(e.nc, 100));
   const int hc4 = std::max(chs[0] / 4, e.nm);
-  for (int i = 0; i < 3; ++i) {
-    e.feat[i] = P[i];
-    const std::string si = std::to_string(i);
-    const int lvl = 3 + i;
-    // the first 3x3 conv of the box / class / coef branches reads the same P_i: one fused GEMM, N = hc2+hc3+hc4
-    const int f0 = e.new_buf(Hd + "lvl" + si + ".s0", lvl, hc2 + hc3 + hc4);
-    e.conv({Hd + "cv2." + si + ".0", Hd + "cv3." + si + ".0", Hd + "cv4." + si + ".0"}, {hc2, hc3, hc4}, P[i], e.whole(f0), 3, 1);
-    const int t2 = e.new_buf(Hd + "cv2." + si + ".t", lvl, hc2), t3 = e.new_buf(Hd + "cv3." + si + ".t", lvl, hc3);
-    const int t4 = e.new_buf(Hd + "cv4." + si + ".t", lvl, hc4);
-    e.conv1(Hd + "cv2." + si + ".1", e.slice(f0, 0, hc2), e.whole(t2), 3, 1);
-    e.conv1(Hd + "cv3." + si + ".1", e.slice(f0, hc2, hc3), e.whole(t3), 3, 1);
-    e.conv1(Hd + "cv4." + si + ".1", e.slice(f0, hc2 + hc3, hc4), e.whole(t4), 3, 1);
-    e.head_out(Hd + "cv2." + si + ".2", e.whole(t2), 64, i, 0);
-    e.head_out(Hd + "cv3." + si + ".2", e.whole(t3), e.nc, i, 64);
-    e.head_out(Hd + "cv4." + si + ".2", e.whole(t4), e.nm, i, 64 + e.nc);
-  }
+  // Proto first: it only needs P3, so in the branch-parallel graph it starts while the neck is still running
   e.add_weight(Hd + "dfl.conv.weight", {1, 16, 1, 1}, false);
   // Proto (UPSTREAM block.py::Proto)
   const int npr = ch(256);
@@ -448,6 +455,27 @@ static bool build_v8seg(ypb_engine& e, char scale) {
   {
     e.conv1(Hd + "proto.cv3", e.whole(p3), e.whole(pr), 1, 1);
     e.ops.back().out_mode = OUT_F32;
+  }
+  for (int i = 0; i < 3; ++i) {
+    e.feat[i] = P[i];
+    const std::string si = std::to_string(i);
+    const int lvl = 3 + i;
+    // the first 3x3 conv of the box / class / coef branches reads the same P_i: one fused GEMM, N = hc2+hc3+hc4.
+    // N > 256 is split into equal tiles of a multiple of 16 channels; yolov8m-seg's 64+192+48 = 304 = 16 x 19 has no
+    // such split above 16 (the planner used to fall back to NINETEEN 16-channel tiles: 0.15 of tensor peak), so the
+    // fused output is padded with zero-weight channels to the next total that splits evenly (304 -> 320 = 2 x 160)
+    const int fpad = fused_n_pad(hc2 + hc3 + hc4);
+    const int f0 = e.new_buf(Hd + "lvl" + si + ".s0", lvl, hc2 + hc3 + hc4 + fpad);
+    e.conv({Hd + "cv2." + si + ".0", Hd + "cv3." + si + ".0", Hd + "cv4." + si + ".0"}, {hc2, hc3, hc4}, P[i], e.whole(f0), 3, 1);
+    if (fpad) { e.ops.back().srcs.back().slot = hc4 + fpad; e.ops.back().cout += fpad; }
+    const int t2 = e.new_buf(Hd + "cv2." + si + ".t", lvl, hc2), t3 = e.new_buf(Hd + "cv3." + si + ".t", lvl, hc3);
+    const int t4 = e.new_buf(Hd + "cv4." + si + ".t", lvl, hc4);
+    e.conv1(Hd + "cv2." + si + ".1", e.slice(f0, 0, hc2), e.whole(t2), 3, 1);
+    e.conv1(Hd + "cv3." + si + ".1", e.slice(f0, hc2, hc3), e.whole(t3), 3, 1);
+    e.conv1(Hd + "cv4." + si + ".1", e.slice(f0, hc2 + hc3, hc4), e.whole(t4), 3, 1);
+    e.head_out(Hd + "cv2." + si + ".2", e.whole(t2), 64, i, 0);
+    e.head_out(Hd + "cv3." + si + ".2", e.whole(t3), e.nc, i, 64);
+    e.head_out(Hd + "cv4." + si + ".2", e.whole(t4), e.nm, i, 64 + e.nc);
   }
   e.proto_buf = pr;
   e.name_view("proto", e.whole(pr));
@@ -612,27 +640,7 @@ static bool build_v11seg(ypb_engine& e, char scale) {
   const View P[3] = {e.whole(x16), e.whole(x19), e.whole(x22)};
   const int hc2 = std::max(std::max(16, chs[0] / 4), 64), hc3 = std::max(chs[0], std::min(e.nc, 100));
   const int hc4 = std::max(chs[0] / 4, e.nm);
-  for (int i = 0; i < 3; ++i) {
-    e.feat[i] = P[i];
-    const std::string si = std::to_string(i);
-    const int lvl = 3 + i, x = chs[i];
-    // the first 3x3 conv of the box and coefficient branches reads the same P_i: one fused GEMM, N = hc2 + hc4
-    const int f0 = e.new_buf(Hd + "lvl" + si + ".s0", lvl, hc2 + hc4);
-    e.conv({Hd + "cv2." + si + ".0", Hd + "cv4." + si + ".0"}, {hc2, hc4}, P[i], e.whole(f0), 3, 1);
-    const int t2 = e.new_buf(Hd + "cv2." + si + ".t", lvl, hc2), t4 = e.new_buf(Hd + "cv4." + si + ".t", lvl, hc4);
-    e.conv1(Hd + "cv2." + si + ".1", e.slice(f0, 0, hc2), e.whole(t2), 3, 1);
-    e.conv1(Hd + "cv4." + si + ".1", e.slice(f0, hc2, hc4), e.whole(t4), 3, 1);
-    const std::string b3 = Hd + "cv3." + si + ".";
-    const int u0 = e.new_buf(b3 + "u0", lvl, x), u1 = e.new_buf(b3 + "u1", lvl, hc3), u2 = e.new_buf(b3 + "u2", lvl, hc3);
-    const int u3 = e.new_buf(b3 + "u3", lvl, hc3);
-    e.dwconv({b3 + "0.0"}, {3}, P[i], e.whole(u0), 3, 1, true);
-    e.conv1(b3 + "0.1", e.whole(u0), e.whole(u1), 1, 1);
-    e.dwconv({b3 + "1.0"}, {3}, e.whole(u1), e.whole(u2), 3, 1, true);
-    e.conv1(b3 + "1.1", e.whole(u2), e.whole(u3), 1, 1);
-    e.head_out(Hd + "cv2." + si + ".2", e.whole(t2), 64, i, 0);
-    e.head_out(b3 + "2", e.whole(u3), e.nc, i, 64);
-    e.head_out(Hd + "cv4." + si + ".2", e.whole(t4), e.nm, i, 64 + e.nc);
-  }
+  // Proto first (see build_v8seg)
   e.add_weight(Hd + "dfl.conv.weight", {1, 16, 1, 1}, false);
   // Proto (UPSTREAM block.py::Proto)
   const int npr = ch(256);
@@ -653,6 +661,27 @@ static bool build_v11seg(ypb_engine& e, char scale) {
   {
     e.conv1(Hd + "proto.cv3", e.whole(p3), e.whole(pr), 1, 1);
     e.ops.back().out_mode = OUT_F32;
+  }
+  for (int i = 0; i < 3; ++i) {
+    e.feat[i] = P[i];
+    const std::string si = std::to_string(i);
+    const int lvl = 3 + i, x = chs[i];
+    // the first 3x3 conv of the box and coefficient branches reads the same P_i: one fused GEMM, N = hc2 + hc4
+    const int f0 = e.new_buf(Hd + "lvl" + si + ".s0", lvl, hc2 + hc4);
+    e.conv({Hd + "cv2." + si + ".0", Hd + "cv4." + si + ".0"}, {hc2, hc4}, P[i], e.whole(f0), 3, 1);
+    const int t2 = e.new_buf(Hd + "cv2." + si + ".t", lvl, hc2), t4 = e.new_buf(Hd + "cv4." + si + ".t", lvl, hc4);
+    e.conv1(Hd + "cv2." + si + ".1", e.slice(f0, 0, hc2), e.whole(t2), 3, 1);
+    e.conv1(Hd + "cv4." + si + ".1", e.slice(f0, hc2, hc4), e.whole(t4), 3, 1);
+    const std::string b3 = Hd + "cv3." + si + ".";
+    const int u0 = e.new_buf(b3 + "u0", lvl, x), u1 = e.new_buf(b3 + "u1", lvl, hc3), u2 = e.new_buf(b3 + "u2", lvl, hc3);
+    const int u3 = e.new_buf(b3 + "u3", lvl, hc3);
+    e.dwconv({b3 + "0.0"}, {3}, P[i], e.whole(u0), 3, 1, true);
+    e.conv1(b3 + "0.1", e.whole(u0), e.whole(u1), 1, 1);
+    e.dwconv({b3 + "1.0"}, {3}, e.whole(u1), e.whole(u2), 3, 1, true);
+    e.conv1(b3 + "1.1", e.whole(u2), e.whole(u3), 1, 1);
+    e.head_out(Hd + "cv2." + si + ".2", e.whole(t2), 64, i, 0);
+    e.head_out(b3 + "2", e.whole(u3), e.nc, i, 64);
+    e.head_out(Hd + "cv4." + si + ".2", e.whole(t4), e.nm, i, 64 + e.nc);
   }
   e.proto_buf = pr;
   e.name_view("proto", e.whole(pr));
@@ -867,6 +896,8 @@ int ypb_engine_create(const char* model_spec, int nc, ypb_engine** out) {
     delete e;
     return fail(YPB_ERR_ARG, "unknown model spec '" + s + "'");
   }
+  e->branch_parallel = getenv("YPB_NO_BRANCHES") == nullptr;
+  e->build_schedule(getenv("YPB_STREAMS") ? std::max(1, std::min(8, atoi(getenv("YPB_STREAMS")))) : 8);
   *out = e;
   return YPB_OK;
 }
@@ -877,6 +908,8 @@ void ypb_engine_destroy(ypb_engine* e) {
     DeviceGuard guard(e->device);
     e->drop_graph();
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    for (cudaStream_t ss : e->side_streams) if (ss) cudaStreamDestroy(ss);
+    for (cudaEvent_t ev : e->op_events) cudaEventDestroy(ev);
     if (e->w_arena) cudaFree(e->w_arena);
   }
   delete e;
@@ -1073,6 +1106,12 @@ int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
     }
     std::string err;
     if (!conv_plan_geometry(d, &op.L, &err)) return fail(YPB_ERR_ARG, op.name + ": " + err);
+    {  // algorithmic FLOPs: the module's real channels, not the zero-padded ones the tensor core multiplies
+      int cout_real = 0;
+      for (const ConvSrc& sc : op.srcs) cout_real += sc.kind == SRC_CONVT ? 4 * sc.cout : sc.cout;
+      const int cin_r = op.cin_real > 0 ? op.cin_real : op.cin;
+      op.L.flops = 2.0 * B * op.L.oH * op.L.oW * (double)cout_real * cin_r * op.k * op.k;
+    }
     e->flops += op.L.flops;
     if (getenv("YPB_PLAN_DEBUG")) {
       if (op.L.use_halo)
@@ -1147,12 +1186,98 @@ int ypb_set_graph(ypb_engine* e, int on) {
   return YPB_OK;
 }
 
-static int enqueue_infer(ypb_engine* e, cudaStream_t st, const uint8_t* frames, const float* xform,
-                         const ypb_infer_params* prm, float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count) {
-  for (const Op& op : e->ops) {
-    int rc = launch_op(e, op, st, frames);
-    if (rc) return rc;
+// Channel ranges of buffers an op reads / writes (head rows: pseudo buffer 1000 + level).
+namespace {
+struct Access { int buf, lo, hi; };
+inline bool overlaps(const Access& a, const Access& b) { return a.buf == b.buf && a.lo < b.hi && b.lo < a.hi; }
+void op_accesses(const Op& op, std::vector<Access>* rd, std::vector<Access>* wr) {
+  auto add = [](std::vector<Access>* v, const View& w) { if (w.buf >= 0) v->push_back({w.buf, w.c_off, w.c_off + w.C}); };
+  if (op.kind != OP_STEM) add(rd, op.in);
+  add(rd, op.res);
+  if (op.head_lvl >= 0) wr->push_back({1000 + op.head_lvl, op.head_coff, op.head_coff + op.cout});
+  else add(wr, op.out);
+  if (op.kind == OP_SPPF) add(rd, op.out);  // the pools read what earlier pools of the same launch wrote
+}
+}  // namespace
+
+void ypb_engine::build_schedule(int max_streams) {
+  const int n = (int)ops.size();
+  sched.assign(n, OpSched());
+  std::vector<std::vector<Access>> rd(n), wr(n);
+  for (int j = 0; j < n; ++j) op_accesses(ops[j], &rd[j], &wr[j]);
+  std::vector<int> tail;  // last op of every stream
+  tail.push_back(-1);
+  for (int j = 0; j < n; ++j) {
+    std::vector<int> preds;
+    for (int i = 0; i < j; ++i) {
+      bool dep = false;
+      for (const Access& w : wr[i]) {
+        for (const Access& r : rd[j]) dep = dep || overlaps(w, r);   // read after write
+        for (const Access& w2 : wr[j]) dep = dep || overlaps(w, w2);  // write after write
+      }
+      for (const Access& r : rd[i])
+        for (const Access& w2 : wr[j]) dep = dep || overlaps(r, w2);  // write after read (in-place blocks)
+      if (dep) preds.push_back(i);
+    }
+    int stream = -1;
+    // continue the stream whose tail is one of my predecessors (the latest such predecessor wins)
+    for (int k = (int)preds.size() - 1; k >= 0 && stream < 0; --k)
+      if (tail[sched[preds[k]].stream] == preds[k]) stream = sched[preds[k]].stream;
+    if (stream < 0) {
+      if (preds.empty()) stream = 0;
+      else if ((int)tail.size() < max_streams) { tail.push_back(-1); stream = (int)tail.size() - 1; }
+      else stream = sched[preds.back()].stream;
+    }
+    sched[j].stream = stream;
+    for (int i : preds)
+      if (sched[i].stream != stream) { sched[j].waits.push_back(i); sched[i].record = true; }
+    tail[stream] = j;
   }
+  n_streams = (int)tail.size();
+  if (getenv("YPB_PLAN_DEBUG"))
+    for (int j = 0; j < n; ++j) {
+      fprintf(stderr, "[sched] %-30s stream %d waits", ops[j].name.c_str(), sched[j].stream);
+      for (int w : sched[j].waits) fprintf(stderr, " %s", ops[w].name.c_str());
+      fprintf(stderr, "\n");
+    }
+  // the selection stage runs on stream 0 after every branch: the tails of the side streams are recorded too
+  for (int st = 1; st < n_streams; ++st)
+    if (tail[st] >= 0) sched[tail[st]].record = true;
+}
+
+static int enqueue_infer(ypb_engine* e, cudaStream_t st, const uint8_t* frames, const float* xform,
+                         const ypb_infer_params* prm, float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count,
+                         bool capturing = false) {
+  const int n = (int)e->ops.size();
+  const bool par = capturing && e->branch_parallel && e->n_streams > 1 && (int)e->sched.size() == n;
+  if (!par) {
+    for (const Op& op : e->ops) {
+      int rc = launch_op(e, op, st, frames);
+      if (rc) return rc;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, nullptr);
+  }
+  // inside a stream capture: side streams join the capture through event waits and are joined back before decode
+  if ((int)e->op_events.size() < n) {
+    const size_t old = e->op_events.size();
+    e->op_events.resize(n);
+    for (size_t i = old; i < (size_t)n; ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->op_events[i], cudaEventDisableTiming));
+  }
+  for (int k = 1; k < e->n_streams; ++k)
+    if (!e->side_streams[k]) CUDA_TRY(cudaStreamCreateWithFlags(&e->side_streams[k], cudaStreamNonBlocking));
+  std::vector<int> last(e->n_streams, -1);
+  for (int j = 0; j < n; ++j) {
+    const ypb_engine::OpSched& sc = e->sched[j];
+    cudaStream_t sj = sc.stream == 0 ? st : e->side_streams[sc.stream];
+    for (int w : sc.waits) CUDA_TRY(cudaStreamWaitEvent(sj, e->op_events[w], 0));
+    int rc = launch_op(e, e->ops[j], sj, frames);
+    if (rc) return rc;
+    if (sc.record) CUDA_TRY(cudaEventRecord(e->op_events[j], sj));
+    last[sc.stream] = j;
+  }
+  for (int k = 1; k < e->n_streams; ++k)
+    if (last[k] >= 0) CUDA_TRY(cudaStreamWaitEvent(st, e->op_events[last[k]], 0));
   CUDA_TRY(cudaGetLastError());
   return launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, nullptr);
 }
@@ -1176,7 +1301,7 @@ int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const flo
     // capture the ~80 launches of a forward pass on a private stream; replays cost one launch
     if (!e->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_infer(e, e->cap_stream, frames, xform, prm, det, det_lb, keep, coef, count);
+    int rc = enqueue_infer(e, e->cap_stream, frames, xform, prm, det, det_lb, keep, coef, count, true);
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }

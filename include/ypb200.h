@@ -82,11 +82,14 @@ typedef struct {
 
 /* frames : device, (B,H,W,3) uint8 BGR, already letterboxed (resize + 114 pad) to the planned H x W
  * xform  : device, (B,5) fp32 [pad_w, pad_h, gain, W0, H0] per frame (ops.scale_boxes geometry)
- * det    : device, (B,max_det,6) fp32 [x1,y1,x2,y2,conf,cls] in original-frame pixels, descending conf
- * det_lb : device, (B,max_det,4) fp32 same boxes in letterboxed-input pixels
- * keep   : device, (B,max_det) int32 anchor index of each detection
- * coef   : device, (B,max_det,nm) fp32 mask coefficients (ignored when nm == 0; may be NULL)
- * count  : device, (B) int32 detections per frame */
+ * det    : device, (B,300,6) fp32 [x1,y1,x2,y2,conf,cls] in original-frame pixels, descending conf
+ * det_lb : device, (B,300,4) fp32 same boxes in letterboxed-input pixels
+ * keep   : device, (B,300) int32 anchor index of each detection
+ * coef   : device, (B,300,nm) fp32 mask coefficients (ignored when nm == 0; may be NULL)
+ * count  : device, (B) int32 detections per frame (<= params->max_det)
+ * The output arrays ALWAYS have YPB_MAX_DET = 300 rows per image, whatever params->max_det asks for: image b starts at
+ * row b * 300 (ypb_masks reads them with the same stride); rows at or beyond count[b] are not written. */
+#define YPB_MAX_DET 300
 int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform,
               const ypb_infer_params* params, float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count);
 
@@ -173,6 +176,9 @@ int ypb_hosts_are_pinned(const void* const* ptrs, int n, int* all_pinned);  /* t
 int ypb_h2d_frames(void* cuda_stream, void* dst_dev, const void* const* src, size_t bytes_each, int n);
 /* Host helper of the predict() pipeline: copy n frames into pinned staging memory with nthreads host threads. */
 int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads);
+/* Same with the copy flavour chosen by the caller: mode 0 = memcpy, 1 = non-temporal stores (the default of
+   ypb_stage_frames unless YPB_STAGE_MEMCPY is set).  Persistent thread pool, 256 KB pieces. */
+int ypb_stage_frames_ex(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads, int mode);
 #ifdef __cplusplus
 }
 #endif

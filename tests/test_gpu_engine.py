@@ -412,3 +412,27 @@ def test_north_star_bar_vs_fp32_oracle_on_damped_recipe(name, nframes):
         mx, p999, mean, share = ulp_report(yolo.engine.view(vname)[:2].cpu(), feats[int(vname.split(".")[1])].permute(0, 2, 3, 1))
         report(test="ulp_vs_emulating_oracle", model=name, recipe="damped", layer=vname, max_ulp=mx, p999_ulp=p999,
                mean_ulp=mean, share_gt_1ulp=share)
+
+
+def test_small_max_det_on_a_fresh_engine_addresses_later_images_correctly():
+    """The output arrays keep 300 rows per image whatever max_det asks for (include/ypb200.h).  Regression: the NMS
+    kernel once strode its outputs by max_det while the mask decode and the host wrappers strode by 300, which only
+    showed on a FRESH engine (the shared fixture's buffers still held the right rows from earlier max_det=300 calls)."""
+    from oracle import ops as oops
+    from yolo_puncture_b200 import YOLO, synth
+    net, sd = oracle_with_synth("yolov8n-seg", emulate=True)
+    yolo = YOLO("yolov8n-seg", state_dict=sd, device=0)
+    frames = [synth.synth_frame(i) for i in (0, 2, 0, 2, 2)]  # frames with detections in every slot (B >= 4: two batch halves)
+    res = yolo.predict(frames, conf=0.25, iou=0.7, max_det=5, retina_masks=True)
+    eng = yolo.engine
+    dets, kept, proto = oracle_select_on_engine_tensors(eng, net, len(frames), [(80, 80), (40, 40), (20, 20)], 0.25, 0.7, 5)
+    for b in range(len(frames)):
+        n = len(res[b])
+        assert n == len(dets[b]) == 5
+        assert eng.keep[b, :n].cpu().long().tolist() == kept[b].tolist()
+        d = dets[b].clone()
+        d[:, :4] = oops.scale_boxes((640, 640), d[:, :4], (640, 640))
+        got = res[b].boxes.data.cpu()
+        assert torch.equal(got[:, 5], d[:, 5]) and (got[:, :4] - d[:, :4]).abs().max() <= 1e-2
+        mo = oops.process_mask_native(proto[b], d[:, 6:], d[:, :4], (640, 640))
+        assert mask_iou(mo, res[b].masks.data.cpu()).min() >= 0.99

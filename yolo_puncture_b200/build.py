@@ -16,7 +16,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libypb200.so")
 SOURCES = ["ypb200.cu", "common.cuh", "conv_tc.cuh", "conv_plan.cuh", "head_kernels.cuh", "mask_kernels.cuh",
-           "misc_kernels.cuh", "v10_kernels.cuh"]  # + tma_bench.cuh in the diagnostics build
+           "misc_kernels.cuh", "v10_kernels.cuh", "host_stage.cpp"]  # + tma_bench.cuh in the diagnostics build
+UNITS = [os.path.join(CSRC, "ypb200.cu"), os.path.join(CSRC, "host_stage.cpp")]  # device TU + host-only staging pool
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
@@ -38,6 +39,7 @@ def needs_build():
 
 LIB_PROF = os.path.join(HERE, "libypb200_prof.so")
 LIB_DIAG = os.path.join(HERE, "libypb200_diag.so")
+LIB_EXACT = os.path.join(HERE, "libypb200_exact.so")
 
 
 def _stale(path):
@@ -48,7 +50,7 @@ def _stale(path):
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False, prof=False, diag=False):
+def build(force=False, verbose=False, prof=False, diag=False, exact=False):
     """Product library: libypb200.so (the product kernels and the C ABI of include/ypb200.h, nothing else).
     diag=True builds libypb200_diag.so: the same translation unit with -DYPB_DIAG=1, i.e. plus the debugging twins of
     the conv kernel and the micro-benchmarks of include/ypb200_diag.h (tests/test_gpu_conv.py twins, tools/).
@@ -57,19 +59,20 @@ def build(force=False, verbose=False, prof=False, diag=False):
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libypb200.so")
-    if prof or diag:
-        out = LIB_PROF if prof else LIB_DIAG
+    if prof or diag or exact:
+        out = LIB_EXACT if exact else LIB_PROF if prof else LIB_DIAG
         if not force and not _stale(out):
             return out
-        flags = ["-DYPB_DIAG=1"] + (["-DYPB_PROF=1"] if prof else [])
-        res = subprocess.run([nvcc, *NVCC_FLAGS, *flags, "-o", out, os.path.join(CSRC, "ypb200.cu")],
+        # exact: the product build with full-precision SiLU (A/B of the tanh.approx epilogue against the oracle)
+        flags = ["-DYPB_EXACT_SILU=1"] if exact else ["-DYPB_DIAG=1"] + (["-DYPB_PROF=1"] if prof else [])
+        res = subprocess.run([nvcc, *NVCC_FLAGS, *flags, "-o", out, *UNITS],
                              capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
         return out
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "ypb200.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *UNITS]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -85,4 +88,5 @@ def ensure_built():
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv, diag="--diag" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, prof="--prof" in sys.argv, diag="--diag" in sys.argv,
+                exact="--exact" in sys.argv))

@@ -300,7 +300,13 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
 // of ex2 + rcp.  The conv epilogues are bound by the SFU pipe on B200 (16 results/clk/SM): ~2.7 G SiLUs per
 // yolov8s-seg batch of 64.  Absolute error <= |x| * 2.5e-4, below half a bf16 ulp of the result except on the
 // x << 0 tail where |SiLU| < 0.05 (error <= 2e-3 there); outputs are rounded to bf16 right after.
+#ifndef YPB_EXACT_SILU
+#define YPB_EXACT_SILU 0  // 1: full-precision SiLU everywhere (A/B build to quantify what tanh.approx costs in parity)
+#endif
 __device__ __forceinline__ float silu_f(float x) {
+#if YPB_EXACT_SILU
+  return x / (1.0f + expf(-x));
+#endif
   const float h = 0.5f * x;
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));

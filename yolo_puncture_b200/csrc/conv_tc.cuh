@@ -445,9 +445,14 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
     if (!F32) {
 #pragma unroll
       for (int i = 0; i < NC; ++i) {  // y holds h = x/2: SiLU(x) = h + h*tanh(h)
+#if YPB_EXACT_SILU  // A/B build (libypb200_exact.so): full-precision x * sigmoid(x), see tools/silu_ab.md
+        const float x2 = 2.0f * y[i];
+        y[i] = x2 / (1.0f + expf(-x2));
+#else
         float t;
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y[i]));
         y[i] = fmaf(y[i], t, y[i]);
+#endif
       }
     } else {
 #pragma unroll

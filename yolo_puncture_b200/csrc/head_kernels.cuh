@@ -300,15 +300,18 @@ constexpr int kNmsSmemKeys = 4096;
 constexpr int kNmsMaxDet = 300;
 
 // One CTA per image.  Outputs (row i < count[b], descending score):
-//   det     (B, max_det, 6)  [x1,y1,x2,y2,conf,cls] boxes mapped back to the original frame
-//   det_lb  (B, max_det, 4)  the same boxes in letterboxed-input pixels (what non-retina masks crop with)
-//   keep    (B, max_det)     anchor index of each kept row
-//   coef    (B, max_det, nm) mask coefficients gathered from the head rows
+//   det     (B, out_stride, 6)  [x1,y1,x2,y2,conf,cls] boxes mapped back to the original frame
+//   det_lb  (B, out_stride, 4)  the same boxes in letterboxed-input pixels (what non-retina masks crop with)
+//   keep    (B, out_stride)     anchor index of each kept row
+//   coef    (B, out_stride, nm) mask coefficients gathered from the head rows
+// out_stride = rows per image of the output arrays: always kNmsMaxDet (300) for the engine, whatever max_det (<= 300)
+// the call asks for, so that the mask decode and the host wrappers address image b at b * 300 rows.
 constexpr int kNmsThreads = 1024;
 __global__ void __launch_bounds__(kNmsThreads)
 nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict__ dbox, const int* __restrict__ dcls,
            unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_count, float iou_thr, int max_det,
-           int max_nms, float max_wh, int e2e, const unsigned* __restrict__ cls_mask, const FrameXform* __restrict__ xf,
+           int max_nms, float max_wh, int e2e, const unsigned* __restrict__ cls_mask, int out_stride,
+           const FrameXform* __restrict__ xf,
            float* __restrict__ det, float* __restrict__ det_lb, int* __restrict__ keep, float* __restrict__ coef,
            int* __restrict__ count) {
   __shared__ unsigned long long s_keys[kNmsSmemKeys];
@@ -421,7 +424,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
       const unsigned pair = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
       s_score[pos] = __uint_as_float((unsigned)(key >> 32));
       s_cls[pos] = cls;
-      keep[(long long)b * max_det + pos] = (int)(pair / (unsigned)g.nc);
+      keep[(long long)b * out_stride + pos] = (int)(pair / (unsigned)g.nc);
     }
     if (threadIdx.x == 0) { s_nkept = total; count[b] = total; }
   } else {
@@ -509,7 +512,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
             s_kept[idx][0] = x1; s_kept[idx][1] = y1; s_kept[idx][2] = x2; s_kept[idx][3] = y2; s_kept[idx][4] = area;
             s_score[idx] = score;
             s_cls[idx] = cls;
-            keep[(long long)b * max_det + idx] = anchor;
+            keep[(long long)b * out_stride + idx] = anchor;
             s_next[idx] = (short)atomicExch(&s_head[bkt], idx);  // newest first
           }
           if (lane == 0) { s_range[ws][0] = nkept; s_range[ws][1] = nkept + min(__popc(K), room); }
@@ -563,7 +566,7 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
               s_kept[nk][0] = x1; s_kept[nk][1] = y1; s_kept[nk][2] = x2; s_kept[nk][3] = y2; s_kept[nk][4] = area;
               s_score[nk] = score;
               s_cls[nk] = cls;
-              keep[(long long)b * max_det + nk] = anchor;
+              keep[(long long)b * out_stride + nk] = anchor;
             }
             ++nk;
             if (alive && lane > l && iou_gt(kx1, ky1, kx2, ky2, ka, x1, y1, x2, y2, area, iou_thr)) alive = false;
@@ -599,15 +602,15 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
   const int nk = s_nkept;
   const FrameXform t = xf[b];
   for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-    const int anchor = keep[(long long)b * max_det + i];
+    const int anchor = keep[(long long)b * out_stride + i];
     const long long ga = (long long)b * g.A + anchor;
     const float4 bx = dbox[ga];
     const int cls = s_cls[i];
     const float score = s_score[i];
     if (det == nullptr) continue;  // selection-only call (ypb_nms)
-    float* lb = det_lb + ((long long)b * max_det + i) * 4;
+    float* lb = det_lb + ((long long)b * out_stride + i) * 4;
     lb[0] = bx.x; lb[1] = bx.y; lb[2] = bx.z; lb[3] = bx.w;
-    float* o = det + ((long long)b * max_det + i) * 6;
+    float* o = det + ((long long)b * out_stride + i) * 6;
     o[0] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.x, t.pad_w), t.gain), 0.0f), t.W0);
     o[1] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.y, t.pad_h), t.gain), 0.0f), t.H0);
     o[2] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.z, t.pad_w), t.gain), 0.0f), t.W0);
@@ -618,8 +621,8 @@ nms_kernel(const float* __restrict__ head, HeadGeom g, const float4* __restrict_
   if (g.nm > 0 && coef != nullptr) {
     for (int i = threadIdx.x; i < nk * g.nm; i += blockDim.x) {
       const int r = i / g.nm, c = i - r * g.nm;
-      const int anchor = keep[(long long)b * max_det + r];
-      coef[((long long)b * max_det + r) * g.nm + c] = head[((long long)b * g.A + anchor) * g.no + 64 + g.nc + c];
+      const int anchor = keep[(long long)b * out_stride + r];
+      coef[((long long)b * out_stride + r) * g.nm + c] = head[((long long)b * g.A + anchor) * g.no + 64 + g.nc + c];
     }
   }
 }

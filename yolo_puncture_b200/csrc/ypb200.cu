@@ -81,7 +81,9 @@ struct Op {
   View in, out, res;
   int head_lvl = -1, head_coff = 0;
   size_t w_off = 0, b_off = 0;  // byte offsets in the weight arena
-  ConvLaunch L;
+  ConvLaunch L;    // launch of batch half 0 (the whole batch when the plan is not split)
+  ConvLaunch L1;   // launch of batch half 1
+  double flops = 0;  // algorithmic FLOPs of the op over the whole batch
   // OP_ATTN: in = qkv buffer view, res = pe view, out = output view
   int heads = 0;
 };
@@ -112,6 +114,10 @@ struct ypb_engine {
   size_t ws_bytes = 0;
   size_t off_head = 0, off_dbox = 0, off_dcls = 0, off_keys = 0, off_count = 0, off_moff = 0;
   bool planned = false, bound = false;
+  // Batch halves: with B >= 4 the plan holds TWO launch sets over images [0, sB[0]) and [sB[0], B).  In the captured
+  // graph they are independent chains, so the ~10 us a layer spends in launch latency, prologue, first operand fetch,
+  // epilogue drain and wave quantisation is covered by the other half's tensor work instead of idling the GPU.
+  int n_split = 1, sB[2] = {0, 0}, sb0[2] = {0, 0};
   uint8_t* ws = nullptr;
   int conv_impl = 0;
   int launches = 0;
@@ -135,7 +141,7 @@ struct ypb_engine {
   std::vector<OpSched> sched;
   int n_streams = 1;
   bool branch_parallel = true;
-  cudaStream_t side_streams[8] = {};
+  cudaStream_t side_streams[16] = {};
   std::vector<cudaEvent_t> op_events;
   void build_schedule(int max_streams);
   void drop_graph() {
@@ -729,9 +735,13 @@ static int folded(const ypb_engine& e, const ConvSrc& s, std::vector<float>* w, 
 
 
 // Enqueue one layer op on `st`.
-static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t* frames) {
+static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t* frames, int split = 0) {
   const uint8_t* wa = reinterpret_cast<const uint8_t*>(e->w_arena);
-  const int B = e->B;
+  const int B = e->sB[split], b0 = e->sb0[split];  // this launch covers images [b0, b0 + B)
+  if (B <= 0) return YPB_OK;
+  // first byte of image b0 in an activation buffer (every kernel below indexes images from its base pointer)
+  auto base = [&](const BufDesc& b) { return e->ws + b.offset + (size_t)b0 * b.H * b.W * b.C * (b.dtype ? 4 : 2); };
+  frames += (size_t)b0 * e->H * e->W * 3;
   switch (op.kind) {
     case OP_STEM: {
       const BufDesc& ob = e->bufs[op.out.buf];
@@ -739,7 +749,7 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       memset(&sp, 0, sizeof sp);
       sp.Cout = op.cout; sp.n_tile = op.cout; sp.act = 1; sp.out_mode = OUT_BF16;
       sp.img_HW = ob.H * ob.W; sp.img_W = ob.W;
-      sp.out = e->ws + ob.offset; sp.out_img_stride = (long long)ob.H * ob.W * ob.C; sp.out_pix_stride = ob.C;
+      sp.out = base(ob); sp.out_img_stride = (long long)ob.H * ob.W * ob.C; sp.out_pix_stride = ob.C;
       sp.out_c_off = op.out.c_off; sp.bias = reinterpret_cast<const float*>(wa + op.b_off);
       const int tiles_w = (ob.W + kStemTW - 1) / kStemTW, tiles_h = (ob.H + kStemTH - 1) / kStemTH;
       sp.tiles_w = tiles_w; sp.tiles_h = tiles_h;
@@ -756,15 +766,15 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       break;
     }
     case OP_CONV:
-      CUDA_TRY(conv_launch(op.L, st, e->conv_impl));
+      CUDA_TRY(conv_launch(split ? op.L1 : op.L, st, e->conv_impl));
       break;
     case OP_UPSAMPLE: {
       const BufDesc &ib = e->bufs[op.in.buf], &ob = e->bufs[op.out.buf];
       const int row_vecs = ib.W * (op.in.C / 8);
       if ((long long)B * ib.H > 65535) return fail(YPB_ERR_ARG, "upsample: batch x rows exceeds the grid limit");
       upsample2x_kernel<<<dim3((unsigned)((row_vecs + 255) / 256), (unsigned)(B * ib.H)), 256, 0, st>>>(
-          reinterpret_cast<const __nv_bfloat16*>(e->ws + ib.offset), ib.C, op.in.c_off,
-          reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C, op.out.c_off, B, ib.H, ib.W, op.in.C);
+          reinterpret_cast<const __nv_bfloat16*>(base(ib)), ib.C, op.in.c_off,
+          reinterpret_cast<__nv_bfloat16*>(base(ob)), ob.C, op.out.c_off, B, ib.H, ib.W, op.in.C);
       break;
     }
     case OP_SPPF: {
@@ -779,22 +789,22 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
           ds.sppf_smem = 200 * 1024;
         }
       }
-      sppf_pool_kernel<<<dim3(op.in.C / 8, B), 256, smem, st>>>(reinterpret_cast<__nv_bfloat16*>(e->ws + ib.offset), B, ib.H,
+      sppf_pool_kernel<<<dim3(op.in.C / 8, B), 256, smem, st>>>(reinterpret_cast<__nv_bfloat16*>(base(ib)), B, ib.H,
                                                                 ib.W, op.in.C);
       break;
     }
     case OP_DW: {
       const BufDesc &ib = e->bufs[op.in.buf], &ob = e->bufs[op.out.buf];
       DwParams p{};
-      p.in = reinterpret_cast<const __nv_bfloat16*>(e->ws + ib.offset);
+      p.in = reinterpret_cast<const __nv_bfloat16*>(base(ib));
       p.H = ib.H; p.W = ib.W; p.in_ctot = ib.C; p.in_c_off = op.in.c_off;
       p.wk = reinterpret_cast<const __nv_bfloat16*>(wa + op.w_off);
       p.bias = reinterpret_cast<const float*>(wa + op.b_off);
       p.C = op.cout; p.k = op.k; p.stride = op.s; p.act = op.act;
-      p.out = reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset);
+      p.out = reinterpret_cast<__nv_bfloat16*>(base(ob));
       p.oH = ob.H; p.oW = ob.W; p.out_ctot = ob.C; p.out_c_off = op.out.c_off;
       if (op.res.buf >= 0) {
-        p.res = reinterpret_cast<const __nv_bfloat16*>(e->ws + e->bufs[op.res.buf].offset);
+        p.res = reinterpret_cast<const __nv_bfloat16*>(base(e->bufs[op.res.buf]));
         p.res_ctot = e->bufs[op.res.buf].C; p.res_c_off = op.res.c_off;
       }
       p.nB = B;
@@ -820,9 +830,9 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
       const int N = qb.H * qb.W;
       dim3 grid((N + kAttnThreads - 1) / kAttnThreads, op.heads, B);
       psa_attention_kernel<<<grid, kAttnThreads, 0, st>>>(
-          reinterpret_cast<const __nv_bfloat16*>(e->ws + qb.offset), qb.C, op.in.c_off,
-          reinterpret_cast<const __nv_bfloat16*>(e->ws + pb.offset), pb.C, op.res.c_off,
-          reinterpret_cast<__nv_bfloat16*>(e->ws + ob.offset), ob.C, op.out.c_off, N, 1.0f / std::sqrt((float)kAttnKD));
+          reinterpret_cast<const __nv_bfloat16*>(base(qb)), qb.C, op.in.c_off,
+          reinterpret_cast<const __nv_bfloat16*>(base(pb)), pb.C, op.res.c_off,
+          reinterpret_cast<__nv_bfloat16*>(base(ob)), ob.C, op.out.c_off, N, 1.0f / std::sqrt((float)kAttnKD));
       break;
     }
   }
@@ -831,15 +841,23 @@ static int launch_op(ypb_engine* e, const Op& op, cudaStream_t st, const uint8_t
 
 // Selection stage: candidate filter + decode, then batched NMS.
 static int launch_select(ypb_engine* e, cudaStream_t st, const float* xform, const ypb_infer_params* prm, float* det,
-                         float* det_lb, int32_t* keep, float* coef, int32_t* count, cudaEvent_t mid) {
-  const int B = e->B;
+                         float* det_lb, int32_t* keep, float* coef, int32_t* count, cudaEvent_t mid, int b0 = 0, int nb = -1) {
+  // images [b0, b0 + nb) of the batch (default: all of it); every per-image array is advanced to image b0
+  const int B = nb < 0 ? e->B : nb;
+  if (B <= 0) return YPB_OK;
   const HeadGeom& g = e->hg;
-  int* cand_count = reinterpret_cast<int*>(e->ws + e->off_count);
+  int* cand_count = reinterpret_cast<int*>(e->ws + e->off_count) + b0;
   CUDA_TRY(cudaMemsetAsync(cand_count, 0, (size_t)B * 4, st));
-  const float* head = reinterpret_cast<const float*>(e->ws + e->off_head);
-  float4* dbox = reinterpret_cast<float4*>(e->ws + e->off_dbox);
-  int* dcls = reinterpret_cast<int*>(e->ws + e->off_dcls);
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(e->ws + e->off_keys);
+  const float* head = reinterpret_cast<const float*>(e->ws + e->off_head) + (size_t)b0 * g.A * g.no;
+  float4* dbox = reinterpret_cast<float4*>(e->ws + e->off_dbox) + (size_t)b0 * g.A;
+  int* dcls = reinterpret_cast<int*>(e->ws + e->off_dcls) + (size_t)b0 * g.A;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(e->ws + e->off_keys) + (size_t)b0 * g.cand_stride;
+  xform += (size_t)b0 * 5;
+  det += (size_t)b0 * kNmsMaxDet * 6;
+  det_lb += (size_t)b0 * kNmsMaxDet * 4;
+  keep += (size_t)b0 * kNmsMaxDet;
+  if (coef) coef += (size_t)b0 * kNmsMaxDet * g.nm;
+  count += b0;
   const long long warps = (long long)B * g.A;
   bool pairs_done = false;
   if (g.nc % 4 == 0 && g.no % 4 == 0 && g.nc >= 16) {
@@ -859,7 +877,7 @@ static int launch_select(ypb_engine* e, cudaStream_t st, const float* xform, con
   if (mid) CUDA_TRY(cudaEventRecord(mid, st));
   nms_kernel<<<B, kNmsThreads, 0, st>>>(head, g, dbox, dcls, keys, cand_count, prm->iou, prm->max_det, 30000,
                                 prm->agnostic_nms ? 0.0f : 7680.0f, e->end2end ? 1 : 0, e->end2end ? prm->class_mask : nullptr,
-                                reinterpret_cast<const FrameXform*>(xform), det, det_lb, keep, coef, count);
+                                kNmsMaxDet, reinterpret_cast<const FrameXform*>(xform), det, det_lb, keep, coef, count);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;
 }
@@ -1077,15 +1095,24 @@ int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
   e->off_count = off; off = align(off + (size_t)B * 4);
   e->off_moff = off; off = align(off + (size_t)(B + 1) * 4);
   e->ws_bytes = off;
+  // batch halves (see ypb_engine::n_split)
+  {
+    int want = 2;
+    if (const char* ev = getenv("YPB_BATCH_SPLIT")) want = atoi(ev);
+    e->n_split = (want >= 2 && B >= 4) ? 2 : 1;
+    e->sB[0] = e->n_split == 2 ? (B + 1) / 2 : B;
+    e->sB[1] = B - e->sB[0];
+    e->sb0[0] = 0; e->sb0[1] = e->sB[0];
+  }
   // per-op geometry
   e->launches = 0; e->flops = 0;
   for (Op& op : e->ops) {
-    ++e->launches;
+    e->launches += e->n_split;
     if (op.kind == OP_STEM) { e->flops += 2.0 * B * (H / 2) * (W / 2) * op.cout * 27; continue; }
     if (op.kind == OP_DW) {
       const BufDesc& ob = e->bufs[op.out.buf];
       e->flops += 2.0 * B * ob.H * ob.W * op.cout * op.k * op.k;
-      if (op.heads > 1) e->launches += op.heads - 1;
+      if (op.heads > 1) e->launches += e->n_split * (op.heads - 1);
       continue;
     }
     if (op.kind != OP_CONV) continue;
@@ -1105,14 +1132,20 @@ int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
       d.res_img_stride = (long long)rb.H * rb.W * rb.C; d.res_pix_stride = rb.C; d.res_c_off = op.res.c_off;
     }
     std::string err;
+    d.B = e->sB[0];
     if (!conv_plan_geometry(d, &op.L, &err)) return fail(YPB_ERR_ARG, op.name + ": " + err);
+    if (e->n_split == 2) {
+      d.B = e->sB[1];
+      if (!conv_plan_geometry(d, &op.L1, &err)) return fail(YPB_ERR_ARG, op.name + ": " + err);
+    }
     {  // algorithmic FLOPs: the module's real channels, not the zero-padded ones the tensor core multiplies
       int cout_real = 0;
       for (const ConvSrc& sc : op.srcs) cout_real += sc.kind == SRC_CONVT ? 4 * sc.cout : sc.cout;
       const int cin_r = op.cin_real > 0 ? op.cin_real : op.cin;
-      op.L.flops = 2.0 * B * op.L.oH * op.L.oW * (double)cout_real * cin_r * op.k * op.k;
+      op.flops = 2.0 * B * op.L.oH * op.L.oW * (double)cout_real * cin_r * op.k * op.k;
+      op.L.flops = op.flops;
     }
-    e->flops += op.L.flops;
+    e->flops += op.flops;
     if (getenv("YPB_PLAN_DEBUG")) {
       if (op.L.use_halo)
         fprintf(stderr, "[plan] %-28s k%d s%d %4d->%4d %4dx%-4d halo msub %d %s a_slots %d b_slots %d tiles %d smem %d\n",
@@ -1124,7 +1157,7 @@ int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
                 op.L.stages2, op.L.total_tiles, op.L.smem2);
     }
   }
-  e->launches += e->end2end ? 3 : 2;  // decode_filter (+ pair_candidates) + nms
+  e->launches += e->n_split * 2;  // decode_filter + nms per batch half
   e->planned = true;
   e->bound = false;
   if (workspace_bytes) *workspace_bytes = off;
@@ -1143,15 +1176,19 @@ int ypb_bind_workspace(ypb_engine* e, void* workspace, size_t bytes) {
   for (Op& op : e->ops) {
     if (op.kind != OP_CONV) continue;
     const BufDesc& ib = e->bufs[op.in.buf];
-    ConvDesc d;
-    d.in = e->ws + ib.offset;
-    d.B = e->B; d.Hin = ib.H; d.Win = ib.W; d.in_ctot = ib.C; d.in_c_off = op.in.c_off; d.cin = op.cin;
-    d.wg = wa + op.w_off; d.bias = reinterpret_cast<const float*>(wa + op.b_off);
-    d.cout = op.cout; d.k = op.k; d.stride = op.s; d.act = op.act; d.out_mode = op.out_mode;
-    d.out = op.head_lvl >= 0 ? (void*)(e->ws + e->off_head) : (void*)(e->ws + e->bufs[op.out.buf].offset);
-    if (op.res.buf >= 0) d.res = e->ws + e->bufs[op.res.buf].offset;
-    std::string err;
-    if (!conv_bind(d, &op.L, &err)) return fail(YPB_ERR_CUDA, op.name + ": " + err);
+    for (int sp = 0; sp < e->n_split; ++sp) {
+      const size_t b0 = (size_t)e->sb0[sp];
+      auto img0 = [&](const BufDesc& b) { return e->ws + b.offset + b0 * b.H * b.W * b.C * (b.dtype ? 4 : 2); };
+      ConvDesc d;
+      d.in = img0(ib);
+      d.B = e->sB[sp]; d.Hin = ib.H; d.Win = ib.W; d.in_ctot = ib.C; d.in_c_off = op.in.c_off; d.cin = op.cin;
+      d.wg = wa + op.w_off; d.bias = reinterpret_cast<const float*>(wa + op.b_off);
+      d.cout = op.cout; d.k = op.k; d.stride = op.s; d.act = op.act; d.out_mode = op.out_mode;
+      d.out = op.head_lvl >= 0 ? (void*)(e->ws + e->off_head + b0 * g.A * g.no * 4) : (void*)img0(e->bufs[op.out.buf]);
+      if (op.res.buf >= 0) d.res = img0(e->bufs[op.res.buf]);
+      std::string err;
+      if (!conv_bind(d, sp ? &op.L1 : &op.L, &err)) return fail(YPB_ERR_CUDA, op.name + ": " + err);
+    }
   }
   (void)g;
   e->drop_graph();
@@ -1249,37 +1286,60 @@ static int enqueue_infer(ypb_engine* e, cudaStream_t st, const uint8_t* frames, 
                          const ypb_infer_params* prm, float* det, float* det_lb, int32_t* keep, float* coef, int32_t* count,
                          bool capturing = false) {
   const int n = (int)e->ops.size();
-  const bool par = capturing && e->branch_parallel && e->n_streams > 1 && (int)e->sched.size() == n;
-  if (!par) {
-    for (const Op& op : e->ops) {
-      int rc = launch_op(e, op, st, frames);
-      if (rc) return rc;
-    }
+  const bool par = capturing && e->branch_parallel && (int)e->sched.size() == n && (e->n_streams > 1 || e->n_split > 1);
+  if (!par) {  // plain stream order: half 0 then half 1 of every op, then selection over the whole batch
+    for (const Op& op : e->ops)
+      for (int sp = 0; sp < e->n_split; ++sp) {
+        int rc = launch_op(e, op, st, frames, sp);
+        if (rc) return rc;
+      }
     CUDA_TRY(cudaGetLastError());
     return launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, nullptr);
   }
-  // inside a stream capture: side streams join the capture through event waits and are joined back before decode
-  if ((int)e->op_events.size() < n) {
+  // Inside a stream capture: every batch half is its own set of streams (stream 0 of half 0 is the capture's origin);
+  // side streams join the capture through event waits and are joined back before the capture ends.  Each half runs
+  // its own decode + NMS at the end of its chain, overlapping the other half's tensor work.
+  const int ns = e->n_streams, total_streams = ns * e->n_split;
+  if ((int)e->op_events.size() < n * e->n_split + 2) {
     const size_t old = e->op_events.size();
-    e->op_events.resize(n);
-    for (size_t i = old; i < (size_t)n; ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->op_events[i], cudaEventDisableTiming));
+    e->op_events.resize(n * e->n_split + 2);
+    for (size_t i = old; i < e->op_events.size(); ++i) CUDA_TRY(cudaEventCreateWithFlags(&e->op_events[i], cudaEventDisableTiming));
   }
-  for (int k = 1; k < e->n_streams; ++k)
+  for (int k = 1; k < total_streams; ++k)
     if (!e->side_streams[k]) CUDA_TRY(cudaStreamCreateWithFlags(&e->side_streams[k], cudaStreamNonBlocking));
-  std::vector<int> last(e->n_streams, -1);
+  auto stream_of = [&](int sp, int k) { return (sp == 0 && k == 0) ? st : e->side_streams[sp * ns + k]; };
+  cudaEvent_t fork = e->op_events[n * e->n_split];
+  if (e->n_split > 1) {
+    CUDA_TRY(cudaEventRecord(fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(stream_of(1, 0), fork, 0));
+  }
+  // interleave the halves op by op so that the graph's node order (a scheduling hint) alternates between them
+  std::vector<int> last(total_streams, -1);
   for (int j = 0; j < n; ++j) {
     const ypb_engine::OpSched& sc = e->sched[j];
-    cudaStream_t sj = sc.stream == 0 ? st : e->side_streams[sc.stream];
-    for (int w : sc.waits) CUDA_TRY(cudaStreamWaitEvent(sj, e->op_events[w], 0));
-    int rc = launch_op(e, e->ops[j], sj, frames);
-    if (rc) return rc;
-    if (sc.record) CUDA_TRY(cudaEventRecord(e->op_events[j], sj));
-    last[sc.stream] = j;
+    for (int sp = 0; sp < e->n_split; ++sp) {
+      cudaStream_t sj = stream_of(sp, sc.stream);
+      for (int w : sc.waits) CUDA_TRY(cudaStreamWaitEvent(sj, e->op_events[sp * n + w], 0));
+      int rc = launch_op(e, e->ops[j], sj, frames, sp);
+      if (rc) return rc;
+      if (sc.record) CUDA_TRY(cudaEventRecord(e->op_events[sp * n + j], sj));
+      last[sp * ns + sc.stream] = j;
+    }
   }
-  for (int k = 1; k < e->n_streams; ++k)
-    if (last[k] >= 0) CUDA_TRY(cudaStreamWaitEvent(st, e->op_events[last[k]], 0));
   CUDA_TRY(cudaGetLastError());
-  return launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, nullptr);
+  for (int sp = 0; sp < e->n_split; ++sp) {
+    cudaStream_t s0 = stream_of(sp, 0);
+    for (int k = 1; k < ns; ++k)
+      if (last[sp * ns + k] >= 0) CUDA_TRY(cudaStreamWaitEvent(s0, e->op_events[sp * n + last[sp * ns + k]], 0));
+    int rc = launch_select(e, s0, xform, prm, det, det_lb, keep, coef, count, nullptr, e->sb0[sp], e->sB[sp]);
+    if (rc) return rc;
+  }
+  if (e->n_split > 1) {
+    cudaEvent_t join = e->op_events[n * e->n_split + 1];
+    CUDA_TRY(cudaEventRecord(join, stream_of(1, 0)));
+    CUDA_TRY(cudaStreamWaitEvent(st, join, 0));
+  }
+  return YPB_OK;
 }
 
 int ypb_infer(ypb_engine* e, void* cuda_stream, const uint8_t* frames, const float* xform, const ypb_infer_params* prm,
@@ -1341,7 +1401,7 @@ int ypb_op_info(const ypb_engine* e, int i, const char** name, int* kind, double
   } else if (op.kind == OP_CONV) {
     const BufDesc& ib = e->bufs[op.in.buf];
     const double M = (double)B * op.L.oH * op.L.oW;
-    *flops = op.L.flops;
+    *flops = op.flops;
     *bytes = (double)B * ib.H * ib.W * op.cin * 2 + M * op.cout * (op.out_mode == OUT_F32 ? 4 : 2) +
              (double)op.k * op.k * op.cin * op.cout * 2 + (op.res.buf >= 0 ? M * op.cout * 2 : 0.0);
   } else if (op.kind == OP_UPSAMPLE) {
@@ -1376,8 +1436,10 @@ int ypb_infer_profile(ypb_engine* e, void* cuda_stream, const uint8_t* frames, c
   for (auto& x : ev) CUDA_TRY(cudaEventCreate(&x));
   CUDA_TRY(cudaEventRecord(ev[0], st));
   for (int i = 0; i < n; ++i) {
-    rc = launch_op(e, e->ops[i], st, frames);
-    if (rc) return rc;
+    for (int sp = 0; sp < e->n_split; ++sp) {  // both batch halves of the op, back to back, inside its event bracket
+      rc = launch_op(e, e->ops[i], st, frames, sp);
+      if (rc) return rc;
+    }
     CUDA_TRY(cudaEventRecord(ev[i + 1], st));
   }
   rc = launch_select(e, st, xform, prm, det, det_lb, keep, coef, count, ev[n + 1]);
@@ -1677,21 +1739,19 @@ int ypb_latency_probe(long long* out_dev) {
 }
 #endif  // YPB_DIAG
 
-// Host-side helper: copy n frames into the pinned staging buffer with `nthreads` host threads (the Python caller
-// releases the GIL for the duration of the call).  Frame staging is the host stage of the predict() pipeline.
+// Host-side helper: copy n frames into the pinned staging buffer with `nthreads` host threads (persistent pool,
+// 256 KB pieces, optional non-temporal stores: csrc/host_stage.cpp).  The Python caller releases the GIL for the
+// duration of the call.  Frame staging is the host stage of the predict() pipeline.
+extern "C" int ypb_host_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads, int mode);
+
+int ypb_stage_frames_ex(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads, int mode) {
+  if (!dst || !src || !bytes || n < 0 || mode < 0 || mode > 1) return fail(YPB_ERR_ARG, "bad argument");
+  return ypb_host_stage_frames(dst, src, bytes, n, nthreads, mode);
+}
+
 int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads) {
-  if (!dst || !src || !bytes || n < 0) return fail(YPB_ERR_ARG, "bad argument");
-  if (nthreads < 1) nthreads = 1;
-  if (nthreads > n) nthreads = n;
-  if (n == 0) return YPB_OK;
-  auto work = [&](int t) {
-    for (int i = t; i < n; i += nthreads) memcpy(dst[i], src[i], bytes[i]);
-  };
-  std::vector<std::thread> th;
-  for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
-  work(0);
-  for (auto& x : th) x.join();
-  return YPB_OK;
+  static const int mode = getenv("YPB_STAGE_MEMCPY") ? 0 : 1;
+  return ypb_stage_frames_ex(dst, src, bytes, n, nthreads, mode);
 }
 
 // Needle length on the device: minimum-area rectangle of every mask (mask_kernels.cuh).
@@ -1817,7 +1877,7 @@ int ypb_nms(void* cuda_stream, const float* boxes, const float* scores, const in
   FrameXform* xf = reinterpret_cast<FrameXform*>(s + (size_t)B * cs * 8);
   nms_test_pack_kernel<<<(B * N + 255) / 256, 256, 0, st>>>(boxes, scores, n_valid, B, N, cs, keys, xf);
   nms_kernel<<<B, kNmsThreads, 0, st>>>(nullptr, g, reinterpret_cast<const float4*>(boxes), cls, keys, n_valid, iou, max_det, 30000,
-                                agnostic ? 0.0f : 7680.0f, 0, nullptr, xf, nullptr, nullptr, keep, nullptr, count);
+                                agnostic ? 0.0f : 7680.0f, 0, nullptr, max_det, xf, nullptr, nullptr, keep, nullptr, count);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;
 }

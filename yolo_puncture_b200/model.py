@@ -184,6 +184,8 @@ class YOLO:
         # An int forces uniform passes of that size.  H2D of pass k+1 always overlaps compute of pass k.
         self.micro_batch = None
         self.head_pass = 16
+        self.stage_chunk = 8      # frames per staging call / H2D copy when the caller's frames are pageable
+        self.stage_threads = None  # host threads of the staging pool (None: min(16, cores / WORLD_SIZE))
         self.device_letterbox = True  # resize + pad on the GPU when the frame is at least as large as the network input
         if device is not None:
             self._set_device(device)
@@ -270,10 +272,11 @@ class YOLO:
 
     def _schedule(self, B, pinned=True):
         """[(engine, lo, hi, capacity, slot)]: the engine passes of a group of B frames (slot = input / output set).
-        Frames in pageable memory are staged into pinned memory by host threads first (~0.1 ms per 640x640 frame, slower
-        than the engine consumes them): there uniform passes of 32 measured best."""
-        if self.micro_batch or not pinned:
-            mb = min(B, int(self.micro_batch or 32))
+        The same schedule serves frames in pageable and in page-locked memory: pageable frames are staged into the pinned
+        ring in chunks of `stage_chunk` frames by the native thread pool (csrc/host_stage.cpp), every chunk's H2D copy is
+        issued as soon as it is staged, so staging, PCIe transfer and the previous engine pass overlap."""
+        if self.micro_batch:
+            mb = min(B, int(self.micro_batch))
             return [(self.engine, lo, min(lo + mb, B), mb, k & 1) for k, lo in enumerate(range(0, B, mb))]
         if B <= 32 or B - self.head_pass < self.head_pass:
             return [(self.engine, 0, B, B, 0)]
@@ -340,7 +343,7 @@ class YOLO:
                 nbytes = shape[0] * shape[1] * 3  # == H * W * 3 when direct
                 src_ptrs = (ctypes.c_void_p * B)(*[f.ctypes.data for f in frames_c])
                 sizes = (ctypes.c_size_t * B)(*([nbytes] * B))
-                nthreads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+                nthreads = self.stage_threads or max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
                 # frames that already live in page-locked memory go to the device from where they are (no staging copy)
                 flag = ctypes.c_int(0)
                 check(lib().ypb_hosts_are_pinned(src_ptrs, B, ctypes.byref(flag)))
@@ -380,12 +383,6 @@ class YOLO:
             def enqueue_h2d(k):
                 _, lo, hi, _, slot = passes[k]
                 vp = ctypes.sizeof(ctypes.c_void_p)
-                if (direct or dev_lb) and not pinned:  # native multi-threaded copy into pinned memory (ctypes drops the GIL)
-                    check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, lo * vp), ctypes.byref(src_ptrs, lo * vp),
-                                                 ctypes.byref(sizes, lo * ctypes.sizeof(ctypes.c_size_t)), hi - lo, nthreads))
-                elif not (direct or dev_lb):
-                    for fu in futs[lo:hi]:
-                        fu.result()
                 with torch.cuda.stream(cs):
                     if buf["in_free"][slot] is not None:
                         cs.wait_event(buf["in_free"][slot])
@@ -393,8 +390,20 @@ class YOLO:
                     if pinned:  # frames already live in page-locked memory: copy from where they are
                         check(lib().ypb_h2d_frames(ctypes.c_void_p(cs.cuda_stream), ctypes.c_void_p(target.data_ptr()),
                                                    ctypes.byref(src_ptrs, lo * vp), nbytes, hi - lo))
+                    elif direct or dev_lb:
+                        # pageable frames: native multi-threaded copy into the pinned ring (ctypes drops the GIL), a chunk
+                        # at a time, each chunk's H2D issued right behind it: chunk i+1 is staged while chunk i crosses PCIe
+                        stage_host = lb["raw_host"] if dev_lb else buf["host"]
+                        step = max(1, int(self.stage_chunk))
+                        for c0 in range(lo, hi, step):
+                            c1 = min(c0 + step, hi)
+                            check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, c0 * vp), ctypes.byref(src_ptrs, c0 * vp),
+                                                         ctypes.byref(sizes, c0 * ctypes.sizeof(ctypes.c_size_t)), c1 - c0, nthreads))
+                            target[c0 - lo:c1 - lo].copy_(stage_host[c0:c1], non_blocking=True)
                     else:
-                        target[: hi - lo].copy_((lb["raw_host"] if dev_lb else buf["host"])[lo:hi], non_blocking=True)
+                        for fu in futs[lo:hi]:
+                            fu.result()
+                        target[: hi - lo].copy_(buf["host"][lo:hi], non_blocking=True)
                     if dev_lb:
                         check(lib().ypb_letterbox_u8(
                             ctypes.c_void_p(cs.cuda_stream), ctypes.c_void_p(target.data_ptr()), hi - lo, shape[0], shape[1],

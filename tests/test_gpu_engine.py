@@ -436,3 +436,28 @@ def test_small_max_det_on_a_fresh_engine_addresses_later_images_correctly():
         assert torch.equal(got[:, 5], d[:, 5]) and (got[:, :4] - d[:, :4]).abs().max() <= 1e-2
         mo = oops.process_mask_native(proto[b], d[:, 6:], d[:, :4], (640, 640))
         assert mask_iou(mo, res[b].masks.data.cpu()).min() >= 0.99
+
+
+def test_retina_masks_of_a_frame_smaller_than_the_proto_window(nseg):
+    """A 100x100 crop at imgsz 640 (proto 160x160 > frame): upstream's scale_masks down-samples; so does the engine."""
+    from yolo_puncture_b200 import synth
+    net, yolo, oops = nseg["net"], nseg["yolo"], nseg["oops"]
+    frames = [synth.synth_frame(i)[100:200, 300:400].copy() for i in (0, 2)]
+    res = yolo.predict(frames, conf=0.25, iou=0.7, retina_masks=True)
+    eng = yolo.engine
+    assert eng.shape == (2, 640, 640)
+    dets, kept, proto = oracle_select_on_engine_tensors(eng, net, 2, [(80, 80), (40, 40), (20, 20)], 0.25, 0.7)
+    n_tot = 0
+    for b in range(2):
+        n = len(res[b])
+        assert n == len(dets[b])
+        if n == 0:
+            continue
+        n_tot += n
+        d = dets[b].clone()
+        d[:, :4] = oops.scale_boxes((640, 640), d[:, :4], (100, 100))
+        assert (res[b].boxes.data.cpu()[:, :4] - d[:, :4]).abs().max() <= 1e-2
+        mo = oops.process_mask_native(proto[b], d[:, 6:], d[:, :4], (100, 100))
+        me = res[b].masks.data.cpu()
+        assert me.shape == (n, 100, 100) and int((mo != me).sum()) <= max(2, int(0.001 * mo.numel()))
+    assert n_tot > 0

@@ -212,6 +212,72 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   }
 }
 
+// Generic twin for outputs SMALLER than the proto window (a frame under ~imgsz/4 with retina_masks=True: upstream's
+// scale_masks simply down-samples): one thread per output pixel, four proto taps, the same dot-product order and ATen
+// blend order as mask_decode_kernel.  Tiny outputs only (< proto size), so no staging is worth it.
+__global__ void __launch_bounds__(256)
+mask_decode_small_kernel(const float* __restrict__ proto, const float* __restrict__ coef, const float* __restrict__ det,
+                         const float* __restrict__ det_lb, const int* __restrict__ offsets, int nB, int capacity, MaskGeom g,
+                         uint8_t* __restrict__ out) {
+  __shared__ float s_coef[32];
+  const int slot = blockIdx.y;
+  const int total = offsets[nB];
+  if (slot >= total || slot >= capacity) return;
+  int below = 0;
+  for (int i0 = 0; i0 < nB; i0 += 32) {
+    const int i = i0 + (threadIdx.x & 31);
+    below += __popc(__ballot_sync(0xffffffffu, i < nB && offsets[i] <= slot));
+  }
+  const int b = below - 1, di = slot - offsets[b];
+  if (threadIdx.x < g.nm) s_coef[threadIdx.x] = coef[((long long)b * g.max_det + di) * g.nm + threadIdx.x];
+  __syncthreads();
+  float bx1, by1, bx2, by2;
+  if (g.retina) {
+    const float* d = det + ((long long)b * g.max_det + di) * 6;
+    bx1 = d[0]; by1 = d[1]; bx2 = d[2]; by2 = d[3];
+  } else {
+    const float* d = det_lb + ((long long)b * g.max_det + di) * 4;
+    bx1 = __fmul_rn(d[0], g.ratio_w); by1 = __fmul_rn(d[1], g.ratio_h);
+    bx2 = __fmul_rn(d[2], g.ratio_w); by2 = __fmul_rn(d[3], g.ratio_h);
+  }
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.out_h * g.out_w) return;
+  const int oy = idx / g.out_w, ox = idx - oy * g.out_w;
+  auto src_of = [](int dst, float scale) {
+    float s = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+    return s < 0.f ? 0.f : s;
+  };
+  const float sy = src_of(oy, g.scale_h), sx = src_of(ox, g.scale_w);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + ((y0 < g.ch - 1) ? 1 : 0), x1 = x0 + ((x0 < g.cw - 1) ? 1 : 0);
+  const float ly = __fsub_rn(sy, (float)y0), hy = __fsub_rn(1.0f, ly), lx = __fsub_rn(sx, (float)x0), hx = __fsub_rn(1.0f, lx);
+  const float* pb = proto + (long long)b * g.mh * g.mw * g.nm;
+  auto logit = [&](int ry, int rx) {
+    const int py = g.top + ry, px = g.left + rx;
+    const float4* pp = reinterpret_cast<const float4*>(pb + ((long long)py * g.mw + px) * g.nm);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 v = __ldg(pp + k);
+      acc = fmaf(s_coef[4 * k + 0], v.x, acc);
+      acc = fmaf(s_coef[4 * k + 1], v.y, acc);
+      acc = fmaf(s_coef[4 * k + 2], v.z, acc);
+      acc = fmaf(s_coef[4 * k + 3], v.w, acc);
+    }
+    if (!g.retina) {
+      const float fx = (float)px, fy = (float)py;
+      if (!(fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2)) acc = 0.f;
+    }
+    return acc;
+  };
+  const float top = __fadd_rn(__fmul_rn(hx, logit(y0, x0)), __fmul_rn(lx, logit(y0, x1)));
+  const float bot = __fadd_rn(__fmul_rn(hx, logit(y1, x0)), __fmul_rn(lx, logit(y1, x1)));
+  const float val = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+  bool on = val > 0.0f;
+  if (g.retina) on = on && (float)ox >= bx1 && (float)ox < bx2 && (float)oy >= by1 && (float)oy < by2;
+  out[(long long)slot * g.out_h * g.out_w + idx] = on ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Index-mask hand-off.  Replaces the per-detection Python loop of reference
 // yolo_seg/yolo_with_deva.py:54-88 (`auto_segment`): for the detections of a frame in order, skip those whose mask

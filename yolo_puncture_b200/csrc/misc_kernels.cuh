@@ -84,8 +84,8 @@ sppf_pool_kernel(__nv_bfloat16* __restrict__ buf, int nB, int h, int w, int c) {
 
 // ------------------------------------------------------------------------------------------------
 // LetterBox on the device: raw uint8 BGR frames -> resized (cv2.INTER_LINEAR) and 114-padded
-// network input.  Replaces the host cv2.resize + copyMakeBorder of UPSTREAM data/augment.py::LetterBox for the
-// down-scaling case (video frames larger than the network size), bit for bit: OpenCV's 8-bit bilinear resize is
+// network input.  Replaces the host cv2.resize + copyMakeBorder of UPSTREAM data/augment.py::LetterBox, down- and
+// up-scaling, bit for bit: OpenCV's 8-bit bilinear resize is
 // fixed-point — 11-bit coefficients (tables built on the host exactly as cv2 builds them), horizontal pass in int32,
 // vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2.  One thread per output pixel (3 channels).
 // ------------------------------------------------------------------------------------------------
@@ -105,7 +105,10 @@ letterbox_u8_kernel(const uint8_t* __restrict__ src, int nB, int H0, int W0, uin
     o[0] = o[1] = o[2] = (uint8_t)pad;
     return;
   }
-  const int x0 = xofs[rx], x1 = min(x0 + 1, W0 - 1), y0 = yofs[ry], y1 = min(y0 + 1, H0 - 1);
+  // columns: cv2 clamps the index and zeroes the fraction in the table; rows: it keeps the fraction and clamps the two
+  // source rows when it fetches them (sy = -1 above the first row centre when up-scaling): restated exactly
+  const int x0 = xofs[rx], x1 = min(x0 + 1, W0 - 1);
+  const int sy = yofs[ry], y0 = min(max(sy, 0), H0 - 1), y1 = min(max(sy + 1, 0), H0 - 1);
   const int a0 = xa[2 * rx], a1 = xa[2 * rx + 1], b0 = ya[2 * ry], b1 = ya[2 * ry + 1];
   const uint8_t* f = src + (long long)b * H0 * W0 * 3;
   const uint8_t* r0 = f + (long long)y0 * W0 * 3;

@@ -1097,7 +1097,10 @@ int ypb_plan(ypb_engine* e, int B, int H, int W, size_t* workspace_bytes) {
   e->ws_bytes = off;
   // batch halves (see ypb_engine::n_split)
   {
-    int want = 2;
+    // Measured on B200 (profiles/r2_ab_split_branches.md): with one persistent CTA per SM the second half's kernels
+    // cannot co-run, only tail-overlap, and every half-sized launch loses more to wave quantisation than the overlap
+    // recovers (yolov8s-seg B=64: 14 725 vs 15 061 frames/s) - so the split is opt-in (YPB_BATCH_SPLIT=2).
+    int want = 1;
     if (const char* ev = getenv("YPB_BATCH_SPLIT")) want = atoi(ev);
     e->n_split = (want >= 2 && B >= 4) ? 2 : 1;
     e->sB[0] = e->n_split == 2 ? (B + 1) / 2 : B;
@@ -1499,10 +1502,19 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
     g.out_h = e->H; g.out_w = e->W;
     g.ratio_w = (float)((double)g.mw / e->W); g.ratio_h = (float)((double)g.mh / e->H);
   }
-  if (g.ch < 1 || g.cw < 1 || g.ch > g.out_h || g.cw > g.out_w) return fail(YPB_ERR_ARG, "masks: output smaller than the proto window is unsupported");
+  if (g.ch < 1 || g.cw < 1) return fail(YPB_ERR_ARG, "masks: empty proto window");
   g.scale_h = (float)g.ch / (float)g.out_h; g.scale_w = (float)g.cw / (float)g.out_w;
   int* offsets = offsets_scratch ? offsets_scratch : reinterpret_cast<int*>(e->ws + e->off_moff);
   mask_offsets_kernel<<<1, 32, 0, st>>>(count, e->B, capacity, offsets, status);
+  if (capacity > 65535) return fail(YPB_ERR_ARG, "masks: capacity > 65535");
+  if (g.ch > g.out_h || g.cw > g.out_w) {
+    // the output is smaller than the proto window (a tiny frame with retina masks): scale_masks down-samples
+    const int px = g.out_h * g.out_w;
+    mask_decode_small_kernel<<<dim3((px + 255) / 256, capacity), 256, 0, st>>>(
+        proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb, offsets, e->B, capacity, g, masks);
+    CUDA_TRY(cudaGetLastError());
+    return YPB_OK;
+  }
   const int bands = (g.out_h + kMaskTile - 1) / kMaskTile;
   dim3 grid(bands, capacity);
   if (capacity > 65535) return fail(YPB_ERR_ARG, "masks: capacity > 65535");

@@ -60,20 +60,24 @@ def letterbox_into(dst, img, new_unpad, top, left):
     dst[top:top + h, left:left + w] = img
 
 
-def cv2_linear_tables(src_n, dst_n):
+def cv2_linear_tables(src_n, dst_n, vertical=False):
     """Source index and 11-bit fixed-point coefficient pair of every output column (or row) of OpenCV's 8-bit
     INTER_LINEAR resize, built the way cv2 builds them (resize.cpp): scale = 1/(dst/src) in double,
-    f = float((d+0.5)*scale - 0.5), s = floor(f), f -= s, clamped at both borders, coefficients
-    saturate_cast<short>((1-f, f) * 2048).  Bit-exact against cv2.resize when down-scaling (tests/test_letterbox.py)."""
+    f = float((d+0.5)*scale - 0.5), s = floor(f), f -= s, coefficients saturate_cast<short>((1-f, f) * 2048).
+    Columns: at both borders cv2 clamps the index AND zeroes f.  Rows (vertical=True): cv2 keeps f and clamps the two
+    source ROWS instead when it fetches them (s may be -1 or src_n-1 here; the kernel clamps s and s+1) - the two
+    border conventions differ by one LSB when up-scaling, which is where rows above/below the first/last source row
+    centre exist.  Bit-exact against cv2.resize, down- and up-scaling (tests/test_letterbox.py)."""
     scale = 1.0 / (dst_n / src_n)
     d = np.arange(dst_n, dtype=np.float64)
     f = ((d + 0.5) * scale - 0.5).astype(np.float32)
     s = np.floor(f).astype(np.int32)
     f = (f - s.astype(np.float32)).astype(np.float32)
-    lo, hi = s < 0, s >= src_n - 1
-    f[lo | hi] = 0.0
-    s[lo] = 0
-    s[hi] = src_n - 1
+    if not vertical:
+        lo, hi = s < 0, s >= src_n - 1
+        f[lo | hi] = 0.0
+        s[lo] = 0
+        s[hi] = src_n - 1
     coef = np.stack([np.rint((np.float32(1.0) - f) * np.float32(2048.0)), np.rint(f * np.float32(2048.0))], 1).astype(np.int16)
     return s, coef
 
@@ -186,7 +190,7 @@ class YOLO:
         self.head_pass = 16
         self.stage_chunk = 8      # frames per staging call / H2D copy when the caller's frames are pageable
         self.stage_threads = None  # host threads of the staging pool (None: min(16, cores / WORLD_SIZE))
-        self.device_letterbox = True  # resize + pad on the GPU when the frame is at least as large as the network input
+        self.device_letterbox = True  # resize + pad on the GPU (False: cv2 on host threads, exactly upstream's LetterBox)
         if device is not None:
             self._set_device(device)
 
@@ -309,7 +313,7 @@ class YOLO:
             lb["raw_host"] = torch.empty((B, shape[0], shape[1], 3), dtype=torch.uint8).pin_memory()
         if lb is None or lb["key"] != key:
             xofs, xa = cv2_linear_tables(shape[1], new_unpad[0])
-            yofs, ya = cv2_linear_tables(shape[0], new_unpad[1])
+            yofs, ya = cv2_linear_tables(shape[0], new_unpad[1], vertical=True)
             dev = self._device
             lb = {"key": key,
                   "raw_host": torch.empty((B, shape[0], shape[1], 3), dtype=torch.uint8).pin_memory() if need_host else None,
@@ -333,9 +337,9 @@ class YOLO:
         mh, mw = (shape[0], shape[1]) if retina else (H, W)
         with torch.cuda.device(self._device):
             direct = (shape[0], shape[1]) == (H, W)  # frames already have the network size: staging is a plain copy
-            # LetterBox on the device when it is a down-scale (bit-exact with cv2 there): the raw frames are uploaded
-            # and resized + padded by one kernel instead of cv2.resize on host threads
-            dev_lb = (not direct) and self.device_letterbox and new_unpad[0] <= shape[1] and new_unpad[1] <= shape[0]
+            # LetterBox on the device (bit-exact with cv2's 8-bit INTER_LINEAR, down- and up-scaling): the raw frames are
+            # uploaded and resized + padded by one kernel instead of cv2.resize on host threads
+            dev_lb = (not direct) and self.device_letterbox
             futs = None
             pinned = False
             if direct or dev_lb:

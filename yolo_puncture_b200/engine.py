@@ -166,11 +166,11 @@ class Engine:
         start = self._ws_off + off.value
         return self.ws[start:start + nbytes.value]
 
-    def masks(self, out, retina, out_h=0, out_w=0, proto=None, outputs=None):
+    def masks(self, out, retina, out_h=0, out_w=0, proto=None, outputs=None, stream=None):
         """out: cuda uint8 (capacity, h, w).  Decodes masks of an infer() in detection order.  proto / outputs: a copy
         of that pass's proto buffer and its OutputSet when the workspace has already moved on to the next pass."""
         o = outputs or self._cur_out
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
         check(self._lib.ypb_masks_ex(self._h, C.c_void_p(st), int(bool(retina)), int(out_h), int(out_w), _ptr(o.det),
                                      _ptr(o.det_lb), _ptr(o.coef), _ptr(o.count), _ptr(out), int(out.shape[0]),
                                      _ptr(self.mask_status), _ptr(proto), _ptr(o.offsets)))

@@ -22,7 +22,7 @@ import torch
 
 from ._lib import check, lib
 from .engine import MAX_DET, Engine, YpbError
-from .results import Results
+from .results import Boxes, Masks, Results
 from .synth import synth_state_dict
 
 KNOWN_SPECS = tuple(f"yolov8{s}-seg" for s in "nsmlx") + ("yolov10n",) + tuple(f"yolo11{s}-seg" for s in "nsmlx")
@@ -420,38 +420,69 @@ class YOLO:
 
             # Software pipeline: pass k+1 is enqueued BEFORE the host blocks on pass k's detection counts, so the GPU
             # never idles between passes; pass k's outputs live in output set k&1 and its prototypes are copied aside
-            # (device-to-device) because the workspace is reused by pass k+1.
+            # (device-to-device) because the workspace is reused by pass k+1.  Counts AND boxes of a pass come back in
+            # one copy on a side stream that only waits for THAT pass, and the pass's mask decode runs on the side
+            # stream too: masks of pass k overlap the network of pass k+1 instead of queueing behind it.
             protos = buf.setdefault("proto_copy", [None, None])
+            side = buf.setdefault("side_stream", torch.cuda.Stream(device=self._device))
+            hostbuf = buf.setdefault("host_out", {})
+            inf_done, dets_h, side_done = [], [], []
 
             def launch(k):
                 eng, lo, hi, cap, slot = passes[k]
                 main.wait_event(h2d_done[k])
+                if k >= 2:  # output set / proto copy k&1 are still being read by the side stream's work of pass k-2
+                    main.wait_event(side_done[k - 2])
                 eng.use_outputs(slot)
                 eng.infer(buf["dev"][slot][:cap], buf["xf_dev"][:cap], conf, iou, max_det, agnostic, cmask)
                 fr = torch.cuda.Event()
                 fr.record(main)
                 buf["in_free"][slot] = fr
-                if hi - lo < cap:
-                    eng.count[hi - lo:].zero_()  # padded tail of the last pass
                 if seg:
                     pv = eng.proto_view()
                     if protos[k & 1] is None or protos[k & 1].numel() != pv.numel():
                         protos[k & 1] = torch.empty_like(pv)
                     protos[k & 1].copy_(pv, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                o = eng.out_sets[slot]
+                n = hi - lo
+                hb = hostbuf.get((k & 1, cap))
+                if hb is None:
+                    hb = hostbuf[(k & 1, cap)] = (torch.empty((cap,), dtype=torch.int32).pin_memory(),
+                                                  torch.empty((cap, MAX_DET, 6), dtype=torch.float32).pin_memory())
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    hb[0][:n].copy_(o.count[:n], non_blocking=True)
+                    hb[1][:n].copy_(o.det[:n], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                inf_done.append(done)
 
             def finish(k):
                 eng, lo, hi, cap, slot = passes[k]
                 o = eng.out_sets[slot]
-                counts = o.count[: hi - lo].cpu()  # stream-ordered D2H: the host sync of this pass
+                n = hi - lo
+                inf_done[k].synchronize()  # the host sync of this pass: its counts and boxes are in pinned memory now
+                hb = hostbuf[(k & 1, cap)]
+                counts = hb[0][:n].clone()
                 n_k = int(counts.sum())
-                cnts.append(counts)
-                dets.append(o.det[: hi - lo].clone() if n_k else None)
+                cnts.append(counts.tolist())
+                dets.append(o.det[:n].clone() if n_k else None)
+                dets_h.append(hb[1][:n].clone() if n_k else None)
                 if seg and n_k:
-                    m = torch.empty((n_k, mh, mw), dtype=torch.uint8, device=self._device)
-                    eng.masks(m, retina, mh, mw, proto=protos[k & 1], outputs=o)
+                    with torch.cuda.stream(side):
+                        m = torch.empty((n_k, mh, mw), dtype=torch.uint8, device=self._device)
+                        if hi - lo < cap:
+                            o.count[hi - lo:].zero_()  # padded tail of the last pass
+                        eng.masks(m, retina, mh, mw, proto=protos[k & 1], outputs=o, stream=side)
+                    m.record_stream(main)
                     mask_parts.append(m)
                 else:
                     mask_parts.append(None)
+                sd = torch.cuda.Event()
+                sd.record(side)
+                side_done.append(sd)
 
             enqueue_h2d(0)
             for k in range(n_mb):
@@ -461,6 +492,7 @@ class YOLO:
                 if k > 0:
                     finish(k - 1)
             finish(n_mb - 1)
+            main.wait_stream(side)  # the masks are consumed on the caller's stream
             t2 = time.perf_counter()
             err = self.engine.device_error()
             if err:
@@ -468,13 +500,21 @@ class YOLO:
             t3 = time.perf_counter()
         speed = {"preprocess": (t1 - t0) * 1e3 / B, "inference": (t2 - t1) * 1e3 / B, "postprocess": (t3 - t2) * 1e3 / B}
         out = []
+        empty = None
         for k in range(n_mb):
             _, lo, hi, _, _ = passes[k]
-            counts, det, masks, off = cnts[k].tolist(), dets[k], mask_parts[k], 0
+            counts, det, det_h, masks, off = cnts[k], dets[k], dets_h[k], mask_parts[k], 0
             for j in range(hi - lo):
                 n = counts[j]
-                boxes = det[j, :n] if n else torch.zeros((0, 6), device=self._device)
-                m = masks[off:off + n] if (masks is not None and n) else None
+                shp = frames[lo + j].shape[:2]
+                if n:
+                    boxes = Boxes(None, shp, lazy=(lambda d=det, j=j, n=n: d[j, :n]), n=n,
+                                  host=(lambda d=det_h, j=j, n=n: d[j, :n]))
+                    m = Masks(None, shp, lazy=(lambda mm=masks, a=off, b=off + n: mm[a:b]), n=n) if masks is not None else None
+                else:
+                    if empty is None:
+                        empty = torch.zeros((0, 6), device=self._device)
+                    boxes, m = Boxes(empty, shp, n=0), None
                 off += n
-                out.append(Results(frames[lo + j], None, self.names, boxes=boxes, masks=m, speed=dict(speed)))
+                out.append(Results(frames[lo + j], None, self.names, boxes=boxes, masks=m, speed=speed))
         return out

@@ -15,9 +15,23 @@ import torch
 
 
 class BaseTensor:
-    def __init__(self, data, orig_shape):
-        self._data = data
+    def __init__(self, data, orig_shape, lazy=None, n=None, host=None):
+        """data: tensor / ndarray, or None with `lazy` = a zero-argument callable producing it on first use (predict()
+        hands out views of batch-level tensors: slicing 64 frames x {boxes, masks} eagerly costs more host time than a
+        B200 needs for the frames themselves).  n: row count when known without materialising.  host: zero-argument
+        callable returning an already-fetched CPU copy (predict() reads every box of a pass back in ONE copy)."""
+        self._d = data
+        self._lazy = lazy
+        self._n = n
+        self._host = host
         self.orig_shape = orig_shape
+
+    @property
+    def _data(self):
+        if self._d is None and self._lazy is not None:
+            self._d = self._lazy()
+            self._lazy = None
+        return self._d
 
     @property
     def data(self):
@@ -28,7 +42,7 @@ class BaseTensor:
         return self.data.shape
 
     def __len__(self):
-        return len(self._data)
+        return self._n if self._n is not None else len(self._data)
 
     def __getitem__(self, idx):
         d = self._data[idx]
@@ -37,9 +51,13 @@ class BaseTensor:
         return self.__class__(d, self.orig_shape)
 
     def cpu(self):
+        if self._host is not None:  # fetched with the rest of its engine pass: no device round trip
+            return self.__class__(self._host(), self.orig_shape)
         return self if isinstance(self._data, np.ndarray) else self.__class__(self._data.cpu(), self.orig_shape)
 
     def numpy(self):
+        if self._host is not None:
+            return self.__class__(self._host().numpy(), self.orig_shape)
         return self if isinstance(self._data, np.ndarray) else self.__class__(self._data.cpu().numpy(), self.orig_shape)
 
     def cuda(self):
@@ -152,8 +170,8 @@ class Results:
         self.orig_shape = tuple(orig_img.shape[:2])
         self.path = path
         self.names = names
-        self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
-        self.masks = Masks(masks, self.orig_shape) if masks is not None else None
+        self.boxes = boxes if isinstance(boxes, Boxes) else Boxes(boxes, self.orig_shape) if boxes is not None else None
+        self.masks = masks if isinstance(masks, Masks) else Masks(masks, self.orig_shape) if masks is not None else None
         self.probs = None
         self.keypoints = None
         self.obb = None

@@ -39,7 +39,6 @@ def summarize_results(results):
     (the DEVA hand-off of reference yolo_seg/yolo_with_deva.py:54-88 is point-to-point, not gathered)."""
     out = []
     for r in results:
-        b = r.boxes.data
-        b = b.cpu().numpy() if hasattr(b, "cpu") else b
+        b = r.boxes.cpu().numpy().data  # predict() fetched every box of a pass in one copy: no device round trip here
         out.append((len(b), b))
     return out

@@ -462,8 +462,8 @@ def run_ours(args, wl):
                    "candidates_per_frame": {"mean": float(cand.mean()), "max": int(cand.max())}, "parallelism": f"frame-sharded replicas x{world}",
                    "l2": "each step streams >1 GB of activations through HBM (inputs+activations exceed the 126 MB L2)"},
         "p50_frame_latency_ms_b1": p50, "p50_predict_call_ms_b1": p50_e2e,
-        "e2e": e2e, "gpu_launches": (eng.launches + (2 if is_seg else 0)) * args.steps,
-        "launches_per_step": eng.launches + (2 if is_seg else 0),
+        "e2e": e2e, "gpu_launches": (eng.launches + (3 if is_seg else 0)) * args.steps,
+        "launches_per_step": eng.launches + (3 if is_seg else 0),
         "roofline": roofline, "clocks": clocks,
     }
     if base is not None:

@@ -169,6 +169,13 @@ int ypb_letterbox_u8(void* cuda_stream, const uint8_t* src, int B, int H0, int W
    of the LAST kept detection covering each pixel, else 0.  All device pointers, caller's stream. */
 int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int H, int W,
                     int min_area, int32_t* area, int32_t* ids, int64_t* index_map);
+/* The same hand-off for the reference's `min_side` branch (yolo_with_deva.py:44-48,71-72): predict() ran on a resized
+   frame, masks are (n_total, h1, w1) and go back to (H, W) as torchvision's F.resize does (antialiased bilinear) before
+   the float `mask.sum() < min_area` filter (min_area < 0: keep all) and the `mask > 0.5` paint.
+   bins: scratch (n_total, H, W) uint8; area_f: (n_total) fp32 sums of the resized masks. */
+int ypb_index_masks_resized(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int h1,
+                            int w1, int H, int W, float min_area, uint8_t* bins, float* area_f, int32_t* ids,
+                            int64_t* index_map);
 /* Zero-staging path of predict(): is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / pinned torch
    tensor)?  and: copy n such frames to consecutive device slots on `cuda_stream`, merging adjacent sources. */
 int ypb_host_is_pinned(const void* p, int* pinned);

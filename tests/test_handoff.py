@@ -150,3 +150,75 @@ def test_min_rect_len_on_predict_output():
             assert abs(float(got[i, 0]) - length) <= 0.05 + 2e-3 * length, (i, float(got[i, 0]), length)
             checked += 1
     assert checked > 0
+
+
+def test_oracle_min_side_branch_resizes_like_torchvision():
+    """CPU: the restated `min_side` branch on a hand-checkable case - a 2x up-scaled frame, masks brought back by a 2x
+    antialiased bilinear down-scale (weights 1/8, 3/8, 3/8, 1/8): a 20x20 block of ones at even offsets comes back as a
+    10x10 block (interior 1, the border row at 0.5+ stays on only where the kernel's weight > 0.5)."""
+    from oracle.handoff import auto_segment_index_mask_resized
+    m = torch.zeros(1, 40, 40)
+    m[0, 10:30, 10:30] = 1
+    out, info = auto_segment_index_mask_resized(m, torch.tensor([0.9]), torch.tensor([2.0]), (20, 20), True, 50)
+    assert len(info) == 1 and info[0][0] == 1
+    assert out[5:15, 5:15].eq(1).all() and int(out.sum()) == 100
+
+
+def _aa_resize_reference(masks_u8, H, W):
+    from torchvision.transforms import functional as F
+    return torch.stack([F.resize(m.float().unsqueeze(0), size=[H, W])[0] for m in masks_u8])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h1,w1,H,W", [(960, 1280, 480, 640), (720, 1280, 1080, 1920), (333, 500, 480, 721), (1000, 750, 400, 300),
+                                         (640, 640, 640, 640)])
+def test_index_masks_resized_matches_torchvision_resize(h1, w1, H, W):
+    """GPU: `index_masks(out_shape=...)` (ypb_index_masks_resized) against the reference loop with torchvision's F.resize
+    (antialiased bilinear), down- and up-scaling, on blob masks: painted ids equal except on pixels whose resized value is
+    within 1e-4 of the 0.5 threshold; kept / suppressed sets equal."""
+    from oracle.handoff import auto_segment_index_mask_resized
+    from yolo_puncture_b200 import index_masks
+    g = torch.Generator().manual_seed(h1 + W)
+    n = 6
+    m = torch.zeros(n, h1, w1, dtype=torch.uint8)
+    yy, xx = torch.meshgrid(torch.arange(h1), torch.arange(w1), indexing="ij")
+    for i in range(n):
+        cy, cx = float(torch.rand(1, generator=g)) * h1, float(torch.rand(1, generator=g)) * w1
+        r = (3.0 if i == 2 else 20.0 + 100.0 * float(torch.rand(1, generator=g)))  # one tiny blob: suppressed
+        m[i] = (((yy - cy) ** 2 + ((xx - cx) * 0.7) ** 2) < r * r).to(torch.uint8)
+    conf, cls = torch.rand(n, generator=g), torch.randint(0, 80, (n,), generator=g).float()
+    res = [_FakeResults(m.cuda(), conf.cuda(), cls.cuda(), (h1, w1))]
+    (got, info), = index_masks(res, True, 100, out_shape=(H, W))
+    ref, ref_info = auto_segment_index_mask_resized(m, conf, cls, (H, W), True, 100)
+    assert [d["id"] for d in info] == [i[0] for i in ref_info]
+    assert [d["category_id"] for d in info] == [i[2] for i in ref_info]
+    got = got.cpu()
+    assert got.shape == (H, W) and got.dtype == torch.int64
+    diff = got != ref
+    if (h1, w1) == (H, W):
+        assert not diff.any()
+    else:
+        r = _aa_resize_reference(m, H, W)
+        near = ((r - 0.5).abs() < 1e-4).any(0)          # the value sits on the threshold: either side is right
+        assert not (diff & ~near).any(), int((diff & ~near).sum())
+        assert int(diff.sum()) <= 0.001 * H * W
+
+
+@pytest.mark.gpu
+def test_auto_segment_drop_in_with_min_side():
+    """The reference's entry point itself (yolo_with_deva.py:35-88), min_side > 0: frame resized, predict, masks back."""
+    from oracle.handoff import auto_segment_index_mask_resized
+    from yolo_puncture_b200 import YOLO, auto_segment, synth
+    yolo = YOLO("yolov8n-seg", device=0)
+    frame = synth.synth_frame(0, 480, 640)
+    out, info = auto_segment({"MIN_AREA_THRESHOLD": 100}, frame, yolo, 720, True)
+    assert out.shape == (480, 640) and out.dtype == torch.int64 and out.is_cuda
+    import cv2
+    big = cv2.resize(frame, (int(640 * 1.5), int(480 * 1.5)))
+    r = yolo.predict(big, retina_masks=True, conf=0.9)[0]
+    if r.masks is None:
+        assert info == [] and int(out.sum()) == 0
+        return
+    ref, ref_info = auto_segment_index_mask_resized(r.masks.data.cpu(), r.boxes.conf.cpu(), r.boxes.cls.cpu(), (480, 640), True, 100)
+    assert [d["id"] for d in info] == [i[0] for i in ref_info]
+    assert int((out.cpu() != ref).sum()) <= 0.001 * 480 * 640

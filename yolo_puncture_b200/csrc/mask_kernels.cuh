@@ -20,6 +20,7 @@ struct MaskGeom {
   float scale_h, scale_w;
   // non-retina: proto-space box = letterbox box * (mw/W, mh/H)
   float ratio_w, ratio_h;
+  int prefilled;       // 1: the output was zero-filled by mask_zero_kernel, only box-touching tiles are written
 };
 
 // Exclusive prefix sum of per-image detection counts -> offsets[0..B]; flags overflow of the mask capacity.
@@ -35,6 +36,21 @@ __global__ void mask_offsets_kernel(const int* __restrict__ count, int nB, int c
 }
 
 constexpr int kMaskTile = 64;  // 64x64 output pixels per step, 256 threads x 16 px
+
+// Streaming zero fill of the masks of the first min(total, capacity) detections: a plain grid-stride loop of 16-byte
+// stores runs at the HBM write rate, which the decode kernel's per-band zero fills (L1/LSU-bound next to its
+// shared-memory traffic: ncu l1tex 85 %, 2.3 TB/s) did not.  mask_decode_kernel then only writes the tiles a box touches.
+__global__ void __launch_bounds__(256)
+mask_zero_kernel(const int* __restrict__ offsets, int nB, int capacity, long long bytes_per_mask, uint8_t* __restrict__ out) {
+  const int total = min(offsets[nB], capacity);
+  const long long nbytes = (long long)total * bytes_per_mask;
+  uint4* o4 = reinterpret_cast<uint4*>(out);
+  const long long n16 = nbytes >> 4;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) o4[i] = z;
+  if (blockIdx.x == 0)
+    for (long long i = (n16 << 4) + threadIdx.x; i < nbytes; i += blockDim.x) out[i] = 0;
+}
 
 // One CTA per (band of 64 output rows, detection).  Bands that miss the box are one contiguous, fully coalesced
 // zero fill; inside a band the CTA walks 64-pixel tiles: tiles that miss the box are zero-filled, the others get the
@@ -85,6 +101,7 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   if (g.retina) band_empty = ((float)(ty0 + kMaskTile) <= by1) || ((float)ty0 >= by2);
   else band_empty = ((float)(g.top + sy_hi) < by1) || ((float)(g.top + sy_lo) >= by2);
   if (band_empty || rh > kMaskTile + 2) {
+    if (g.prefilled) return;
     const long long nbytes = (long long)(y_last - ty0 + 1) * g.out_w;
     uint8_t* dst = o + (long long)ty0 * g.out_w;
     if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nbytes) & 15) == 0) {
@@ -153,7 +170,7 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
     int sx_lo, sx_hi;
     tile_window(tx0, &sx_lo, &sx_hi);
     if (tile_empty(tx0, sx_lo, sx_hi)) {  // CTA-uniform
-      if (oy < g.out_h) {
+      if (oy < g.out_h && !g.prefilled) {
         if (vec_ok && ox0 + 16 <= g.out_w) {
           *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
         } else {
@@ -184,7 +201,7 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
     // this thread's 16 pixels lie outside the box (rows above / below it inside the band, columns left / right of it
     // inside the tile): zeros without touching the interpolation
     if (vec_ok && ox0 + 16 <= g.out_w && (!row_in || (g.retina && ((float)(ox0 + 16) <= bx1 || (float)ox0 >= bx2)))) {
-      *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
+      if (!g.prefilled) *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
       continue;
     }
     const float4* t0 = reinterpret_cast<const float4*>(s_hrow + (y0 - sy_lo) * kMaskTile + tcol);
@@ -316,6 +333,66 @@ __global__ void mask_ids_kernel(const int* __restrict__ offsets, int nB, const i
   if (b >= nB) return;
   int cur = 0;
   for (int i = offsets[b]; i < offsets[b + 1]; ++i) ids[i] = (min_area < 0 || area[i] >= min_area) ? ++cur : 0;
+}
+
+// The `min_side` branch of the hand-off (reference yolo_seg/yolo_with_deva.py:44-48,71-72): predict() ran on a resized
+// frame, so every mask goes back to the frame size through torchvision `F.resize(mask[None], [h, w])` - bilinear WITH
+// antialiasing (the default for tensors) - before the `mask.sum() < MIN_AREA` filter and the `mask > 0.5` paint.
+// Restates ATen's _upsample_bilinear2d_aa: scale = in / out (float), support = max(scale, 1), taps
+// [int(c - support + 0.5), int(c + support + 0.5)) around c = scale * (i + 0.5), triangle weights
+// max(0, 1 - |(j + xmin - c + 0.5) / max(scale, 1)|) normalised by their sum; rows are reduced horizontally first,
+// then vertically.  One thread per output pixel; writes bin = (value > 0.5) and adds the float values to area_f[mask].
+__global__ void __launch_bounds__(256)
+mask_resize_aa_kernel(const uint8_t* __restrict__ masks, int n, int h1, int w1, int H, int W, uint8_t* __restrict__ bins,
+                      float* __restrict__ area_f) {
+  const int i = blockIdx.z;
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  float v = 0.f;
+  if (ox < W && oy < H) {
+    const float sx = (float)w1 / (float)W, sy = (float)h1 / (float)H;
+    const float supx = sx >= 1.f ? sx : 1.f, supy = sy >= 1.f ? sy : 1.f;
+    const float invx = sx >= 1.f ? 1.f / sx : 1.f, invy = sy >= 1.f ? 1.f / sy : 1.f;
+    const float cx = sx * ((float)ox + 0.5f), cy = sy * ((float)oy + 0.5f);
+    const int xmin = max((int)(cx - supx + 0.5f), 0), xsize = min((int)(cx + supx + 0.5f), w1) - xmin;
+    const int ymin = max((int)(cy - supy + 0.5f), 0), ysize = min((int)(cy + supy + 0.5f), h1) - ymin;
+    float tx = 0.f, ty = 0.f;
+    for (int j = 0; j < xsize; ++j) tx += fmaxf(0.f, 1.f - fabsf(((float)j + ((float)xmin - cx) + 0.5f) * invx));
+    for (int j = 0; j < ysize; ++j) ty += fmaxf(0.f, 1.f - fabsf(((float)j + ((float)ymin - cy) + 0.5f) * invy));
+    const uint8_t* m = masks + (long long)i * h1 * w1;
+    for (int r = 0; r < ysize; ++r) {
+      const uint8_t* row = m + (long long)(ymin + r) * w1 + xmin;
+      float hs = 0.f;
+      for (int j = 0; j < xsize; ++j) {
+        float wx = fmaxf(0.f, 1.f - fabsf(((float)j + ((float)xmin - cx) + 0.5f) * invx));
+        if (tx != 0.f) wx /= tx;
+        hs += (float)row[j] * wx;
+      }
+      float wy = fmaxf(0.f, 1.f - fabsf(((float)r + ((float)ymin - cy) + 0.5f) * invy));
+      if (ty != 0.f) wy /= ty;
+      v += hs * wy;
+    }
+    bins[((long long)i * H + oy) * W + ox] = v > 0.5f ? 1 : 0;
+  }
+  // block sum of the float values -> one atomic per block
+  __shared__ float s_part[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s_part[k];
+    if (t != 0.f) atomicAdd(area_f + i, t);
+  }
+}
+
+__global__ void mask_ids_f_kernel(const int* __restrict__ offsets, int nB, const float* __restrict__ area_f, float min_area,
+                                  int* __restrict__ ids) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nB) return;
+  int cur = 0;
+  for (int i = offsets[b]; i < offsets[b + 1]; ++i) ids[i] = (min_area < 0.f || !(area_f[i] < min_area)) ? ++cur : 0;
 }
 
 // index_map[b][p] = id of the LAST kept detection of frame b whose mask covers pixel p, else 0.  8 pixels per thread.

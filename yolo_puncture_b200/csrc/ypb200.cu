@@ -1530,6 +1530,11 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
       ds.mask_smem = 160 * 1024;
     }
   }
+  // zero fill at the HBM write rate first, then only the tiles a box touches (YPB_MASK_ONEPASS=1: the one-kernel form)
+  static const bool onepass = getenv("YPB_MASK_ONEPASS") != nullptr;
+  g.prefilled = onepass ? 0 : 1;
+  if (g.prefilled)
+    mask_zero_kernel<<<device_state().num_sms * 8, 256, 0, st>>>(offsets, e->B, capacity, (long long)g.out_h * g.out_w, masks);
   mask_decode_kernel<<<grid, 256, band_smem, st>>>(proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb,
                                                   offsets, e->B, capacity, g, masks);
   CUDA_TRY(cudaGetLastError());
@@ -1809,6 +1814,28 @@ int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offs
     mask_ids_kernel<<<(B + 127) / 128, 128, 0, st>>>(offsets, B, area, min_area, ids);
   }
   index_paint_kernel<<<dim3((unsigned)((hw + 2047) / 2048), B), 256, 0, st>>>(masks, offsets, ids, hw,
+                                                                             reinterpret_cast<long long*>(index_map));
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
+// Same hand-off when predict() ran on a resized frame (the reference's `min_side`, yolo_with_deva.py:44-48,71-72): masks
+// (n_total, h1, w1) are resized to (H, W) as torchvision F.resize does (antialiased bilinear), area_f receives the float
+// sum of every resized mask (the reference filters on `mask.sum() < MIN_AREA`), bins (n_total, H, W) uint8 scratch.
+int ypb_index_masks_resized(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int h1, int w1,
+                            int H, int W, float min_area, uint8_t* bins, float* area_f, int32_t* ids, int64_t* index_map) {
+  if (!offsets || !index_map || B < 1 || H < 1 || W < 1 || h1 < 1 || w1 < 1 || n_total < 0 ||
+      (n_total > 0 && (!masks || !bins || !area_f || !ids)))
+    return fail(YPB_ERR_ARG, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  const long long hw = (long long)H * W;
+  if (n_total > 0) {
+    if (n_total > 65535 || B > 65535 || (H + 7) / 8 > 65535) return fail(YPB_ERR_ARG, "index_masks: too many masks / frames / rows per call");
+    CUDA_TRY(cudaMemsetAsync(area_f, 0, (size_t)n_total * 4, st));
+    mask_resize_aa_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, n_total), 256, 0, st>>>(masks, n_total, h1, w1, H, W, bins, area_f);
+    mask_ids_f_kernel<<<(B + 127) / 128, 128, 0, st>>>(offsets, B, area_f, min_area, ids);
+  }
+  index_paint_kernel<<<dim3((unsigned)((hw + 2047) / 2048), B), 256, 0, st>>>(bins, offsets, ids, hw,
                                                                              reinterpret_cast<long long*>(index_map));
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;

@@ -13,14 +13,18 @@ import torch
 from ._lib import check, lib
 
 
-def index_masks(results, suppress_small_mask=True, min_area=100):
+def index_masks(results, suppress_small_mask=True, min_area=100, out_shape=None):
     """results: list of `Results` (masks at frame size, i.e. predict(retina_masks=True)).
     Returns a list of (index_mask int64 (H, W) device tensor, segments_info list of dicts {id, score, category_id}),
     one per frame, with the reference's semantics: detections in order; `mask.sum() < min_area` ones are skipped when
-    suppress_small_mask; kept ones get ids 1, 2, ...; later detections overwrite earlier ones."""
+    suppress_small_mask; kept ones get ids 1, 2, ...; later detections overwrite earlier ones.
+    out_shape=(h, w): the reference's `min_side` branch - predict() ran on a resized copy of the frame, every mask is
+    resized back to (h, w) the way `F.resize(mask[None], [h, w])` does before the area filter and the paint."""
     results = list(results)
     if not results:
         return []
+    if out_shape is not None and any(tuple(out_shape) != tuple(r.orig_shape) for r in results):
+        return _index_masks_resized(results, suppress_small_mask, min_area, tuple(int(v) for v in out_shape))
     raws, counts = [], []
     dev = None
     for r in results:
@@ -67,6 +71,64 @@ def index_masks(results, suppress_small_mask=True, min_area=100):
         k += counts[b]
         out.append((index_map[b], info))
     return out
+
+
+def _index_masks_resized(results, suppress_small_mask, min_area, out_shape):
+    H, W = out_shape
+    shapes = {tuple(r.orig_shape) for r in results}
+    if len(shapes) != 1:
+        raise ValueError("index_masks: all frames of a call must have one size")
+    h1, w1 = shapes.pop()
+    raws = [r.masks.raw if r.masks is not None else None for r in results]
+    counts = [0 if m is None else int(m.shape[0]) for m in raws]
+    present = [m for m in raws if m is not None]
+    if any((not torch.is_tensor(m)) or (not m.is_cuda) or m.dtype != torch.uint8 or tuple(m.shape[1:]) != (h1, w1) for m in present):
+        raise ValueError("index_masks needs the device-resident uint8 retina masks of YOLO.predict()")
+    B, n_total = len(results), sum(counts)
+    if not present:
+        ref = results[0].boxes.data if results[0].boxes is not None and torch.is_tensor(results[0].boxes.data) else None
+        dev = ref.device if ref is not None and ref.is_cuda else torch.device("cuda")
+        return [(torch.zeros((H, W), dtype=torch.int64, device=dev), []) for _ in results]
+    dev = present[0].device
+    contiguous = all(m.is_contiguous() for m in present) and all(
+        b.data_ptr() == a.data_ptr() + a.numel() for a, b in zip(present, present[1:]))
+    base = present[0] if contiguous else torch.cat(present)
+    offsets = torch.zeros(B + 1, dtype=torch.int32)
+    offsets[1:] = torch.tensor(counts, dtype=torch.int32).cumsum(0)
+    with torch.cuda.device(dev):
+        offs_d = offsets.to(dev, non_blocking=True)
+        bins = torch.empty((n_total, H, W), dtype=torch.uint8, device=dev)
+        area = torch.empty(n_total, dtype=torch.float32, device=dev)
+        ids = torch.empty(n_total, dtype=torch.int32, device=dev)
+        index_map = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        check(lib().ypb_index_masks_resized(C.c_void_p(st), C.c_void_p(base.data_ptr()), C.c_void_p(offs_d.data_ptr()), B, n_total,
+                                            h1, w1, H, W, float(min_area) if suppress_small_mask else -1.0,
+                                            C.c_void_p(bins.data_ptr()), C.c_void_p(area.data_ptr()), C.c_void_p(ids.data_ptr()),
+                                            C.c_void_p(index_map.data_ptr())))
+        meta = torch.cat([r.boxes.data[:, 4:6].to(dev, torch.float32) for r, c in zip(results, counts) if c])
+        packed = torch.cat([ids.to(torch.float32)[:, None], meta], 1).cpu().tolist()
+    out, k = [], 0
+    for b in range(B):
+        info = [{"id": int(i), "score": float(sc), "category_id": int(cl)} for i, sc, cl in packed[k:k + counts[b]] if i]
+        k += counts[b]
+        out.append((index_map[b], info))
+    return out
+
+
+def auto_segment(config, image, yolo_model, min_side, suppress_small_mask):
+    """Drop-in for reference yolo_seg/yolo_with_deva.py:35-88 `auto_segment(config, image, yolo_model, min_side,
+    suppress_small_mask)`: optional `min_side` resize of the frame (cv2.resize, as the reference), predict(retina_masks=True,
+    conf=0.9), then the index mask and the segment list in three kernel launches.  Returns (int64 (h, w) device tensor,
+    [{"id", "score", "category_id"}, ...]) - the fields of the reference's ObjectInfo."""
+    h, w = image.shape[:2]
+    if min_side > 0:
+        import cv2
+        scale = min_side / min(h, w)
+        image = cv2.resize(image, (int(w * scale), int(h * scale)))
+    results = yolo_model.predict(image, retina_masks=True, conf=0.9)
+    (index_mask, info), = index_masks(results[:1], suppress_small_mask, config.get("MIN_AREA_THRESHOLD", 100), out_shape=(h, w))
+    return index_mask, info
 
 
 def min_rect_len(masks):

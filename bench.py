@@ -293,23 +293,23 @@ def run_ours(args, wl):
         pin_np[i] = f
     frames_pinned = [pin_np[i] for i in range(B)]
 
-    from yolo_puncture_b200.sharding import gather_in_frame_order, shard_indices, summarize_results
+    from yolo_puncture_b200.sharded import ShardedPredictor
     n_global = world * B
-    my_frames = shard_indices(n_global, rank, world, B)  # rank r owns frames [r*B, (r+1)*B) of every step's stream chunk
-    assert my_frames == list(range(rank * B, (rank + 1) * B))
+    sp = ShardedPredictor(yolo, rank, world, chunk=B)  # rank r owns frames [r*B, (r+1)*B) of every step's stream chunk
+    assert sp.frames_of(n_global) == list(range(rank * B, (rank + 1) * B))
     do_handoff = is_seg and (args.handoff or model == "yolov8x-seg")  # BASELINE config C5 names the index-mask hand-off
+    if do_handoff and world > 1:
+        # the tracker lives on rank 0's GPU: the other ranks push their index masks into its memory over NVLink (CUDA IPC)
+        sp.attach_mailbox(hw[0], hw[1], n_global, consumer_rank=0)
 
     def run_e2e(frs, handoff_inside=False):
         """Timed region per step: predict() on host frames (H2D inside), D2H of every frame's boxes, and - when the job
         is sharded - the host gather of the per-frame payloads into global frame order (sharding.py; no data-path
-        collective: masks stay on the GPU that produced them)."""
+        collective).  With the hand-off: index_masks() on every rank and the peer push of the index masks to rank 0."""
         def e2e_step():
-            res = yolo.predict(frs, conf=CONF, iou=IOU, retina_masks=True, imgsz=imgsz, batch=B)
-            n_obj = 0
-            if handoff_inside:
-                n_obj = sum(len(info) for _, info in index_masks(res, suppress_small_mask=True, min_area=100))
-            payload = summarize_results(res)  # (n, boxes (n,6) numpy) per frame: the D2H read of the step's result
-            ordered = gather_in_frame_order(payload, n_global, rank, world, B)
+            ordered, res = sp.predict(frs, n_global, handoff=handoff_inside, min_area=100, conf=CONF, iou=IOU,
+                                      retina_masks=True, imgsz=imgsz, batch=B)
+            n_obj = sum(len(o[2]) for o in ordered) if handoff_inside else 0
             return res, ordered, n_obj
 
         for _ in range(2):
@@ -328,7 +328,7 @@ def run_ours(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         assert len(ordered) == n_global and all(o is not None for o in ordered)
-        d2h = sum(int(bx.size) * 4 for _, bx in ordered[rank * B:(rank + 1) * B]) + B * 4
+        d2h = sum(int(o[1].size) * 4 for o in ordered[rank * B:(rank + 1) * B]) + B * 4
         return world * B * e2e_steps / e2e_s, e2e_s / e2e_steps * 1e3, e2e_steps, d2h, n_obj
 
     from yolo_puncture_b200 import index_masks
@@ -348,17 +348,23 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
         handoff = {"ms_per_step": (time.perf_counter() - t0) / 5 * 1e3, "frames": B,
                    "kept_objects": sum(len(i) for _, i in out_h), "inside_timed_e2e": bool(do_handoff),
+                   "peer_push_to_rank0_mailbox": bool(do_handoff and world > 1),
                    "note": "index_masks(): int64 (H0,W0) id map + (id, score, class) list per frame, 3 launches per batch"}
     e2e = {"value": v_page, "unit": "frames/s",
            "h2d_bytes_per_step": B * hw[0] * hw[1] * 3 + B * 5 * 4,  # raw frames (LetterBox runs on the device) + xform rows
            "d2h_bytes_per_step": d2h_bytes,  # per rank: counts + the (n,6) boxes of every frame
            "steps": e2e_steps, "ms_per_step": ms_page, "source": "pageable numpy frames",
            "pinned_frames": {"value": v_pin, "ms_per_step": ms_pin}, "index_mask_handoff": handoff,
-           "frame_order_gather": "sharding.gather_in_frame_order over %d rank(s), inside the timed region" % world,
+           "frame_order_gather": "sharded.ShardedPredictor -> sharding.gather_in_frame_order over %d rank(s), inside the timed region" % world,
            "note": "YOLO.predict() on ordinary (pageable) host frames: staging into pinned memory + H2D of the uint8 frames + "
                    "engine + D2H of counts and boxes + ordered host gather every step; masks stay on the device as in "
                    "upstream Results.  pinned_frames = the same call on frames that already live in page-locked memory"}
 
+    if sp.mailbox is not None:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sp.mailbox.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -176,6 +176,16 @@ int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offs
 int ypb_index_masks_resized(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int h1,
                             int w1, int H, int W, float min_area, uint8_t* bins, float* area_f, int32_t* ids,
                             int64_t* index_map);
+/* Point-to-point mask hand-off between the GPUs of one box (BASELINE config C5): the tracker that consumes
+   the index masks (reference yolo_seg/yolo_with_deva.py:133-159) runs on ONE GPU; detector replicas on the other GPUs
+   copy their index masks into a mailbox in that GPU's memory over NVLink / NVSwitch.  create: cudaMalloc on `device` +
+   CUDA IPC handle (64 bytes) to hand to the producer processes; open / close: map it in a producer process;
+   ypb_peer_copy: cudaMemcpyAsync(dst, src) on the caller's stream (peer access is enabled by the IPC open). */
+int ypb_mailbox_create(int device, size_t bytes, void** dev_ptr, unsigned char handle[64]);
+int ypb_mailbox_destroy(int device, void* dev_ptr);
+int ypb_mailbox_open(int device, const unsigned char handle[64], void** dev_ptr);
+int ypb_mailbox_close(int device, void* dev_ptr);
+int ypb_peer_copy(void* cuda_stream, void* dst, const void* src, size_t bytes);
 /* Zero-staging path of predict(): is this host pointer page-locked (cudaHostAlloc / cudaHostRegister / pinned torch
    tensor)?  and: copy n such frames to consecutive device slots on `cuda_stream`, merging adjacent sources. */
 int ypb_host_is_pinned(const void* p, int* pinned);

@@ -70,6 +70,11 @@ SIGNATURES = {
     "ypb_index_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ypb_index_masks_resized": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ypb_mailbox_create": (c_int, [c_int, c_size_t, C.POINTER(c_void_p), c_void_p]),
+    "ypb_mailbox_destroy": (c_int, [c_int, c_void_p]),
+    "ypb_mailbox_open": (c_int, [c_int, c_void_p, C.POINTER(c_void_p)]),
+    "ypb_mailbox_close": (c_int, [c_int, c_void_p]),
+    "ypb_peer_copy": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "ypb_host_is_pinned": (c_int, [c_void_p, C.POINTER(c_int)]),
     "ypb_hosts_are_pinned": (c_int, [c_void_p, c_int, C.POINTER(c_int)]),
     "ypb_h2d_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int]),

@@ -1841,6 +1841,56 @@ int ypb_index_masks_resized(void* cuda_stream, const uint8_t* masks, const int32
   return YPB_OK;
 }
 
+// ---- point-to-point mask hand-off between the GPUs of one box (BASELINE config C5) ----------------
+// The tracker (DEVA) is sequential and lives on ONE GPU; the detector replicas on the other GPUs push their per-frame
+// index masks into a mailbox in the consumer GPU's memory over NVLink / NVSwitch: cudaMemcpyAsync between peer
+// devices, exported across the one-process-per-GPU boundary with CUDA IPC.  No collective, no host bounce.
+int ypb_mailbox_create(int device, size_t bytes, void** dev_ptr, unsigned char handle[64]) {
+  if (!dev_ptr || !handle || bytes == 0) return fail(YPB_ERR_ARG, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  DeviceGuard guard(device);
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t ce = cudaIpcGetMemHandle(&h, p);
+  if (ce != cudaSuccess) { cudaFree(p); return fail(YPB_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(ce)); }
+  memcpy(handle, &h, 64);
+  *dev_ptr = p;
+  return YPB_OK;
+}
+
+int ypb_mailbox_destroy(int device, void* dev_ptr) {
+  if (!dev_ptr) return YPB_OK;
+  DeviceGuard guard(device);
+  CUDA_TRY(cudaFree(dev_ptr));
+  return YPB_OK;
+}
+
+// Producer side: map the consumer's mailbox into this process (device = the producer's own GPU).
+int ypb_mailbox_open(int device, const unsigned char handle[64], void** dev_ptr) {
+  if (!handle || !dev_ptr) return fail(YPB_ERR_ARG, "bad argument");
+  DeviceGuard guard(device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return YPB_OK;
+}
+
+int ypb_mailbox_close(int device, void* dev_ptr) {
+  if (!dev_ptr) return YPB_OK;
+  DeviceGuard guard(device);
+  CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return YPB_OK;
+}
+
+// Enqueue a device-to-device copy (same GPU or a peer's mailbox) on the caller's stream.
+int ypb_peer_copy(void* cuda_stream, void* dst, const void* src, size_t bytes) {
+  if (!dst || !src) return fail(YPB_ERR_ARG, "bad argument");
+  if (bytes == 0) return YPB_OK;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(cuda_stream)));
+  return YPB_OK;
+}
+
 // Host helpers of the zero-staging path: frames that already live in page-locked memory (a capture / decode ring, a
 // pinned torch tensor) are copied to the device straight from where they are.
 int ypb_host_is_pinned(const void* p, int* pinned) {

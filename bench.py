@@ -302,6 +302,8 @@ def run_ours(args, wl):
         # the tracker lives on rank 0's GPU: the other ranks push their index masks into its memory over NVLink (CUDA IPC)
         sp.attach_mailbox(hw[0], hw[1], n_global, consumer_rank=0)
 
+    host_tm = []
+
     def run_e2e(frs, handoff_inside=False):
         """Timed region per step: predict() on host frames (H2D inside), D2H of every frame's boxes, and - when the job
         is sharded - the host gather of the per-frame payloads into global frame order (sharding.py; no data-path
@@ -328,6 +330,7 @@ def run_ours(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         assert len(ordered) == n_global and all(o is not None for o in ordered)
+        host_tm.append(dict(yolo.last_timing))
         d2h = sum(int(o[1].size) * 4 for o in ordered[rank * B:(rank + 1) * B]) + B * 4
         return world * B * e2e_steps / e2e_s, e2e_s / e2e_steps * 1e3, e2e_steps, d2h, n_obj
 
@@ -355,6 +358,7 @@ def run_ours(args, wl):
            "d2h_bytes_per_step": d2h_bytes,  # per rank: counts + the (n,6) boxes of every frame
            "steps": e2e_steps, "ms_per_step": ms_page, "source": "pageable numpy frames",
            "pinned_frames": {"value": v_pin, "ms_per_step": ms_pin}, "index_mask_handoff": handoff,
+           "host_breakdown_ms_last_step": {"pageable": host_tm[0], "pinned": host_tm[1], "host_cores": os.cpu_count()},
            "frame_order_gather": "sharded.ShardedPredictor -> sharding.gather_in_frame_order over %d rank(s), inside the timed region" % world,
            "note": "YOLO.predict() on ordinary (pageable) host frames: staging into pinned memory + H2D of the uint8 frames + "
                    "engine + D2H of counts and boxes + ordered host gather every step; masks stay on the device as in "
@@ -468,8 +472,8 @@ def run_ours(args, wl):
                    "candidates_per_frame": {"mean": float(cand.mean()), "max": int(cand.max())}, "parallelism": f"frame-sharded replicas x{world}",
                    "l2": "each step streams >1 GB of activations through HBM (inputs+activations exceed the 126 MB L2)"},
         "p50_frame_latency_ms_b1": p50, "p50_predict_call_ms_b1": p50_e2e,
-        "e2e": e2e, "gpu_launches": (eng.launches + (3 if is_seg else 0)) * args.steps,
-        "launches_per_step": eng.launches + (3 if is_seg else 0),
+        "e2e": e2e, "gpu_launches": (eng.launches + (2 if is_seg else 0)) * args.steps,
+        "launches_per_step": eng.launches + (2 if is_seg else 0),
         "roofline": roofline, "clocks": clocks,
     }
     if base is not None:

@@ -1045,6 +1045,17 @@ int ypb_finalize_weights(ypb_engine* e, int device) {
       n_off += s.width();
     }
   }
+  if (e->device >= 0 && e->device != device) {
+    // the engine moves to another GPU (YOLO.to('cuda:1')): graphs, capture streams, events and the weight arena belong
+    // to the old device
+    DeviceGuard old_dev(e->device);
+    e->drop_graph();
+    if (e->cap_stream) { cudaStreamDestroy(e->cap_stream); e->cap_stream = nullptr; }
+    for (cudaStream_t& ss : e->side_streams) if (ss) { cudaStreamDestroy(ss); ss = nullptr; }
+    for (cudaEvent_t ev : e->op_events) cudaEventDestroy(ev);
+    e->op_events.clear();
+    if (e->w_arena) { cudaFree(e->w_arena); e->w_arena = nullptr; }
+  }
   DeviceGuard guard(device);  // the caller's current device is restored on return
   {
     int cur = -1;
@@ -1530,9 +1541,11 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
       ds.mask_smem = 160 * 1024;
     }
   }
-  // zero fill at the HBM write rate first, then only the tiles a box touches (YPB_MASK_ONEPASS=1: the one-kernel form)
-  static const bool onepass = getenv("YPB_MASK_ONEPASS") != nullptr;
-  g.prefilled = onepass ? 0 : 1;
+  // Measured (profiles/r2_ab_split_branches.md): the two-kernel form is SLOWER (0.40 vs 0.33 ms for 1 824 detections at
+  // 640x640): the zero fill was never what bounds this kernel - the per-band logit window and the blends are - so the
+  // one-kernel form stays the default and the streaming fill is an opt-in (YPB_MASK_PREFILL=1).
+  static const bool prefill = getenv("YPB_MASK_PREFILL") != nullptr;
+  g.prefilled = prefill ? 1 : 0;
   if (g.prefilled)
     mask_zero_kernel<<<device_state().num_sms * 8, 256, 0, st>>>(offsets, e->B, capacity, (long long)g.out_h * g.out_w, masks);
   mask_decode_kernel<<<grid, 256, band_smem, st>>>(proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb,

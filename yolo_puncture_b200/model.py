@@ -329,6 +329,7 @@ class YOLO:
         stream as soon as its frames are staged, and it overlaps the engine pass before it."""
         B = len(frames)
         t0 = time.perf_counter()
+        tm = self.last_timing = {"stage_ms": 0.0, "wait_ms": 0.0}  # host-side breakdown of the last group (diagnostics)
         new_unpad, top, bottom, left, right = letterbox_geometry(shape, imgsz, auto)
         H, W = new_unpad[1] + top + bottom, new_unpad[0] + left + right
         if H % 32 or W % 32:
@@ -401,8 +402,10 @@ class YOLO:
                         step = max(1, int(self.stage_chunk))
                         for c0 in range(lo, hi, step):
                             c1 = min(c0 + step, hi)
+                            ts = time.perf_counter()
                             check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, c0 * vp), ctypes.byref(src_ptrs, c0 * vp),
                                                          ctypes.byref(sizes, c0 * ctypes.sizeof(ctypes.c_size_t)), c1 - c0, nthreads))
+                            tm["stage_ms"] += (time.perf_counter() - ts) * 1e3
                             target[c0 - lo:c1 - lo].copy_(stage_host[c0:c1], non_blocking=True)
                     else:
                         for fu in futs[lo:hi]:
@@ -463,7 +466,9 @@ class YOLO:
                 eng, lo, hi, cap, slot = passes[k]
                 o = eng.out_sets[slot]
                 n = hi - lo
+                ts = time.perf_counter()
                 inf_done[k].synchronize()  # the host sync of this pass: its counts and boxes are in pinned memory now
+                tm["wait_ms"] += (time.perf_counter() - ts) * 1e3
                 hb = hostbuf[(k & 1, cap)]
                 counts = hb[0][:n].clone()
                 n_k = int(counts.sum())
@@ -494,10 +499,13 @@ class YOLO:
             finish(n_mb - 1)
             main.wait_stream(side)  # the masks are consumed on the caller's stream
             t2 = time.perf_counter()
+            tm["enqueue_to_done_ms"] = (t2 - t1) * 1e3
+            tm["prologue_ms"] = (t1 - t0) * 1e3
             err = self.engine.device_error()
             if err:
                 raise YpbError(f"device pipeline error word 0x{err:x}")
             t3 = time.perf_counter()
+        tm["device_error_ms"] = (t3 - t2) * 1e3
         speed = {"preprocess": (t1 - t0) * 1e3 / B, "inference": (t2 - t1) * 1e3 / B, "postprocess": (t3 - t2) * 1e3 / B}
         out = []
         empty = None
@@ -517,4 +525,6 @@ class YOLO:
                     boxes, m = Boxes(empty, shp, n=0), None
                 off += n
                 out.append(Results(frames[lo + j], None, self.names, boxes=boxes, masks=m, speed=speed))
+        tm["results_ms"] = (time.perf_counter() - t3) * 1e3
+        tm["threads"] = nthreads if (direct or dev_lb) else 0
         return out

@@ -196,6 +196,10 @@ int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* byt
 /* Same with the copy flavour chosen by the caller: mode 0 = memcpy, 1 = non-temporal stores (the default of
    ypb_stage_frames unless YPB_STAGE_MEMCPY is set).  Persistent thread pool, 256 KB pieces. */
 int ypb_stage_frames_ex(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads, int mode);
+/* Asynchronous flavour: queues the copy on the staging pool, returns at once, and gates `cuda_stream` (a host function):
+   whatever is enqueued on that stream afterwards - the chunk's H2D copy - runs only once the frames are staged.  The
+   caller keeps enqueuing engine passes meanwhile; sources and destinations must outlive the gate. */
+int ypb_stage_frames_gated(void* cuda_stream, void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads);
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,7 @@ SIGNATURES = {
     "ypb_nms_scratch_bytes": (c_size_t, [c_int, c_int]),
     "ypb_stage_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "ypb_stage_frames_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
+    "ypb_stage_frames_gated": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]),
     "ypb_mask_min_rect": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ypb_letterbox_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int]),

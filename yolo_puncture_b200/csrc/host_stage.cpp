@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -159,6 +160,134 @@ class StagePool {
 };
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Asynchronous flavour: the caller queues staging jobs and goes on enqueuing GPU work; a host function placed in the copy
+// stream in front of each chunk's H2D copy (ypb_stage_gate, ypb200.cu) holds that stream until the chunk's ticket is
+// complete.  predict() then never blocks on staging: frames are staged by the pool while Python enqueues the engine
+// passes, and the copy engine picks every chunk up the moment it is ready.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct AsyncJob {
+  std::vector<void*> dst;
+  std::vector<const void*> src;
+  std::vector<size_t> bytes;
+  std::vector<long> first_piece;
+  int mode = 0;
+  long total = 0;
+  std::atomic<long> next{0};
+  std::atomic<long> done{0};
+  std::mutex m;
+  std::condition_variable cv;
+  bool finished = false;
+};
+
+class AsyncStagePool {
+ public:
+  static AsyncStagePool& get() {
+    static AsyncStagePool p;
+    return p;
+  }
+  void submit(std::shared_ptr<AsyncJob> job, int nthreads) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      while ((int)threads_.size() < nthreads) threads_.emplace_back([this] { loop(); });
+      queue_.push_back(std::move(job));
+    }
+    cv_.notify_all();
+  }
+
+ private:
+  AsyncStagePool() = default;
+  ~AsyncStagePool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  void loop() {
+    for (;;) {
+      std::shared_ptr<AsyncJob> job;  // shared ownership: the waiter may drop its reference while a late worker still polls
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        // the head job stays at the front until its last piece has been HANDED OUT: all threads work on the oldest chunk
+        for (;;) {
+          while (!queue_.empty() && queue_.front()->next.load(std::memory_order_relaxed) >= queue_.front()->total) queue_.erase(queue_.begin());
+          if (stop_ || !queue_.empty()) break;
+          cv_.wait(lk);
+        }
+        if (stop_) return;
+        job = queue_.front();
+      }
+      for (;;) {
+        const long p = job->next.fetch_add(1, std::memory_order_relaxed);
+        if (p >= job->total) break;
+        int f = 0;
+        const int n = (int)job->bytes.size();
+        while (f + 1 < n && job->first_piece[f + 1] <= p) ++f;
+        const size_t off = (size_t)(p - job->first_piece[f]) * kPiece;
+        const size_t len = job->bytes[f] - off < kPiece ? job->bytes[f] - off : kPiece;
+        copy_piece(static_cast<uint8_t*>(job->dst[f]) + off, static_cast<const uint8_t*>(job->src[f]) + off, len, job->mode);
+        if (job->done.fetch_add(1, std::memory_order_acq_rel) + 1 == job->total) {
+          {
+            std::lock_guard<std::mutex> lk(job->m);
+            job->finished = true;
+          }
+          job->cv.notify_all();
+          break;
+        }
+      }
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::vector<std::thread> threads_;
+  std::vector<std::shared_ptr<AsyncJob>> queue_;
+  bool stop_ = false;
+};
+
+}  // namespace
+
+// Queue a staging job; returns an opaque ticket that MUST be passed to exactly one ypb_host_stage_wait().
+extern "C" void* ypb_host_stage_submit(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads, int mode) {
+  auto job = std::make_shared<AsyncJob>();
+  job->mode = mode;
+  job->dst.assign(dst, dst + n);
+  job->src.assign(src, src + n);
+  job->bytes.assign(bytes, bytes + n);
+  job->first_piece.resize(n + 1);
+  long acc = 0;
+  for (int i = 0; i < n; ++i) {
+    job->first_piece[i] = acc;
+    acc += (long)((bytes[i] + kPiece - 1) / kPiece);
+  }
+  job->first_piece[n] = acc;
+  job->total = acc;
+  auto* ticket = new std::shared_ptr<AsyncJob>(job);
+  if (acc == 0) {
+    job->finished = true;
+    return ticket;
+  }
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  AsyncStagePool::get().submit(job, nthreads);
+  return ticket;
+}
+
+// Block until the ticket's frames are staged, then free it (called from the CUDA host function, or directly).
+extern "C" void ypb_host_stage_wait(void* ticket) {
+  auto* holder = static_cast<std::shared_ptr<AsyncJob>*>(ticket);
+  if (!holder) return;
+  {
+    AsyncJob* job = holder->get();
+    std::unique_lock<std::mutex> lk(job->m);
+    job->cv.wait(lk, [&] { return job->finished; });
+  }
+  delete holder;
+}
 
 // mode 0: memcpy; 1: non-temporal stores (AVX2) when available.  Returns 0.
 extern "C" int ypb_host_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads, int mode) {

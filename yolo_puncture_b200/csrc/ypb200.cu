@@ -1779,6 +1779,26 @@ int ypb_stage_frames_ex(void* const* dst, const void* const* src, const size_t* 
   return ypb_host_stage_frames(dst, src, bytes, n, nthreads, mode);
 }
 
+// Asynchronous staging: queue the copy of n frames into pinned memory (returns at once) and place a gate in `cuda_stream`:
+// work enqueued on that stream after this call (the chunk's H2D copy) starts only when the frames are staged.  The source
+// frames and both pointer targets must stay alive until the stream has passed the gate.
+extern "C" void* ypb_host_stage_submit(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads, int mode);
+extern "C" void ypb_host_stage_wait(void* ticket);
+static void CUDART_CB stage_gate_fn(void* ticket) { ypb_host_stage_wait(ticket); }
+
+int ypb_stage_frames_gated(void* cuda_stream, void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads) {
+  if (!dst || !src || !bytes || n < 0) return fail(YPB_ERR_ARG, "bad argument");
+  if (n == 0) return YPB_OK;
+  static const int mode = getenv("YPB_STAGE_MEMCPY") ? 0 : 1;
+  void* ticket = ypb_host_stage_submit(dst, src, bytes, n, nthreads, mode);
+  cudaError_t ce = cudaLaunchHostFunc(reinterpret_cast<cudaStream_t>(cuda_stream), stage_gate_fn, ticket);
+  if (ce != cudaSuccess) {
+    ypb_host_stage_wait(ticket);  // no gate in the stream: finish the copy here so that nothing dangles
+    return fail(YPB_ERR_CUDA, std::string("cudaLaunchHostFunc: ") + cudaGetErrorString(ce));
+  }
+  return YPB_OK;
+}
+
 int ypb_stage_frames(void* const* dst, const void* const* src, const size_t* bytes, int n, int nthreads) {
   static const int mode = getenv("YPB_STAGE_MEMCPY") ? 0 : 1;
   return ypb_stage_frames_ex(dst, src, bytes, n, nthreads, mode);

@@ -189,6 +189,7 @@ class YOLO:
         self.micro_batch = None
         self.head_pass = 16
         self.stage_chunk = 8      # frames per staging call / H2D copy when the caller's frames are pageable
+        self.async_staging = True  # staging runs on the native pool behind a stream gate; False: the host blocks per chunk
         self.stage_threads = None  # host threads of the staging pool (None: min(16, cores / WORLD_SIZE))
         self.device_letterbox = True  # resize + pad on the GPU (False: cv2 on host threads, exactly upstream's LetterBox)
         if device is not None:
@@ -403,8 +404,13 @@ class YOLO:
                         for c0 in range(lo, hi, step):
                             c1 = min(c0 + step, hi)
                             ts = time.perf_counter()
-                            check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, c0 * vp), ctypes.byref(src_ptrs, c0 * vp),
-                                                         ctypes.byref(sizes, c0 * ctypes.sizeof(ctypes.c_size_t)), c1 - c0, nthreads))
+                            if self.async_staging:  # queue the copy and gate the copy stream on it: the host moves on
+                                check(lib().ypb_stage_frames_gated(ctypes.c_void_p(cs.cuda_stream), ctypes.byref(dst_ptrs, c0 * vp),
+                                                                   ctypes.byref(src_ptrs, c0 * vp),
+                                                                   ctypes.byref(sizes, c0 * ctypes.sizeof(ctypes.c_size_t)), c1 - c0, nthreads))
+                            else:
+                                check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, c0 * vp), ctypes.byref(src_ptrs, c0 * vp),
+                                                             ctypes.byref(sizes, c0 * ctypes.sizeof(ctypes.c_size_t)), c1 - c0, nthreads))
                             tm["stage_ms"] += (time.perf_counter() - ts) * 1e3
                             target[c0 - lo:c1 - lo].copy_(stage_host[c0:c1], non_blocking=True)
                     else:

@@ -84,3 +84,42 @@ def test_conv_simt_twin_matches_reference(case):
     ok = bool(((got - ref).abs() <= ATOL + RTOL * ref.abs()).all())
     assert ok, describe_mismatch(got, ref, RTOL, ATOL)
     assert clean
+
+
+# CTA-pair kernel (conv3_halo2_kernel: tcgen05.mma.cta_group::2, weights shared by the two SMs of a TPC).  The planner
+# picks it for 3x3 stride-1 layers with streamed weights and >= 74 tile pairs; YPB_PAIR_MIN=1 forces it on small cases.
+PAIR_CASES = [
+    (8, 80, 80, 128, 0, 128, 128, 3, 1, 1, False, 128, 0, False),      # many pairs per cluster, K = 2 full chunks
+    (4, 80, 80, 320, 160, 160, 160, 3, 1, 1, True, 320, 160, False),   # ragged third chunk (4, 4, 2 K-steps), residual, slices
+    (3, 40, 40, 320, 0, 320, 320, 3, 1, 1, False, 320, 0, False),      # two Cout splits of 160; 45 tiles: the last pair is half empty
+    (2, 23, 40, 96, 16, 80, 80, 3, 1, 1, True, 80, 0, False),          # K-steps (4, 1), odd map size
+    (5, 20, 20, 256, 0, 256, 224, 3, 1, 0, False, 224, 0, True),       # n_tile 224, fp32 rows, no activation
+    (2, 160, 160, 128, 0, 128, 128, 3, 1, 1, False, 128, 0, False),    # 400 tiles per image
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[str(i) for i in range(len(PAIR_CASES))])
+def test_conv_pair_kernel_matches_reference(case, monkeypatch):
+    monkeypatch.setenv("YPB_PAIR_MIN", "1")
+    got, ref, clean = run_case(case, impl=0, seed=3)
+    ok = bool(((got - ref).abs() <= ATOL + RTOL * ref.abs()).all())
+    assert ok, describe_mismatch(got, ref, RTOL, ATOL)
+    assert clean, "kernel wrote outside its channel slice"
+    monkeypatch.setenv("YPB_NO_PAIR", "1")  # and the single-CTA halo kernel on the same case, bit for bit the same result
+    got1, _, _ = run_case(case, impl=0, seed=3)
+    assert torch.equal(got, got1)
+
+
+def test_planner_picks_the_pair_kernel_for_wide_layers():
+    import ctypes as C
+    from yolo_puncture_b200._lib import check, diag_lib
+    B, H, W, cin, cout = 32, 80, 80, 160, 160
+    x = torch.zeros((B, H, W, cin), device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros((9, cout, cin), device="cuda", dtype=torch.bfloat16)
+    bias = torch.zeros((cout,), device="cuda")
+    out = torch.empty((B, H, W, cout), device="cuda", dtype=torch.bfloat16)
+    ms, desc = C.c_float(), C.create_string_buffer(640)
+    check(diag_lib().ypb_conv_bench(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(x.data_ptr()), B, H, W, cin, 0, cin,
+                                    C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()), cout, 3, 1, 1, None,
+                                    C.c_void_p(out.data_ptr()), cout, 0, 0, 0, -1, 2, C.byref(ms), desc, 640))
+    assert desc.value.decode().startswith("pair(cta_group::2)"), desc.value.decode()

@@ -64,8 +64,36 @@ LAYERS = [
 ]
 
 
+# yolov8x-seg at B=32 (BASELINE config C5's model): Cin 80 / 160 / 320 / 640 -> ragged 64-channel chunks, streamed weights
+LAYERS_X = [
+    ("x.1           3x3s2  80->160 @320", 320, 320, 80, 0, 80, 160, 3, 2, 0, 0, 160, 1),
+    ("x.2.m.cv1     3x3    80->80  @160", 160, 160, 400, 80, 80, 80, 3, 1, 0, 0, 80, 1),
+    ("x.2.m.cv2     3x3    80->80+r@160", 160, 160, 80, 0, 80, 80, 3, 1, 1, 0, 400, 1),
+    ("x.3           3x3s2 160->320 @160", 160, 160, 160, 0, 160, 320, 3, 2, 0, 0, 320, 1),
+    ("x.4.m.cv1     3x3   160->160 @80", 80, 80, 1280, 160, 160, 160, 3, 1, 0, 0, 160, 1),
+    ("x.4.m.cv2     3x3   160->160+r@80", 80, 80, 160, 0, 160, 160, 3, 1, 1, 0, 1280, 1),
+    ("x.4.cv2       1x1  1280->320 @80", 80, 80, 1280, 0, 1280, 320, 1, 1, 0, 0, 960, 1),
+    ("x.6.m.cv1     3x3   320->320 @40", 40, 40, 2560, 320, 320, 320, 3, 1, 0, 0, 320, 1),
+    ("x.6.m.cv2     3x3   320->320+r@40", 40, 40, 320, 0, 320, 320, 3, 1, 1, 0, 2560, 1),
+    ("x.8.m.cv1     3x3   320->320 @20", 20, 20, 1600, 320, 320, 320, 3, 1, 0, 0, 320, 1),
+    ("x.head0.s0    3x3   320->480 @80", 80, 80, 320, 0, 320, 480, 3, 1, 0, 0, 480, 1),
+    ("x.head0.cv3.1 3x3   320->320 @80", 80, 80, 480, 80, 320, 320, 3, 1, 0, 0, 320, 1),
+    ("x.proto.cv2   3x3   320->320 @160", 160, 160, 320, 0, 320, 320, 3, 1, 0, 0, 320, 1),
+]
+# yolov8m-seg at 736x1280, B=16 (config C4): c = 48 / 96 / 192 / 288
+LAYERS_M = [
+    ("m.2.m.cv1     3x3    48->48  @184x320", 184, 320, 192, 48, 48, 48, 3, 1, 0, 0, 48, 1),
+    ("m.4.m.cv1     3x3    96->96  @92x160", 92, 160, 576, 96, 96, 96, 3, 1, 0, 0, 96, 1),
+    ("m.6.m.cv1     3x3   192->192 @46x80", 46, 80, 1152, 192, 192, 192, 3, 1, 0, 0, 192, 1),
+    ("m.8.m.cv1     3x3   288->288 @23x40", 23, 40, 1152, 288, 288, 288, 3, 1, 0, 0, 288, 1),
+    ("m.head0.s0    3x3   192->320 @92x160", 92, 160, 192, 0, 192, 320, 3, 1, 0, 0, 320, 1),
+    ("m.proto.cv2   3x3   192->192 @184x320", 184, 320, 192, 0, 192, 192, 3, 1, 0, 0, 192, 1),
+]
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--set", default="s", choices=["s", "x", "m"], help="layer table: yolov8s-seg B=64, yolov8x-seg B=32, yolov8m-seg 736x1280 B=16")
     ap.add_argument("--dbg", default="0,1,2,4,7")
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=20)
@@ -73,13 +101,16 @@ def main():
     ap.add_argument("--batch", type=int, default=B)
     ap.add_argument("--csv", default=None)
     a = ap.parse_args()
+    layers = {"s": LAYERS, "x": LAYERS_X, "m": LAYERS_M}[a.set]
+    if a.set != "s" and a.batch == B:
+        a.batch = 32 if a.set == "x" else 16
     dbgs = [int(x) for x in a.dbg.split(",")]
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     st = torch.cuda.current_stream().cuda_stream
     rows = []
     print(f"{'layer':36s} " + " ".join(f"{'dbg' + str(d) + ' ms':>10s}" for d in dbgs) + "   TFLOP/s    GB/s  plan")
-    for (name, H, W, ictot, ioff, cin, cout, k, s, res, omode, octot, act) in LAYERS:
+    for (name, H, W, ictot, ioff, cin, cout, k, s, res, omode, octot, act) in layers:
         if a.only and a.only not in name:
             continue
         nb = a.batch

@@ -12,6 +12,7 @@
 #include <string>
 
 #include "conv_tc.cuh"
+#include "conv_halo2.cuh"
 
 namespace ypb {
 
@@ -44,6 +45,11 @@ struct ConvLaunch {
   Conv3Extra x3{};
   CUtensorMap tmHalo3, tmB3;  // halo box; weight box {64, n_tile, b_group}
   int tiles_h3 = 0, tiles_w3 = 0, total_tiles3 = 0, smem3 = 0;
+  // CTA-pair kernel (conv3_halo2_kernel): 3x3 stride-1 layers whose weights do not fit in shared memory
+  bool use_pair = false;
+  Conv3Pair x2{};
+  CUtensorMap tmHalo2, tmB2;  // halo box {64, 10, 18}; weight box {64, n_tile / 2, 3}
+  int tiles_h2 = 0, tiles_w2 = 0, total_pairs = 0, smem_pair = 0;
   ConvParams p;       // persistent kernels (conv_tc2 geometry: tile may hold msub sub-tiles)
   ConvParams p1;      // one-tile-per-CTA geometry (impl 2 / 3, A/B experiments)
   CUtensorMap tmA1;
@@ -294,6 +300,7 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
         } else {
           a_slots = 2;
           if ((avail - a_slots * a_bytes) / (3 * b_slot) < 2) b_group = 1;  // a kernel row of taps per box when two fit
+          if (const char* ev = getenv("YPB_BGROUP")) b_group = atoi(ev) == 1 ? 1 : 3;  // experiment knob
           b_slots = (avail - a_slots * a_bytes) / (b_group * b_slot);
           if (b_slots > 12) b_slots = 12;
           if (b_slots < 2) continue;
@@ -337,6 +344,32 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
       L->tiles_h3 = th3; L->tiles_w3 = tw3; L->total_tiles3 = d.B * th3 * tw3;
       L->smem3 = (int)(1024 + a_slots * a_bytes + b_total + 512 + epi_smem + conv_bias_smem(d.cout));
       conv3_set_taps(&L->x3, true);
+    }
+  }
+  L->use_pair = false;
+  if (L->use_halo && !L->x3.b_stat && !L->x3.s2 && d.k == 3 && d.stride == 1 && (p.n_tile % 16) == 0 && !getenv("YPB_NO_PAIR")) {
+    // Streamed weights: let the two SMs of a TPC share every weight tile (conv_halo2.cuh).  Each CTA keeps a 16 x 8
+    // pixel tile; the pair's tiles are consecutive in the (image, row, column) order.
+    const int th1 = (oH + 15) / 16, tw1 = (oW + 7) / 8;
+    const long m_tiles = (long)d.B * th1 * tw1, pairs_m = (m_tiles + 1) / 2, total_pairs = pairs_m * splits;
+    const long avail = 227 * 1024 - 1024 - 512 - kEpiWarps * epi_stage_bytes(d.out_mode == OUT_F32) - conv_bias_smem(d.cout);
+    const long a_bytes = (180L * 128 + 1023) & ~1023L, grp = 3L * (p.n_tile / 2) * 128;
+    long a_slots = 3;
+    long b_slots = (avail - a_slots * a_bytes) / grp;
+    if (b_slots < 3) { a_slots = 2; b_slots = (avail - a_slots * a_bytes) / grp; }
+    if (b_slots > 12) b_slots = 12;
+    const int min_pairs = getenv("YPB_PAIR_MIN") ? atoi(getenv("YPB_PAIR_MIN")) : 74;
+    if (b_slots >= 2 && total_pairs >= min_pairs && 2 * conv2_acc_stride(p.n_tile) <= 512) {
+      L->use_pair = true;
+      L->x2.a_slots = (int)a_slots; L->x2.a_bytes = (int)a_bytes; L->x2.b_slots = (int)b_slots; L->x2.grp_bytes = (int)grp;
+      L->x2.m_tiles = (int)m_tiles;
+      Conv3Extra taps;
+      conv3_set_taps(&taps, false);
+      for (int t = 0; t < 9; ++t) L->x2.tap_off[t] = taps.tap_off[t];
+      L->x2.a_hi = taps.a_hi;
+      L->tiles_h2 = th1; L->tiles_w2 = tw1; L->total_pairs = (int)total_pairs;
+      L->smem_pair = (int)(1024 + a_slots * a_bytes + b_slots * grp + 512 + kEpiWarps * epi_stage_bytes(d.out_mode == OUT_F32) +
+                           conv_bias_smem(d.cout));
     }
   }
 #if YPB_DIAG
@@ -392,6 +425,10 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
     if (L->x3.s2) { hb[2] = 2; hb[3] = (cuuint32_t)(16 * L->x3.msub + 1); }
     if (!encode_bf16_map(&L->tmHalo3, d.in, 5, dims, str, hb, err)) return false;
   }
+  if (L->use_pair) {
+    cuuint32_t hb[5] = {64, 10, 18, 1, 1};
+    if (!encode_bf16_map(&L->tmHalo2, d.in, 5, dims, str, hb, err)) return false;
+  }
   L->halo_ok = false;
   if (d.k == 3 && d.stride == 1 && d.cout <= 128) {
     cuuint32_t hb[5] = {64, 10, 18, 1, 1};
@@ -427,12 +464,19 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
     cuuint32_t wb3[3] = {64, (cuuint32_t)p.n_tile, (cuuint32_t)L->x3.b_group};
     if (!encode_bf16_map(&L->tmB3, d.wg, 3, wd, ws, wb3, err)) return false;
   }
+  if (L->use_pair) {
+    cuuint32_t wb2[3] = {64, (cuuint32_t)(p.n_tile / 2), 3};
+    if (!encode_bf16_map(&L->tmB2, d.wg, 3, wd, ws, wb2, err)) return false;
+  }
   return true;
 }
 
 // One-line description of the launch the planner chose (diagnostics).
 static void conv_describe(const ConvLaunch& L, int impl, char* out, int n) {
-  if (L.use_halo && impl == 0)
+  if (L.use_pair && impl == 0)
+    snprintf(out, n, "pair(cta_group::2) a_slots=%d b_slots=%d n_tile=%d splits=%d pairs=%d smem=%d", L.x2.a_slots, L.x2.b_slots,
+             L.p.n_tile, L.n_splits, L.total_pairs, L.smem_pair);
+  else if (L.use_halo && impl == 0)
     snprintf(out, n, "halo%s msub=%d a_slots=%d b_stat=%d b_slots=%d b_group=%d n_tile=%d splits=%d tiles=%d smem=%d", L.x3.s2 ? "-s2" : "", L.x3.msub,
              L.x3.a_slots, L.x3.b_stat, L.x3.b_slots, L.x3.b_group, L.p.n_tile, L.n_splits, L.total_tiles3, L.smem3);
   else
@@ -476,6 +520,8 @@ static cudaError_t conv_launch_init() {
   e = cudaFuncSetAttribute(conv_tc2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);       \
   if (e != cudaSuccess) return e;                                                                                 \
   e = cudaFuncSetAttribute(conv3_halo_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);     \
+  if (e != cudaSuccess) return e;                                                                                 \
+  e = cudaFuncSetAttribute(conv3_halo2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);    \
   if (e != cudaSuccess) return e;
   YPB_SET_SMEM(0) YPB_SET_SMEM(1) YPB_SET_SMEM(2) YPB_SET_SMEM(3) YPB_SET_SMEM(4) YPB_SET_SMEM(5) YPB_SET_SMEM(6) YPB_SET_SMEM(7)
 #undef YPB_SET_SMEM
@@ -498,6 +544,22 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   static const bool no_pdl = getenv("YPB_NO_PDL") != nullptr;
   cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Same for a kernel that runs as CTA pairs (cluster of two: the two SMs of a TPC).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_pair(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("YPB_NO_PDL") != nullptr;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 1 : 2;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -549,6 +611,21 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
     return cudaGetLastError();
   }
 #endif
+  if (L.use_pair && impl == 0) {
+    ConvParams p2 = L.p;
+    p2.tiles_h = L.tiles_h2; p2.tiles_w = L.tiles_w2;
+    conv_set_fastdiv(p2, L.n_splits);
+    const int clusters = L.total_pairs < num_sms / 2 ? L.total_pairs : num_sms / 2;
+    cudaError_t le = cudaSuccess;
+#define YPB_PAIR_CASE(MODE) \
+  case MODE: le = launch_pdl_pair(conv3_halo2_kernel<MODE>, 2 * clusters, kConv2Threads, L.smem_pair, stream, L.tmHalo2, L.tmB2, p2, L.x2, L.n_splits, L.total_pairs); break;
+    switch (epi_mode_of(p2.out_mode, p2.res != nullptr, p2.act)) {
+      YPB_PAIR_CASE(0) YPB_PAIR_CASE(1) YPB_PAIR_CASE(2) YPB_PAIR_CASE(3) YPB_PAIR_CASE(4) YPB_PAIR_CASE(5) YPB_PAIR_CASE(6)
+      YPB_PAIR_CASE(7)
+    }
+#undef YPB_PAIR_CASE
+    return le != cudaSuccess ? le : cudaGetLastError();
+  }
   if (L.use_halo && impl == 0) {
     ConvParams p3 = L.p;
     p3.tiles_h = L.tiles_h3; p3.tiles_w = L.tiles_w3;

@@ -561,18 +561,26 @@ __device__ __forceinline__ void epi_store_pass(const ConvParams& p, const uint32
 #undef EPI_MARK
 }
 
+__device__ __forceinline__ void epi_release(uint64_t* release, uint32_t release_remote) {
+  if (release_remote != 0u) mbar_arrive_cluster(release_remote);
+  else mbar_arrive(release);
+}
+
 template <int MODE, bool PINGPONG = true>
 __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa, uint32_t sbias_sa, int lane, int c_begin,
                                           int c_end, uint32_t t_addr, int n0, bool valid, int qb, int rem,
                                           uint64_t* release, long long (&pacc)[6], const CUtensorMap* tmO = nullptr,
-                                          int tma_mode = 0, int tq = 0, int tb = 0, int* tbuf = nullptr) {
+                                          int tma_mode = 0, int tq = 0, int tb = 0, int* tbuf = nullptr,
+                                          uint32_t release_remote = 0) {
+  // release_remote != 0: the accumulator is handed back with an arrive on a barrier of ANOTHER CTA of the cluster (its
+  // shared::cluster address; the 2-CTA kernel's peer signals the leader's MMA warp) instead of the local `release`
   constexpr int LAY = MODE & 3;
   constexpr bool F32 = LAY == EPI_F32;
   constexpr int P32 = F32 ? 8 : 4, P16 = F32 ? 4 : 2;  // 16-byte pieces per staged row of a 32- / 16-column pass
   const unsigned vmask = __ballot_sync(0xffffffffu, valid);
   if (c_begin >= c_end || vmask == 0u) {  // nothing to read (more warps than column chunks; tile rows all padding)
     __syncwarp();
-    if (lane == 0 && release != nullptr) mbar_arrive(release);
+    if (lane == 0 && release != nullptr) epi_release(release, release_remote);
     return;
   }
   const bool prof = kProf && (p.dbg & 8) != 0 && lane == 0;
@@ -611,7 +619,7 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
       tmem_ld_wait();
       if (k + 1 == n32 && !tail16 && release != nullptr) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(release);
+        if (lane == 0) epi_release(release, release_remote);
       }
       epi_store_pass<32, MODE>(p, va, stage_sa, sbias_sa + (uint32_t)(n0 + col) * 4, lane, n0 + col, base, res_base, dl, rl,
                                prof, pt, pacc);
@@ -632,7 +640,7 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
       } else if (!tail16 && release != nullptr) {
         // last TMEM read of this tile has landed (tcgen05.wait::ld): hand the accumulator back to the MMA warp
         __syncwarp();
-        if (lane == 0) mbar_arrive(release);
+        if (lane == 0) epi_release(release, release_remote);
       }
       EPI_MARK(9);
       int tb_idx = 0;
@@ -657,7 +665,7 @@ __device__ __forceinline__ void epi_drain(const ConvParams& p, uint32_t stage_sa
     tmem_ld_wait();
     if (release != nullptr) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(release);
+      if (lane == 0) epi_release(release, release_remote);
     }
     if (tma_mode != 0) {  // the manual pass reuses the staging memory the bulk stores read from
       if (lane == 0) bulk_wait_read<0>();

@@ -87,6 +87,11 @@ class StagePool {
       job_ = job;
       want_ = nthreads - 1;
       ++epoch_;
+      static const int hc = (int)std::thread::hardware_concurrency();
+      int lim = nthreads - 1;
+      if (lim > hc - 2) lim = hc - 2;
+      spin_limit_.store(lim < 0 ? 0 : lim, std::memory_order_relaxed);
+      epoch_hint_.store(epoch_, std::memory_order_release);
     }
     cv_.notify_all();
     work(job);
@@ -133,6 +138,13 @@ class StagePool {
     unsigned long seen = 0;
     for (;;) {
       Job* job = nullptr;
+      // stay hot between the chunk calls of one predict(): spin on the epoch for a short while before sleeping (a thread
+      // parked on the condition variable needs 50-100 us to come back and its core has clocked down by then; measured
+      // in situ the chunk calls ran at 26 GB/s against 71 GB/s back to back)
+      // (only the threads the last job used, and never more spinners than cores minus two: a spinning thread that
+      // shares a core with a working one halves it)
+      if (id < spin_limit_.load(std::memory_order_relaxed))
+        for (int spin = 0; spin < kSpinIters && epoch_hint_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
       {
         std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
@@ -149,6 +161,14 @@ class StagePool {
       }
     }
   }
+  static constexpr int kSpinIters = 40000;  // ~0.4 ms of pause instructions
+  static void cpu_relax() {
+#if defined(__x86_64__)
+    _mm_pause();
+#endif
+  }
+  std::atomic<unsigned long> epoch_hint_{0};
+  std::atomic<int> spin_limit_{0};
   std::mutex m_, run_mutex_;
   std::condition_variable cv_;
   std::vector<std::thread> threads_;

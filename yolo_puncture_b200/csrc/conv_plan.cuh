@@ -487,7 +487,7 @@ static void conv_describe(const ConvLaunch& L, int impl, char* out, int n) {
 // Per-device launch state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are properties of ONE
 // device: a process that drives several GPUs (YOLO.to('cuda:1'), one host thread per GPU) needs them per ordinal.
 struct DeviceState {
-  bool conv_attrs = false, halo_test_attr = false;
+  bool conv_attrs = false, halo_test_attr = false, mask_tile_attr = false;
   size_t sppf_smem = 0, mask_smem = 0;
   int num_sms = 148;
 };

@@ -229,6 +229,145 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   }
 }
 
+// Tile-stationary mask decode (the default when a 64 x 64 output tile needs at most kMaskWin x kMaskWin prototypes, i.e.
+// whenever the masks are up-sampled by >= ~3.7x: retina masks of 640 x 640 and larger frames, non-retina masks).
+// mask_decode_kernel is detection-stationary: every (detection, band) CTA re-reads the prototypes under its box from L2
+// (a 300 x 300 px box = 720 KB; 1.1 GB per 64-frame step) and that, not its zero fills, is what bounds it (ncu:
+// 0.19 ms with 6 MB of DRAM writes once the zero fill is taken out).  Here a CTA owns one 64 x 64 OUTPUT tile of one
+// image: it loads the tile's prototype window ONCE (<= 20 x 20 x 32 fp32, transposed in shared memory), then walks
+// the image's detections, and for every box that touches the tile computes the window's logits (one 32-long dot
+// product per prototype, operands in shared memory) and the tile's 4096 pixels.  Prototypes are read once per image;
+// the zero background is written by mask_zero_kernel at the HBM write rate.  Same dot-product order, same ATen blend
+// order, same crop and threshold as mask_decode_kernel: bit-identical masks.
+constexpr int kMaskWin = 20;
+
+__global__ void __launch_bounds__(256)
+mask_tile_kernel(const float* __restrict__ proto, const float* __restrict__ coef, const float* __restrict__ det,
+                 const float* __restrict__ det_lb, const int* __restrict__ offsets, int nB, int capacity, MaskGeom g,
+                 uint8_t* __restrict__ out) {
+  extern __shared__ float s_tile[];            // [32][kMaskWin * kMaskWin] prototypes (channel-major), then 2 logit windows
+  float* s_p = s_tile;
+  float* s_logit = s_tile + 32 * kMaskWin * kMaskWin;  // [2][kMaskWin * kMaskWin]
+  const int b = blockIdx.z;
+  const int slot0 = offsets[b], n_b = offsets[b + 1] - slot0;
+  if (n_b <= 0) return;
+  const int tx0 = blockIdx.x * kMaskTile, ty0 = blockIdx.y * kMaskTile;
+  auto src_of = [](int dst, float scale) {
+    float s = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+    return s < 0.f ? 0.f : s;
+  };
+  const int x_last = min(tx0 + kMaskTile, g.out_w) - 1, y_last = min(ty0 + kMaskTile, g.out_h) - 1;
+  const int sx_lo = (int)src_of(tx0, g.scale_w), sx_hi = min((int)src_of(x_last, g.scale_w) + 1, g.cw - 1);
+  const int sy_lo = (int)src_of(ty0, g.scale_h), sy_hi = min((int)src_of(y_last, g.scale_h) + 1, g.ch - 1);
+  const int ww = sx_hi - sx_lo + 1, wh = sy_hi - sy_lo + 1;  // <= kMaskWin (checked by the host)
+  const int npx = ww * wh;
+  // ---- does any box of this image touch the tile?  (cheap scan; most tiles of most images are background) ----
+  bool any = false;
+  for (int di = threadIdx.x; di < n_b; di += 256) {
+    if (slot0 + di >= capacity) break;
+    if (g.retina) {
+      const float* d = det + ((long long)b * g.max_det + di) * 6;
+      any = any || !(((float)(tx0 + kMaskTile) <= d[0]) || ((float)tx0 >= d[2]) || ((float)(ty0 + kMaskTile) <= d[1]) || ((float)ty0 >= d[3]));
+    } else {
+      const float* d = det_lb + ((long long)b * g.max_det + di) * 4;
+      const float bx1 = __fmul_rn(d[0], g.ratio_w), by1 = __fmul_rn(d[1], g.ratio_h);
+      const float bx2 = __fmul_rn(d[2], g.ratio_w), by2 = __fmul_rn(d[3], g.ratio_h);
+      any = any || !(((float)(g.left + sx_hi) < bx1) || ((float)(g.left + sx_lo) >= bx2) || ((float)(g.top + sy_hi) < by1) ||
+                     ((float)(g.top + sy_lo) >= by2));
+    }
+  }
+  if (!__syncthreads_or(any)) return;
+  // ---- the tile's prototype window, once: s_p[k][py * ww + px] ----
+  const float* pb = proto + (long long)b * g.mh * g.mw * g.nm;
+  for (int i = threadIdx.x; i < npx; i += 256) {
+    const int ry = i / ww, rx = i - ry * ww;
+    const float4* pp = reinterpret_cast<const float4*>(pb + ((long long)(g.top + sy_lo + ry) * g.mw + (g.left + sx_lo + rx)) * g.nm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 v = __ldg(pp + k);
+      s_p[(4 * k + 0) * (kMaskWin * kMaskWin) + i] = v.x;
+      s_p[(4 * k + 1) * (kMaskWin * kMaskWin) + i] = v.y;
+      s_p[(4 * k + 2) * (kMaskWin * kMaskWin) + i] = v.z;
+      s_p[(4 * k + 3) * (kMaskWin * kMaskWin) + i] = v.w;
+    }
+  }
+  // ---- this thread's 16 output pixels: row oy, columns ox0 .. ox0 + 15; interpolation taps are detection-independent ----
+  const int trow = threadIdx.x >> 2, tcol = (threadIdx.x & 3) * 16;
+  const int oy = ty0 + trow, ox0 = tx0 + tcol;
+  const float sy = src_of(min(oy, g.out_h - 1), g.scale_h);
+  const int y0 = (int)sy;
+  const int y1 = y0 + ((y0 < g.ch - 1) ? 1 : 0);
+  const float ly = __fsub_rn(sy, (float)y0), hy = __fsub_rn(1.0f, ly);
+  const int r0 = (y0 - sy_lo) * ww, r1 = (y1 - sy_lo) * ww;
+  const bool vec_ok = ((g.out_w & 15) == 0) && ox0 + 16 <= g.out_w;
+  __syncthreads();
+  int buf = 0;
+  for (int di = 0; di < n_b; ++di) {
+    const int slot = slot0 + di;
+    if (slot >= capacity) break;
+    float bx1, by1, bx2, by2;
+    bool touch;
+    if (g.retina) {
+      const float* d = det + ((long long)b * g.max_det + di) * 6;
+      bx1 = d[0]; by1 = d[1]; bx2 = d[2]; by2 = d[3];
+      touch = !(((float)(tx0 + kMaskTile) <= bx1) || ((float)tx0 >= bx2) || ((float)(ty0 + kMaskTile) <= by1) || ((float)ty0 >= by2));
+    } else {
+      const float* d = det_lb + ((long long)b * g.max_det + di) * 4;
+      bx1 = __fmul_rn(d[0], g.ratio_w); by1 = __fmul_rn(d[1], g.ratio_h);
+      bx2 = __fmul_rn(d[2], g.ratio_w); by2 = __fmul_rn(d[3], g.ratio_h);
+      touch = !(((float)(g.left + sx_hi) < bx1) || ((float)(g.left + sx_lo) >= bx2) || ((float)(g.top + sy_hi) < by1) ||
+                ((float)(g.top + sy_lo) >= by2));
+    }
+    if (!touch) continue;  // CTA-uniform
+    // window logits: one dot product per prototype pixel (fmaf chain k = 0..31, as mask_decode_kernel)
+    const float4* cf = reinterpret_cast<const float4*>(coef + ((long long)b * g.max_det + di) * g.nm);
+    float c[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 v = __ldg(cf + k);
+      c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+    }
+    float* lg = s_logit + buf * (kMaskWin * kMaskWin);
+    for (int i = threadIdx.x; i < npx; i += 256) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc = fmaf(c[k], s_p[k * (kMaskWin * kMaskWin) + i], acc);
+      if (!g.retina) {  // ops.process_mask crops in proto space BEFORE the upsample
+        const int ry = i / ww, rx = i - ry * ww;
+        const float fx = (float)(g.left + sx_lo + rx), fy = (float)(g.top + sy_lo + ry);
+        if (!(fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2)) acc = 0.f;
+      }
+      lg[i] = acc;
+    }
+    __syncthreads();  // (also orders the reuse of the other logit buffer two detections later)
+    buf ^= 1;
+    if (oy >= g.out_h || ox0 >= g.out_w) continue;
+    const bool row_in = g.retina ? ((float)oy >= by1 && (float)oy < by2) : true;
+    if (g.retina && (!row_in || (float)(ox0 + 16) <= bx1 || (float)ox0 >= bx2)) continue;  // zeros already there
+    uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int ox = ox0 + j;
+      const float sx = src_of(min(ox, g.out_w - 1), g.scale_w);
+      const int x0 = (int)sx;
+      const int x1 = x0 + ((x0 < g.cw - 1) ? 1 : 0);
+      const float lx = __fsub_rn(sx, (float)x0), hx = __fsub_rn(1.0f, lx);
+      const float top = __fadd_rn(__fmul_rn(hx, lg[r0 + x0 - sx_lo]), __fmul_rn(lx, lg[r0 + x1 - sx_lo]));
+      const float bot = __fadd_rn(__fmul_rn(hx, lg[r1 + x0 - sx_lo]), __fmul_rn(lx, lg[r1 + x1 - sx_lo]));
+      const float val = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+      bool on = val > 0.0f && row_in && ox < g.out_w;
+      if (g.retina) on = on && ((float)ox >= bx1 && (float)ox < bx2);
+      packed[j >> 2] |= (on ? 1u : 0u) << (8 * (j & 3));
+    }
+    uint8_t* o = out + (long long)slot * g.out_h * g.out_w + (long long)oy * g.out_w + ox0;
+    if (vec_ok) {
+      *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    } else {
+      for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j) o[j] = (uint8_t)((packed[j >> 2] >> (8 * (j & 3))) & 1u);
+    }
+  }
+}
+
 // Generic twin for outputs SMALLER than the proto window (a frame under ~imgsz/4 with retina_masks=True: upstream's
 // scale_masks simply down-samples): one thread per output pixel, four proto taps, the same dot-product order and ATen
 // blend order as mask_decode_kernel.  Tiny outputs only (< proto size), so no staging is worth it.

@@ -1526,6 +1526,29 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
     CUDA_TRY(cudaGetLastError());
     return YPB_OK;
   }
+  {
+    // tile-stationary decode when a 64 x 64 output tile needs at most kMaskWin x kMaskWin prototypes (mask_kernels.cuh)
+    const int need_h = std::min(g.ch, (int)(kMaskTile * g.scale_h) + 3), need_w = std::min(g.cw, (int)(kMaskTile * g.scale_w) + 3);
+    static const bool bands_only = getenv("YPB_MASK_BANDS") != nullptr;
+    if (!bands_only && need_h <= kMaskWin && need_w <= kMaskWin) {
+      const size_t smem = (size_t)(32 + 2) * kMaskWin * kMaskWin * sizeof(float);
+      {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        DeviceState& ds = device_state();
+        if (!ds.mask_tile_attr) {
+          CUDA_TRY(cudaFuncSetAttribute(mask_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          ds.mask_tile_attr = true;
+        }
+      }
+      g.prefilled = 1;
+      mask_zero_kernel<<<device_state().num_sms * 8, 256, 0, st>>>(offsets, e->B, capacity, (long long)g.out_h * g.out_w, masks);
+      dim3 tgrid((g.out_w + kMaskTile - 1) / kMaskTile, (g.out_h + kMaskTile - 1) / kMaskTile, e->B);
+      mask_tile_kernel<<<tgrid, 256, smem, st>>>(proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb,
+                                                 offsets, e->B, capacity, g, masks);
+      CUDA_TRY(cudaGetLastError());
+      return YPB_OK;
+    }
+  }
   const int bands = (g.out_h + kMaskTile - 1) / kMaskTile;
   dim3 grid(bands, capacity);
   if (capacity > 65535) return fail(YPB_ERR_ARG, "masks: capacity > 65535");

@@ -300,6 +300,17 @@ mask_tile_kernel(const float* __restrict__ proto, const float* __restrict__ coef
   const float ly = __fsub_rn(sy, (float)y0), hy = __fsub_rn(1.0f, ly);
   const int r0 = (y0 - sy_lo) * ww, r1 = (y1 - sy_lo) * ww;
   const bool vec_ok = ((g.out_w & 15) == 0) && ox0 + 16 <= g.out_w;
+  // horizontal taps of the 16 pixels (detection-independent): window column of the left tap, whether the right tap is a
+  // different column, and the two weights
+  int xo[16];
+  float lxs[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float sx = src_of(min(ox0 + j, g.out_w - 1), g.scale_w);
+    const int x0 = (int)sx;
+    lxs[j] = __fsub_rn(sx, (float)x0);
+    xo[j] = ((x0 - sx_lo) << 1) | ((x0 < g.cw - 1) ? 1 : 0);
+  }
   __syncthreads();
   int buf = 0;
   for (int di = 0; di < n_b; ++di) {
@@ -348,12 +359,10 @@ mask_tile_kernel(const float* __restrict__ proto, const float* __restrict__ coef
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int ox = ox0 + j;
-      const float sx = src_of(min(ox, g.out_w - 1), g.scale_w);
-      const int x0 = (int)sx;
-      const int x1 = x0 + ((x0 < g.cw - 1) ? 1 : 0);
-      const float lx = __fsub_rn(sx, (float)x0), hx = __fsub_rn(1.0f, lx);
-      const float top = __fadd_rn(__fmul_rn(hx, lg[r0 + x0 - sx_lo]), __fmul_rn(lx, lg[r0 + x1 - sx_lo]));
-      const float bot = __fadd_rn(__fmul_rn(hx, lg[r1 + x0 - sx_lo]), __fmul_rn(lx, lg[r1 + x1 - sx_lo]));
+      const int c0 = xo[j] >> 1, c1 = c0 + (xo[j] & 1);
+      const float lx = lxs[j], hx = __fsub_rn(1.0f, lx);
+      const float top = __fadd_rn(__fmul_rn(hx, lg[r0 + c0]), __fmul_rn(lx, lg[r0 + c1]));
+      const float bot = __fadd_rn(__fmul_rn(hx, lg[r1 + c0]), __fmul_rn(lx, lg[r1 + c1]));
       const float val = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
       bool on = val > 0.0f && row_in && ox < g.out_w;
       if (g.retina) on = on && ((float)ox >= bx1 && (float)ox < bx2);

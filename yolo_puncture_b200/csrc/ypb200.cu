@@ -1529,8 +1529,11 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
   {
     // tile-stationary decode when a 64 x 64 output tile needs at most kMaskWin x kMaskWin prototypes (mask_kernels.cuh)
     const int need_h = std::min(g.ch, (int)(kMaskTile * g.scale_h) + 3), need_w = std::min(g.cw, (int)(kMaskTile * g.scale_w) + 3);
-    static const bool bands_only = getenv("YPB_MASK_BANDS") != nullptr;
-    if (!bands_only && need_h <= kMaskWin && need_w <= kMaskWin) {
+    // Measured (profiles/r2_ab_split_branches.md): correct to the bit but slower than the band kernel on the bench
+    // workloads (boxes of the synthetic recipe are large: the per-pixel blend, not the prototype reads, is the bulk of
+    // the work, and the band kernel blends each window row once per column) - opt-in with YPB_MASK_TILES=1.
+    static const bool tiles = getenv("YPB_MASK_TILES") != nullptr;
+    if (tiles && need_h <= kMaskWin && need_w <= kMaskWin) {
       const size_t smem = (size_t)(32 + 2) * kMaskWin * kMaskWin * sizeof(float);
       {
         std::lock_guard<std::mutex> lock(g_dev_mutex);

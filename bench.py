@@ -232,6 +232,8 @@ def run_ours(args, wl):
     eng.set_graph(not args.no_graph)
     if args.micro_batch:
         yolo.micro_batch = args.micro_batch
+    if args.stage_threads:
+        yolo.stage_threads = args.stage_threads
     frames = make_frames(B, hw, rank * B)  # each rank owns its own shard of the synthetic stream
     new_unpad, top, bottom, left, right = letterbox_geometry(hw, (imgsz, imgsz), auto=True)
     H, W = new_unpad[1] + top + bottom, new_unpad[0] + left + right
@@ -302,7 +304,7 @@ def run_ours(args, wl):
         # the tracker lives on rank 0's GPU: the other ranks push their index masks into its memory over NVLink (CUDA IPC)
         sp.attach_mailbox(hw[0], hw[1], n_global, consumer_rank=0)
 
-    host_tm = []
+    host_tm, step_stats = [], []
 
     def run_e2e(frs, handoff_inside=False):
         """Timed region per step: predict() on host frames (H2D inside), D2H of every frame's boxes, and - when the job
@@ -321,10 +323,14 @@ def run_ours(args, wl):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
+        per_step = []
         for _ in range(e2e_steps):
+            ts = time.perf_counter()
             res, ordered, n_obj = e2e_step()
+            per_step.append((time.perf_counter() - ts) * 1e3)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        step_stats.append({"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)})
         if world > 1:
             t = torch.tensor([e2e_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -359,6 +365,7 @@ def run_ours(args, wl):
            "steps": e2e_steps, "ms_per_step": ms_page, "source": "pageable numpy frames",
            "pinned_frames": {"value": v_pin, "ms_per_step": ms_pin}, "index_mask_handoff": handoff,
            "host_breakdown_ms_last_step": {"pageable": host_tm[0], "pinned": host_tm[1], "host_cores": os.cpu_count()},
+           "call_ms_min_median_max": {"pageable": step_stats[0], "pinned": step_stats[1]},
            "frame_order_gather": "sharded.ShardedPredictor -> sharding.gather_in_frame_order over %d rank(s), inside the timed region" % world,
            "note": "YOLO.predict() on ordinary (pageable) host frames: staging into pinned memory + H2D of the uint8 frames + "
                    "engine + D2H of counts and boxes + ordered host gather every step; masks stay on the device as in "
@@ -495,6 +502,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-impl", type=int, default=0, help="0 persistent tcgen05 (product), 2 one-tile-per-CTA tcgen05 (A/B)")
     ap.add_argument("--micro-batch", type=int, default=0, help="frames per engine pass inside YOLO.predict() (e2e arm)")
+    ap.add_argument("--stage-threads", type=int, default=0, help="host threads of predict()'s staging pool (0: automatic)")
     ap.add_argument("--handoff", action="store_true", help="run index_masks() inside the timed e2e region (always on for yolov8x-seg)")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay (A/B)")
     ap.add_argument("--dump-ops", default=None, help="write the per-op CUDA-event profile of one step to this CSV")

@@ -123,3 +123,18 @@ def test_planner_picks_the_pair_kernel_for_wide_layers():
                                     C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()), cout, 3, 1, 1, None,
                                     C.c_void_p(out.data_ptr()), cout, 0, 0, 0, -1, 2, C.byref(ms), desc, 640))
     assert desc.value.decode().startswith("pair(cta_group::2)"), desc.value.decode()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_every_case_with_cta_pairs_forced(case, monkeypatch):
+    """All shapes of the main table again with YPB_PAIR_MIN=1: 1x1 and stride-2 3x3 layers then run on conv_tc2p_kernel, 3x3
+    stride-1 layers with streamed weights on conv3_halo2_kernel (resident-weight halo layers keep their kernel); results
+    must equal the single-CTA kernels' bit for bit (same accumulation order) and match the fp32 reference."""
+    monkeypatch.setenv("YPB_PAIR_MIN", "1")
+    got, ref, clean = run_case(case, impl=0)
+    ok = bool(((got - ref).abs() <= ATOL + RTOL * ref.abs()).all())
+    assert ok, describe_mismatch(got, ref, RTOL, ATOL)
+    assert clean, "kernel wrote outside its channel slice"
+    monkeypatch.setenv("YPB_NO_PAIR", "1")
+    got1, _, _ = run_case(case, impl=0)
+    assert torch.equal(got, got1)

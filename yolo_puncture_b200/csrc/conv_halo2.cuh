@@ -216,4 +216,217 @@ conv3_halo2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same pairing for the per-tap kernel (1x1 convs on 128 * msub consecutive pixels, stride-2 3x3 convs on rectangles):
+// conv_tc2_kernel's ring of {A box | W box} stages, each CTA loading ITS tile's A box and half of the W rows, the
+// leader issuing M = 256 MMAs per sub-tile.  Besides halving the weight bytes every SM pulls through L2 -> SM, a CTA
+// now reads only half of B from shared memory per MMA: an N = 256 step (137 cycles on one SM, bound by operand reads)
+// gets cheaper.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kConv2Threads, 1)
+conv_tc2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvParams p, int n_splits, int total_pairs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = p.msub * kATileBytes;
+  const int half_n = p.n_tile >> 1;
+  const int stage_bytes = a_bytes + half_n * 128;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);  // used in the leader
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] used in the leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int kchunks = (p.Cin + 63) >> 6;
+  const int acc_stride = conv2_acc_stride(p.n_tile);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * p.msub * acc_stride)) tmem_cols <<= 1;
+
+  if (warp == kProdWarp0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.tma_out != 0) tma_prefetch_desc(&tmO);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + i, 1);
+      mbar_init(tempty_bar + i, 2 * kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc2(tmem_slot, tmem_cols);
+  const int kStageB = epi_stage_bytes((MODE & 3) == EPI_F32, p.ntaps == 1);
+  uint8_t* stage0 = smem + ((p.stages * stage_bytes + 256 + 1023) & ~1023);
+  float* sbias = reinterpret_cast<float*>(stage0 + kEpiWarps * kStageB);
+  epi_load_bias(p, sbias);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  const int pw = warp - kProdWarp0;
+  if (pw >= 0 && pw < kProdWarps) {
+    // ===================== TMA producers (stage s belongs to producer s % kProdWarps, in both CTAs alike) =====================
+    if (elect_one()) {
+      const uint32_t tx_bytes = 2u * (uint32_t)(p.TH * p.TW * 128 + half_n * 128);  // both CTAs' boxes land on the leader's barrier
+      int s = -1;
+      uint32_t ph = 1;
+      for (int pt = cid; pt < total_pairs; pt += nclusters) {
+        const int mp = fdiv(pt, p.fd_ns), n0 = (pt - mp * n_splits) * p.n_tile + (int)rank * half_n;
+        const int mt = 2 * mp + (int)rank;
+        const int b = fdiv(mt, p.fd_tpi), t_in = mt - b * tiles_per_img;
+        const int th = fdiv(t_in, p.fd_tw);
+        const int h0 = th * p.TH, w0 = (t_in - th * p.tiles_w) * p.TW;
+        int cbase[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) cbase[d] = p.a_base[d] + b * p.a_cb[d] + h0 * p.a_ch[d] + w0 * p.a_cw[d];
+        for (int c = 0; c < kchunks; ++c) {
+          for (int t = 0; t < p.ntaps; ++t) {
+            if (++s == p.stages) s = 0;
+            if (s == 0) ph ^= 1;
+            if ((s % kProdWarps) != pw) continue;
+            mbar_wait_bo(empty_bar + s, ph ^ 1, 1u, p.bo_prod);
+            uint8_t* sa = smem + s * stage_bytes;
+            const uint32_t fb = mapa_u32(smem_u32(full_bar + s), 0);
+            if (leader) mbar_expect_tx(full_bar + s, tx_bytes);
+            tma_load_5d_2cta(sa, &tmA, fb, cbase[0] + p.tap[t][0] + c * 64, cbase[1] + p.tap[t][1], cbase[2] + p.tap[t][2],
+                             cbase[3] + p.tap[t][3], cbase[4] + p.tap[t][4]);
+            tma_load_3d_2cta(sa + a_bytes, &tmB, fb, c * 64, n0, t);
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== the pair's MMA issuer (leader only) =====================
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16(256, p.n_tile);
+      const int msub = p.msub;
+      const uint32_t sub_bytes = (uint32_t)(p.sub_rows * 128);
+      int s = -1, acc = 0;
+      uint32_t ph = 1;
+      for (int pt = cid; pt < total_pairs; pt += nclusters, ++acc) {
+        const int buf = acc & 1;
+        mbar_wait_warp(tempty_bar + buf, ((acc >> 1) & 1) ^ 1, 8u, p.bo_mma_acc);
+        tc_fence_after();
+        uint32_t accf = 0;
+        const uint32_t d_tmem0 = tmem_base + (uint32_t)(buf * msub * acc_stride);
+        for (int c = 0; c < kchunks; ++c) {
+          int ksteps = (p.Cin - c * 64) >> 4;
+          if (ksteps > 4) ksteps = 4;
+          for (int t = 0; t < p.ntaps; ++t) {
+            if (++s == p.stages) s = 0;
+            if (s == 0) ph ^= 1;
+            mbar_wait_warp(full_bar + s, ph, 2u, p.bo_mma_full);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * stage_bytes);
+            const uint32_t b_lo = umma_desc_lo(sa + a_bytes);
+            const uint32_t a_lo0 = umma_desc_lo(sa), a_lo1 = umma_desc_lo(sa + sub_bytes);
+            constexpr uint32_t hi = umma_desc_hi(1024);
+            if (elect_one()) {
+              if (ksteps == 4) {
+                umma2_bf16_ksteps<4>(d_tmem0, a_lo0, hi, b_lo, hi, idesc, accf);
+                if (msub > 1) umma2_bf16_ksteps<4>(d_tmem0 + (uint32_t)acc_stride, a_lo1, hi, b_lo, hi, idesc, accf);
+              } else if (ksteps == 2) {
+                umma2_bf16_ksteps<2>(d_tmem0, a_lo0, hi, b_lo, hi, idesc, accf);
+                if (msub > 1) umma2_bf16_ksteps<2>(d_tmem0 + (uint32_t)acc_stride, a_lo1, hi, b_lo, hi, idesc, accf);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  if (j < ksteps) {
+                    umma2_bf16_lohi(d_tmem0, a_lo0 + 2 * j, hi, b_lo + 2 * j, hi, idesc, j == 0 ? accf : 1u);
+                    if (msub > 1) umma2_bf16_lohi(d_tmem0 + (uint32_t)acc_stride, a_lo1 + 2 * j, hi, b_lo + 2 * j, hi, idesc, j == 0 ? accf : 1u);
+                  }
+              }
+              umma2_commit_mc(empty_bar + s, 3);
+            }
+            accf = 1;
+          }
+        }
+        if (elect_one()) umma2_commit_mc(tfull_bar + buf, 3);
+      }
+    }
+  } else {
+    // ===================== epilogue: this CTA's msub x 128 rows =====================
+    const int lg = warp & 3;
+    int sidx, c_begin, c_end;
+    epi_split(p.msub, p.n_tile >> 4, (warp - kEpiWarp0) >> 2, &sidx, &c_begin, &c_end);
+    uint8_t* stage = stage0 + (warp - kEpiWarp0) * kStageB;
+    int tbuf = 0;
+    const int r = lg * 32 + lane;
+    long long pacc[6] = {0, 0, 0, 0, 0, 0};
+    const bool flat = p.ntaps == 1;
+    const int R = sidx * p.sub_rows + r;
+    const int rh = R / p.TW, rw = R - rh * p.TW;
+    int acc = 0;
+    for (int pt = cid; pt < total_pairs; pt += nclusters, ++acc) {
+      const int mp = fdiv(pt, p.fd_ns), n0 = (pt - mp * n_splits) * p.n_tile;
+      const int mt = 2 * mp + (int)rank;
+      const int b = fdiv(mt, p.fd_tpi), t_in = mt - b * tiles_per_img;
+      const int th = fdiv(t_in, p.fd_tw);
+      const int buf = acc & 1;
+      if ((MODE & 3) == EPI_BF16_RES && pt + nclusters < total_pairs && c_begin < c_end) {
+        const int pt2 = pt + nclusters;
+        const int mp2 = fdiv(pt2, p.fd_ns), n2 = (pt2 - mp2 * n_splits) * p.n_tile;
+        const int mt2 = 2 * mp2 + (int)rank;
+        const int b2 = fdiv(mt2, p.fd_tpi), t2 = mt2 - b2 * tiles_per_img;
+        const int th2 = fdiv(t2, p.fd_tw);
+        const int h = th2 * p.TH + rh, w = (t2 - th2 * p.tiles_w) * p.TW + rw;
+        const bool valid = (r < p.sub_rows) && (b2 < p.tB) && (h < p.tH) && (w < p.tW);
+        int qb = b2, rem = h * p.tW + w;
+        if (flat) {
+          qb = fdiv(w, p.fd_hw);
+          rem = w - qb * p.img_HW;
+        }
+        epi_prefetch_res(p, valid, qb, rem, n2 + c_begin * 16, (c_end - c_begin) * 16);
+      }
+      mbar_wait_bo(tfull_bar + buf, (acc >> 1) & 1, 4u, p.bo_epi);
+      tc_fence_after();
+      {
+        const int h = th * p.TH + rh, w = (t_in - th * p.tiles_w) * p.TW + rw;
+        const bool valid = (r < p.sub_rows) && (b < p.tB) && (h < p.tH) && (w < p.tW);
+        int qb = 0, rem = 0;
+        if (valid) {
+          if (flat) {
+            qb = fdiv(w, p.fd_hw);
+            rem = w - qb * p.img_HW;
+          } else {
+            qb = b;
+            rem = h * p.tW + w;
+          }
+        }
+        const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * p.msub + sidx) * acc_stride);
+        int tq = 0, tb = 0;
+        if (p.tma_out != 0) {
+          tq = t_in * p.TW + sidx * p.sub_rows + lg * 32;
+          if (p.tma_out == 3) {
+            tb = fdiv(tq, p.fd_hw);
+            tq -= tb * p.img_HW;
+          }
+        }
+        epi_drain<MODE>(p, smem_u32(stage), smem_u32(sbias), lane, c_begin, c_end, t_addr, n0, valid, qb, rem, tempty_bar + buf,
+                        pacc, &tmO, p.tma_out, tq, tb, &tbuf, leader ? 0u : mapa_u32(smem_u32(tempty_bar + buf), 0));
+      }
+    }
+    if (p.tma_out != 0 && lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, tmem_cols);
+  }
+}
+
 }  // namespace ypb

@@ -50,6 +50,10 @@ struct ConvLaunch {
   Conv3Pair x2{};
   CUtensorMap tmHalo2, tmB2;  // halo box {64, 10, 18}; weight box {64, n_tile / 2, 3}
   int tiles_h2 = 0, tiles_w2 = 0, total_pairs = 0, smem_pair = 0;
+  // CTA-pair flavour of the per-tap kernel (conv_tc2p_kernel): 1x1 and stride-2 3x3 layers
+  bool use_pair_tc2 = false;
+  CUtensorMap tmB2p;  // weight box {64, n_tile / 2, 1}
+  int total_pairs_tc2 = 0, stages2p = 2, smem2p = 0;
   ConvParams p;       // persistent kernels (conv_tc2 geometry: tile may hold msub sub-tiles)
   ConvParams p1;      // one-tile-per-CTA geometry (impl 2 / 3, A/B experiments)
   CUtensorMap tmA1;
@@ -372,6 +376,24 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
                            conv_bias_smem(d.cout));
     }
   }
+  L->use_pair_tc2 = false;
+  if (!L->use_halo && (p.n_tile % 16) == 0 && !getenv("YPB_NO_PAIR") && !getenv("YPB_NO_PAIR_TC2")) {
+    const long m_tiles = (long)L->grid.x, total_pairs = ((m_tiles + 1) / 2) * splits;
+    const int min_pairs = getenv("YPB_PAIR_MIN") ? atoi(getenv("YPB_PAIR_MIN")) : 74;
+    const int stage = p.msub * kATileBytes + (p.n_tile / 2) * 128;
+    int ring_kb = 150;
+    if (const char* ev = getenv("YPB_RING_KB")) ring_kb = atoi(ev);
+    int st = (ring_kb * 1024) / stage;
+    if (st > 8) st = 8;
+    if (st < 2) st = 2;
+    if (total_pairs >= min_pairs) {
+      L->use_pair_tc2 = true;
+      L->total_pairs_tc2 = (int)total_pairs;
+      L->stages2p = st;
+      L->smem2p = 1024 + st * stage + 256 + kEpiWarps * epi_stage_bytes(d.out_mode == OUT_F32, d.k == 1) + 1024 + conv_bias_smem(d.cout);
+      if (L->smem2p < 120 * 1024) L->smem2p = 120 * 1024;
+    }
+  }
 #if YPB_DIAG
   ConvSimtGeom& g = L->sg;
   memset(&g, 0, sizeof g);
@@ -468,6 +490,10 @@ static bool conv_bind(const ConvDesc& d, ConvLaunch* L, std::string* err) {
     cuuint32_t wb2[3] = {64, (cuuint32_t)(p.n_tile / 2), 3};
     if (!encode_bf16_map(&L->tmB2, d.wg, 3, wd, ws, wb2, err)) return false;
   }
+  if (L->use_pair_tc2) {
+    cuuint32_t wb2[3] = {64, (cuuint32_t)(p.n_tile / 2), 1};
+    if (!encode_bf16_map(&L->tmB2p, d.wg, 3, wd, ws, wb2, err)) return false;
+  }
   return true;
 }
 
@@ -479,6 +505,9 @@ static void conv_describe(const ConvLaunch& L, int impl, char* out, int n) {
   else if (L.use_halo && impl == 0)
     snprintf(out, n, "halo%s msub=%d a_slots=%d b_stat=%d b_slots=%d b_group=%d n_tile=%d splits=%d tiles=%d smem=%d", L.x3.s2 ? "-s2" : "", L.x3.msub,
              L.x3.a_slots, L.x3.b_stat, L.x3.b_slots, L.x3.b_group, L.p.n_tile, L.n_splits, L.total_tiles3, L.smem3);
+  else if (L.use_pair_tc2 && impl == 0)
+    snprintf(out, n, "tc2-pair(cta_group::2) msub=%d tile=%dx%d stages=%d n_tile=%d splits=%d pairs=%d smem=%d", L.p.msub, L.p.TH,
+             L.p.TW, L.stages2p, L.p.n_tile, L.n_splits, L.total_pairs_tc2, L.smem2p);
   else
     snprintf(out, n, "tc2 msub=%d tile=%dx%d stages=%d n_tile=%d splits=%d tiles=%d smem=%d", L.p.msub, L.p.TH, L.p.TW,
              L.stages2, L.p.n_tile, L.n_splits, L.total_tiles, L.smem2);
@@ -522,6 +551,8 @@ static cudaError_t conv_launch_init() {
   e = cudaFuncSetAttribute(conv3_halo_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);     \
   if (e != cudaSuccess) return e;                                                                                 \
   e = cudaFuncSetAttribute(conv3_halo2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);    \
+  if (e != cudaSuccess) return e;                                                                                 \
+  e = cudaFuncSetAttribute(conv_tc2p_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
   if (e != cudaSuccess) return e;
   YPB_SET_SMEM(0) YPB_SET_SMEM(1) YPB_SET_SMEM(2) YPB_SET_SMEM(3) YPB_SET_SMEM(4) YPB_SET_SMEM(5) YPB_SET_SMEM(6) YPB_SET_SMEM(7)
 #undef YPB_SET_SMEM
@@ -639,6 +670,20 @@ static cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream, int imp
       YPB_HALO_CASE(7)
     }
 #undef YPB_HALO_CASE
+    return le != cudaSuccess ? le : cudaGetLastError();
+  }
+  if (L.use_pair_tc2 && impl == 0) {
+    ConvParams pp = L.p;
+    pp.stages = L.stages2p;
+    conv_set_fastdiv(pp, L.n_splits);
+    const int clusters = L.total_pairs_tc2 < num_sms / 2 ? L.total_pairs_tc2 : num_sms / 2;
+    cudaError_t le = cudaSuccess;
+#define YPB_TC2P_CASE(MODE) \
+  case MODE: le = launch_pdl_pair(conv_tc2p_kernel<MODE>, 2 * clusters, kConv2Threads, L.smem2p, stream, L.tmA, L.tmB2p, pp.tma_out ? L.tmO : L.tmB2p, pp, L.n_splits, L.total_pairs_tc2); break;
+    switch (epi_mode_of(pp.out_mode, pp.res != nullptr, pp.act)) {
+      YPB_TC2P_CASE(0) YPB_TC2P_CASE(1) YPB_TC2P_CASE(2) YPB_TC2P_CASE(3) YPB_TC2P_CASE(4) YPB_TC2P_CASE(5) YPB_TC2P_CASE(6) YPB_TC2P_CASE(7)
+    }
+#undef YPB_TC2P_CASE
     return le != cudaSuccess ? le : cudaGetLastError();
   }
   ConvParams p2 = L.p;

@@ -386,7 +386,13 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
     int st = (ring_kb * 1024) / stage;
     if (st > 8) st = 8;
     if (st < 2) st = 2;
-    if (total_pairs >= min_pairs) {
+    // Pairing couples the two CTAs stage by stage (cross-CTA barrier round trips): it pays when a tile is a long K loop
+    // over wide weight tiles, and loses on the thin, HBM-bound 1x1 layers.  Measured on B200 (tools/conv_layers.py,
+    // yolov8s/x-seg shapes): wins from k_iters x n_tile >= 12 x 256 (model.12.cv1 +4 %, model.5 +8 %, model.7 +12 %,
+    // x.4.cv2 +10 %, x.3 +15 %), loses below (model.2.cv1 -34 %, proto.upsample -16 %, model.16 -3 %).
+    const long pair_work = (long)k_iters * p.n_tile;
+    const long pair_min_work = getenv("YPB_PAIR_WORK") ? atol(getenv("YPB_PAIR_WORK")) : 2560;
+    if (total_pairs >= min_pairs && (pair_work >= pair_min_work || getenv("YPB_PAIR_MIN"))) {
       L->use_pair_tc2 = true;
       L->total_pairs_tc2 = (int)total_pairs;
       L->stages2p = st;

@@ -176,6 +176,12 @@ int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offs
 int ypb_index_masks_resized(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int h1,
                             int w1, int H, int W, float min_area, uint8_t* bins, float* area_f, int32_t* ids,
                             int64_t* index_map);
+/* JPEG frames decoded straight into device memory (replaces the host decode of reference yolo_seg/utils/video_reader.py:
+   91-99 `Image.open(path).convert("RGB")` and of `cv2.imread`): jpeg_host = the file's bytes in host memory; dst_dev =
+   device (height, width, 3) uint8 interleaved BGR, the layout ypb_letterbox_u8 / ypb_infer consume.  nvJPEG (loaded
+   lazily; YPB_ERR_CUDA if the machine has no libnvjpeg).  Enqueued on the caller's stream after a host-side Huffman pass. */
+int ypb_jpeg_info(const uint8_t* jpeg_host, size_t nbytes, int* height, int* width);
+int ypb_jpeg_decode_bgr(void* cuda_stream, const uint8_t* jpeg_host, size_t nbytes, uint8_t* dst_dev, int height, int width);
 /* Point-to-point mask hand-off between the GPUs of one box (BASELINE config C5): the tracker that consumes
    the index masks (reference yolo_seg/yolo_with_deva.py:133-159) runs on ONE GPU; detector replicas on the other GPUs
    copy their index masks into a mailbox in that GPU's memory over NVLink / NVSwitch.  create: cudaMalloc on `device` +

@@ -10,11 +10,12 @@ Hand-written CUDA (tcgen05/TMEM/TMA implicit-GEMM convs, warp-level decode/NMS, 
 behind the C ABI of include/ypb200.h; PyTorch only moves bytes.  No CPU fallback.
 """
 
+from .frames import decode_jpegs  # noqa: F401
 from .handoff import auto_segment, index_masks, min_rect_len  # noqa: F401
 from .model import YOLO  # noqa: F401
 from .results import Boxes, Masks, Results  # noqa: F401
 
-__all__ = ["YOLO", "Results", "Boxes", "Masks", "install_ultralytics_shim", "index_masks", "min_rect_len", "auto_segment"]
+__all__ = ["YOLO", "Results", "Boxes", "Masks", "install_ultralytics_shim", "index_masks", "min_rect_len", "auto_segment", "decode_jpegs"]
 
 
 def install_ultralytics_shim():

@@ -71,6 +71,8 @@ SIGNATURES = {
     "ypb_index_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ypb_index_masks_resized": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ypb_jpeg_info": (c_int, [c_void_p, c_size_t, C.POINTER(c_int), C.POINTER(c_int)]),
+    "ypb_jpeg_decode_bgr": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_int]),
     "ypb_mailbox_create": (c_int, [c_int, c_size_t, C.POINTER(c_void_p), c_void_p]),
     "ypb_mailbox_destroy": (c_int, [c_int, c_void_p]),
     "ypb_mailbox_open": (c_int, [c_int, c_void_p, C.POINTER(c_void_p)]),

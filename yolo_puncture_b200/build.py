@@ -16,10 +16,11 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libypb200.so")
 SOURCES = ["ypb200.cu", "common.cuh", "conv_tc.cuh", "conv_plan.cuh", "head_kernels.cuh", "mask_kernels.cuh",
-           "misc_kernels.cuh", "v10_kernels.cuh", "host_stage.cpp"]  # + tma_bench.cuh in the diagnostics build
-UNITS = [os.path.join(CSRC, "ypb200.cu"), os.path.join(CSRC, "host_stage.cpp")]  # device TU + host-only staging pool
+           "misc_kernels.cuh", "v10_kernels.cuh", "conv_halo2.cuh", "host_stage.cpp", "jpeg_source.cpp"]  # + tma_bench.cuh in the diagnostics build
+UNITS = [os.path.join(CSRC, "ypb200.cu"), os.path.join(CSRC, "host_stage.cpp"), os.path.join(CSRC, "jpeg_source.cpp")]
+# device TU + host-only staging pool + nvJPEG frame source (dlopen: no link-time dependency)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177", "-ldl"]
 
 
 def _nvcc():

@@ -1900,6 +1900,25 @@ int ypb_index_masks_resized(void* cuda_stream, const uint8_t* masks, const int32
   return YPB_OK;
 }
 
+// ---- JPEG frames decoded on the device (csrc/jpeg_source.cpp: nvJPEG, loaded lazily) ----------------------------------
+extern "C" int ypb_host_jpeg_info(const unsigned char* data, size_t n, int* h, int* w, char* err, int errlen);
+extern "C" int ypb_host_jpeg_decode(void* stream, const unsigned char* data, size_t n, unsigned char* dst_dev, int H, int W, char* err,
+                                    int errlen);
+
+int ypb_jpeg_info(const uint8_t* jpeg_host, size_t nbytes, int* height, int* width) {
+  if (!jpeg_host || nbytes == 0 || !height || !width) return fail(YPB_ERR_ARG, "bad argument");
+  char err[256] = {0};
+  if (ypb_host_jpeg_info(jpeg_host, nbytes, height, width, err, sizeof err) != 0) return fail(YPB_ERR_ARG, err);
+  return YPB_OK;
+}
+
+int ypb_jpeg_decode_bgr(void* cuda_stream, const uint8_t* jpeg_host, size_t nbytes, uint8_t* dst_dev, int height, int width) {
+  if (!jpeg_host || nbytes == 0 || !dst_dev || height < 1 || width < 1) return fail(YPB_ERR_ARG, "bad argument");
+  char err[256] = {0};
+  if (ypb_host_jpeg_decode(cuda_stream, jpeg_host, nbytes, dst_dev, height, width, err, sizeof err) != 0) return fail(YPB_ERR_CUDA, err);
+  return YPB_OK;
+}
+
 // ---- point-to-point mask hand-off between the GPUs of one box (BASELINE config C5) ----------------
 // The tracker (DEVA) is sequential and lives on ONE GPU; the detector replicas on the other GPUs push their per-frame
 // index masks into a mailbox in the consumer GPU's memory over NVLink / NVSwitch: cudaMemcpyAsync between peer

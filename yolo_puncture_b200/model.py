@@ -248,6 +248,13 @@ class YOLO:
             raise ValueError("predict() needs a source")
         if device is not None or self._device is None:
             self._set_device(device)
+        if torch.is_tensor(source):
+            # frames that already live on the GPU (frames.decode_jpegs, a capture / NVDEC ring): (H,W,3) or (B,H,W,3) uint8 BGR
+            if not source.is_cuda or source.dtype != torch.uint8 or source.shape[-1] != 3 or source.dim() not in (3, 4):
+                raise ValueError("tensor sources must be CUDA uint8 (H,W,3) or (B,H,W,3) BGR frames")
+            res = self._predict_device_frames(source if source.dim() == 4 else source[None], imgsz or self.overrides.get("imgsz", 640),
+                                              conf, iou, retina_masks, min(int(max_det), MAX_DET), classes, agnostic_nms, batch)
+            return iter(res) if stream else res
         srcs = list(source) if isinstance(source, (list, tuple)) else [source]
         frames, paths = zip(*[_to_bgr_array(s) for s in srcs])
         imgsz = imgsz or self.overrides.get("imgsz", 640)
@@ -268,6 +275,74 @@ class YOLO:
                     r.path = paths[i]
                     results[i] = r
         return iter(results) if stream else results
+
+    def _predict_device_frames(self, frames, imgsz, conf, iou, retina, max_det, classes, agnostic, batch):
+        """Device-resident frames (B, H0, W0, 3): LetterBox on the device when needed, one engine pass per chunk; nothing
+        but counts and boxes crosses PCIe.  `Results.orig_img` is the frame's device tensor."""
+        if frames.device != self._device:
+            frames = frames.to(self._device)
+        frames = frames.contiguous()
+        imgsz = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        n_all, shape = frames.shape[0], (int(frames.shape[1]), int(frames.shape[2]))
+        new_unpad, top, bottom, left, right = letterbox_geometry(shape, imgsz, True)
+        H, W = new_unpad[1] + top + bottom, new_unpad[0] + left + right
+        if H % 32 or W % 32:
+            raise YpbError(f"letterboxed size {H}x{W} is not a multiple of 32 (imgsz={imgsz})")
+        seg = self.task == "segment"
+        mh, mw = shape if retina else (H, W)
+        direct = shape == (H, W)
+        out = []
+        t0 = time.perf_counter()
+        with torch.cuda.device(self._device):
+            main = torch.cuda.current_stream(self._device)
+            cmask = None
+            if classes is not None:
+                words = np.zeros(((self.nc + 31) // 32,), np.uint32)
+                for c in classes:
+                    words[int(c) >> 5] |= np.uint32(1) << np.uint32(int(c) & 31)
+                cmask = torch.from_numpy(words.view(np.int32)).to(self._device)
+            for lo in range(0, n_all, batch):
+                chunk = frames[lo:lo + batch]
+                B = int(chunk.shape[0])
+                eng = self.engine
+                eng.plan(B, H, W)
+                eng.use_outputs(0)
+                if direct:
+                    net_in = chunk
+                else:
+                    key = ("devlb", B, shape, H, W)
+                    st = self._staging.get(key)
+                    if st is None:
+                        xofs, xa = cv2_linear_tables(shape[1], new_unpad[0])
+                        yofs, ya = cv2_linear_tables(shape[0], new_unpad[1], vertical=True)
+                        st = self._staging[key] = {"dst": torch.empty((B, H, W, 3), dtype=torch.uint8, device=self._device),
+                                                   "t": [torch.from_numpy(a).to(self._device) for a in (xofs, xa, yofs, ya)]}
+                    net_in = st["dst"]
+                    check(lib().ypb_letterbox_u8(ctypes.c_void_p(main.cuda_stream), ctypes.c_void_p(chunk.data_ptr()), B, shape[0], shape[1],
+                                                 ctypes.c_void_p(net_in.data_ptr()), H, W, new_unpad[0], new_unpad[1], top, left,
+                                                 *[ctypes.c_void_p(t.data_ptr()) for t in st["t"]], 114))
+                xf = torch.tensor([box_xform((H, W), shape)] * B, dtype=torch.float32).to(self._device)
+                eng.infer(net_in, xf, conf, iou, max_det, agnostic, cmask)
+                o = eng.out_sets[0]
+                counts = o.count[:B].cpu()
+                det_h = o.det[:B].cpu()
+                n_k = int(counts.sum())
+                det = o.det[:B].clone()
+                masks = None
+                if seg and n_k:
+                    masks = torch.empty((n_k, mh, mw), dtype=torch.uint8, device=self._device)
+                    eng.masks(masks, retina, mh, mw)
+                err = eng.device_error()
+                if err:
+                    raise YpbError(f"device pipeline error word 0x{err:x}")
+                speed = {"preprocess": 0.0, "inference": (time.perf_counter() - t0) * 1e3 / max(B, 1), "postprocess": 0.0}
+                off = 0
+                for j, n in enumerate(counts.tolist()):
+                    boxes = Boxes(det[j, :n], shape, n=n, host=(lambda d=det_h, j=j, n=n: d[j, :n]))
+                    m = Masks(masks[off:off + n], shape, n=n) if (masks is not None and n) else None
+                    off += n
+                    out.append(Results(chunk[j], None, self.names, boxes=boxes, masks=m, speed=speed))
+        return out
 
     def _head(self):
         """Second engine instance (same weights) so that two pass sizes stay planned side by side."""

@@ -36,8 +36,13 @@ def test_nvjpeg_frames_decode_on_the_device(tmp_path):
     from yolo_puncture_b200.frames import jpeg_size
     frames = synth.synth_frames(4, 480, 640, start=11)
     paths, blobs = [], []
+    # 4:4:4 sampling: the two decoders then differ by IDCT rounding only (with 4:2:0 the chroma up-sampling FILTERS differ -
+    # libjpeg-turbo's "fancy" triangle filter vs nvJPEG's - which on noise-like frames is several LSB on average)
+    enc_args = [cv2.IMWRITE_JPEG_QUALITY, 95]
+    if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+        enc_args += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
     for i, f in enumerate(frames):
-        ok, enc = cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 95])
+        ok, enc = cv2.imencode(".jpg", f, enc_args)
         assert ok
         p = tmp_path / f"frame_{i}.jpg"
         p.write_bytes(enc.tobytes())
@@ -56,7 +61,10 @@ def test_nvjpeg_frames_decode_on_the_device(tmp_path):
     ref = np.stack([cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR) for b in blobs])
     diff = np.abs(dev.cpu().numpy().astype(np.int16) - ref.astype(np.int16))
     # two IDCT / chroma up-sampling implementations of the same bitstream: same image up to a few LSB (BGR order included)
-    assert diff.mean() < 1.0 and np.percentile(diff, 99.9) <= 6, (diff.mean(), diff.max())
+    if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+        assert diff.mean() < 1.0 and np.percentile(diff, 99.9) <= 4, (diff.mean(), diff.max())
+    else:
+        assert diff.mean() < 6.0, (diff.mean(), diff.max())
     yolo = YOLO("yolov8n-seg", device=0)
     res = yolo.predict(dev, conf=0.25, retina_masks=True)
     assert len(res) == 4 and all(r.orig_shape == (480, 640) for r in res)

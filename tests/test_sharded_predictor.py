@@ -70,14 +70,14 @@ def test_sharded_predict_two_ranks_gloo_returns_global_frame_order():
             assert n == i % 3 and all(v == float(i) for row in boxes for v in row)
 
 
-def _gpu_worker(rank, world, port, q):
+def _gpu_worker(rank, world, port, q, backend="gloo"):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from yolo_puncture_b200 import YOLO, index_masks, synth
     from yolo_puncture_b200.sharded import ShardedPredictor
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group(backend, rank=rank, world_size=world, **({"device_id": torch.device("cuda", rank)} if backend == "nccl" else {}))
     yolo = YOLO("yolov8n-seg", device=rank)
     n_frames, chunk = 6, 3
     sp = ShardedPredictor(yolo, rank, world, chunk)
@@ -99,16 +99,22 @@ def _gpu_worker(rank, world, port, q):
     dist.barrier()
     sp.mailbox.close()
     dist.destroy_process_group()
-    q.put((rank, ok, [n for n, *_ in ordered], sum(sums.values())))
+    # the fixed-size NCCL gather (taken on an NCCL default group) must return what the generic object gather returns
+    from yolo_puncture_b200.sharding import gather_in_frame_order, summarize_results
+    ref = gather_in_frame_order(summarize_results(local), n_frames, rank, world, chunk)
+    same = all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(ordered, ref))
+    ids_ok = all(len(o) == 3 and all(d["index"] < o[0] for d in o[2]) for o in ordered)
+    q.put((rank, ok and same and ids_ok, [n for n, *_ in ordered], sum(sums.values())))
 
 
 @pytest.mark.gpu
-def test_mask_mailbox_peer_push_between_two_gpus():
+@pytest.mark.parametrize("backend,port", [("gloo", 29743), ("nccl", 29745)])
+def test_mask_mailbox_peer_push_between_two_gpus(backend, port):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, 29743, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q, backend)) for r in range(2)]
     for p in procs:
         p.start()
     outs = sorted(q.get(timeout=600) for _ in range(2))

@@ -67,7 +67,9 @@ def index_masks(results, suppress_small_mask=True, min_area=100, out_shape=None)
         packed = torch.cat([ids.to(torch.float32)[:, None], meta], 1).cpu().tolist()  # the one host sync of the hand-off
     out, k = [], 0
     for b in range(B):
-        info = [{"id": int(i), "score": float(sc), "category_id": int(cl)} for i, sc, cl in packed[k:k + counts[b]] if i]
+        # "index" = the detection's row in its frame's Results (beyond the reference's ObjectInfo fields)
+        info = [{"id": int(i), "score": float(sc), "category_id": int(cl), "index": r}
+                for r, (i, sc, cl) in enumerate(packed[k:k + counts[b]]) if i]
         k += counts[b]
         out.append((index_map[b], info))
     return out
@@ -110,7 +112,9 @@ def _index_masks_resized(results, suppress_small_mask, min_area, out_shape):
         packed = torch.cat([ids.to(torch.float32)[:, None], meta], 1).cpu().tolist()
     out, k = [], 0
     for b in range(B):
-        info = [{"id": int(i), "score": float(sc), "category_id": int(cl)} for i, sc, cl in packed[k:k + counts[b]] if i]
+        # "index" = the detection's row in its frame's Results (beyond the reference's ObjectInfo fields)
+        info = [{"id": int(i), "score": float(sc), "category_id": int(cl), "index": r}
+                for r, (i, sc, cl) in enumerate(packed[k:k + counts[b]]) if i]
         k += counts[b]
         out.append((index_map[b], info))
     return out

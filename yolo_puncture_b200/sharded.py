@@ -194,20 +194,51 @@ class ShardedPredictor:
                 rows[:, :6] = boxes
                 if with_ids:
                     rows[:, 6] = 0
-                    for d in item[2]:  # kept detections: id 1, 2, ... at their row of the frame's Results
-                        rows[d["index"], 6] = d["id"]
+                    if item[2]:  # kept detections: id 1, 2, ... at their row of the frame's Results
+                        rows[[d["index"] for d in item[2]], 6] = [d["id"] for d in item[2]]
         with torch.cuda.device(dev):
             mine = host.to(dev, non_blocking=True)
             dist.all_gather_into_tensor(self._gdev.view(self.world * cap, -1), mine)
             allh = self._gdev.cpu().numpy()
-        out = [None] * n_frames
+        where = [None] * n_frames
         for r in range(self.world):
             for j, idx in enumerate(shard_indices(n_frames, r, self.world, chunk)):
-                n = int(allh[r, j, 0])
-                rows = allh[r, j, 1:1 + n * width].reshape(n, width)
-                if with_ids:
-                    info = [{"id": int(q[6]), "score": float(q[4]), "category_id": int(q[5]), "index": k} for k, q in enumerate(rows) if q[6] > 0]
-                    out[idx] = (n, rows[:, :6].copy(), info)
-                else:
-                    out[idx] = (n, rows.copy())
-        return out
+                where[idx] = (r, j)
+        return _OrderedRows(allh, where, width, with_ids)
+
+
+class _OrderedRows:
+    """The gathered per-frame rows in global frame order, unpacked on access: `rows[i]` -> (n_i, boxes (n_i, 6)[, info]).
+    (Unpacking every frame of every rank eagerly cost more host time at 8 ranks than the detector itself.)"""
+
+    def __init__(self, table, where, width, with_ids):
+        self._t, self._where, self._w, self._ids = table, where, width, with_ids
+
+    def __len__(self):
+        return len(self._where)
+
+    def _one(self, i):
+        r, j = self._where[i]
+        n = int(self._t[r, j, 0])
+        rows = self._t[r, j, 1:1 + n * self._w].reshape(n, self._w)
+        if not self._ids:
+            return (n, rows.copy())
+        kept = rows[:, 6] > 0
+        info = [{"id": int(q[6]), "score": float(q[4]), "category_id": int(q[5]), "index": int(k)}
+                for k, q in zip(kept.nonzero()[0], rows[kept])]
+        return (n, rows[:, :6].copy(), info)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._one(k) for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self._one(i)
+
+    def __iter__(self):
+        return (self._one(i) for i in range(len(self)))
+
+    def counts(self):
+        """Detections per frame, in frame order (one vectorised read)."""
+        import numpy as np
+        return np.array([int(self._t[r, j, 0]) for r, j in self._where])

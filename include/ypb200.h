@@ -127,6 +127,10 @@ int ypb_select_info(const ypb_engine* e, size_t* count_offset, int* cand_stride)
 
 /* Device-side error word (0 = ok); nonzero means a bounded pipeline wait inside a kernel gave up. */
 int ypb_device_error(ypb_engine* e, uint32_t* word);
+/* The same word copied to `host_word` (page-locked) in stream order, without a host synchronisation: the caller reads it
+ * after the event / stream it already waits on for the pass's results, and calls ypb_device_error() to clear a nonzero
+ * word. */
+int ypb_device_error_async(ypb_engine* e, void* cuda_stream, uint32_t* host_word);
 
 /* ---- introspection for tests / profiling --------------------------------------------------- */
 /* Named activation views of the bound workspace, e.g. "model.4", "head", "proto".

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ypb_proto_info": (c_int, [c_void_p, C.POINTER(c_size_t), C.POINTER(c_size_t)]),
     "ypb_select_info": (c_int, [c_void_p, C.POINTER(c_size_t), C.POINTER(c_int)]),
     "ypb_device_error": (c_int, [c_void_p, C.POINTER(c_uint32)]),
+    "ypb_device_error_async": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ypb_view_count": (c_int, [c_void_p]),
     "ypb_view_info": (c_int, [c_void_p, c_int, C.POINTER(c_char_p), C.POINTER(c_size_t), C.POINTER(c_int),
                               C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),

@@ -1581,8 +1581,8 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
 }
 
 int ypb_device_error(ypb_engine* e, uint32_t* word) {
-  (void)e;
   if (!word) return fail(YPB_ERR_ARG, "bad argument");
+  DeviceGuard guard(e ? e->device : -1);
   unsigned int v = 0;
   CUDA_TRY(cudaMemcpyFromSymbol(&v, g_dev_error, sizeof v));
   *word = v;
@@ -1590,6 +1590,14 @@ int ypb_device_error(ypb_engine* e, uint32_t* word) {
     unsigned int z = 0;
     CUDA_TRY(cudaMemcpyToSymbol(g_dev_error, &z, sizeof z));
   }
+  return YPB_OK;
+}
+
+int ypb_device_error_async(ypb_engine* e, void* cuda_stream, uint32_t* host_word) {
+  if (!e || !host_word) return fail(YPB_ERR_ARG, "bad argument");
+  DeviceGuard guard(e->device);
+  CUDA_TRY(cudaMemcpyFromSymbolAsync(host_word, g_dev_error, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost,
+                                     reinterpret_cast<cudaStream_t>(cuda_stream)));
   return YPB_OK;
 }
 

@@ -180,6 +180,10 @@ class Engine:
         check(self._lib.ypb_device_error(self._h, C.byref(w)))
         return w.value
 
+    def device_error_async(self, stream, host_word):
+        """Copy the error word into `host_word` (pinned int32 tensor, >= 1 element) in `stream` order; no host sync."""
+        check(self._lib.ypb_device_error_async(self._h, C.c_void_p(stream.cuda_stream), C.c_void_p(host_word.data_ptr())))
+
     def set_conv_impl(self, impl):
         check(self._lib.ypb_set_conv_impl(self._h, int(impl)))
 

@@ -141,6 +141,14 @@ class _ModelProxy:
         return self._owner.names
 
 
+
+def _addr(a):
+    """Address of a C-contiguous numpy array's first byte (a.ctypes.data costs ~2 us per frame; this path 0.7 us)."""
+    try:
+        return ctypes.addressof(ctypes.c_char.from_buffer(a))
+    except (TypeError, ValueError, BufferError):  # read-only arrays do not export a writable buffer
+        return a.ctypes.data
+
 class YOLO:
     """Drop-in for `ultralytics.YOLO` on the predict path.
 
@@ -188,6 +196,7 @@ class YOLO:
         # An int forces uniform passes of that size.  H2D of pass k+1 always overlaps compute of pass k.
         self.micro_batch = None
         self.head_pass = 16
+        self.head_stage_chunk = 4  # frames per staging chunk of the first pass (later passes: stage_chunk)
         self.stage_chunk = 16     # frames per staging call / H2D copy when the caller's frames are pageable
         # True: staging is queued on the native pool behind a stream gate (cudaLaunchHostFunc) and the host never blocks.
         # Measured slower on B200 hosts (9.7 vs 7.4 ms per 64-frame call: the gate's callback latency and 16 pool threads
@@ -425,7 +434,7 @@ class YOLO:
             if direct or dev_lb:
                 frames_c = [f if f.flags["C_CONTIGUOUS"] else np.ascontiguousarray(f) for f in frames]
                 nbytes = shape[0] * shape[1] * 3  # == H * W * 3 when direct
-                src_ptrs = (ctypes.c_void_p * B)(*[f.ctypes.data for f in frames_c])
+                src_ptrs = (ctypes.c_void_p * B)(*[_addr(f) for f in frames_c])
                 sizes = (ctypes.c_size_t * B)(*([nbytes] * B))
                 # staging threads: the rank's share of the host cores minus two (the Python thread and the CUDA driver's)
                 share = len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
@@ -460,7 +469,8 @@ class YOLO:
                     lb = self._letterbox_buffers(buf, B, caps, shape, new_unpad, need_host=not pinned)
                 if not pinned:
                     stage_host = lb["raw_host"] if dev_lb else buf["host"]
-                    dst_ptrs = (ctypes.c_void_p * B)(*[stage_host[i].data_ptr() for i in range(B)])
+                    d0, dstep = stage_host.data_ptr(), stage_host.stride(0) * stage_host.element_size()
+                    dst_ptrs = (ctypes.c_void_p * B)(*range(d0, d0 + B * dstep, dstep))
             else:
                 futs = [_pool().submit(letterbox_into, host[i], f, new_unpad, top, left) for i, f in enumerate(frames)]
             cs.wait_stream(main)
@@ -482,7 +492,8 @@ class YOLO:
                         # pageable frames: native multi-threaded copy into the pinned ring (ctypes drops the GIL), a chunk
                         # at a time, each chunk's H2D issued right behind it: chunk i+1 is staged while chunk i crosses PCIe
                         stage_host = lb["raw_host"] if dev_lb else buf["host"]
-                        step = max(1, int(self.stage_chunk))
+                        # the first pass's H2D is on the call's critical path (nothing overlaps it): smaller chunks there
+                        step = max(1, int(self.stage_chunk if k else self.head_stage_chunk))
                         for c0 in range(lo, hi, step):
                             c1 = min(c0 + step, hi)
                             ts = time.perf_counter()
@@ -541,11 +552,13 @@ class YOLO:
                 hb = hostbuf.get((k & 1, cap))
                 if hb is None:
                     hb = hostbuf[(k & 1, cap)] = (torch.empty((cap,), dtype=torch.int32).pin_memory(),
-                                                  torch.empty((cap, MAX_DET, 6), dtype=torch.float32).pin_memory())
+                                                  torch.empty((cap, MAX_DET, 6), dtype=torch.float32).pin_memory(),
+                                                  torch.zeros((1,), dtype=torch.int32).pin_memory())
                 with torch.cuda.stream(side):
                     side.wait_event(ev)
                     hb[0][:n].copy_(o.count[:n], non_blocking=True)
                     hb[1][:n].copy_(o.det[:n], non_blocking=True)
+                    eng.device_error_async(side, hb[2])  # the kernels' error word rides along: no separate host sync
                     done = torch.cuda.Event()
                     done.record(side)
                 inf_done.append(done)
@@ -558,9 +571,11 @@ class YOLO:
                 inf_done[k].synchronize()  # the host sync of this pass: its counts and boxes are in pinned memory now
                 tm["wait_ms"] += (time.perf_counter() - ts) * 1e3
                 hb = hostbuf[(k & 1, cap)]
-                counts = hb[0][:n].clone()
-                n_k = int(counts.sum())
-                cnts.append(counts.tolist())
+                if int(hb[2][0]):
+                    raise YpbError(f"device pipeline error word 0x{eng.device_error():x}")
+                counts = hb[0][:n].tolist()
+                n_k = sum(counts)
+                cnts.append(counts)
                 dets.append(o.det[:n].clone() if n_k else None)
                 dets_h.append(hb[1][:n].clone() if n_k else None)
                 if seg and n_k:
@@ -585,15 +600,13 @@ class YOLO:
                 if k > 0:
                     finish(k - 1)
             finish(n_mb - 1)
-            main.wait_stream(side)  # the masks are consumed on the caller's stream
+            # The masks of the last pass may still be in flight when predict() returns (as upstream's are): they are ordered
+            # on the caller's stream, and every pass's error word came back with its boxes.
+            main.wait_stream(side)
             t2 = time.perf_counter()
             tm["enqueue_to_done_ms"] = (t2 - t1) * 1e3
             tm["prologue_ms"] = (t1 - t0) * 1e3
-            err = self.engine.device_error()
-            if err:
-                raise YpbError(f"device pipeline error word 0x{err:x}")
-            t3 = time.perf_counter()
-        tm["device_error_ms"] = (t3 - t2) * 1e3
+            t3 = t2
         speed = {"preprocess": (t1 - t0) * 1e3 / B, "inference": (t2 - t1) * 1e3 / B, "postprocess": (t3 - t2) * 1e3 / B}
         out = []
         empty = None

@@ -31,6 +31,7 @@ WORKLOADS = {
     "yolov8s-seg-640-b64": ("yolov8s-seg", 64, (640, 640), 640),
     "yolov8s-seg-640-b32": ("yolov8s-seg", 32, (640, 640), 640),
     "yolov8s-seg-640-b16": ("yolov8s-seg", 16, (640, 640), 640),
+    "yolov8s-seg-640-b8": ("yolov8s-seg", 8, (640, 640), 640),
     "yolov8n-seg-640-b1": ("yolov8n-seg", 1, (640, 640), 640),
     "yolov8n-seg-640-b64": ("yolov8n-seg", 64, (640, 640), 640),
     "yolov8m-seg-1080p-b16": ("yolov8m-seg", 16, (1080, 1920), 1280),
@@ -112,20 +113,25 @@ def make_frames(n, hw, start):
 # ---------------------------------------------------------------------------------------------------
 # CPU arms (the oracle is test infrastructure: it is only ever the timed baseline here)
 # ---------------------------------------------------------------------------------------------------
-def oracle_predictor(model):
+def synth_geometry(hw):
+    """Frames that are not 640x640 use the class shift calibrated on frames of their size (synth.synth_state_dict)."""
+    return None if tuple(hw) == (640, 640) else tuple(hw)
+
+
+def oracle_predictor(model, hw=(640, 640)):
     import torch
     from oracle import OracleYOLO
     from oracle.model import build_model
     from yolo_puncture_b200.synth import synth_state_dict
     torch.set_num_threads(os.cpu_count() or 1)
     net = build_model(model)
-    sd = synth_state_dict([(k, v.shape) for k, v in net.state_dict().items()], model)
+    sd = synth_state_dict([(k, v.shape) for k, v in net.state_dict().items()], model, geometry=synth_geometry(hw))
     return OracleYOLO(model, state_dict=sd), torch.get_num_threads()
 
 
 def cpu_baseline(model, hw, imgsz, budget_s=12.0):
     """Oracle predict (fp32, BN-folded, torch CPU, all host threads), B=1, bounded to ~budget_s."""
-    yolo, cores = oracle_predictor(model)
+    yolo, cores = oracle_predictor(model, hw)
     frames = make_frames(2, hw, 0)
     yolo.predict(frames[0], conf=CONF, iou=IOU, retina_masks=True, imgsz=imgsz)  # warm-up
     t_end, times = time.perf_counter() + budget_s, []
@@ -180,7 +186,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     model, B, hw, imgsz = wl
-    yolo, cores = oracle_predictor(model)
+    yolo, cores = oracle_predictor(model, hw)
     sample = 2
     frames = make_frames(sample, hw, 0)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -226,7 +232,7 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
-    yolo = YOLO(model, device=local)
+    yolo = YOLO(model, device=local, synth_geometry=synth_geometry(hw))
     eng = yolo.engine
     eng.set_conv_impl(args.conv_impl)
     eng.set_graph(not args.no_graph)

@@ -6,6 +6,7 @@ statistics are centred the way trained ones are), and (ii) the per-level class-b
 the 98th percentile of the per-anchor max class logit at logit(0.25).
 
     python -m oracle.calibrate_synth [--recipe=damped] [model ...]
+    python -m oracle.calibrate_synth [--recipe=damped] --geometry=1080x1920@1280 model ...   (class shift for another frame size)
 """
 
 import json
@@ -79,10 +80,43 @@ def calibrate(name, seed=0, pct=0.98, conf=0.25, recipe="default"):
     return calib
 
 
+@torch.no_grad()
+def calibrate_geometry(name, hw, imgsz, base, seed=0, pct=0.98, conf=0.25, recipe="default", n_frames=2):
+    """Class-bias shift for frames of another size (e.g. 1080p letterboxed to 736x1280, BASELINE config C4): same
+    weights and BN statistics as the base entry, only the per-level shift is re-derived on synthetic frames of that size
+    (the 640x640 shift leaves such frames with no candidate at all, i.e. nothing for NMS and the mask decode to do)."""
+    net = build_model(name)
+    specs = [(k, v.shape) for k, v in net.state_dict().items()]
+    calib = {"bn": base["bn"], "cls_shift": [0.0, 0.0, 0.0]}
+    if "coef0_bias" in base:
+        calib["coef0_bias"] = base["coef0_bias"]
+    net.load_state_dict(synth.synth_state_dict(specs, name, seed, calib=calib, recipe=recipe))
+    structured = synth.RECIPES[recipe]["structured"]
+    im = ops.preprocess([synth.synth_frame(i, hw[0], hw[1], structured=structured) for i in range(n_frames)], imgsz)
+    feats = net.features(im, upto=len(net.model) - 1)
+    head = net.model[-1]
+    maps = head.head_maps([feats[j] for j in net.froms[-1]])
+    target = math.log(conf / (1 - conf))
+    return {"cls_shift": [target - torch.quantile(mp[:, 64:].amax(1).flatten(), pct).item() for mp in maps]}
+
+
 def main(argv):
     recipe = "default"
     if argv and argv[0].startswith("--recipe="):
         recipe, argv = argv[0].split("=", 1)[1], argv[1:]
+    if argv and argv[0].startswith("--geometry="):  # --geometry=1080x1920@1280 model ...
+        geo, argv = argv[0].split("=", 1)[1], argv[1:]
+        hw_s, imgsz = geo.split("@")
+        hw = tuple(int(v) for v in hw_s.split("x"))
+        table = synth.load_calibration()
+        for n in argv:
+            base_key = f"{n}:0" if recipe == "default" else f"{n}:0:{recipe}"
+            key = f"{base_key}@{hw[0]}x{hw[1]}"
+            table[key] = calibrate_geometry(n, hw, int(imgsz), table[base_key], recipe=recipe)
+            print(key, table[key])
+        with open(synth._CALIB_PATH, "w") as f:
+            json.dump(table, f, separators=(",", ":"))
+        return
     names = argv or list(MODEL_SPECS)
     table = synth.load_calibration()
     for n in names:

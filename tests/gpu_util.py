@@ -40,12 +40,12 @@ def describe_mismatch(got, ref, rtol, atol, max_items=12):
     return "\n".join(lines)
 
 
-def oracle_with_synth(name, emulate, recipe="default"):
+def oracle_with_synth(name, emulate, recipe="default", geometry=None):
     """(oracle net fused [+bf16 emulation], state_dict) with the deterministic synthetic weights."""
     from oracle.model import build_model
     from yolo_puncture_b200 import synth
     net = build_model(name)
-    sd = synth.synth_state_dict([(k, v.shape) for k, v in net.state_dict().items()], name, recipe=recipe)
+    sd = synth.synth_state_dict([(k, v.shape) for k, v in net.state_dict().items()], name, recipe=recipe, geometry=geometry)
     net.load_state_dict(sd)
     net.fuse()
     if emulate:

@@ -344,9 +344,10 @@ def test_config_c5_model_yolov8x_seg_b4_strict():
 
 
 def test_config_c4_yolov8m_seg_1080p_b2_strict():
-    """The C4 model on the C4 geometry: 1920x1080 frames, imgsz 1280 -> 736x1280 net input (device LetterBox), 1080p masks."""
+    """The C4 model on the C4 geometry: 1920x1080 frames, imgsz 1280 -> 736x1280 net input (device LetterBox), 1080p masks.
+    Weights: the class shift calibrated on 1080p frames (what bench.py's C4 workload runs), ~50 detections per frame."""
     from yolo_puncture_b200 import YOLO, synth
-    net, sd = oracle_with_synth("yolov8m-seg", emulate=True)
+    net, sd = oracle_with_synth("yolov8m-seg", emulate=True, geometry=(1080, 1920))
     yolo = YOLO("yolov8m-seg", state_dict=sd, device=0)
     frames = synth.synth_frames(2, 1080, 1920, start=40)
     res = yolo.predict(frames, conf=0.25, iou=0.7, retina_masks=True, imgsz=1280)
@@ -356,7 +357,7 @@ def test_config_c4_yolov8m_seg_1080p_b2_strict():
     n = _strict_selection_and_masks(yolo, net, res, (736, 1280), (1080, 1920), "m-seg 1080p")
     assert all(r.masks is None or r.masks.data.shape[1:] == (1080, 1920) for r in res)
     report(test="c4", model="yolov8m-seg", B=2, detections=n, worst_layer=worst, head=r_head, proto=r_proto)
-    assert n > 0
+    assert n >= 20
 
 
 def test_config_c3_bench_shape_yolov8s_seg_b64_strict():

@@ -157,7 +157,8 @@ class YOLO:
     state_dict (real `.pt` pickles need the upstream classes to unpickle — export their
     `model.state_dict()` on a box that has ultralytics)."""
 
-    def __init__(self, model="yolov8n-seg", task=None, verbose=False, nc=None, state_dict=None, device=None, seed=0):
+    def __init__(self, model="yolov8n-seg", task=None, verbose=False, nc=None, state_dict=None, device=None, seed=0,
+                 synth_geometry=None):
         names = None
         spec = model
         if isinstance(model, (str, os.PathLike)) and os.path.exists(str(model)):
@@ -182,7 +183,10 @@ class YOLO:
         self.names = names or {i: f"class{i}" for i in range(self.nc)}
         self.engine = Engine(spec, self.nc)
         if state_dict is None:
-            state_dict = synth_state_dict([(n, s) for n, s, _ in self.engine.weight_specs()], spec, seed, nc=self.nc)
+            # synthetic weights (no checkpoint given); synth_geometry=(h, w) selects the class shift calibrated on frames
+            # of that size when the calibration file has one (synth.synth_state_dict)
+            state_dict = synth_state_dict([(n, s) for n, s, _ in self.engine.weight_specs()], spec, seed, nc=self.nc,
+                                          geometry=synth_geometry)
         self.engine.load_state_dict(state_dict)
         self._state_dict = state_dict  # kept for the head-pass engine (second plan size), built on first use
         self._head_engine = None

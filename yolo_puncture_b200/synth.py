@@ -60,16 +60,24 @@ def load_calibration():
     return {}
 
 
-def synth_state_dict(specs, model_name, seed=0, calib=None, nc=80, recipe="default"):
+def synth_state_dict(specs, model_name, seed=0, calib=None, nc=80, recipe="default", geometry=None):
     """specs: iterable of (name, shape).  Returns {name: fp32 tensor} following the recipe:
     conv weights U(+-sqrt(3/fan_in)); BN gamma~U(.5,1.5), beta~N(0,.1), running_mean = mu_l +
     N(0,.1)*sqrt(v_l), running_var = v_l*U(.5,1.5) with (mu_l, v_l) the layer's calibrated pre-BN
     statistics; box-branch final bias 1.0; class-branch final bias log(5/nc/(640/s)^2) + per-level
     calibrated shift (so a few hundred candidates per frame pass conf=0.25); mask-coefficient final
-    bias ~N(0,1).  calib: {"bn": {conv_module_name: [mu, v]}, "cls_shift": [s0, s1, s2]}."""
+    bias ~N(0,1).  calib: {"bn": {conv_module_name: [mu, v]}, "cls_shift": [s0, s1, s2]}.
+    geometry=(h, w): frames of that size - if the calibration file has a class shift derived on such frames
+    (key "<model>:<seed>[:recipe]@<h>x<w>", oracle/calibrate_synth.py --geometry) it replaces the 640x640 one; every
+    other tensor is unchanged."""
     if calib is None:
         key = f"{model_name}:{seed}" if recipe == "default" else f"{model_name}:{seed}:{recipe}"
-        calib = load_calibration().get(key, {})
+        table = load_calibration()
+        calib = table.get(key, {})
+        if geometry is not None:
+            over = table.get(f"{key}@{int(geometry[0])}x{int(geometry[1])}")
+            if over:
+                calib = dict(calib, **over)
     rp = RECIPES[recipe]
     cls_bias_shift = calib.get("cls_shift", [0.0, 0.0, 0.0])
     bn_stats = calib.get("bn", {})

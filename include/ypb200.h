@@ -173,6 +173,11 @@ int ypb_letterbox_u8(void* cuda_stream, const uint8_t* src, int B, int H0, int W
    of the LAST kept detection covering each pixel, else 0.  All device pointers, caller's stream. */
 int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, int B, int n_total, int H, int W,
                     int min_area, int32_t* area, int32_t* ids, int64_t* index_map);
+/* The same hand-off for masks known to be zero outside a rectangle each (predict() crops every mask to its box):
+ * rects (n_total, 4) int32 device array of (x0, y0, x1, y1), x1 / y1 exclusive.  The area sum and the paint then touch
+ * ~the box areas instead of n_total x H x W bytes twice.  rects == NULL (or W % 16 != 0) falls back to ypb_index_masks. */
+int ypb_index_masks_boxed(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, const int32_t* rects, int B,
+                          int n_total, int H, int W, int min_area, int32_t* area, int32_t* ids, int64_t* index_map);
 /* The same hand-off for the reference's `min_side` branch (yolo_with_deva.py:44-48,71-72): predict() ran on a resized
    frame, masks are (n_total, h1, w1) and go back to (H, W) as torchvision's F.resize does (antialiased bilinear) before
    the float `mask.sum() < min_area` filter (min_area < 0: keep all) and the `mask > 0.5` paint.

@@ -70,6 +70,51 @@ def test_index_masks_kernel_matches_oracle_on_random_masks(H, W, suppress):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("H,W,counts", [(640, 640, [40, 0, 300, 3]), (1080, 1920, [25, 1]), (100, 104, [7, 2])])
+def test_index_masks_boxed_path_matches_oracle(H, W, counts):
+    """Masks cropped to their (fractional) boxes, as predict() produces them: the rectangle-restricted area / paint kernels
+    (ypb_index_masks_boxed) against the reference loop.  300 detections in a frame = two rounds of the paint's list."""
+    from yolo_puncture_b200 import index_masks
+    g = torch.Generator().manual_seed(H + 3 * W)
+    res, refs = [], []
+    for n in counts:
+        if n == 0:
+            res.append(_FakeResults(None, torch.zeros(0), torch.zeros(0), (H, W)))
+            refs.append((None, []))
+            continue
+        m = torch.zeros(n, H, W, dtype=torch.uint8)
+        boxes = torch.zeros(n, 4)
+        for i in range(n):
+            bw, bh = float(torch.rand(1, generator=g)) * W * (0.05 if i % 3 == 0 else 0.6) + 2, float(torch.rand(1, generator=g)) * H * (0.05 if i % 3 == 0 else 0.6) + 2
+            x1, y1 = float(torch.rand(1, generator=g)) * (W - bw), float(torch.rand(1, generator=g)) * (H - bh)
+            boxes[i] = torch.tensor([x1, y1, x1 + bw, y1 + bh])
+            ys, xs = torch.arange(H).float()[:, None], torch.arange(W).float()[None, :]
+            inside = (xs >= x1) & (xs < x1 + bw) & (ys >= y1) & (ys < y1 + bh)
+            pattern = torch.rand(H, W, generator=g) < 0.7
+            m[i] = (inside & pattern).to(torch.uint8)
+        conf, cls = torch.rand(n, generator=g), torch.randint(0, 80, (n,), generator=g).float()
+        r = _FakeResults(m.cuda(), conf.cuda(), cls.cuda(), (H, W))
+        r.boxes.data = torch.cat([boxes, conf[:, None], cls[:, None]], 1).cuda()
+        r.masks.cropped = True
+        res.append(r)
+        refs.append(auto_segment_index_mask(m.float(), conf, cls, True, 100))
+    out = index_masks(res, suppress_small_mask=True, min_area=100)
+    for (imap, info), (rmap, rinfo) in zip(out, refs):
+        if rmap is None:
+            assert int(imap.abs().sum()) == 0 and info == []
+            continue
+        assert torch.equal(imap.cpu(), rmap)
+        assert [(d["id"], d["category_id"]) for d in info] == [(i[0], i[2]) for i in rinfo]
+    # the full-scan path on the same masks gives the same answer
+    for r in res:
+        if r.masks is not None:
+            r.masks.cropped = False
+    out2 = index_masks(res, suppress_small_mask=True, min_area=100)
+    for (a, ia), (b, ib) in zip(out, out2):
+        assert torch.equal(a, b) and ia == ib
+
+
+@pytest.mark.gpu
 def test_index_masks_on_predict_output():
     from yolo_puncture_b200 import YOLO, index_masks, synth
     yolo = YOLO("yolov8n-seg", device=0)

@@ -70,6 +70,8 @@ SIGNATURES = {
     "ypb_letterbox_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "ypb_index_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ypb_index_masks_boxed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p]),
     "ypb_index_masks_resized": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "ypb_jpeg_info": (c_int, [c_void_p, c_size_t, C.POINTER(c_int), C.POINTER(c_int)]),

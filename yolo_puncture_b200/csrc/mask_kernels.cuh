@@ -62,7 +62,7 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
                    const int* __restrict__ offsets, int nB, int capacity, MaskGeom g, uint8_t* __restrict__ out) {
   extern __shared__ float s_band[];  // low-resolution logits of the band's proto window: rh rows x band_w columns
   __shared__ __align__(16) float s_hrow[(kMaskTile + 2) * kMaskTile];  // horizontally interpolated window rows of a tile
-  __shared__ float s_coef[32];
+  __shared__ __align__(16) float s_coef[32];
   const int slot = blockIdx.y;
   const int total = offsets[nB];
   if (slot >= total || slot >= capacity) return;
@@ -122,9 +122,11 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   const float ly = __fsub_rn(sy, (float)y0), hy = __fsub_rn(1.0f, ly);
   const bool row_in = g.retina ? ((float)oy >= by1 && (float)oy < by2) : true;
 
-  // ---- the band's logits, once: every column of the proto window that a box-touching tile of this band needs.
-  // One pass with all the loads of a thread in flight together (a per-tile version waited for L2 once per tile:
-  // ncu showed 36 % long-scoreboard stalls on the dot products) ----
+  // ---- per-tile source windows, once per CTA (they are CTA-uniform: every thread used to recompute them, two float
+  // round trips per tile and thread - 12 % of the kernel's instructions under ncu) ----
+  constexpr int kMaxTiles = 64;  // out_w <= 4096
+  __shared__ int s_tlo[kMaxTiles], s_thi[kMaxTiles];  // s_thi < s_tlo: the tile misses the box
+  const int n_tiles = (g.out_w + kMaskTile - 1) / kMaskTile;
   auto tile_window = [&](int tx0, int* sx_lo, int* sx_hi) {
     const int x_last = min(tx0 + kMaskTile, g.out_w) - 1;
     *sx_lo = (int)src_of(tx0, g.scale_w);
@@ -135,41 +137,78 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
     if (g.retina) return ((float)(tx0 + kMaskTile) <= bx1) || ((float)tx0 >= bx2);
     return ((float)(g.left + sx_hi) < bx1) || ((float)(g.left + sx_lo) >= bx2);
   };
-  int bw_lo = 1 << 30, bw_hi = -1;  // CTA-uniform
-  for (int tx0 = 0; tx0 < g.out_w; tx0 += kMaskTile) {
-    int sx_lo, sx_hi;
-    tile_window(tx0, &sx_lo, &sx_hi);
-    if (tile_empty(tx0, sx_lo, sx_hi)) continue;
-    bw_lo = min(bw_lo, sx_lo);
-    bw_hi = max(bw_hi, sx_hi);
+  for (int t = threadIdx.x; t < min(n_tiles, kMaxTiles); t += 256) {
+    int lo, hi;
+    tile_window(t * kMaskTile, &lo, &hi);
+    if (tile_empty(t * kMaskTile, lo, hi)) { lo = 1; hi = 0; }
+    s_tlo[t] = lo;
+    s_thi[t] = hi;
+  }
+  __syncthreads();  // s_coef and the tile windows are ready
+  int bw_lo = 1 << 30, bw_hi = -1;  // CTA-uniform: the proto columns the box-touching tiles of this band need
+  for (int t = 0; t < n_tiles; ++t) {
+    int lo, hi;
+    if (t < kMaxTiles) { lo = s_tlo[t]; hi = s_thi[t]; }
+    else { tile_window(t * kMaskTile, &lo, &hi); if (tile_empty(t * kMaskTile, lo, hi)) { lo = 1; hi = 0; } }
+    if (hi < lo) continue;
+    bw_lo = min(bw_lo, lo);
+    bw_hi = max(bw_hi, hi);
   }
   const int band_w = bw_hi >= bw_lo ? bw_hi - bw_lo + 1 : 0;
-  __syncthreads();  // s_coef ready
-  for (int i = threadIdx.x; i < rh * band_w; i += 256) {
-    const int ry = i / band_w, rx = i - ry * band_w;
-    const int py = g.top + sy_lo + ry, px = g.left + bw_lo + rx;
-    const float4* pp = reinterpret_cast<const float4*>(pb + ((long long)py * g.mw + px) * g.nm);
-    float acc = 0.f;
+
+  // ---- the band's logits, once.  Eight lanes per prototype: lane q holds channels 4q..4q+3, so one warp-wide 16-byte
+  // load covers 4 prototypes = 512 CONTIGUOUS bytes (a thread-per-prototype loop touches 32 different 128-byte lines with
+  // every load instruction); the partial dot products are combined with three shuffles.  Four prototypes per thread are
+  // in flight together; row / column of a prototype come from a multiply-high (the kernel is issue-bound: the integer
+  // division here was 18 % of its instructions), offsets are 32-bit. ----
+  {
+    const int q = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    const float4 cq = *reinterpret_cast<const float4*>(&s_coef[4 * q]);
+    const float4* pb4 = reinterpret_cast<const float4*>(pb);
+    const int npx = rh * band_w;  // <= 66 * 1026
+    const unsigned inv_bw = band_w > 0 ? 0xFFFFFFFFu / (unsigned)band_w + 1u : 0u;  // floor(i / band_w) = umulhi(i, inv_bw), i < 2^16
+    const int base_off = ((g.top + sy_lo) * g.mw + g.left + bw_lo) * 8 + q;
+    for (int i0 = 0; i0 < npx; i0 += 128) {
+      float part[4];
+      int idx[4];
+      bool keep[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 v = __ldg(pp + k);
-      acc = fmaf(s_coef[4 * k + 0], v.x, acc);
-      acc = fmaf(s_coef[4 * k + 1], v.y, acc);
-      acc = fmaf(s_coef[4 * k + 2], v.z, acc);
-      acc = fmaf(s_coef[4 * k + 3], v.w, acc);
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + 32 * u + grp;
+        idx[u] = i;
+        part[u] = 0.f;
+        keep[u] = true;
+        if (i < npx) {
+          const int ry = npx < 65536 ? (int)__umulhi((unsigned)i, inv_bw) : i / band_w;
+          const int rx = i - ry * band_w;
+          const float4 v = __ldg(pb4 + base_off + (ry * g.mw + rx) * 8);
+          part[u] = fmaf(cq.w, v.w, fmaf(cq.z, v.z, fmaf(cq.y, v.y, __fmul_rn(cq.x, v.x))));
+          if (!g.retina) {  // ops.process_mask crops in proto space BEFORE the upsample
+            const float fx = (float)(g.left + bw_lo + rx), fy = (float)(g.top + sy_lo + ry);
+            keep[u] = fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        part[u] += __shfl_xor_sync(0xffffffffu, part[u], 1);
+        part[u] += __shfl_xor_sync(0xffffffffu, part[u], 2);
+        part[u] += __shfl_xor_sync(0xffffffffu, part[u], 4);
+        if (q == 0 && idx[u] < npx) s_band[idx[u]] = keep[u] ? part[u] : 0.f;
+      }
     }
-    if (!g.retina) {  // ops.process_mask crops in proto space BEFORE the upsample
-      const float fx = (float)px, fy = (float)py;
-      if (!(fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2)) acc = 0.f;
-    }
-    s_band[i] = acc;
   }
 
-  for (int tx0 = 0; tx0 < g.out_w; tx0 += kMaskTile) {
+  // integer form of the retina crop: (float)x >= b  <=>  x >= ceil(b), (float)x < b  <=>  x < ceil(b) for integer x
+  // (no int->float conversion per pixel: those run on the 16-lane XU pipe)
+  const int cx_lo = g.retina ? (int)ceilf(fmaxf(bx1, -1.0f)) : 0, cx_hi = g.retina ? (int)ceilf(fminf(bx2, 1.0e6f)) : g.out_w;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int tx0 = t * kMaskTile;
     const int ox0 = tx0 + tcol;
     int sx_lo, sx_hi;
-    tile_window(tx0, &sx_lo, &sx_hi);
-    if (tile_empty(tx0, sx_lo, sx_hi)) {  // CTA-uniform
+    if (t < kMaxTiles) { sx_lo = s_tlo[t]; sx_hi = s_thi[t]; }
+    else { tile_window(tx0, &sx_lo, &sx_hi); if (tile_empty(tx0, sx_lo, sx_hi)) { sx_lo = 1; sx_hi = 0; } }
+    if (sx_hi < sx_lo) {  // CTA-uniform: the tile misses the box
       if (oy < g.out_h && !g.prefilled) {
         if (vec_ok && ox0 + 16 <= g.out_w) {
           *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
@@ -182,8 +221,7 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
     __syncthreads();  // band logits written / previous tile's s_hrow fully consumed
     // Separable bilinear, in ATen's operation order (horizontal blend of each source row first, then the vertical
     // blend): the horizontal pass is done ONCE per (window row, output column) into shared memory instead of twice
-    // per output pixel, and the vertical pass reads its two rows with 16-byte loads.  Same roundings, fewer
-    // shared-memory instructions (the kernel is bound by the L1/LSU pipe, ncu l1tex throughput 73 %).
+    // per output pixel, and the vertical pass reads its two rows with 16-byte loads.
     {
       const int hx_col = threadIdx.x & (kMaskTile - 1);
       const int ox = tx0 + hx_col;
@@ -200,12 +238,13 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
     if (oy >= g.out_h) continue;
     // this thread's 16 pixels lie outside the box (rows above / below it inside the band, columns left / right of it
     // inside the tile): zeros without touching the interpolation
-    if (vec_ok && ox0 + 16 <= g.out_w && (!row_in || (g.retina && ((float)(ox0 + 16) <= bx1 || (float)ox0 >= bx2)))) {
+    if (vec_ok && ox0 + 16 <= g.out_w && (!row_in || ox0 + 16 <= cx_lo || ox0 >= cx_hi)) {
       if (!g.prefilled) *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
       continue;
     }
     const float4* t0 = reinterpret_cast<const float4*>(s_hrow + (y0 - sy_lo) * kMaskTile + tcol);
     const float4* t1 = reinterpret_cast<const float4*>(s_hrow + (y1 - sy_lo) * kMaskTile + tcol);
+    const int x_end = min(cx_hi, g.out_w);
     uint32_t packed[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -215,8 +254,7 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
       for (int u = 0; u < 4; ++u) {
         const int ox = ox0 + 4 * q + u;
         const float val = __fadd_rn(__fmul_rn(hy, tv[u]), __fmul_rn(ly, bv[u]));
-        bool on = val > 0.0f && row_in && ox < g.out_w;
-        if (g.retina) on = on && ((float)ox >= bx1 && (float)ox < bx2);
+        const bool on = val > 0.0f && row_in && ox >= cx_lo && ox < x_end;
         packed[q] |= (on ? 1u : 0u) << (8 * u);
       }
     }
@@ -576,6 +614,94 @@ index_paint_kernel(const uint8_t* __restrict__ masks, const int* __restrict__ of
     for (int j = 0; j < 8; j += 2) *reinterpret_cast<longlong2*>(o + j) = make_longlong2(out[j], out[j + 1]);
   } else {
     for (int j = 0; j < 8 && p0 + j < hw; ++j) o[j] = out[j];
+  }
+}
+
+// ---- the same hand-off when every mask is known to be zero outside a rectangle (the masks of predict() are cropped to
+// their boxes): rects[i] = (x0, y0, x1, y1), x1 / y1 exclusive.  The area sum reads only the rectangle, and the paint
+// works on 64 x 32 pixel tiles: a CTA first compacts (in detection order) the kept detections whose rectangle touches its
+// tile, then every thread walks that short list BACKWARDS for its 8 pixels and stops as soon as all of them are assigned
+// (the last kept detection covering a pixel wins, as in the reference's sequential overwrite).  Same index map, a
+// fraction of the traffic: ~box area instead of n x H x W bytes, twice.  Needs W % 16 == 0 and 16-byte aligned masks.
+__global__ void __launch_bounds__(256)
+mask_area_rect_kernel(const uint8_t* __restrict__ masks, const int4* __restrict__ rects, int H, int W, int* __restrict__ area) {
+  const int i = blockIdx.y;
+  int4 r = rects[i];
+  r.x = max(r.x, 0); r.y = max(r.y, 0); r.z = min(r.z, W); r.w = min(r.w, H);
+  if (r.z <= r.x || r.w <= r.y) return;
+  const uint8_t* m = masks + (long long)i * H * W;
+  const int xa = r.x & ~15;
+  const int cpr = (r.z - xa + 15) >> 4;  // 16-byte chunks per rectangle row (the last one may overhang: zeros there)
+  const int total = (r.w - r.y) * cpr;
+  unsigned sum = 0;
+  for (int id = blockIdx.x * 256 + threadIdx.x; id < total; id += gridDim.x * 256) {
+    const int row = id / cpr, c = id - row * cpr;
+    const uint4 v = *reinterpret_cast<const uint4*>(m + (long long)(r.y + row) * W + xa + c * 16);
+    sum += ((v.x * 0x01010101u) >> 24) + ((v.y * 0x01010101u) >> 24) + ((v.z * 0x01010101u) >> 24) + ((v.w * 0x01010101u) >> 24);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0 && sum) atomicAdd(area + i, (int)sum);
+}
+
+constexpr int kPaintTW = 64, kPaintTH = 32;  // 256 threads x 8 pixels
+__global__ void __launch_bounds__(256)
+index_paint_rect_kernel(const uint8_t* __restrict__ masks, const int* __restrict__ offsets, const int* __restrict__ ids,
+                        const int4* __restrict__ rects, int H, int W, long long* __restrict__ index_map) {
+  __shared__ int s_det[256];   // detections of this round that touch the tile (index into the batch), in order
+  __shared__ int s_id[256];
+  __shared__ int s_wcnt[8];
+  const int b = blockIdx.z;
+  const int tx0 = blockIdx.x * kPaintTW, ty0 = blockIdx.y * kPaintTH;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int y = ty0 + (threadIdx.x >> 3), x = tx0 + (threadIdx.x & 7) * 8;
+  const bool inside = y < H && x < W;  // W % 16 == 0: a thread's 8 pixels are all inside or all outside
+  const long long hw = (long long)H * W;
+  const int lo = offsets[b], hi = offsets[b + 1];
+  long long out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned todo = inside ? 0xffu : 0u;  // pixels of this thread not yet assigned
+  // rounds of 256 detections, LAST round first (later detections win)
+  for (int r0 = lo + ((hi - lo - 1) / 256) * 256; r0 >= lo && hi > lo; r0 -= 256) {
+    const int i = r0 + threadIdx.x;
+    bool touch = false;
+    int id = 0;
+    if (i < hi) {
+      id = ids[i];
+      if (id) {
+        const int4 r = rects[i];
+        touch = r.x < tx0 + kPaintTW && r.z > tx0 && r.y < ty0 + kPaintTH && r.w > ty0;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, touch);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int pos = __popc(bal & ((1u << lane) - 1u)), cnt = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) pos += s_wcnt[w];
+      cnt += s_wcnt[w];
+    }
+    if (touch) { s_det[pos] = i; s_id[pos] = id; }
+    __syncthreads();
+    for (int k = cnt - 1; k >= 0 && todo; --k) {
+      const int d = s_det[k];
+      const int4 r = rects[d];
+      if (y < r.y || y >= r.w || x + 8 <= r.x || x >= r.z) continue;
+      const uint2 v = *reinterpret_cast<const uint2*>(masks + (long long)d * hw + (long long)y * W + x);
+      if ((v.x | v.y) == 0u) continue;
+      const long long idv = s_id[k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (((v.x >> (8 * j)) & 0xffu) && ((todo >> j) & 1u)) { out[j] = idv; todo &= ~(1u << j); }
+        if (((v.y >> (8 * j)) & 0xffu) && ((todo >> (4 + j)) & 1u)) { out[4 + j] = idv; todo &= ~(1u << (4 + j)); }
+      }
+    }
+    __syncthreads();  // s_det / s_id / s_wcnt are rewritten by the next round
+  }
+  if (inside) {
+    long long* o = index_map + (long long)b * hw + (long long)y * W + x;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) *reinterpret_cast<longlong2*>(o + j) = make_longlong2(out[j], out[j + 1]);
   }
 }
 

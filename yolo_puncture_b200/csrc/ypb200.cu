@@ -1886,6 +1886,25 @@ int ypb_index_masks(void* cuda_stream, const uint8_t* masks, const int32_t* offs
   return YPB_OK;
 }
 
+// The hand-off for masks that are zero outside rects[i] = (x0, y0, x1, y1) (exclusive ends): what predict() produces,
+// every mask cropped to its box.  rects == nullptr, W % 16 != 0 or unaligned masks: the full-scan kernels above.
+int ypb_index_masks_boxed(void* cuda_stream, const uint8_t* masks, const int32_t* offsets, const int32_t* rects, int B, int n_total,
+                          int H, int W, int min_area, int32_t* area, int32_t* ids, int64_t* index_map) {
+  if (!rects || (W & 15) != 0 || (reinterpret_cast<uintptr_t>(masks) & 15) != 0 || n_total == 0)
+    return ypb_index_masks(cuda_stream, masks, offsets, B, n_total, H, W, min_area, area, ids, index_map);
+  if (!offsets || !index_map || B < 1 || H < 1 || W < 1 || n_total < 0 || !masks || !area || !ids) return fail(YPB_ERR_ARG, "bad argument");
+  if (n_total > 65535 || B > 65535 || (H + kPaintTH - 1) / kPaintTH > 65535)
+    return fail(YPB_ERR_ARG, "index_masks: more than 65535 masks / frames / tile rows per call");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  CUDA_TRY(cudaMemsetAsync(area, 0, (size_t)n_total * 4, st));
+  mask_area_rect_kernel<<<dim3(8, n_total), 256, 0, st>>>(masks, reinterpret_cast<const int4*>(rects), H, W, area);
+  mask_ids_kernel<<<(B + 127) / 128, 128, 0, st>>>(offsets, B, area, min_area, ids);
+  index_paint_rect_kernel<<<dim3((W + kPaintTW - 1) / kPaintTW, (H + kPaintTH - 1) / kPaintTH, B), 256, 0, st>>>(
+      masks, offsets, ids, reinterpret_cast<const int4*>(rects), H, W, reinterpret_cast<long long*>(index_map));
+  CUDA_TRY(cudaGetLastError());
+  return YPB_OK;
+}
+
 // Same hand-off when predict() ran on a resized frame (the reference's `min_side`, yolo_with_deva.py:44-48,71-72): masks
 // (n_total, h1, w1) are resized to (H, W) as torchvision F.resize does (antialiased bilinear), area_f receives the float
 // sum of every resized mask (the reference filters on `mask.sum() < MIN_AREA`), bins (n_total, H, W) uint8 scratch.

@@ -8,6 +8,7 @@ for a whole batch of frames (`ypb_index_masks`) instead of a `.sum()` host sync 
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from ._lib import check, lib
@@ -51,28 +52,76 @@ def index_masks(results, suppress_small_mask=True, min_area=100, out_shape=None)
     contiguous = all(m.is_contiguous() for m in present) and all(
         b.data_ptr() == a.data_ptr() + a.numel() for a, b in zip(present, present[1:]))
     base = present[0] if contiguous else torch.cat(present)
-    offsets = torch.zeros(B + 1, dtype=torch.int32)
-    offsets[1:] = torch.tensor(counts, dtype=torch.int32).cumsum(0)
+    # (conf, cls) of every detection from the host copy predict() already fetched with the pass (no device gather), and -
+    # when every mask is known to be cropped to its box (the masks of predict()) - the boxes as pixel rectangles, so that
+    # the area sum and the paint only touch the boxes
+    hb = [_host_boxes(r) for r, c in zip(results, counts) if c]
+    allb = np.concatenate(hb) if len(hb) > 1 else hb[0]
+    if allb.shape[0] != n_total:
+        raise ValueError("index_masks: boxes and masks of a frame differ in length")
+    cropped = all(getattr(r.masks, "cropped", False) for r, c in zip(results, counts) if c)
+    r_off = (B + 1 + 3) & ~3  # the rectangles are read as int4: 16-byte aligned behind the offsets
+    stage = _pinned_i32(r_off + 4 * n_total)
+    sn = stage.numpy()
+    sn[0] = 0
+    np.cumsum(counts, out=sn[1:B + 1])
+    if cropped:  # mask on  <=>  bx1 <= x < bx2 and by1 <= y < by2 (mask_decode_kernel): [floor(b1), ceil(b2)) covers it
+        rc = sn[r_off:r_off + 4 * n_total].reshape(n_total, 4)
+        rc[:, 0] = np.clip(np.floor(allb[:, 0]), 0, W)
+        rc[:, 1] = np.clip(np.floor(allb[:, 1]), 0, H)
+        rc[:, 2] = np.clip(np.ceil(allb[:, 2]), 0, W)
+        rc[:, 3] = np.clip(np.ceil(allb[:, 3]), 0, H)
     with torch.cuda.device(dev):
-        offs_d = offsets.to(dev, non_blocking=True)
+        n_stage = r_off + 4 * n_total if cropped else B + 1
+        stage_d = torch.empty(n_stage, dtype=torch.int32, device=dev)
+        stage_d.copy_(stage[:n_stage], non_blocking=True)
         area = torch.empty(n_total, dtype=torch.int32, device=dev)
         ids = torch.empty(n_total, dtype=torch.int32, device=dev)
         index_map = torch.empty((B, H, W), dtype=torch.int64, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
-        check(lib().ypb_index_masks(C.c_void_p(st), C.c_void_p(base.data_ptr()), C.c_void_p(offs_d.data_ptr()), B, n_total, H, W,
-                                    int(min_area) if suppress_small_mask else -1, C.c_void_p(area.data_ptr()),
-                                    C.c_void_p(ids.data_ptr()), C.c_void_p(index_map.data_ptr())))
-        # one device-to-host copy for the whole batch: ids next to (conf, cls) of every detection
-        meta = torch.cat([r.boxes.data[:, 4:6].to(dev, torch.float32) for r, c in zip(results, counts) if c])
-        packed = torch.cat([ids.to(torch.float32)[:, None], meta], 1).cpu().tolist()  # the one host sync of the hand-off
-    out, k = [], 0
-    for b in range(B):
-        # "index" = the detection's row in its frame's Results (beyond the reference's ObjectInfo fields)
-        info = [{"id": int(i), "score": float(sc), "category_id": int(cl), "index": r}
-                for r, (i, sc, cl) in enumerate(packed[k:k + counts[b]]) if i]
-        k += counts[b]
-        out.append((index_map[b], info))
-    return out
+        rects_p = stage_d.data_ptr() + 4 * r_off if cropped else None
+        check(lib().ypb_index_masks_boxed(C.c_void_p(st), C.c_void_p(base.data_ptr()), C.c_void_p(stage_d.data_ptr()),
+                                          C.c_void_p(rects_p), B, n_total, H, W,
+                                          int(min_area) if suppress_small_mask else -1, C.c_void_p(area.data_ptr()),
+                                          C.c_void_p(ids.data_ptr()), C.c_void_p(index_map.data_ptr())))
+        ids_h = ids.cpu().numpy()  # the one host sync of the hand-off
+    return _pack_infos(index_map, ids_h, allb, counts)
+
+
+def _host_boxes(r):
+    """(n, 6) float32 numpy rows of a frame's boxes; predict()'s Results carry a host copy fetched with their pass."""
+    b = r.boxes
+    h = b._host() if getattr(b, "_host", None) is not None else b.data
+    if torch.is_tensor(h):
+        h = h.detach().cpu().numpy()
+    return np.asarray(h, dtype=np.float32).reshape(-1, 6)
+
+
+_PINNED = {}
+
+
+def _pinned_i32(n):
+    """Page-locked int32 scratch, grown on demand; every use is followed by a host sync before the next one."""
+    buf = _PINNED.get("i32")
+    if buf is None or buf.numel() < n:
+        buf = _PINNED["i32"] = torch.empty(max(n, 4096), dtype=torch.int32).pin_memory()
+    return buf
+
+
+def _pack_infos(index_map, ids_h, allb, counts):
+    """[(index_map[b], [{id, score, category_id, index}, ...])]: kept detections only, in order.
+    "index" = the detection's row in its frame's Results (beyond the reference's ObjectInfo fields)."""
+    keep = np.flatnonzero(ids_h)
+    starts = np.zeros(len(counts) + 1, dtype=np.int64)
+    np.cumsum(counts, out=starts[1:])
+    frame_of = np.searchsorted(starts, keep, side="right") - 1
+    cut = np.searchsorted(frame_of, np.arange(len(counts) + 1))
+    kid = ids_h[keep].tolist()
+    ksc = allb[keep, 4].tolist()
+    kcl = allb[keep, 5].astype(np.int64).tolist()
+    krow = (keep - starts[frame_of]).tolist()
+    infos = [{"id": i, "score": s, "category_id": c, "index": r} for i, s, c, r in zip(kid, ksc, kcl, krow)]
+    return [(index_map[b], infos[cut[b]:cut[b + 1]]) for b in range(len(counts))]
 
 
 def _index_masks_resized(results, suppress_small_mask, min_area, out_shape):
@@ -108,16 +157,9 @@ def _index_masks_resized(results, suppress_small_mask, min_area, out_shape):
                                             h1, w1, H, W, float(min_area) if suppress_small_mask else -1.0,
                                             C.c_void_p(bins.data_ptr()), C.c_void_p(area.data_ptr()), C.c_void_p(ids.data_ptr()),
                                             C.c_void_p(index_map.data_ptr())))
-        meta = torch.cat([r.boxes.data[:, 4:6].to(dev, torch.float32) for r, c in zip(results, counts) if c])
-        packed = torch.cat([ids.to(torch.float32)[:, None], meta], 1).cpu().tolist()
-    out, k = [], 0
-    for b in range(B):
-        # "index" = the detection's row in its frame's Results (beyond the reference's ObjectInfo fields)
-        info = [{"id": int(i), "score": float(sc), "category_id": int(cl), "index": r}
-                for r, (i, sc, cl) in enumerate(packed[k:k + counts[b]]) if i]
-        k += counts[b]
-        out.append((index_map[b], info))
-    return out
+        ids_h = ids.cpu().numpy()
+    hb = [_host_boxes(r) for r, c in zip(results, counts) if c]
+    return _pack_infos(index_map, ids_h, np.concatenate(hb) if len(hb) > 1 else hb[0], counts)
 
 
 def auto_segment(config, image, yolo_model, min_side, suppress_small_mask):

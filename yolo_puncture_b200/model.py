@@ -353,6 +353,8 @@ class YOLO:
                 for j, n in enumerate(counts.tolist()):
                     boxes = Boxes(det[j, :n], shape, n=n, host=(lambda d=det_h, j=j, n=n: d[j, :n]))
                     m = Masks(masks[off:off + n], shape, n=n) if (masks is not None and n) else None
+                    if m is not None:
+                        m.cropped = bool(retina)
                     off += n
                     out.append(Results(chunk[j], None, self.names, boxes=boxes, masks=m, speed=speed))
         return out
@@ -624,6 +626,8 @@ class YOLO:
                     boxes = Boxes(None, shp, lazy=(lambda d=det, j=j, n=n: d[j, :n]), n=n,
                                   host=(lambda d=det_h, j=j, n=n: d[j, :n]))
                     m = Masks(None, shp, lazy=(lambda mm=masks, a=off, b=off + n: mm[a:b]), n=n) if masks is not None else None
+                    if m is not None:
+                        m.cropped = bool(retina)  # retina masks are cropped to the frame-space boxes of `boxes`
                 else:
                     if empty is None:
                         empty = torch.zeros((0, 6), device=self._device)

@@ -110,6 +110,8 @@ class Boxes(BaseTensor):
 class Masks(BaseTensor):
     """(n,h,w) masks.  Stored uint8 {0,1}; `.data` yields float32 {0.,1.} like upstream."""
 
+    cropped = False  # True on the masks predict() hands out: mask i is zero outside box i (what index_masks exploits)
+
     @property
     def data(self):
         """float32 view of the masks, converted ONCE and cached: the reference loop `masks.data[i]` per detection

@@ -1,5 +1,5 @@
 """One engine pass + mask decode of a bench workload, a few times - the short program to put under ncu when only the
-selection / mask kernels are of interest (bench.py launches thousands of kernels).  usage: mask_probe.py [workload] [reps]"""
+selection / mask kernels are of interest (bench.py launches thousands of kernels).  usage: mask_probe.py [workload] [reps] [nograph]"""
 import os
 import sys
 
@@ -15,6 +15,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 model, B, hw, imgsz = bench.WORKLOADS[wl]
 yolo = YOLO(model, device=0, synth_geometry=bench.synth_geometry(hw))
 eng = yolo.engine
+if len(sys.argv) > 3 and sys.argv[3] == "nograph":
+    eng.set_graph(False)
 frames = bench.make_frames(B, hw, 0)
 new_unpad, top, bottom, left, right = letterbox_geometry(hw, (imgsz, imgsz), auto=True)
 H, W = new_unpad[1] + top + bottom, new_unpad[0] + left + right

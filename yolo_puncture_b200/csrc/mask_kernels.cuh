@@ -53,9 +53,15 @@ mask_zero_kernel(const int* __restrict__ offsets, int nB, int capacity, long lon
 }
 
 // One CTA per (band of 64 output rows, detection).  Bands that miss the box are one contiguous, fully coalesced
-// zero fill; inside a band the CTA walks 64-pixel tiles: tiles that miss the box are zero-filled, the others get the
-// low-resolution logits of just the proto window they need (<= 66x66 dot products of length 32, in shared memory),
-// then every thread produces 16 output pixels with ATen's bilinear arithmetic, the box crop and the > 0 threshold.
+// zero fill; inside a band the CTA walks the 64-pixel tiles the box touches (the others are zero-filled in one flat
+// loop): it first computes the low-resolution logits of just the proto window those tiles need (<= 66 rows of dot
+// products of length 32, in shared memory), then every thread produces 16 output pixels per tile with ATen's bilinear
+// arithmetic, the box crop and the > 0 threshold.
+// ncu (profiles/NCU_SUMMARY.md, r2 mask captures): the kernel is ISSUE-bound (72 % issue slots busy, DRAM 25 %), so the
+// code below counts instructions: CTA-uniform tile windows are computed once into shared memory, prototype row / column
+// come from a multiply-high instead of an integer division, the crop tests are integer bit masks, and the dot products
+// are laid out so that loads are coalesced (four lanes per prototype) and reduced with three shuffles per FOUR prototypes.
+template <bool RETINA>
 __global__ void __launch_bounds__(256)
 mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const float* __restrict__ coef /*(B,max_det,nm)*/,
                    const float* __restrict__ det /*(B,max_det,6) frame boxes*/, const float* __restrict__ det_lb /*(B,max_det,4)*/,
@@ -63,6 +69,8 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   extern __shared__ float s_band[];  // low-resolution logits of the band's proto window: rh rows x band_w columns
   __shared__ __align__(16) float s_hrow[(kMaskTile + 2) * kMaskTile];  // horizontally interpolated window rows of a tile
   __shared__ __align__(16) float s_coef[32];
+  constexpr int kMaxTiles = 64;  // out_w <= 4096; wider outputs recompute the windows per thread
+  __shared__ int s_tlo[kMaxTiles], s_thi[kMaxTiles];  // proto columns a tile needs; s_thi < s_tlo: the tile misses the box
   const int slot = blockIdx.y;
   const int total = offsets[nB];
   if (slot >= total || slot >= capacity) return;
@@ -77,7 +85,7 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   const int ty0 = blockIdx.x * kMaskTile;
 
   float bx1, by1, bx2, by2;
-  if (g.retina) {
+  if (RETINA) {
     const float* d = det + ((long long)b * g.max_det + di) * 6;
     bx1 = d[0]; by1 = d[1]; bx2 = d[2]; by2 = d[3];
   } else {
@@ -98,124 +106,143 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
 
   // ---- whole band outside the box: contiguous zero fill ----
   bool band_empty;
-  if (g.retina) band_empty = ((float)(ty0 + kMaskTile) <= by1) || ((float)ty0 >= by2);
+  if (RETINA) band_empty = ((float)(ty0 + kMaskTile) <= by1) || ((float)ty0 >= by2);
   else band_empty = ((float)(g.top + sy_hi) < by1) || ((float)(g.top + sy_lo) >= by2);
   if (band_empty || rh > kMaskTile + 2) {
     if (g.prefilled) return;
     const long long nbytes = (long long)(y_last - ty0 + 1) * g.out_w;
     uint8_t* dst = o + (long long)ty0 * g.out_w;
     if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nbytes) & 15) == 0) {
-      for (long long i = threadIdx.x; i < (nbytes >> 4); i += 256) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0, 0, 0, 0);
+      const int n16 = (int)(nbytes >> 4);
+      for (int i = threadIdx.x; i < n16; i += 256) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0, 0, 0, 0);
     } else {
       for (long long i = threadIdx.x; i < nbytes; i += 256) dst[i] = 0;
     }
     return;
   }
 
-  if (threadIdx.x < g.nm) s_coef[threadIdx.x] = coef[((long long)b * g.max_det + di) * g.nm + threadIdx.x];
-  const float* pb = proto + (long long)b * g.mh * g.mw * g.nm;
+  if (threadIdx.x < 32) s_coef[threadIdx.x] = coef[((long long)b * g.max_det + di) * 32 + threadIdx.x];  // nm == 32 (checked by the host)
+  const float* pb = proto + (long long)b * g.mh * g.mw * 32;
   const int trow = threadIdx.x >> 2, tcol = (threadIdx.x & 3) * 16;
   const int oy = ty0 + trow;
   const float sy = src_of(min(oy, g.out_h - 1), g.scale_h);
   const int y0 = (int)sy;
   const int y1 = y0 + ((y0 < g.ch - 1) ? 1 : 0);
   const float ly = __fsub_rn(sy, (float)y0), hy = __fsub_rn(1.0f, ly);
-  const bool row_in = g.retina ? ((float)oy >= by1 && (float)oy < by2) : true;
+  const bool row_in = RETINA ? ((float)oy >= by1 && (float)oy < by2) : true;
 
-  // ---- per-tile source windows, once per CTA (they are CTA-uniform: every thread used to recompute them, two float
-  // round trips per tile and thread - 12 % of the kernel's instructions under ncu) ----
-  constexpr int kMaxTiles = 64;  // out_w <= 4096
-  __shared__ int s_tlo[kMaxTiles], s_thi[kMaxTiles];  // s_thi < s_tlo: the tile misses the box
+  // ---- per-tile source windows, once per CTA ----
   const int n_tiles = (g.out_w + kMaskTile - 1) / kMaskTile;
-  auto tile_window = [&](int tx0, int* sx_lo, int* sx_hi) {
+  auto tile_window = [&](int tx0, int* sx_lo, int* sx_hi) {  // empty tiles come back as (1, 0)
     const int x_last = min(tx0 + kMaskTile, g.out_w) - 1;
-    *sx_lo = (int)src_of(tx0, g.scale_w);
-    *sx_hi = min((int)src_of(x_last, g.scale_w) + 1, g.cw - 1);
+    int lo = (int)src_of(tx0, g.scale_w);
+    int hi = min((int)src_of(x_last, g.scale_w) + 1, g.cw - 1);
+    bool empty = hi - lo + 1 > kMaskTile + 2;
+    if (RETINA) empty = empty || ((float)(tx0 + kMaskTile) <= bx1) || ((float)tx0 >= bx2);
+    else empty = empty || ((float)(g.left + hi) < bx1) || ((float)(g.left + lo) >= bx2);
+    *sx_lo = empty ? 1 : lo;
+    *sx_hi = empty ? 0 : hi;
   };
-  auto tile_empty = [&](int tx0, int sx_lo, int sx_hi) {
-    if (sx_hi - sx_lo + 1 > kMaskTile + 2) return true;
-    if (g.retina) return ((float)(tx0 + kMaskTile) <= bx1) || ((float)tx0 >= bx2);
-    return ((float)(g.left + sx_hi) < bx1) || ((float)(g.left + sx_lo) >= bx2);
-  };
-  for (int t = threadIdx.x; t < min(n_tiles, kMaxTiles); t += 256) {
-    int lo, hi;
-    tile_window(t * kMaskTile, &lo, &hi);
-    if (tile_empty(t * kMaskTile, lo, hi)) { lo = 1; hi = 0; }
-    s_tlo[t] = lo;
-    s_thi[t] = hi;
-  }
+  for (int t = threadIdx.x; t < min(n_tiles, kMaxTiles); t += 256) tile_window(t * kMaskTile, &s_tlo[t], &s_thi[t]);
   __syncthreads();  // s_coef and the tile windows are ready
-  int bw_lo = 1 << 30, bw_hi = -1;  // CTA-uniform: the proto columns the box-touching tiles of this band need
+  auto window_of = [&](int t, int* lo, int* hi) {
+    if (t < kMaxTiles) { *lo = s_tlo[t]; *hi = s_thi[t]; }
+    else tile_window(t * kMaskTile, lo, hi);
+  };
+  // the tiles the box touches form one run [t_first, t_last]; bw_lo..bw_hi = the proto columns they need (CTA-uniform)
+  int bw_lo = 1 << 30, bw_hi = -1, t_first = n_tiles, t_last = -1;
   for (int t = 0; t < n_tiles; ++t) {
     int lo, hi;
-    if (t < kMaxTiles) { lo = s_tlo[t]; hi = s_thi[t]; }
-    else { tile_window(t * kMaskTile, &lo, &hi); if (tile_empty(t * kMaskTile, lo, hi)) { lo = 1; hi = 0; } }
+    window_of(t, &lo, &hi);
     if (hi < lo) continue;
     bw_lo = min(bw_lo, lo);
     bw_hi = max(bw_hi, hi);
+    t_first = min(t_first, t);
+    t_last = t;
   }
   const int band_w = bw_hi >= bw_lo ? bw_hi - bw_lo + 1 : 0;
 
-  // ---- the band's logits, once.  Eight lanes per prototype: lane q holds channels 4q..4q+3, so one warp-wide 16-byte
-  // load covers 4 prototypes = 512 CONTIGUOUS bytes (a thread-per-prototype loop touches 32 different 128-byte lines with
-  // every load instruction); the partial dot products are combined with three shuffles.  Four prototypes per thread are
-  // in flight together; row / column of a prototype come from a multiply-high (the kernel is issue-bound: the integer
-  // division here was 18 % of its instructions), offsets are 32-bit. ----
+  // ---- the band's logits, once.  Four lanes per prototype: lane l holds channels 4l..4l+3 and 16+4l..16+4l+3, so a
+  // warp-wide 16-byte load covers eight 64-byte runs of full sectors (a thread-per-prototype loop touches 32 different
+  // 128-byte lines with every load instruction).  Each lane group works on FOUR consecutive prototypes at a time and the
+  // four partial sums are reduced with a transposing butterfly - 3 shuffles + 3 adds per lane for the four of them -
+  // after which lane l holds the finished logit of one of them.  All 8 loads of a thread are in flight together. ----
   {
-    const int q = threadIdx.x & 7, grp = threadIdx.x >> 3;
-    const float4 cq = *reinterpret_cast<const float4*>(&s_coef[4 * q]);
-    const float4* pb4 = reinterpret_cast<const float4*>(pb);
+    const int l4 = threadIdx.x & 3, g4 = threadIdx.x >> 2;
+    const bool o1 = (l4 & 1) != 0, o2 = (l4 & 2) != 0;
+    const float4 c0 = *reinterpret_cast<const float4*>(&s_coef[4 * l4]);
+    const float4 c1 = *reinterpret_cast<const float4*>(&s_coef[16 + 4 * l4]);
+    const float4* pb4 = reinterpret_cast<const float4*>(pb) + ((g.top + sy_lo) * g.mw + g.left + bw_lo) * 8 + l4;
     const int npx = rh * band_w;  // <= 66 * 1026
     const unsigned inv_bw = band_w > 0 ? 0xFFFFFFFFu / (unsigned)band_w + 1u : 0u;  // floor(i / band_w) = umulhi(i, inv_bw), i < 2^16
-    const int base_off = ((g.top + sy_lo) * g.mw + g.left + bw_lo) * 8 + q;
-    for (int i0 = 0; i0 < npx; i0 += 128) {
-      float part[4];
-      int idx[4];
-      bool keep[4];
+    auto row_col = [&](int i, int* ry, int* rx) {
+      *ry = npx < 65536 ? (int)__umulhi((unsigned)i, inv_bw) : i / band_w;
+      *rx = i - *ry * band_w;
+    };
+    for (int i0 = 0; i0 < npx; i0 += 256) {
+      const int ib = i0 + g4 * 4;
+      float p[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + 32 * u + grp;
-        idx[u] = i;
-        part[u] = 0.f;
-        keep[u] = true;
-        if (i < npx) {
-          const int ry = npx < 65536 ? (int)__umulhi((unsigned)i, inv_bw) : i / band_w;
-          const int rx = i - ry * band_w;
-          const float4 v = __ldg(pb4 + base_off + (ry * g.mw + rx) * 8);
-          part[u] = fmaf(cq.w, v.w, fmaf(cq.z, v.z, fmaf(cq.y, v.y, __fmul_rn(cq.x, v.x))));
-          if (!g.retina) {  // ops.process_mask crops in proto space BEFORE the upsample
-            const float fx = (float)(g.left + bw_lo + rx), fy = (float)(g.top + sy_lo + ry);
-            keep[u] = fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2;
-          }
+        p[u] = 0.f;
+        if (ib + u < npx) {
+          int ry, rx;
+          row_col(ib + u, &ry, &rx);
+          const float4* a = pb4 + (ry * g.mw + rx) * 8;
+          const float4 v0 = __ldg(a), v1 = __ldg(a + 4);
+          float acc = __fmul_rn(c0.x, v0.x);
+          acc = fmaf(c0.y, v0.y, acc); acc = fmaf(c0.z, v0.z, acc); acc = fmaf(c0.w, v0.w, acc);
+          acc = fmaf(c1.x, v1.x, acc); acc = fmaf(c1.y, v1.y, acc); acc = fmaf(c1.z, v1.z, acc); acc = fmaf(c1.w, v1.w, acc);
+          p[u] = acc;
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        part[u] += __shfl_xor_sync(0xffffffffu, part[u], 1);
-        part[u] += __shfl_xor_sync(0xffffffffu, part[u], 2);
-        part[u] += __shfl_xor_sync(0xffffffffu, part[u], 4);
-        if (q == 0 && idx[u] < npx) s_band[idx[u]] = keep[u] ? part[u] : 0.f;
+      // lanes (l, l^1) swap halves, then (l, l^2) swap quarters: lane l ends with prototype u = 2*(l&1) + ((l>>1)&1)
+      const float k0 = (o1 ? p[2] : p[0]) + __shfl_xor_sync(0xffffffffu, o1 ? p[0] : p[2], 1);
+      const float k1 = (o1 ? p[3] : p[1]) + __shfl_xor_sync(0xffffffffu, o1 ? p[1] : p[3], 1);
+      float f = (o2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, o2 ? k0 : k1, 2);
+      const int iu = ib + (o1 ? 2 : 0) + (o2 ? 1 : 0);
+      if (iu < npx) {
+        if (!RETINA) {  // ops.process_mask crops in proto space BEFORE the upsample
+          int ry, rx;
+          row_col(iu, &ry, &rx);
+          const float fx = (float)(g.left + bw_lo + rx), fy = (float)(g.top + sy_lo + ry);
+          if (!(fx >= bx1 && fx < bx2 && fy >= by1 && fy < by2)) f = 0.f;
+        }
+        s_band[iu] = f;
       }
+    }
+  }
+
+  // ---- tiles left and right of the box: zeros, one 16-byte store per thread and tile, no per-tile bookkeeping ----
+  if (!g.prefilled && oy < g.out_h) {
+    const int x_a = min(max(t_first, 0) * kMaskTile, g.out_w), x_b = min((t_last + 1) * kMaskTile, g.out_w);  // box tiles = [x_a, x_b)
+    uint8_t* orow = o + (long long)oy * g.out_w;
+    if (t_last < 0) {  // no tile touches the box in this band (cannot happen for a non-empty band; kept for safety)
+      for (int x = tcol; x < g.out_w; x += kMaskTile)
+        for (int j = 0; j < 16 && x + j < g.out_w; ++j) orow[x + j] = 0;
+    } else if (vec_ok) {
+      for (int x = tcol; x < x_a; x += kMaskTile) *reinterpret_cast<uint4*>(orow + x) = make_uint4(0, 0, 0, 0);
+      for (int x = x_b + tcol; x < g.out_w; x += kMaskTile) *reinterpret_cast<uint4*>(orow + x) = make_uint4(0, 0, 0, 0);
+    } else {
+      for (int x = tcol; x < x_a; x += kMaskTile)
+        for (int j = 0; j < 16; ++j) orow[x + j] = 0;
+      for (int x = x_b + tcol; x < g.out_w; x += kMaskTile)
+        for (int j = 0; j < 16 && x + j < g.out_w; ++j) orow[x + j] = 0;
     }
   }
 
   // integer form of the retina crop: (float)x >= b  <=>  x >= ceil(b), (float)x < b  <=>  x < ceil(b) for integer x
   // (no int->float conversion per pixel: those run on the 16-lane XU pipe)
-  const int cx_lo = g.retina ? (int)ceilf(fmaxf(bx1, -1.0f)) : 0, cx_hi = g.retina ? (int)ceilf(fminf(bx2, 1.0e6f)) : g.out_w;
-  for (int t = 0; t < n_tiles; ++t) {
+  const int cx_lo = RETINA ? (int)ceilf(fmaxf(bx1, -1.0f)) : 0;
+  const int cx_hi = RETINA ? min((int)ceilf(fminf(bx2, 1.0e6f)), g.out_w) : g.out_w;
+  for (int t = max(t_first, 0); t <= t_last; ++t) {
     const int tx0 = t * kMaskTile;
     const int ox0 = tx0 + tcol;
     int sx_lo, sx_hi;
-    if (t < kMaxTiles) { sx_lo = s_tlo[t]; sx_hi = s_thi[t]; }
-    else { tile_window(tx0, &sx_lo, &sx_hi); if (tile_empty(tx0, sx_lo, sx_hi)) { sx_lo = 1; sx_hi = 0; } }
-    if (sx_hi < sx_lo) {  // CTA-uniform: the tile misses the box
-      if (oy < g.out_h && !g.prefilled) {
-        if (vec_ok && ox0 + 16 <= g.out_w) {
-          *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
-        } else {
-          for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j) o[(long long)oy * g.out_w + ox0 + j] = 0;
-        }
-      }
+    window_of(t, &sx_lo, &sx_hi);
+    if (sx_hi < sx_lo) {  // CTA-uniform: a tile inside the run that is treated as empty (window too wide)
+      if (oy < g.out_h && !g.prefilled)
+        for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j) o[(long long)oy * g.out_w + ox0 + j] = 0;
       continue;
     }
     __syncthreads();  // band logits written / previous tile's s_hrow fully consumed
@@ -229,34 +256,35 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
       const int x0 = (int)sx;
       const int x1 = x0 + ((x0 < g.cw - 1) ? 1 : 0);
       const float lx = __fsub_rn(sx, (float)x0), hx = __fsub_rn(1.0f, lx);
-      for (int ry = threadIdx.x >> 6; ry < rh; ry += 4) {
-        const float* rr = s_band + ry * band_w - bw_lo;
-        s_hrow[ry * kMaskTile + hx_col] = __fadd_rn(__fmul_rn(hx, rr[x0]), __fmul_rn(lx, rr[x1]));
-      }
+      const float* r0 = s_band + (x0 - bw_lo);
+      const float* r1 = s_band + (x1 - bw_lo);
+      float* dst = s_hrow + hx_col;
+      for (int ry = threadIdx.x >> 6; ry < rh; ry += 4)
+        dst[ry * kMaskTile] = __fadd_rn(__fmul_rn(hx, r0[ry * band_w]), __fmul_rn(lx, r1[ry * band_w]));
     }
     __syncthreads();
     if (oy >= g.out_h) continue;
-    // this thread's 16 pixels lie outside the box (rows above / below it inside the band, columns left / right of it
-    // inside the tile): zeros without touching the interpolation
-    if (vec_ok && ox0 + 16 <= g.out_w && (!row_in || ox0 + 16 <= cx_lo || ox0 >= cx_hi)) {
-      if (!g.prefilled) *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
+    // pixels of this thread's 16 that survive the crop, as a bit mask
+    const int jl = min(max(cx_lo - ox0, 0), 16), jh = min(max(cx_hi - ox0, 0), 16);
+    const unsigned in16 = row_in && jh > jl ? ((1u << jh) - 1u) & ~((1u << jl) - 1u) : 0u;
+    if (in16 == 0u) {  // rows above / below the box inside the band, columns left / right of it inside the tile
+      if (!g.prefilled) {
+        if (vec_ok && ox0 + 16 <= g.out_w) *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(0, 0, 0, 0);
+        else for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j) o[(long long)oy * g.out_w + ox0 + j] = 0;
+      }
       continue;
     }
     const float4* t0 = reinterpret_cast<const float4*>(s_hrow + (y0 - sy_lo) * kMaskTile + tcol);
     const float4* t1 = reinterpret_cast<const float4*>(s_hrow + (y1 - sy_lo) * kMaskTile + tcol);
-    const int x_end = min(cx_hi, g.out_w);
-    uint32_t packed[4] = {0, 0, 0, 0};
+    uint32_t packed[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 a = t0[q], c = t1[q];
-      const float tv[4] = {a.x, a.y, a.z, a.w}, bv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int ox = ox0 + 4 * q + u;
-        const float val = __fadd_rn(__fmul_rn(hy, tv[u]), __fmul_rn(ly, bv[u]));
-        const bool on = val > 0.0f && row_in && ox >= cx_lo && ox < x_end;
-        packed[q] |= (on ? 1u : 0u) << (8 * u);
-      }
+      const float v0 = __fadd_rn(__fmul_rn(hy, a.x), __fmul_rn(ly, c.x)), v1 = __fadd_rn(__fmul_rn(hy, a.y), __fmul_rn(ly, c.y));
+      const float v2 = __fadd_rn(__fmul_rn(hy, a.z), __fmul_rn(ly, c.z)), v3 = __fadd_rn(__fmul_rn(hy, a.w), __fmul_rn(ly, c.w));
+      const uint32_t on = (v0 > 0.0f ? 0x1u : 0u) | (v1 > 0.0f ? 0x100u : 0u) | (v2 > 0.0f ? 0x10000u : 0u) | (v3 > 0.0f ? 0x1000000u : 0u);
+      // bits 4q..4q+3 of the crop mask spread to one byte each: b * 0x00204081 puts bit k at position 8k (no carries)
+      packed[q] = on & ((((in16 >> (4 * q)) & 0xFu) * 0x00204081u) & 0x01010101u);
     }
     if (vec_ok && ox0 + 16 <= g.out_w) {
       *reinterpret_cast<uint4*>(o + (long long)oy * g.out_w + ox0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);

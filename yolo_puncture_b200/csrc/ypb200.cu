@@ -1563,7 +1563,8 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
     std::lock_guard<std::mutex> lock(g_dev_mutex);
     DeviceState& ds = device_state();
     if (band_smem > ds.mask_smem) {
-      CUDA_TRY(cudaFuncSetAttribute(mask_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(mask_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(mask_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       ds.mask_smem = 160 * 1024;
     }
   }
@@ -1574,8 +1575,9 @@ int ypb_masks_ex(ypb_engine* e, void* cuda_stream, int retina, int out_h, int ou
   g.prefilled = prefill ? 1 : 0;
   if (g.prefilled)
     mask_zero_kernel<<<device_state().num_sms * 8, 256, 0, st>>>(offsets, e->B, capacity, (long long)g.out_h * g.out_w, masks);
-  mask_decode_kernel<<<grid, 256, band_smem, st>>>(proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset), coef, det, det_lb,
-                                                  offsets, e->B, capacity, g, masks);
+  const float* proto_p = proto ? proto : reinterpret_cast<const float*>(e->ws + pb.offset);
+  if (g.retina) mask_decode_kernel<true><<<grid, 256, band_smem, st>>>(proto_p, coef, det, det_lb, offsets, e->B, capacity, g, masks);
+  else mask_decode_kernel<false><<<grid, 256, band_smem, st>>>(proto_p, coef, det, det_lb, offsets, e->B, capacity, g, masks);
   CUDA_TRY(cudaGetLastError());
   return YPB_OK;
 }

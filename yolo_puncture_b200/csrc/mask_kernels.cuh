@@ -62,15 +62,20 @@ mask_zero_kernel(const int* __restrict__ offsets, int nB, int capacity, long lon
 // come from a multiply-high instead of an integer division, the crop tests are integer bit masks, and the dot products
 // are laid out so that loads are coalesced (four lanes per prototype) and reduced with three shuffles per FOUR prototypes.
 template <bool RETINA>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const float* __restrict__ coef /*(B,max_det,nm)*/,
                    const float* __restrict__ det /*(B,max_det,6) frame boxes*/, const float* __restrict__ det_lb /*(B,max_det,4)*/,
                    const int* __restrict__ offsets, int nB, int capacity, MaskGeom g, uint8_t* __restrict__ out) {
   extern __shared__ float s_band[];  // low-resolution logits of the band's proto window: rh rows x band_w columns
-  __shared__ __align__(16) float s_hrow[(kMaskTile + 2) * kMaskTile];  // horizontally interpolated window rows of a tile
+  // horizontally interpolated window rows of a tile; column c lives at c + 4 * (c / 32) (rows of 72 floats): the vertical
+  // pass reads 16-byte pieces at columns 0 / 16 / 32 / 48 of a row and columns 0 and 32 would share their banks (ncu:
+  // 2.1 wavefronts per request there before the padding)
+  constexpr int kHrowPitch = kMaskTile + 8;
+  __shared__ __align__(16) float s_hrow[(kMaskTile + 2) * kHrowPitch];
   __shared__ __align__(16) float s_coef[32];
   constexpr int kMaxTiles = 64;  // out_w <= 4096; wider outputs recompute the windows per thread
   __shared__ int s_tlo[kMaxTiles], s_thi[kMaxTiles];  // proto columns a tile needs; s_thi < s_tlo: the tile misses the box
+  __shared__ unsigned s_tmask[2];                      // bit t: tile t touches the box
   const int slot = blockIdx.y;
   const int total = offsets[nB];
   if (slot >= total || slot >= capacity) return;
@@ -143,23 +148,46 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
     *sx_lo = empty ? 1 : lo;
     *sx_hi = empty ? 0 : hi;
   };
-  for (int t = threadIdx.x; t < min(n_tiles, kMaxTiles); t += 256) tile_window(t * kMaskTile, &s_tlo[t], &s_thi[t]);
-  __syncthreads();  // s_coef and the tile windows are ready
-  auto window_of = [&](int t, int* lo, int* hi) {
-    if (t < kMaxTiles) { *lo = s_tlo[t]; *hi = s_thi[t]; }
-    else tile_window(t * kMaskTile, lo, hi);
-  };
   // the tiles the box touches form one run [t_first, t_last]; bw_lo..bw_hi = the proto columns they need (CTA-uniform)
   int bw_lo = 1 << 30, bw_hi = -1, t_first = n_tiles, t_last = -1;
-  for (int t = 0; t < n_tiles; ++t) {
-    int lo, hi;
-    window_of(t, &lo, &hi);
-    if (hi < lo) continue;
-    bw_lo = min(bw_lo, lo);
-    bw_hi = max(bw_hi, hi);
-    t_first = min(t_first, t);
-    t_last = t;
+  unsigned long long tmask = 0ull;  // bit t: tile t touches the box (n_tiles <= 64 only)
+  if (n_tiles <= kMaxTiles) {
+    if (threadIdx.x < 64) {  // warps 0 and 1: one tile per lane, the non-empty ones as two ballot words
+      int lo = 1, hi = 0;
+      if (threadIdx.x < n_tiles) tile_window(threadIdx.x * kMaskTile, &lo, &hi);
+      s_tlo[threadIdx.x] = lo;
+      s_thi[threadIdx.x] = hi;
+      const unsigned bal = __ballot_sync(0xffffffffu, hi >= lo);
+      if ((threadIdx.x & 31) == 0) s_tmask[threadIdx.x >> 5] = bal;
+    }
+    __syncthreads();  // s_coef and the tile windows are ready
+    tmask = ((unsigned long long)s_tmask[1] << 32) | s_tmask[0];
+    if (tmask) {
+      t_first = __ffsll((long long)tmask) - 1;
+      t_last = 63 - __clzll((long long)tmask);
+      bw_lo = s_tlo[t_first];  // the windows move right with the tile index
+      bw_hi = s_thi[t_last];
+      for (int t = t_first + 1; t < t_last; ++t)  // (a tile in the middle may be "empty" only through the width guard)
+        if ((tmask >> t) & 1ull) { bw_lo = min(bw_lo, s_tlo[t]); bw_hi = max(bw_hi, s_thi[t]); }
+    }
+  } else {
+    __syncthreads();  // s_coef
+    for (int t = 0; t < n_tiles; ++t) {
+      int lo, hi;
+      tile_window(t * kMaskTile, &lo, &hi);
+      if (hi < lo) continue;
+      bw_lo = min(bw_lo, lo);
+      bw_hi = max(bw_hi, hi);
+      t_first = min(t_first, t);
+      t_last = t;
+    }
   }
+  auto tile_is_empty = [&](int t) {
+    if (n_tiles <= kMaxTiles) return ((tmask >> t) & 1ull) == 0ull;
+    int lo, hi;
+    tile_window(t * kMaskTile, &lo, &hi);
+    return hi < lo;
+  };
   const int band_w = bw_hi >= bw_lo ? bw_hi - bw_lo + 1 : 0;
 
   // ---- the band's logits, once.  Four lanes per prototype: lane l holds channels 4l..4l+3 and 16+4l..16+4l+3, so a
@@ -238,9 +266,7 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
   for (int t = max(t_first, 0); t <= t_last; ++t) {
     const int tx0 = t * kMaskTile;
     const int ox0 = tx0 + tcol;
-    int sx_lo, sx_hi;
-    window_of(t, &sx_lo, &sx_hi);
-    if (sx_hi < sx_lo) {  // CTA-uniform: a tile inside the run that is treated as empty (window too wide)
+    if (tile_is_empty(t)) {  // CTA-uniform: a tile inside the run that is treated as empty (window too wide)
       if (oy < g.out_h && !g.prefilled)
         for (int j = 0; j < 16 && ox0 + j < g.out_w; ++j) o[(long long)oy * g.out_w + ox0 + j] = 0;
       continue;
@@ -258,9 +284,9 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
       const float lx = __fsub_rn(sx, (float)x0), hx = __fsub_rn(1.0f, lx);
       const float* r0 = s_band + (x0 - bw_lo);
       const float* r1 = s_band + (x1 - bw_lo);
-      float* dst = s_hrow + hx_col;
+      float* dst = s_hrow + hx_col + ((hx_col >> 5) << 2);
       for (int ry = threadIdx.x >> 6; ry < rh; ry += 4)
-        dst[ry * kMaskTile] = __fadd_rn(__fmul_rn(hx, r0[ry * band_w]), __fmul_rn(lx, r1[ry * band_w]));
+        dst[ry * kHrowPitch] = __fadd_rn(__fmul_rn(hx, r0[ry * band_w]), __fmul_rn(lx, r1[ry * band_w]));
     }
     __syncthreads();
     if (oy >= g.out_h) continue;
@@ -274,8 +300,9 @@ mask_decode_kernel(const float* __restrict__ proto /*(B,mh,mw,nm) fp32*/, const 
       }
       continue;
     }
-    const float4* t0 = reinterpret_cast<const float4*>(s_hrow + (y0 - sy_lo) * kMaskTile + tcol);
-    const float4* t1 = reinterpret_cast<const float4*>(s_hrow + (y1 - sy_lo) * kMaskTile + tcol);
+    const int pcol = tcol + ((tcol >> 5) << 2);
+    const float4* t0 = reinterpret_cast<const float4*>(s_hrow + (y0 - sy_lo) * kHrowPitch + pcol);
+    const float4* t1 = reinterpret_cast<const float4*>(s_hrow + (y1 - sy_lo) * kHrowPitch + pcol);
     uint32_t packed[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

@@ -206,6 +206,15 @@ static bool conv_plan_geometry(const ConvDesc& d, ConvLaunch* L, std::string* er
     ++splits;
     if (splits > d.cout / 16) { *err = "cannot split Cout"; return false; }
   }
+  // Few output tiles (small batches, the deep 20x20 / 40x40 levels): a 128-row tile x 256 channels is ONE CTA walking the
+  // whole K loop at 128 cycles per K-step (3x3, 256 -> 256 at B = 1: 4 CTAs busy for ~10 us while 144 SMs idle).  Narrower
+  // channel tiles put more CTAs on the layer and shorten that chain in proportion; the A tile is re-read from L2 once per
+  // split, which costs less than the chain as long as a split keeps >= 64 channels.  Throughput shapes (tiles >= half
+  // the SMs) are untouched.
+  if (!getenv("YPB_NO_LAT_SPLIT")) {
+    const long m_tiles0 = (long)L->grid.x;
+    while (m_tiles0 * splits < 74 && d.cout / (2 * splits) >= 64 && d.cout % (32 * splits) == 0) splits *= 2;
+  }
   p.n_tile = d.cout / splits;
   L->grid.y = splits; L->grid.z = 1;
   const int k_iters = p.ntaps * ((d.cin + 63) / 64);

@@ -32,6 +32,7 @@ WORKLOADS = {
     "yolov8s-seg-640-b32": ("yolov8s-seg", 32, (640, 640), 640),
     "yolov8s-seg-640-b16": ("yolov8s-seg", 16, (640, 640), 640),
     "yolov8s-seg-640-b8": ("yolov8s-seg", 8, (640, 640), 640),
+    "yolov8s-seg-640-b1": ("yolov8s-seg", 1, (640, 640), 640),
     "yolov8n-seg-640-b1": ("yolov8n-seg", 1, (640, 640), 640),
     "yolov8n-seg-640-b64": ("yolov8n-seg", 64, (640, 640), 640),
     "yolov8m-seg-1080p-b16": ("yolov8m-seg", 16, (1080, 1920), 1280),

@@ -360,16 +360,17 @@ def run_ours(args, wl):
     handoff = None
     if is_seg:  # index-mask hand-off to the tracker (reference yolo_with_deva.py:54-88) on one step's Results
         res_h = yolo.predict(frames_pinned, conf=CONF, iou=IOU, retina_masks=True, imgsz=imgsz, batch=B)
-        index_masks(res_h)
+        for _ in range(3):  # the first calls pay for the allocator's first (B, H, W) int64 block
+            index_masks(res_h, suppress_small_mask=True, min_area=100)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(5):
+        for _ in range(10):
             out_h = index_masks(res_h, suppress_small_mask=True, min_area=100)
         torch.cuda.synchronize()
-        handoff = {"ms_per_step": (time.perf_counter() - t0) / 5 * 1e3, "frames": B,
+        handoff = {"ms_per_step": (time.perf_counter() - t0) / 10 * 1e3, "frames": B,
                    "kept_objects": sum(len(i) for _, i in out_h), "inside_timed_e2e": bool(do_handoff),
                    "peer_push_to_rank0_mailbox": bool(do_handoff and world > 1),
-                   "note": "index_masks(): int64 (H0,W0) id map + (id, score, class) list per frame, 3 launches per batch"}
+                   "note": "index_masks(): int64 (H0,W0) id map + (id, score, class) list per frame, 3 launches per batch, area sum and paint restricted to the boxes"}
     e2e = {"value": v_page, "unit": "frames/s",
            "h2d_bytes_per_step": B * hw[0] * hw[1] * 3 + B * 5 * 4,  # raw frames (LetterBox runs on the device) + xform rows
            "d2h_bytes_per_step": d2h_bytes,  # per rank: counts + the (n,6) boxes of every frame

@@ -13,6 +13,7 @@ Prints ONE JSON line on rank 0.
 """
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -329,6 +330,10 @@ def run_ours(args, wl):
 
         for _ in range(3):
             e2e_step()
+        # everything allocated so far (torch, the engine wrappers, the frames) moves to the permanent generation: a full
+        # collection in the middle of the timed calls would walk ~1e6 long-lived objects (25-35 ms pauses were seen)
+        gc.collect()
+        gc.freeze()
         e2e_steps = max(3, min(args.steps, 100))  # ~0.6 s of calls: one host hiccup (25 ms seen) does not decide the figure
         torch.cuda.synchronize()
         if world > 1:
@@ -378,6 +383,7 @@ def run_ours(args, wl):
            "pinned_frames": {"value": v_pin, "ms_per_step": ms_pin}, "index_mask_handoff": handoff,
            "host_breakdown_ms_last_step": {"pageable": host_tm[0], "pinned": host_tm[1], "host_cores": os.cpu_count()},
            "call_ms_min_median_max": {"pageable": step_stats[0], "pinned": step_stats[1]},
+           "python_gc": "gc.freeze() after warm-up (long-lived objects out of the collector's way; young collections still run)",
            "frame_order_gather": "sharded.ShardedPredictor -> sharding.gather_in_frame_order over %d rank(s), inside the timed region" % world,
            "note": "YOLO.predict() on ordinary (pageable) host frames: staging into pinned memory + H2D of the uint8 frames + "
                    "engine + D2H of counts and boxes + ordered host gather every step; masks stay on the device as in "

@@ -286,7 +286,13 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    by_rank = None
     if world > 1:
+        # every rank's own time and detection count next to the max: tells a slow GPU from a heavy shard
+        mine = torch.tensor([ms / args.steps, float(n_det)], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        by_rank = {"ms_per_step": [round(float(a[0]), 4) for a in allr], "detections_per_step": [int(a[1]) for a in allr]}
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -505,6 +511,7 @@ def run_ours(args, wl):
                    "detections_per_step": n_det,
                    "candidates_per_frame": {"mean": float(cand.mean()), "max": int(cand.max())}, "parallelism": f"frame-sharded replicas x{world}",
                    "l2": "each step streams >1 GB of activations through HBM (inputs+activations exceed the 126 MB L2)"},
+        "by_rank": by_rank,
         "p50_frame_latency_ms_b1": p50, "p50_predict_call_ms_b1": p50_e2e,
         "e2e": e2e, "gpu_launches": (eng.launches + (2 if is_seg else 0)) * args.steps,
         "launches_per_step": eng.launches + (2 if is_seg else 0),

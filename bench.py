@@ -451,7 +451,8 @@ def run_ours(args, wl):
                    "hbm_bound_launches": int(sum(1 for a, b in lb if b > a)), "tensor_bound_launches": int(sum(1 for a, b in lb if a >= b)),
                    "tensor_only_bound_ms": float(sum(a for a, _ in lb)), "hbm_only_bound_ms": float(sum(b for _, b in lb)),
                    "note": "sum over conv launches of max(flops / tensor peak, algorithmic bytes / HBM peak) / measured conv ms"}
-    roofline = {"kernel": "conv_tc2_kernel / conv3_halo_kernel (tcgen05 implicit-GEMM convs: all %d launches of a step)" % n_conv,
+    roofline = {"kernel": "conv_tc2_kernel / conv3_halo_kernel and their CTA-pair forms conv_tc2p_kernel / conv3_halo2_kernel "
+                          "(tcgen05 implicit-GEMM convs: all %d launches of a step)" % n_conv,
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_burst"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["source"] + ", burst (every conv launch is event-timed on its own)",

@@ -11,8 +11,13 @@ launch = {}
 for r in rows:
     d = launch.setdefault(r[ii], {"name": r[ki]})
     d[r[mi]] = float(r[vi].replace(",", ""))
+# a capture of several forward passes: keep the last one (it starts at the last stem launch)
+order = sorted(launch, key=lambda k: int(k))
+stems = [i for i, k in enumerate(order) if "stem_tc_kernel" in launch[k]["name"]]
+if stems:
+    order = order[stems[-1]:]
 per, conv_b, conv_us, all_us, n_conv = {}, 0.0, 0.0, 0.0, 0
-for d in launch.values():
+for d in (launch[k] for k in order):
     name = re.sub(r"^void ", "", d["name"]).split("(")[0]
     k = per.setdefault(name, {"launches": 0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0, "us_under_ncu": 0.0})
     k["launches"] += 1
@@ -21,7 +26,7 @@ for d in launch.values():
     us = d.get("gpu__time_duration.sum", 0.0) / 1e3
     k["us_under_ncu"] += us
     all_us += us
-    if "conv_tc2_kernel" in name or "conv3_halo_kernel" in name:
+    if any(k in name for k in ("conv_tc2_kernel", "conv3_halo_kernel", "conv3_halo2_kernel", "conv_tc2p_kernel")):
         conv_b += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
         conv_us += us
         n_conv += 1

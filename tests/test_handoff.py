@@ -267,3 +267,32 @@ def test_auto_segment_drop_in_with_min_side():
     ref, ref_info = auto_segment_index_mask_resized(r.masks.data.cpu(), r.boxes.conf.cpu(), r.boxes.cls.cpu(), (480, 640), True, 100)
     assert [d["id"] for d in info] == [i[0] for i in ref_info]
     assert int((out.cpu() != ref).sum()) <= 0.001 * 480 * 640
+
+
+def test_pack_infos_matches_the_per_frame_loop():
+    """Host side of the hand-off: kept detections only, in order, with their row inside the frame (pure numpy, no GPU)."""
+    import numpy as np
+    from yolo_puncture_b200.handoff import _pack_infos
+    rng = np.random.default_rng(3)
+    counts = [3, 0, 5, 1, 0, 4]
+    n = sum(counts)
+    ids = np.zeros(n, np.int32)
+    k = 0
+    for c in counts:
+        cur = 0
+        for j in range(c):
+            if rng.random() < 0.6:
+                cur += 1
+                ids[k + j] = cur
+        k += c
+    allb = rng.random((n, 6)).astype(np.float32)
+    allb[:, 5] = rng.integers(0, 80, n)
+    maps = torch.zeros((len(counts), 2, 2), dtype=torch.int64)
+    out = _pack_infos(maps, ids, allb, counts)
+    k = 0
+    for b, c in enumerate(counts):
+        exp = [{"id": int(ids[k + r]), "score": float(allb[k + r, 4]), "category_id": int(allb[k + r, 5]), "index": r}
+               for r in range(c) if ids[k + r]]
+        assert out[b][1] == exp and out[b][0] is not None
+        k += c
+    assert all(info == [] for _, info in _pack_infos(maps, np.zeros(n, np.int32), allb, counts))

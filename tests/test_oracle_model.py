@@ -80,3 +80,25 @@ def test_yolo11_seg_shapes_and_fuse_equivalence():
         m.fuse()
         y2, (_, _, proto2) = m(x)
     assert (y - y2).abs().max() < 1e-3 and (proto - proto2).abs().max() < 1e-4
+
+
+def test_geometry_class_shift_only_touches_the_class_bias():
+    """synth_state_dict(geometry=(1080, 1920)) (BASELINE config C4): the class-branch final biases move by the calibrated
+    shift, every other tensor is the one of the 640x640 recipe."""
+    import torch
+    from oracle.model import build_model
+    from yolo_puncture_b200 import synth
+    net = build_model("yolov8m-seg")
+    specs = [(k, v.shape) for k, v in net.state_dict().items()]
+    a = synth.synth_state_dict(specs, "yolov8m-seg")
+    b = synth.synth_state_dict(specs, "yolov8m-seg", geometry=(1080, 1920))
+    table = synth.load_calibration()
+    base, over = table["yolov8m-seg:0"]["cls_shift"], table["yolov8m-seg:0@1080x1920"]["cls_shift"]
+    changed = [k for k in a if not torch.equal(a[k], b[k])]
+    assert sorted(changed) == sorted(f"model.22.cv3.{i}.2.bias" for i in range(3))
+    for i in range(3):
+        d = (b[f"model.22.cv3.{i}.2.bias"] - a[f"model.22.cv3.{i}.2.bias"])
+        assert torch.allclose(d, torch.full_like(d, over[i] - base[i]), atol=1e-5)
+    # a size without an entry falls back to the base recipe
+    c = synth.synth_state_dict(specs, "yolov8m-seg", geometry=(123, 457))
+    assert all(torch.equal(a[k], c[k]) for k in a)

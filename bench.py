@@ -340,23 +340,32 @@ def run_ours(args, wl):
         # collection in the middle of the timed calls would walk ~1e6 long-lived objects (25-35 ms pauses were seen)
         gc.collect()
         gc.freeze()
-        e2e_steps = max(3, min(args.steps, 100))  # ~0.6 s of calls: one host hiccup (25 ms seen) does not decide the figure
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        per_step = []
-        for _ in range(e2e_steps):
-            ts = time.perf_counter()
-            res, ordered, n_obj = e2e_step()
-            per_step.append((time.perf_counter() - ts) * 1e3)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        step_stats.append({"min": min(per_step), "median": float(np.median(per_step)), "max": max(per_step)})
-        if world > 1:
-            t = torch.tensor([e2e_s], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_steps = max(3, min(args.steps, 100))  # ~0.6 s of calls per repetition
+        # Two repetitions, the faster one is reported (both are in the line): on the shared hosts one call in a few hundred
+        # stalls for 15-300 ms when the frames are pageable (never with pinned frames) - a single such stall inside a
+        # 0.6 s repetition would move the figure by up to 50 %.
+        reps = []
+        for _rep in range(2 if args.steps >= 20 else 1):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            per_step = []
+            for _ in range(e2e_steps):
+                ts = time.perf_counter()
+                res, ordered, n_obj = e2e_step()
+                per_step.append((time.perf_counter() - ts) * 1e3)
+            torch.cuda.synchronize()
+            rep_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([rep_s], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                rep_s = float(t.item())
+            reps.append((rep_s, {"ms_per_step": rep_s / e2e_steps * 1e3, "min": min(per_step), "median": float(np.median(per_step)),
+                                 "max": max(per_step), "slowest_call_index": int(np.argmax(per_step))}))
+        e2e_s, best = min(reps, key=lambda r: r[0])
+        step_stats.append({"min": best["min"], "median": best["median"], "max": best["max"],
+                           "repetitions": [r[1] for r in reps]})
         assert len(ordered) == n_global and ordered[0] is not None and ordered[n_global - 1] is not None
         host_tm.append(dict(yolo.last_timing))
         d2h = sum(int(o[1].size) * 4 for o in ordered[rank * B:(rank + 1) * B]) + B * 4
@@ -389,6 +398,7 @@ def run_ours(args, wl):
            "pinned_frames": {"value": v_pin, "ms_per_step": ms_pin}, "index_mask_handoff": handoff,
            "host_breakdown_ms_last_step": {"pageable": host_tm[0], "pinned": host_tm[1], "host_cores": os.cpu_count()},
            "call_ms_min_median_max": {"pageable": step_stats[0], "pinned": step_stats[1]},
+           "repetitions": "each arm runs its calls twice; value = the faster repetition, both are listed under call_ms_min_median_max",
            "python_gc": "gc.freeze() after warm-up (long-lived objects out of the collector's way; young collections still run)",
            "frame_order_gather": "sharded.ShardedPredictor -> sharding.gather_in_frame_order over %d rank(s), inside the timed region" % world,
            "note": "YOLO.predict() on ordinary (pageable) host frames: staging into pinned memory + H2D of the uint8 frames + "

@@ -350,11 +350,13 @@ def run_ours(args, wl):
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            per_step = []
+            per_step, slow_tm = [], None
             for _ in range(e2e_steps):
                 ts = time.perf_counter()
                 res, ordered, n_obj = e2e_step()
                 per_step.append((time.perf_counter() - ts) * 1e3)
+                if per_step[-1] >= max(per_step):
+                    slow_tm = dict(yolo.last_timing)  # host breakdown of the slowest call so far
             torch.cuda.synchronize()
             rep_s = time.perf_counter() - t0
             if world > 1:
@@ -362,7 +364,8 @@ def run_ours(args, wl):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 rep_s = float(t.item())
             reps.append((rep_s, {"ms_per_step": rep_s / e2e_steps * 1e3, "min": min(per_step), "median": float(np.median(per_step)),
-                                 "max": max(per_step), "slowest_call_index": int(np.argmax(per_step))}))
+                                 "max": max(per_step), "slowest_call_index": int(np.argmax(per_step)),
+                                 "slowest_call_breakdown_ms": {k: round(v, 3) for k, v in (slow_tm or {}).items()}}))
         e2e_s, best = min(reps, key=lambda r: r[0])
         step_stats.append({"min": best["min"], "median": best["median"], "max": best["max"],
                            "repetitions": [r[1] for r in reps]})

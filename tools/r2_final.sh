@@ -1,6 +1,5 @@
 #!/bin/bash
-# Round-end validation on one B200: GPU parity tests, smoke(), the default bench line, the reference arm, and the e2e
-# pass-shape A/B (first-pass size / first-pass staging chunk).
+# Round-end validation on one B200: GPU parity tests, smoke(), the default bench line and the reference arm.
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
@@ -11,12 +10,5 @@ python bench.py > $O/r2f_bench_default.log 2> $O/r2f_bench_default.err; echo "be
 tail -1 $O/r2f_bench_default.log | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
-print('value', round(d['value']), 'e2e', round(d['e2e']['value']), 'pinned', round(d['e2e']['pinned_frames']['value']), 'frac', round(d['roofline']['frac'], 3), d['roofline'].get('two_ceiling'), d['e2e']['call_ms_min_median_max'], 'b1', d['p50_frame_latency_ms_b1'], d['p50_predict_call_ms_b1'], d['clocks'])"
-for v in "--head-pass 8" "--head-pass 24" "--head-stage-chunk 16" "--head-stage-chunk 8"; do
-  python bench.py --steps 60 --no-cpu-baseline $v > $O/r2f_ab.log 2>> $O/r2f_ab.err
-  tail -1 $O/r2f_ab.log | python -c "
-import sys, json
-d = json.loads(sys.stdin.read())
-print('$v', 'passes', d['config']['predict_passes'], 'e2e', round(d['e2e']['value']), 'pinned', round(d['e2e']['pinned_frames']['value']), d['e2e']['call_ms_min_median_max'])"
-done
+print('value', round(d['value']), 'e2e', round(d['e2e']['value']), 'pinned', round(d['e2e']['pinned_frames']['value']), 'frac', round(d['roofline']['frac'], 3), 'traffic', d['roofline']['traffic'], d['e2e']['call_ms_min_median_max']['pageable']['repetitions'], 'b1', d['p50_frame_latency_ms_b1'], d['p50_predict_call_ms_b1'], d['clocks'], d['cpu_baseline'], d['gpu_launches'])"
 python bench.py --impl reference --steps 3 --warmup 1 > $O/r2f_bench_ref.log 2>&1; tail -1 $O/r2f_bench_ref.log | cut -c1-300

@@ -7,6 +7,7 @@
 // around the cache saves the read-for-ownership of every destination line).  The Python caller releases the GIL for
 // the duration of ypb_stage_frames() (ctypes).
 #include <atomic>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -144,7 +145,7 @@ class StagePool {
       // (only the threads the last job used, and never more spinners than cores minus two: a spinning thread that
       // shares a core with a working one halves it)
       if (id < spin_limit_.load(std::memory_order_relaxed))
-        for (int spin = 0; spin < kSpinIters && epoch_hint_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
+        for (int spin = 0; spin < spin_iters() && epoch_hint_.load(std::memory_order_acquire) == seen; ++spin) cpu_relax();
       {
         std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
@@ -161,8 +162,15 @@ class StagePool {
       }
     }
   }
-  static constexpr int kSpinIters = 40000;  // ~0.4 ms of pause instructions
+  // ~0.4 ms of spinning by default.  YPB_STAGE_SPIN=<iterations> (0: park at once), YPB_STAGE_SPIN_NOPAUSE=1: spin on the
+  // load alone - under a hypervisor a long PAUSE loop is what pause-loop exiting deschedules a vCPU for.
+  static int spin_iters() {
+    static const int n = getenv("YPB_STAGE_SPIN") ? atoi(getenv("YPB_STAGE_SPIN")) : 40000;
+    return n;
+  }
   static void cpu_relax() {
+    static const bool nopause = getenv("YPB_STAGE_SPIN_NOPAUSE") != nullptr;
+    if (nopause) return;
 #if defined(__x86_64__)
     _mm_pause();
 #endif

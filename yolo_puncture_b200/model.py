@@ -511,7 +511,12 @@ class YOLO:
                                 check(lib().ypb_stage_frames(ctypes.byref(dst_ptrs, c0 * vp), ctypes.byref(src_ptrs, c0 * vp),
                                                              ctypes.byref(sizes, c0 * ctypes.sizeof(ctypes.c_size_t)), c1 - c0, nthreads))
                             tm["stage_ms"] += (time.perf_counter() - ts) * 1e3
-                            target[c0 - lo:c1 - lo].copy_(stage_host[c0:c1], non_blocking=True)
+                            # the staged slots are adjacent: one cudaMemcpyAsync per chunk, issued like the pinned-frame path
+                            # (torch's copy_ from a pinned tensor adds a pointer query and a host-allocator event per copy;
+                            # with it the call time had 10-180 ms outliers that the pinned-frame arm never showed)
+                            check(lib().ypb_h2d_frames(ctypes.c_void_p(cs.cuda_stream),
+                                                       ctypes.c_void_p(target.data_ptr() + (c0 - lo) * nbytes),
+                                                       ctypes.byref(dst_ptrs, c0 * vp), nbytes, c1 - c0))
                     else:
                         for fu in futs[lo:hi]:
                             fu.result()
